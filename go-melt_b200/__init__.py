@@ -1,0 +1,11 @@
+"""gomelt_b200 — B200 (sm_100a) implementation of GO-MELT's multilevel explicit FE thermal
+time-step behind the reference's computeFunctions-level entry points.
+
+The directory is ``go-melt_b200/`` (not an importable identifier); ``import gomelt_b200`` works
+through the alias module at the repo root, or use ``importlib.import_module("go-melt_b200")``.
+Sub-modules: ``_lib`` (ctypes binding of the C ABI), ``ops`` (launchers), ``build`` (nvcc).
+"""
+from . import build, _lib, ops  # noqa: F401
+from ._lib import GomeltError, load  # noqa: F401
+
+__all__ = ["build", "ops", "load", "GomeltError"]

@@ -1,0 +1,160 @@
+"""ctypes binding of libgomelt_sm100.so (the C ABI declared in include/gomelt_abi.h).
+
+There is no CPU fallback: importing works without a GPU (so that host-side logic and symbol
+checks run anywhere), but every compute entry point raises if the library is missing or CUDA
+is not available.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+c_float_p = C.POINTER(C.c_float)
+
+
+class Grid(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32),
+                ("hx", C.c_float), ("hy", C.c_float), ("hz", C.c_float)]
+
+
+class Props(C.Structure):
+    _fields_ = [(n, C.c_float) for n in (
+        "k_powder", "k_bulk_a0", "k_bulk_a1", "k_fluid",
+        "cp_solid_a0", "cp_solid_a1", "cp_mushy", "cp_fluid", "rho",
+        "T_amb", "T_solidus", "T_liquidus", "T_boiling",
+        "h_conv", "sigma_sb", "vareps", "evc", "Lev",
+        "CM_coeff", "CT_coeff", "CP_coeff",
+        "laser_radius", "laser_depth", "laser_eta")]
+
+
+class StepArgs(C.Structure):
+    _fields_ = [
+        ("grid", Grid),
+        ("T0", C.c_void_p), ("S1", C.c_void_p), ("rhs", C.c_void_p),
+        ("src_x", C.c_void_p), ("src_y", C.c_void_p), ("src_z", C.c_void_p),
+        ("src_coef", C.c_float),
+        ("topflux", C.c_void_p),
+        ("dt", C.c_float),
+        ("nz_active", C.c_int32),
+        ("n_substrate", C.c_int64),
+        ("flags", C.c_int32),
+        ("bc5", C.c_float * 5),
+        ("T_out", C.c_void_p), ("S1_out", C.c_void_p), ("S2_out", C.c_void_p),
+        ("S2_prev", C.c_void_p), ("accum", C.c_void_p), ("max_accum", C.c_void_p),
+        ("z_chunk", C.c_int32),
+    ]
+
+
+STEP_CLAMP, STEP_WRITE_S1, STEP_WRITE_S2 = 0x01, 0x02, 0x04
+STEP_BC_CONST, STEP_SKIP_FACES, STEP_ACCUM = 0x08, 0x10, 0x20
+
+# name -> (restype, argtypes); kept in one table so tests can check every header symbol loads
+SIGNATURES = {
+    "gomelt_abi_version": (C.c_int, []),
+    "gomelt_last_error": (C.c_char_p, []),
+    "gomelt_level_step_f32": (C.c_int, [C.POINTER(Props), C.POINTER(StepArgs), C.c_void_p]),
+    "gomelt_state_props_f32": (C.c_int, [C.POINTER(Props), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gomelt_surface_flux_f32": (C.c_int, [C.POINTER(Props), C.POINTER(Grid), C.c_void_p, C.c_int32,
+                                          C.c_void_p, C.c_int32, C.c_void_p]),
+    "gomelt_source_tables_f32": (C.c_int, [C.POINTER(Props), C.POINTER(Grid), C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.POINTER(C.c_float * 3), C.c_float, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, c_float_p, C.c_void_p]),
+    "gomelt_diag_fp32_rate": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                        C.POINTER(C.c_double), C.c_void_p]),
+}
+
+_LIB = None
+
+
+class GomeltError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _build.lib_path()
+
+
+def load(build_if_missing=False):
+    """dlopen the library and attach signatures.  Raises GomeltError when it is not there."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        if build_if_missing:
+            _build.build_library()
+        else:
+            raise GomeltError(
+                f"{path} is missing: run `python go-melt_b200/build.py` (or __graft_entry__.build()); "
+                "there is no CPU fallback for the GO-MELT step")
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().gomelt_last_error()
+        raise GomeltError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")
+
+
+def require_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise GomeltError("CUDA device required: the GO-MELT step has no CPU path in this package")
+    return torch
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def make_props(P):
+    """Properties dict (SetupProperties names, cF:267-345) -> gomelt_props_t, float32 like the
+    scalars the reference's jitted functions trace."""
+    p = Props()
+    p.k_powder = P["k_powder"]
+    p.k_bulk_a0 = P["k_bulk_coeff_a0"]
+    p.k_bulk_a1 = P["k_bulk_coeff_a1"]
+    p.k_fluid = P["k_fluid_coeff_a0"]
+    p.cp_solid_a0 = P["cp_solid_coeff_a0"]
+    p.cp_solid_a1 = P["cp_solid_coeff_a1"]
+    p.cp_mushy = P["cp_mushy"]
+    p.cp_fluid = P["cp_fluid"]
+    p.rho = P["rho"]
+    p.T_amb = P["T_amb"]
+    p.T_solidus = P["T_solidus"]
+    p.T_liquidus = P["T_liquidus"]
+    p.T_boiling = P["T_boiling"]
+    p.h_conv = P["h_conv"]
+    p.sigma_sb = P["sigma_sb"]
+    p.vareps = P["vareps"]
+    p.evc = P["evc"]
+    p.Lev = P["Lev"]
+    p.CM_coeff = P["CM_coeff"]
+    p.CT_coeff = P["CT_coeff"]
+    p.CP_coeff = P["CP_coeff"]
+    p.laser_radius = P["laser_radius"]
+    p.laser_depth = P["laser_depth"]
+    p.laser_eta = P["laser_eta"]
+    return p
+
+
+def make_grid(nodes, h):
+    g = Grid()
+    g.nx, g.ny, g.nz = int(nodes[0]), int(nodes[1]), int(nodes[2])
+    g.hx, g.hy, g.hz = float(h[0]), float(h[1]), float(h[2])
+    return g

@@ -1,0 +1,113 @@
+"""Python launchers over the C ABI: torch CUDA tensors own the device memory, the kernels run on
+torch's current stream.  One function per ``extern "C"`` entry point of include/gomelt_abi.h.
+"""
+import ctypes as C
+
+from . import _lib
+from ._lib import (STEP_ACCUM, STEP_BC_CONST, STEP_CLAMP, STEP_SKIP_FACES,  # noqa: F401
+                   STEP_WRITE_S1, STEP_WRITE_S2)
+
+LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _chk_f32(t, n, name):
+    torch = _lib.require_cuda()
+    if t is None:
+        return
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() >= n):
+        raise _lib.GomeltError(f"{name}: need a contiguous float32 CUDA tensor with >= {n} elements")
+
+
+def level_step(props, grid, T0, S1, T_out, dt, *, rhs=None, src=None, topflux=None, nz_active=None,
+               n_substrate=0, flags=0, bc5=None, S1_out=None, S2_out=None, S2_prev=None, accum=None,
+               max_accum=None, z_chunk=0):
+    """K1 (gomelt_level_step_f32): one explicit sweep of one level.  ``src`` = (tx, ty, tz, coef)."""
+    lib = _lib.load()
+    nn = grid.nx * grid.ny * grid.nz
+    for t, name in ((T0, "T0"), (S1, "S1"), (T_out, "T_out"), (rhs, "rhs"), (S1_out, "S1_out"),
+                    (accum, "accum"), (max_accum, "max_accum")):
+        _chk_f32(t, nn, name)
+    a = _lib.StepArgs()
+    a.grid = grid
+    a.T0, a.S1, a.rhs = T0.data_ptr(), S1.data_ptr(), (rhs.data_ptr() if rhs is not None else None)
+    if src is not None:
+        tx, ty, tz, coef = src
+        a.src_x, a.src_y, a.src_z, a.src_coef = tx.data_ptr(), ty.data_ptr(), tz.data_ptr(), float(coef)
+    a.topflux = topflux.data_ptr() if topflux is not None else None
+    a.dt = float(dt)
+    a.nz_active = int(grid.nz if nz_active is None else nz_active)
+    a.n_substrate = int(n_substrate)
+    a.flags = int(flags)
+    if bc5 is not None:
+        a.bc5 = (C.c_float * 5)(*[float(v) for v in bc5])
+    a.T_out = T_out.data_ptr()
+    a.S1_out = S1_out.data_ptr() if S1_out is not None else None
+    a.S2_out = S2_out.data_ptr() if S2_out is not None else None
+    a.S2_prev = S2_prev.data_ptr() if S2_prev is not None else None
+    a.accum = accum.data_ptr() if accum is not None else None
+    a.max_accum = max_accum.data_ptr() if max_accum is not None else None
+    a.z_chunk = int(z_chunk)
+    _lib.check(lib.gomelt_level_step_f32(C.byref(props), C.byref(a), _lib.stream_ptr()), "gomelt_level_step_f32")
+    _count()
+    return T_out
+
+
+def state_props(props, T, S1, n_substrate=0, *, S1_out=None, S2_out=None, k_out=None, rhocp_out=None):
+    """computeStateProperties cF:2567-2614 (gomelt_state_props_f32)."""
+    lib = _lib.load()
+    nn = T.numel()
+    _chk_f32(T, nn, "T")
+    _chk_f32(S1, nn, "S1")
+    _lib.check(lib.gomelt_state_props_f32(C.byref(props), _lib.ptr(T), _lib.ptr(S1), nn, int(n_substrate),
+                                          _lib.ptr(S1_out), _lib.ptr(S2_out), _lib.ptr(k_out),
+                                          _lib.ptr(rhocp_out), _lib.stream_ptr()), "gomelt_state_props_f32")
+    _count()
+
+
+def surface_flux(props, grid, T0, flux, nz_active=None, add=False):
+    """computeConvRadBC cF:2207-2301 (gomelt_surface_flux_f32) -> flux[nx*ny]."""
+    lib = _lib.load()
+    _chk_f32(T0, grid.nx * grid.ny * grid.nz, "T0")
+    _chk_f32(flux, grid.nx * grid.ny, "flux")
+    nza = int(grid.nz if nz_active is None else nz_active)
+    _lib.check(lib.gomelt_surface_flux_f32(C.byref(props), C.byref(grid), _lib.ptr(T0), nza, _lib.ptr(flux),
+                                           int(bool(add)), _lib.stream_ptr()), "gomelt_surface_flux_f32")
+    _count()
+    return flux
+
+
+def source_tables(props, grid, coords, laser_xyz, laserP, tx, ty, tz):
+    """computeSourcesL3 cF:2960-3012 as rank-1 tables (gomelt_source_tables_f32) -> coef."""
+    lib = _lib.load()
+    v = (C.c_float * 3)(float(laser_xyz[0]), float(laser_xyz[1]), float(laser_xyz[2]))
+    coef = C.c_float(0.0)
+    _lib.check(lib.gomelt_source_tables_f32(C.byref(props), C.byref(grid), _lib.ptr(coords[0]),
+                                            _lib.ptr(coords[1]), _lib.ptr(coords[2]), C.byref(v),
+                                            float(laserP), _lib.ptr(tx), _lib.ptr(ty), _lib.ptr(tz),
+                                            C.byref(coef), _lib.stream_ptr()), "gomelt_source_tables_f32")
+    _count(3)
+    return coef.value
+
+
+def diag_fp32_rate(kind, iters=4096, blocks=148 * 8, threads=256):
+    """FP32 issue-rate micro-benchmark; returns lane-ops per second (timed with CUDA events)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    sink = torch.zeros(4, device="cuda")
+    ops = C.c_double(0.0)
+    for _ in range(2):
+        _lib.check(lib.gomelt_diag_fp32_rate(kind, iters, blocks, threads, _lib.ptr(sink), C.byref(ops),
+                                             _lib.stream_ptr()), "diag")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    _lib.check(lib.gomelt_diag_fp32_rate(kind, iters, blocks, threads, _lib.ptr(sink), C.byref(ops),
+                                         _lib.stream_ptr()), "diag")
+    e1.record()
+    torch.cuda.synchronize()
+    return ops.value / (e0.elapsed_time(e1) * 1e-3)

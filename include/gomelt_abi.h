@@ -1,0 +1,127 @@
+/*
+ * gomelt_abi.h — C ABI of libgomelt_sm100.so, the B200 (sm_100a) implementation of
+ * GO-MELT's multilevel explicit FE thermal time-step.
+ *
+ * The reference (JLnorthwestern/GO-MELT) has no FFI: its "operator API" for this path is the
+ * set of computeFunctions.py entry points the driver calls.  Each entry
+ * point below names the reference function(s) it replaces (cF = go_melt/computeFunctions.py,
+ * gm = go_melt/go_melt.py).  The same symbols are what an XLA-FFI shim or a ctypes/cffi
+ * binding would bind.
+ *
+ * Conventions
+ *   - plain C: POD structs, raw device pointers, sizes; no torch / C++ types.
+ *   - every launcher is stream-ordered (`stream` is a cudaStream_t passed as void*),
+ *     never allocates, never synchronises, and is re-entrant.
+ *   - return value: 0 = ok, <0 = bad argument (GOMELT_E_*), >0 = cudaError_t of the launch.
+ *     gomelt_last_error() returns a thread-local message for the last non-zero return.
+ *   - all fields are float32 / int32 like the reference (jax_enable_x64 is never set, cF:15).
+ *   - node numbering is x-fastest: n = ix + iy*nx + iz*nx*ny (cF:646-689).
+ */
+#ifndef GOMELT_ABI_H
+#define GOMELT_ABI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GOMELT_ABI_VERSION 1
+
+#define GOMELT_E_NULL   (-1) /* required pointer is NULL            */
+#define GOMELT_E_SIZE   (-2) /* grid / count out of range           */
+#define GOMELT_E_FLAGS  (-3) /* inconsistent flag combination       */
+#define GOMELT_E_ALIGN  (-4) /* pointer not aligned as required     */
+
+/* Uniform structured hex8 grid of one level (cF:115-157: elements, nodes, h). */
+typedef struct gomelt_grid {
+    int32_t nx, ny, nz;   /* nodes per axis (= elements + 1)                    */
+    float   hx, hy, hz;   /* element size, float32 as Level["h"] holds it        */
+} gomelt_grid_t;
+
+/* Material / process constants, float32 exactly as they are inside jax.jit
+ * (SetupProperties cF:267-345; derived CM/CT/CP cF:339-343; h_conv already *1e6 cF:319). */
+typedef struct gomelt_props {
+    float k_powder, k_bulk_a0, k_bulk_a1, k_fluid;          /* W/m K            */
+    float cp_solid_a0, cp_solid_a1, cp_mushy, cp_fluid;     /* J/kg K           */
+    float rho;                                              /* kg/mm^3          */
+    float T_amb, T_solidus, T_liquidus, T_boiling;          /* K                */
+    float h_conv, sigma_sb, vareps, evc, Lev;               /* surface terms    */
+    float CM_coeff, CT_coeff, CP_coeff;
+    float laser_radius, laser_depth, laser_eta;             /* mm, mm, -        */
+} gomelt_props_t;
+
+/* ---- K1: fused level step -------------------------------------------------------------
+ * Replaces, for one level and one sweep:
+ *   computeStateProperties cF:2567-2614  (S1/S2/k/rhocp from T0,S1 — evaluated per staged node)
+ *   solveMatrixFreeFE      cF:582-642    (element-mean k, rhocp; lumped mass; forward Euler)
+ *   substitute_Tbar        cF:1848-1865  (planes >= nz_active <- T_amb)
+ *   assignBCs              cF:1568-1595  (GOMELT_STEP_BC_CONST: 5 faces <- bc5[y-,y+,x-,x+,z-])
+ *   the "+ Fc + Corr" of cF:642 (rhs array, rank-1 source tables, top-plane flux load)
+ *   jnp.maximum(T_amb, .)  cF:2360-2362 etc. (GOMELT_STEP_CLAMP)
+ *   melt-time bookkeeping  cF:3568-3578  (GOMELT_STEP_ACCUM)
+ * Child levels: GOMELT_STEP_SKIP_FACES leaves the 5 Dirichlet faces of T_out untouched;
+ * gomelt_face_bc_f32 (assignBCsFine cF:1598-1620) writes them.
+ */
+#define GOMELT_STEP_CLAMP      0x01  /* T_out = max(T_amb, T_out)                              */
+#define GOMELT_STEP_WRITE_S1   0x02  /* write thresholded S1 (f32 0/1) to S1_out               */
+#define GOMELT_STEP_WRITE_S2   0x04  /* write S2 = (T0 >= T_liquidus) as uint8 to S2_out       */
+#define GOMELT_STEP_BC_CONST   0x08  /* Level-1 Dirichlet constants on 5 faces (all planes)    */
+#define GOMELT_STEP_SKIP_FACES 0x10  /* do not write the 5 Dirichlet faces (child levels)      */
+#define GOMELT_STEP_ACCUM      0x20  /* update accum / max_accum with S2_prev -> S2 transition */
+
+typedef struct gomelt_step_args {
+    gomelt_grid_t grid;
+    const float  *T0;          /* [nn] temperature at t                                         */
+    const float  *S1;          /* [nn] powder(0)/bulk(1) state, float as in the reference       */
+    const float  *rhs;         /* [nn] or NULL: nodal load (projected source + T' corrections)  */
+    const float  *src_x, *src_y, *src_z; /* rank-1 source tables [nx],[ny],[nz] or all NULL     */
+    float         src_coef;    /* F[n] += src_coef * src_x[ix]*src_y[iy]*src_z[iz]              */
+    const float  *topflux;     /* [nx*ny] or NULL: surface load added on plane nz_active-1      */
+    float         dt;
+    int32_t       nz_active;   /* planes [0,nz_active) are active (tmp_ne_nn, cF:495-517)       */
+    int64_t       n_substrate; /* S1 := 1 for node ids < n_substrate (cF:2592)                  */
+    int32_t       flags;       /* GOMELT_STEP_*                                                 */
+    float         bc5[5];      /* y-, y+, x-, x+, z- values for GOMELT_STEP_BC_CONST            */
+    float        *T_out;       /* [nn] temperature at t+dt (must not alias T0)                  */
+    float        *S1_out;      /* [nn] or NULL (may alias S1)                                   */
+    uint8_t      *S2_out;      /* [nn] or NULL                                                  */
+    const uint8_t *S2_prev;    /* [nn] previous melt flag (ACCUM); may alias S2_out             */
+    float        *accum;       /* [nn] accumulated melt time, updated in place (ACCUM)          */
+    float        *max_accum;   /* [nn] max accumulated melt time, updated in place (ACCUM)      */
+    int32_t       z_chunk;     /* planes per z-chunk, 0 = library default                       */
+} gomelt_step_args_t;
+
+int gomelt_level_step_f32(const gomelt_props_t *props, const gomelt_step_args_t *args, void *stream);
+
+/* computeStateProperties cF:2567-2614 as a stand-alone op (outputs may be NULL). */
+int gomelt_state_props_f32(const gomelt_props_t *props, const float *T, const float *S1, int64_t nn,
+                           int64_t n_substrate, float *S1_out, uint8_t *S2_out, float *k_out,
+                           float *rhocp_out, void *stream);
+
+/* computeConvRadBC cF:2207-2301: convection + radiation + evaporation load of the top face of
+ * element layer (nz_active-2) on the nodes of plane nz_active-1.  flux[nx*ny] is overwritten
+ * (add = 0) or accumulated into (add = 1). */
+int gomelt_surface_flux_f32(const gomelt_props_t *props, const gomelt_grid_t *grid, const float *T0,
+                            int32_t nz_active, float *flux, int32_t add, void *stream);
+
+/* K6 — computeSourcesL3 cF:2960-3012 / computeSourceFunction_jax cF:991-1025 as three 1-D
+ * tables (the Gaussian is separable and N is a tensor product):
+ *   F[n] = coef * tx[ix]*ty[iy]*tz[iz],  coef returned in *coef (host float).
+ * x,y,z are the level's node-coordinate arrays on the device. */
+int gomelt_source_tables_f32(const gomelt_props_t *props, const gomelt_grid_t *grid, const float *x,
+                             const float *y, const float *z, const float laser_xyz[3], float laserP,
+                             float *tx, float *ty, float *tz, float *coef, void *stream);
+
+const char *gomelt_last_error(void);
+int gomelt_abi_version(void);
+
+/* Diagnostics: FP32 issue-rate micro-benchmark.  kind: 0 = FFMA (3-reg),
+ * 1 = FADD, 2 = packed FFMA2 (fma.rn.f32x2).  Returns lane-ops executed in *ops. */
+int gomelt_diag_fp32_rate(int32_t kind, int32_t iters, int32_t blocks, int32_t threads, float *sink,
+                          double *ops, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOMELT_ABI_H */

@@ -1,0 +1,224 @@
+"""GPU parity of K1 (gomelt_level_step_f32) and its helper kernels against the oracle.
+
+Tolerance: BASELINE.json north_star — temperatures within 1e-5 relative (float32); the set of
+nodes with T >= T_liquidus identical (nodes whose oracle T lies within 8 ulp of the threshold are
+counted and excluded).
+"""
+import numpy as np
+import pytest
+
+from oracle import computeFunctions as cF
+from oracle.util import make_level, smooth_field
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _dev(a, dtype=None):
+    import torch
+
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).cuda()
+
+
+def _rel(a, b):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0)))
+
+
+def _setup(gm, example_props, elements, bounds, seed=0, nsub_planes=3):
+    rng = np.random.default_rng(seed)
+    P = cF.SetupProperties(example_props)
+    lv = make_level(elements, bounds)
+    T0 = smooth_field(lv, rng)
+    S1 = (rng.random(lv["nn"]) > 0.5).astype(np.float32)
+    nsub = nsub_planes * lv["nodes"][0] * lv["nodes"][1]
+    return P, lv, T0, S1, nsub
+
+
+def _oracle_step(P, lv, T0, S1, nsub, dt, v, laserP, rhs=None, ne=None, flux=True):
+    ne = lv["ne"] if ne is None else ne
+    ne_nn = (0, lv["ne"], 0, 0, lv["nn"])
+    S1n, S2, k, rc = cF.computeStateProperties(T0, S1, P, nsub)
+    F = cF.computeSourcesL3(lv, v, ne_nn, P, laserP) if laserP else np.zeros(lv["nn"], np.float32)
+    if flux:
+        F = cF.computeConvRadBC(lv, T0, ne, lv["nn"], P, F)
+    T = cF.solveMatrixFreeFE(lv, lv["nn"], ne, k, rc, dt, T0, F, 0 if rhs is None else rhs)
+    return T, S1n, S2
+
+
+def _gpu_step(gm, P, lv, T0, S1, nsub, dt, v, laserP, rhs=None, nz_active=None, flags=0, bc5=None,
+              z_chunk=0, flux=True, extra=None):
+    import torch
+
+    ops = gm.ops
+    props = gm._lib.make_props(P)
+    grid = gm._lib.make_grid(lv["nodes"], lv["h"])
+    dT0, dS1 = _dev(T0), _dev(S1)
+    nn, nx, ny, nz = lv["nn"], *lv["nodes"]
+    src = None
+    if laserP:
+        coords = [_dev(c) for c in lv["node_coords"]]
+        tx, ty, tz = (torch.empty(n, device="cuda") for n in (nx, ny, nz))
+        coef = ops.source_tables(props, grid, coords, v, laserP, tx, ty, tz)
+        src = (tx, ty, tz, coef)
+    top = None
+    if flux:
+        top = torch.empty(nx * ny, device="cuda")
+        ops.surface_flux(props, grid, dT0, top, nz_active=nz_active)
+    Tout = torch.full((nn,), -7.0, device="cuda")
+    S1o = torch.empty(nn, device="cuda")
+    S2o = torch.empty(nn, device="cuda", dtype=torch.uint8)
+    kw = dict(extra or {})
+    ops.level_step(props, grid, dT0, dS1, Tout, dt, rhs=None if rhs is None else _dev(rhs), src=src,
+                   topflux=top, nz_active=nz_active, n_substrate=nsub,
+                   flags=flags | ops.STEP_WRITE_S1 | ops.STEP_WRITE_S2, bc5=bc5, S1_out=S1o, S2_out=S2o,
+                   z_chunk=z_chunk, **kw)
+    torch.cuda.synchronize()
+    return Tout.cpu().numpy(), S1o.cpu().numpy(), S2o.cpu().numpy().astype(bool)
+
+
+@pytest.mark.parametrize("elements,seed", [((36, 28, 12), 0), ((61, 17, 5), 1), ((7, 9, 3), 2), ((100, 100, 10), 3)])
+def test_level3_substep_matches_oracle(gm, example_props, elements, seed):
+    bounds = ((1.0, 1.0 + 0.02 * elements[0]), (1.0, 1.0 + 0.02 * elements[1]), (-0.02 * elements[2], 0.0))
+    P, lv, T0, S1, nsub = _setup(gm, example_props, elements, bounds, seed)
+    v = np.array([0.5 * (bounds[0][0] + bounds[0][1]), 0.5 * (bounds[1][0] + bounds[1][1]), 0.0], np.float32)
+    dt = 1e-5
+    Tref, S1ref, S2ref = _oracle_step(P, lv, T0, S1, nsub, dt, v, 285.0)
+    T, S1g, S2g = _gpu_step(gm, P, lv, T0, S1, nsub, dt, v, 285.0)
+    assert np.isfinite(T).all()
+    assert _rel(T, Tref) <= RTOL, _rel(T, Tref)
+    assert np.array_equal(S1g, S1ref)
+    assert np.array_equal(S2g, S2ref)  # S2 is a pure function of the (identical) input T0: bit-exact
+
+
+def test_z_chunking_is_bit_identical(gm, example_props):
+    elements = (40, 33, 17)
+    bounds = ((0.0, 0.8), (0.0, 0.66), (-0.34, 0.0))
+    P, lv, T0, S1, nsub = _setup(gm, example_props, elements, bounds, 5)
+    v = np.array([0.4, 0.3, 0.0], np.float32)
+    base = _gpu_step(gm, P, lv, T0, S1, nsub, 1e-5, v, 285.0)[0]
+    for zc in (1, 2, 5, 7, 18):
+        T = _gpu_step(gm, P, lv, T0, S1, nsub, 1e-5, v, 285.0, z_chunk=zc)[0]
+        assert np.array_equal(T, base), zc
+
+
+def test_rhs_and_clamp(gm, example_props):
+    elements = (30, 22, 9)
+    bounds = ((0.0, 1.2), (0.0, 0.88), (-0.36, 0.0))
+    P, lv, T0, S1, nsub = _setup(gm, example_props, elements, bounds, 7)
+    rng = np.random.default_rng(11)
+    rhs = (1e-3 * rng.standard_normal(lv["nn"])).astype(np.float32)
+    v = np.array([0.6, 0.4, 0.0], np.float32)
+    Tref, _, _ = _oracle_step(P, lv, T0, S1, nsub, 2e-5, v, 0.0, rhs=rhs)
+    Tref = np.maximum(np.float32(P["T_amb"]), Tref)
+    T, _, _ = _gpu_step(gm, P, lv, T0, S1, nsub, 2e-5, v, 0.0, rhs=rhs, flags=gm.ops.STEP_CLAMP)
+    assert _rel(T, Tref) <= RTOL
+
+
+def test_level1_active_layer_and_dirichlet_constants(gm, example_props):
+    """stepGOMELTDwellTime cF:2617-2664: active elements only, inactive planes <- T_amb, 5 faces
+    <- conditions (assignBCs order y-, y+, x-, x+, z-), no clamp."""
+    elements = (25, 10, 12)
+    bounds = ((0.0, 10.0), (0.0, 4.0), (-2.0, 0.4))
+    P, lv, T0, S1, _ = _setup(gm, example_props, elements, bounds, 9)
+    nx, ny, nz = lv["nodes"]
+    nz_active = 9
+    tmp_ne, tmp_nn = elements[0] * elements[1] * (nz_active - 1), nx * ny * nz_active
+    nsub = 4 * nx * ny
+    cond = {"x": [301.0, 302.0], "y": [303.0, 304.0], "z": [305.0, 306.0]}
+    Levels = [None, dict(lv, T0=T0, S1=S1, conditions=cond)]
+    out = cF.stepGOMELTDwellTime(Levels, (tmp_ne, tmp_nn), (0, 0, lv["nn"]), P, 2e-3, (0, nsub))
+    Tref = out[1]["T0"]
+    bc5 = [cond["y"][0], cond["y"][1], cond["x"][0], cond["x"][1], cond["z"][0]]
+    T, _, _ = _gpu_step(gm, P, lv, T0, S1, nsub, 2e-3, None, 0.0, nz_active=nz_active,
+                        flags=gm.ops.STEP_BC_CONST, bc5=bc5)
+    assert np.isfinite(Tref).all()
+    assert _rel(T, Tref) <= RTOL, _rel(T, Tref)
+
+
+def test_skip_faces_leaves_dirichlet_faces_untouched(gm, example_props):
+    elements = (12, 11, 6)
+    bounds = ((0.0, 0.24), (0.0, 0.22), (-0.12, 0.0))
+    P, lv, T0, S1, nsub = _setup(gm, example_props, elements, bounds, 4)
+    v = np.array([0.1, 0.1, 0.0], np.float32)
+    T, _, _ = _gpu_step(gm, P, lv, T0, S1, nsub, 1e-5, v, 285.0, flags=gm.ops.STEP_SKIP_FACES)
+    full, _, _ = _gpu_step(gm, P, lv, T0, S1, nsub, 1e-5, v, 285.0)
+    nx, ny, nz = lv["nodes"]
+    T3, F3 = T.reshape(nz, ny, nx), full.reshape(nz, ny, nx)
+    face = np.zeros((nz, ny, nx), bool)
+    face[0] = True
+    face[:, 0] = face[:, -1] = True
+    face[:, :, 0] = face[:, :, -1] = True
+    assert (T3[face] == -7.0).all()          # sentinel untouched on the 5 Dirichlet faces
+    assert np.array_equal(T3[~face], F3[~face])  # top plane interior is computed (free surface)
+
+
+def test_melt_time_bookkeeping(gm, example_props):
+    """cF:3568-3578 fused into the step."""
+    import torch
+
+    elements = (20, 20, 6)
+    bounds = ((0.0, 0.4), (0.0, 0.4), (-0.12, 0.0))
+    P, lv, T0, S1, nsub = _setup(gm, example_props, elements, bounds, 13)
+    rng = np.random.default_rng(17)
+    nn = lv["nn"]
+    prev = rng.random(nn) > 0.5
+    acc = rng.random(nn).astype(np.float32) * 1e-3
+    mx = rng.random(nn).astype(np.float32) * 1e-3
+    S2 = T0 >= np.float32(P["T_liquidus"])
+    reset = acc * ((~prev) & S2)
+    mx_ref = np.maximum(reset, mx)
+    acc_ref = (acc + np.float32(1e-5) * S2 - reset).astype(np.float32)
+    dS2 = _dev(prev.astype(np.uint8))
+    dacc, dmx = _dev(acc), _dev(mx)
+    v = np.array([0.2, 0.2, 0.0], np.float32)
+    _gpu_step(gm, P, lv, T0, S1, nsub, 1e-5, v, 285.0, flags=gm.ops.STEP_ACCUM,
+              extra=dict(S2_prev=dS2, accum=dacc, max_accum=dmx))
+    torch.cuda.synchronize()
+    assert np.array_equal(dmx.cpu().numpy(), mx_ref)
+    assert np.allclose(dacc.cpu().numpy(), acc_ref, rtol=1e-6, atol=0)
+
+
+def test_state_props_kernel(gm, example_props):
+    import torch
+
+    rng = np.random.default_rng(3)
+    P = cF.SetupProperties(example_props)
+    n = 100003
+    T = rng.uniform(250, 3500, n).astype(np.float32)
+    T[:7] = np.float32([P["T_liquidus"], P["T_solidus"], np.nextafter(np.float32(P["T_liquidus"]), np.float32(0)),
+                        np.nextafter(np.float32(P["T_solidus"]), np.float32(1e9)), 298.15, 1609.0, 1533.0])
+    S1 = rng.choice(np.float32([0.0, 1.0, 0.3, 0.499, 0.5, 0.7]), n)
+    S1r, S2r, kr, rr = cF.computeStateProperties(T, S1, P, 1000)
+    S1o, ko, ro = (torch.empty(n, device="cuda") for _ in range(3))
+    S2o = torch.empty(n, device="cuda", dtype=torch.uint8)
+    gm.ops.state_props(gm._lib.make_props(P), _dev(T), _dev(S1), 1000, S1_out=S1o, S2_out=S2o, k_out=ko, rhocp_out=ro)
+    assert np.array_equal(S1o.cpu().numpy(), S1r)
+    assert np.array_equal(S2o.cpu().numpy().astype(bool), S2r)
+    assert np.allclose(ko.cpu().numpy(), kr, rtol=3e-7, atol=0)
+    assert np.allclose(ro.cpu().numpy(), rr, rtol=3e-7, atol=0)
+
+
+def test_surface_flux_and_source_tables(gm, example_props):
+    import torch
+
+    elements = (31, 23, 4)
+    bounds = ((0.0, 0.62), (0.0, 0.46), (-0.08, 0.0))
+    P, lv, T0, S1, nsub = _setup(gm, example_props, elements, bounds, 21)
+    T0 = (T0 * 1.3).astype(np.float32)  # push some nodes past T_boiling + 1000 (the min() cap)
+    nx, ny, nz = lv["nodes"]
+    props = gm._lib.make_props(P)
+    grid = gm._lib.make_grid(lv["nodes"], lv["h"])
+    ref = cF.computeConvRadBC(lv, T0, lv["ne"], lv["nn"], P, 0)
+    flux = torch.empty(nx * ny, device="cuda")
+    gm.ops.surface_flux(props, grid, _dev(T0), flux)
+    got = flux.cpu().numpy()
+    top = ref[-nx * ny:]
+    assert np.abs(ref[:-nx * ny]).max() == 0
+    assert np.max(np.abs(got - top)) <= 2e-6 * np.max(np.abs(top))
+    v = np.array([0.3, 0.2, 0.0], np.float32)
+    Fref = cF.computeSourcesL3(lv, v, (0, lv["ne"], 0, 0, lv["nn"]), P, 285.0)
+    coords = [_dev(c) for c in lv["node_coords"]]
+    tx, ty, tz = (torch.empty(n, device="cuda") for n in (nx, ny, nz))
+    coef = gm.ops.source_tables(props, grid, coords, v, 285.0, tx, ty, tz)
+    F = coef * np.einsum("k,j,i->kji", tz.cpu().numpy(), ty.cpu().numpy(), tx.cpu().numpy()).reshape(-1)
+    assert np.max(np.abs(F - Fref)) <= 3e-6 * np.max(np.abs(Fref))

@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 GO-MELT step (contract: task prompt / DESIGN.md section 7).
+
+N = 1  workload "L3-10M": BASELINE.json configs[1] — single laser track, Level-3 melt-pool window
+       512 x 512 x 38 elements (513*513*39 = 10 263 591 nodes), h = 0.02 mm, T-dependent
+       properties (examples/example.json property block), dt = 1e-5 s.  One *step* = one Level-3
+       subcycle block of N3 = 5 explicit substeps (the inner scan of subcycleGOMELT, cF:3367-3412):
+       per substep  source tables (computeSourcesL3) + top-surface flux (computeConvRadBC) +
+       fused level step (computeStateProperties + solveMatrixFreeFE + clamp), laser advancing
+       along +x.  metric = Level-3 DOF-updates/s (1 DOF-update = one node advanced one sweep).
+N > 1  workload "L1-slab": BASELINE.json configs[4] — part-scale Level-1 mesh z-slab-decomposed, one
+       rank per GPU, dwell sweeps (stepGOMELTDwellTime cF:2617-2664) with one-plane halo exchange
+       per sweep over NCCL; weak scaling (fixed slab per GPU).  metric = Level-1 DOF-updates/s.
+
+`--impl reference` times the reference algorithm on the host cores: the NumPy float32 oracle
+(oracle/, "restated reference, not JAX/XLA": JAX is not installable here or on the GPU box) on a
+bounded sample of the same workload, one process per core.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+EXAMPLE_PROPS = {
+    "thermal_conductivity_powder": 0.4, "thermal_conductivity_bulk_a0": 4.23,
+    "thermal_conductivity_bulk_a1": 0.016, "thermal_conductivity_fluid_a0": 29.0,
+    "heat_capacity_solid_a0": 383.1, "heat_capacity_solid_a1": 0.174, "heat_capacity_mushy": 3235.0,
+    "heat_capacity_fluid": 769.0, "density": 8e-06, "laser_radius": 0.1, "laser_depth": 0.1,
+    "laser_power": 285.0, "laser_absorptivity": 0.45, "T_amb": 298.15, "T_solidus": 1533,
+    "T_liquidus": 1609, "T_boiling": 3038.0, "h_conv": 1.5e-05, "emissivity": 0.3,
+    "evaporation_coefficient": 0.82, "latent_heat_evap": 6457000.0, "molar_mass": 58.69,
+    "layer_height": 0.04,
+}
+L3_ELEMENTS = (512, 512, 38)
+L3_H = 0.02
+N3 = 5
+DT = 1e-5
+LASER_V = 1000.0  # mm/s
+B_ALG_L3 = 16     # bytes per Level-3 DOF-update: T0 r4 + S1 r4 + T w4 + S1 w4
+B_ALG_L1 = 12     # Level-1 dwell sweep: T r/w + S1 r
+
+
+def host_properties():
+    """SetupProperties semantics (cF:267-345) without importing the oracle: product-side schema."""
+    import gomelt_b200 as gm
+
+    return gm.schema.SetupProperties(EXAMPLE_PROPS)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                c = float(f[1])
+                smax = float(f[2])
+            except ValueError:
+                continue
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(c)
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                      "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:  # region shorter than one sample: fall back to every sample taken
+            for ts, line in self.rows:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[1]))
+                except (ValueError, IndexError):
+                    pass
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# Level-3 block on the device (N = 1)
+# --------------------------------------------------------------------------------------------
+class L3Block:
+    """Device-resident Level-3 window advanced by subcycle blocks through the product API."""
+
+    def __init__(self, elements=L3_ELEMENTS, h=L3_H, seed=0):
+        import numpy as np
+        import torch
+
+        import gomelt_b200 as gm
+
+        self.gm, self.torch = gm, torch
+        self.P = host_properties()
+        self.props = gm._lib.make_props(self.P)
+        ex, ey, ez = elements
+        self.nodes = (ex + 1, ey + 1, ez + 1)
+        self.grid = gm._lib.make_grid(self.nodes, (h, h, h))
+        self.nn = self.nodes[0] * self.nodes[1] * self.nodes[2]
+        nx, ny, nz = self.nodes
+        x = np.linspace(0.0, ex * h, nx, dtype=np.float32)
+        y = np.linspace(0.0, ey * h, ny, dtype=np.float32)
+        z = np.linspace(-ez * h, 0.0, nz, dtype=np.float32)
+        self.coords_host = (x, y, z)
+        self.coords = [torch.as_tensor(c).cuda() for c in (x, y, z)]
+        # initial state: T_amb + smooth +-50 K perturbation (rng seed 0),
+        # bulk below z = -0.04 (S1 = 1), one powder layer on top (S1 = 0)
+        rng = np.random.default_rng(seed)
+        pert = 50.0 * np.sin(np.linspace(0, 9, nx))[None, None, :] * np.cos(np.linspace(0, 7, ny))[None, :, None] \
+            * np.ones(nz)[:, None, None]
+        pert = pert + rng.uniform(-1.0, 1.0, size=(nz, ny, nx))
+        T0 = (self.P["T_amb"] + 51.0 + pert).astype(np.float32).reshape(-1)
+        S1 = np.repeat((z <= -0.04 + 1e-6).astype(np.float32), nx * ny)
+        self.T0_host, self.S1_host = T0, S1
+        self.n_sub = int((z < 1e-5 - 0.04).sum()) * nx * ny * 0  # no substrate override in the window
+        self.Ta = torch.as_tensor(T0).cuda()
+        self.Tb = torch.empty_like(self.Ta)
+        self.S1 = torch.as_tensor(S1).cuda()
+        self.tx, self.ty, self.tz = (torch.empty(n, device="cuda") for n in (nx, ny, nz))
+        self.top = torch.empty(nx * ny, device="cuda")
+        self.laser = np.array([0.25 * ex * h, 0.5 * ey * h, 0.0], np.float32)
+        self.k1_events = []
+
+    def block(self, time_k1=False):
+        """N3 substeps; returns the tensor holding the newest temperature."""
+        ops, torch = self.gm.ops, self.torch
+        for _ in range(N3):
+            self.laser[0] += LASER_V * DT
+            coef = ops.source_tables(self.props, self.grid, self.coords, self.laser, self.P["laser_power"],
+                                     self.tx, self.ty, self.tz)
+            ops.surface_flux(self.props, self.grid, self.Ta, self.top)
+            if time_k1:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            ops.level_step(self.props, self.grid, self.Ta, self.S1, self.Tb, DT, src=(self.tx, self.ty, self.tz, coef),
+                           topflux=self.top, n_substrate=self.n_sub,
+                           flags=ops.STEP_CLAMP | ops.STEP_WRITE_S1, S1_out=self.S1)
+            if time_k1:
+                e1.record()
+                self.k1_events.append((e0, e1))
+            self.Ta, self.Tb = self.Tb, self.Ta
+        return self.Ta
+
+
+def run_gomelt_single(args):
+    import numpy as np
+    import torch
+
+    import gomelt_b200 as gm
+
+    torch.cuda.set_device(0)
+    gm.load()
+    ops = gm.ops
+    K, W = args.steps, max(args.warmup, 3)
+    blk = L3Block()
+    nn = blk.nn
+    flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")  # 256 MiB > 126 MB L2
+    for _ in range(W):
+        blk.block()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.25)
+    # ---- device-resident timing: per-step CUDA events, L2 flushed between steps -------------
+    evs = []
+    launches0 = ops.LAUNCHES
+    t_wall0 = time.time()
+    torch.cuda.synchronize()
+    for _ in range(K):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        blk.block(time_k1=True)
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    launches = ops.LAUNCHES - launches0
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_s = sum(step_ms) * 1e-3
+    value = K * N3 * nn / total_s
+    k1_ms = [a.elapsed_time(b) for a, b in blk.k1_events]
+    k1_avg_s = (sum(k1_ms) / len(k1_ms)) * 1e-3
+    # ---- end-to-end through the host-buffer API ----------------------------------------------
+    e2e = run_e2e_hostbuffers(blk, K)
+    clocks = sampler.stop(t_wall0, time.time())
+    peaks = read_peaks()
+    achieved = B_ALG_L3 * nn / k1_avg_s / 1e9
+    traffic = read_traffic("level_step_kernel")
+    line = {
+        "metric": "Level-3 DOF-updates/s", "value": value, "unit": "DOF-updates/s", "n_gpus": 1,
+        "steps": K, "warmup": W, "ms_per_step": 1e3 * total_s / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "L3-10M: 512x512x38-element Level-3 window (10263591 nodes), one step = "
+                               "N3=5 substeps (source tables + surface flux + fused level step), "
+                               "T-dependent properties, dt=1e-5, moving laser",
+                   "nodes": nn, "substeps_per_step": N3,
+                   "l2": "flushed between steps (256 MiB write outside the timed events); per-step CUDA "
+                         "events summed", "state": "device-resident (value) / host buffers (e2e)"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
+                     "kernel": "level_step_kernel", "bytes_per_dof": B_ALG_L3,
+                     "kernel_us": k1_avg_s * 1e6, "peak_source": peaks["source"]},
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+    }
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline_sample()
+    print(json.dumps(line))
+
+
+def run_e2e_hostbuffers(blk, K):
+    """Same block through the host-buffer call: pinned host T0,S1 -> device -> N3 substeps -> host.
+    Copies are inside the timed region (one upload + one download per block)."""
+    import torch
+
+    nn = blk.nn
+    hT = torch.empty(nn, dtype=torch.float32).pin_memory()
+    hS = torch.empty(nn, dtype=torch.float32).pin_memory()
+    hT.copy_(torch.as_tensor(blk.T0_host))
+    hS.copy_(torch.as_tensor(blk.S1_host))
+    oT = torch.empty(nn, dtype=torch.float32).pin_memory()
+    oS = torch.empty(nn, dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        blk.Ta.copy_(hT, non_blocking=True)
+        blk.S1.copy_(hS, non_blocking=True)
+        T = blk.block()
+        oT.copy_(T, non_blocking=True)
+        oS.copy_(blk.S1, non_blocking=True)
+        torch.cuda.synchronize()
+        hT, oT = oT, hT
+        hS, oS = oS, hS
+    dt = time.perf_counter() - t0
+    return {"value": K * N3 * nn / dt, "unit": "DOF-updates/s", "h2d_bytes_per_step": 8 * nn,
+            "d2h_bytes_per_step": 8 * nn, "api": "host-buffer Level-3 block: upload T0,S1; N3 substeps; "
+            "download T,S1"}
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": float(d["hbm_gbs"]), "source": "MEASURED_PEAKS.json (of measured)"}
+    return {"hbm_gbs": 6650.0, "source": "B200_PROFILING.md fallback (of fallback)"}
+
+
+def read_traffic(kernel):
+    p = os.path.join(ROOT, "profiles", "roofline_inputs.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        if kernel in d:
+            return d[kernel].get("dram_bytes_per_launch")
+    return None
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle (NumPy f32 restatement of the reference) on a bounded sample
+# --------------------------------------------------------------------------------------------
+CPU_SAMPLE_ELEMENTS = (128, 128, 38)
+
+
+def _oracle_block(elements, nblocks, seed=0):
+    """One worker: nblocks x N3 Level-3 substeps of the reference algorithm on its own window."""
+    import numpy as np
+
+    from oracle import computeFunctions as cF
+    from oracle.util import make_level
+
+    P = cF.SetupProperties(EXAMPLE_PROPS)
+    ex, ey, ez = elements
+    lv = make_level(elements, ((0.0, ex * L3_H), (0.0, ey * L3_H), (-ez * L3_H, 0.0)))
+    nn = lv["nn"]
+    T = np.full(nn, np.float32(P["T_amb"] + 51.0), np.float32)
+    S1 = np.repeat((lv["node_coords"][2] <= -0.04 + 1e-6).astype(np.float32), lv["nodes"][0] * lv["nodes"][1])
+    laser = np.array([0.25 * ex * L3_H, 0.5 * ey * L3_H, 0.0], np.float32)
+    ne_nn = (0, lv["ne"], 0, 0, nn)
+    t0 = time.perf_counter()
+    for _ in range(nblocks * N3):
+        laser[0] += LASER_V * DT
+        S1, _, k, rc = cF.computeStateProperties(T, S1, P, 0)
+        F = cF.computeSourcesL3(lv, laser, ne_nn, P, P["laser_power"])
+        F = cF.computeConvRadBC(lv, T, lv["ne"], nn, P, F)
+        T = np.maximum(np.float32(P["T_amb"]), cF.solveMatrixFreeFE(lv, nn, lv["ne"], k, rc, DT, T, F, 0))
+    return nblocks * N3 * nn, time.perf_counter() - t0
+
+
+def cpu_baseline_sample():
+    dofs, secs = _oracle_block(CPU_SAMPLE_ELEMENTS, 1)
+    return {"value": dofs / secs, "unit": "DOF-updates/s", "cores": 1, "kind": "port",
+            "sample": f"1 block (N3={N3} substeps) of the same Level-3 step on a "
+                      f"{'x'.join(map(str, CPU_SAMPLE_ELEMENTS))}-element window "
+                      f"({dofs // N3} nodes), NumPy float32 restatement of the reference (not JAX/XLA)",
+            "seconds": secs}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    ncores = os.cpu_count() or 1
+    nproc = max(1, min(ncores, 32))
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    K, W = args.steps, args.warmup
+    elements = (96, 96, 38)
+    # bounded: every "step" = one N3-substep block on one window per core; K capped so that the
+    # run ends within a few minutes (~1.2 s per substep per core at this window size)
+    Kb = max(1, min(K, 3))
+    with mp.get_context("fork").Pool(nproc) as pool:
+        if W > 0:
+            pool.starmap(_oracle_block, [((32, 32, 8), 1)] * nproc)
+        t0 = time.perf_counter()
+        res = pool.starmap(_oracle_block, [(elements, Kb, i) for i in range(nproc)])
+        wall = time.perf_counter() - t0
+    dofs = sum(r[0] for r in res)
+    value = dofs / wall
+    sample = (f"{Kb} block(s) x N3={N3} substeps on {nproc} independent "
+              f"{'x'.join(map(str, elements))}-element Level-3 windows (one process per core), NumPy float32 "
+              f"restatement of the reference algorithm (JAX is not installable on this box)")
+    line = {
+        "impl": "reference", "metric": "Level-3 DOF-updates/s", "value": value, "unit": "DOF-updates/s",
+        "n_gpus": args.gpus, "steps": Kb, "warmup": W, "ms_per_step": 1e3 * wall / Kb,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "L3-10M (bounded sample)", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "DOF-updates/s", "cores": nproc, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "DOF-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gomelt", choices=["gomelt", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        from bench_tools.bench_l1_slab import run_gomelt_multi
+
+        run_gomelt_multi(args, read_peaks, ClockSampler, host_properties)
+        return
+    run_gomelt_single(args)
+
+
+if __name__ == "__main__":
+    main()

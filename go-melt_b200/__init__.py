@@ -5,7 +5,7 @@ The directory is ``go-melt_b200/`` (not an importable identifier); ``import gome
 through the alias module at the repo root, or use ``importlib.import_module("go-melt_b200")``.
 Sub-modules: ``_lib`` (ctypes binding of the C ABI), ``ops`` (launchers), ``build`` (nvcc).
 """
-from . import build, _lib, ops  # noqa: F401
+from . import build, _lib, ops, schema  # noqa: F401
 from ._lib import GomeltError, load  # noqa: F401
 
-__all__ = ["build", "ops", "load", "GomeltError"]
+__all__ = ["build", "ops", "schema", "load", "GomeltError"]

@@ -236,6 +236,18 @@ def run_gomelt_single(args):
                      "kernel_us": k1_avg_s * 1e6, "peak_source": peaks["source"]},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
     }
+    # the path that shards (Level-1 z-slabs, the N>1 workload) measured on this one GPU, so that the
+    # N>1 lines have a same-workload denominator
+    try:
+        from bench_tools.bench_l1_slab import run_gomelt_multi
+
+        del blk, flush
+        torch.cuda.empty_cache()
+        ref = run_gomelt_multi(args, read_peaks, lambda i: None, host_properties, single_gpu=True)
+        line["l1_slab_1gpu"] = {k: ref[k] for k in ("metric", "value", "unit", "ms_per_step", "roofline", "e2e")}
+        line["l1_slab_1gpu"]["workload"] = ref["config"]["workload"]
+    except Exception as exc:  # the headline line must still print
+        line["l1_slab_1gpu"] = {"error": repr(exc)}
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_sample()
     print(json.dumps(line))

@@ -9,3 +9,13 @@ from . import build, _lib, ops, schema  # noqa: F401
 from ._lib import GomeltError, load  # noqa: F401
 
 __all__ = ["build", "ops", "schema", "load", "GomeltError"]
+
+_LAZY = ("slab",)  # sub-modules that import torch at module level
+
+
+def __getattr__(name):
+    if name in _LAZY:
+        import importlib
+
+        return importlib.import_module(f"{__name__}.{name}")
+    raise AttributeError(name)

@@ -42,6 +42,7 @@ class StepArgs(C.Structure):
         ("T_out", C.c_void_p), ("S1_out", C.c_void_p), ("S2_out", C.c_void_p),
         ("S2_prev", C.c_void_p), ("accum", C.c_void_p), ("max_accum", C.c_void_p),
         ("z_chunk", C.c_int32),
+        ("z_begin", C.c_int32), ("z_end", C.c_int32),
     ]
 
 

@@ -48,6 +48,7 @@ struct StepParams {
     float bc[5];
     int flags;
     int zchunk;
+    int zbeg, zend;      // planes to finalise
 };
 
 template <int BY>
@@ -62,8 +63,8 @@ __global__ void __launch_bounds__(32 * BY) level_step_kernel(const __grid_consta
     const bool in_dom = (i >= 0) && (i < nx) && (j >= 0) && (j < ny);
     const bool elem_xy = (i >= 0) && (j >= 0) && (i + 1 < nx) && (j + 1 < ny) && (tx < 31) && (ty < BY - 1);
     const bool out_xy = in_dom && (tx >= 1) && (tx <= 30) && (ty >= 1) && (ty <= BY - 2);
-    const int za = blockIdx.z * p.zchunk;
-    const int zb = min(nz, za + p.zchunk);  // this CTA finalises node planes [za, zb)
+    const int za = p.zbeg + blockIdx.z * p.zchunk;
+    const int zb = min(p.zend, za + p.zchunk);  // this CTA finalises node planes [za, zb)
     const int l0 = max(za - 1, 0);
     const int lload_max = min(min(zb, nz - 1), nzl - 1);  // last plane that carries data
     const long long P = (long long)nx * ny;
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(32 * BY) level_step_kernel(const __grid_consta
 static int launch_step(const StepParams& sp, cudaStream_t st) {
     constexpr int BY = 8;
     dim3 block(32, BY);
-    const int nch = (sp.nz + sp.zchunk - 1) / sp.zchunk;
+    const int nch = (sp.zend - sp.zbeg + sp.zchunk - 1) / sp.zchunk;
     dim3 grid((sp.nx + 29) / 30, (sp.ny + BY - 3) / (BY - 2), nch);
     level_step_kernel<BY><<<grid, block, 0, st>>>(sp);
     return check_launch("gomelt_level_step_f32");
@@ -225,7 +226,10 @@ extern "C" int gomelt_level_step_f32(const gomelt_props_t* props, const gomelt_s
         return GOMELT_E_NULL;
     }
     const gomelt_grid_t& g = a->grid;
-    if (g.nx < 2 || g.ny < 2 || g.nz < 2 || a->nz_active < 1 || a->nz_active > g.nz ||
+    const int zbeg = (a->z_begin == 0 && a->z_end == 0) ? 0 : a->z_begin;
+    const int zend = (a->z_begin == 0 && a->z_end == 0) ? g.nz : a->z_end;
+    if (g.nx < 2 || g.ny < 2 || g.nz < 2 || a->nz_active < 0 || a->nz_active > g.nz || zbeg < 0 || zbeg >= zend ||
+        zend > g.nz ||
         (long long)g.nx * g.ny * g.nz > 2000000000LL || !(a->dt > 0.f)) {
         set_error("gomelt_level_step_f32: bad grid %d x %d x %d (nz_active %d, dt %g)", g.nx, g.ny, g.nz,
                   a->nz_active, (double)a->dt);
@@ -273,6 +277,7 @@ extern "C" int gomelt_level_step_f32(const gomelt_props_t* props, const gomelt_s
     sp.S2prev = a->S2_prev; sp.accum = a->accum; sp.maxacc = a->max_accum;
     for (int q = 0; q < 5; ++q) sp.bc[q] = a->bc5[q];
     sp.flags = a->flags;
-    sp.zchunk = a->z_chunk > 0 ? a->z_chunk : g.nz;
+    sp.zbeg = zbeg; sp.zend = zend;
+    sp.zchunk = a->z_chunk > 0 ? a->z_chunk : (zend - zbeg);
     return launch_step(sp, (cudaStream_t)stream);
 }

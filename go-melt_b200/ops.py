@@ -25,7 +25,7 @@ def _chk_f32(t, n, name):
 
 def level_step(props, grid, T0, S1, T_out, dt, *, rhs=None, src=None, topflux=None, nz_active=None,
                n_substrate=0, flags=0, bc5=None, S1_out=None, S2_out=None, S2_prev=None, accum=None,
-               max_accum=None, z_chunk=0):
+               max_accum=None, z_chunk=0, z_range=None):
     """K1 (gomelt_level_step_f32): one explicit sweep of one level.  ``src`` = (tx, ty, tz, coef)."""
     lib = _lib.load()
     nn = grid.nx * grid.ny * grid.nz
@@ -52,6 +52,8 @@ def level_step(props, grid, T0, S1, T_out, dt, *, rhs=None, src=None, topflux=No
     a.accum = accum.data_ptr() if accum is not None else None
     a.max_accum = max_accum.data_ptr() if max_accum is not None else None
     a.z_chunk = int(z_chunk)
+    if z_range is not None:
+        a.z_begin, a.z_end = int(z_range[0]), int(z_range[1])
     _lib.check(lib.gomelt_level_step_f32(C.byref(props), C.byref(a), _lib.stream_ptr()), "gomelt_level_step_f32")
     _count()
     return T_out

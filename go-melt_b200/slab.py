@@ -1,0 +1,136 @@
+"""Level-1 z-slab decomposition across the GPUs of one box (DESIGN.md "Multi-GPU").
+
+The reference is single-device (gm:557).  Here the part-scale Level-1 grid is cut into contiguous
+z-slabs, one rank per GPU.  Node numbering is x-fastest (cF:646-689), so a z-plane is ``nx*ny``
+contiguous floats and a halo is a zero-copy slice.  Each rank stores its owned planes ``[k0, k1)``
+plus one ghost plane per neighbour; an explicit sweep (stepGOMELTDwellTime cF:2617-2664) needs the
+neighbour's boundary plane of T (27-point stencil, radius 1) and - once - of S1.
+
+Per sweep (``Level1Slab.dwell_sweep``):
+  1. fused level step (K1) on the two boundary planes of the owned range,
+  2. those planes go to the neighbours' ghost planes (NCCL send/recv over NVLink, side stream),
+  3. K1 on the interior planes overlaps the transfer,
+  4. the main stream joins the transfer; buffers swap.
+
+Host logic only: the arithmetic is ``ops.level_step`` / ``ops.surface_flux`` (CUDA, no CPU path).
+``partition_planes`` and ``exchange_planes`` are device-agnostic so that the world_size-2 gloo
+tests can exercise the N>1 plumbing on CPU tensors.
+"""
+import torch
+import torch.distributed as dist
+
+
+def partition_planes(nz, world):
+    """Contiguous, balanced plane ranges [(k0, k1)] of ``nz`` planes over ``world`` ranks."""
+    if world < 1 or nz < world:
+        raise ValueError(f"cannot cut {nz} planes into {world} slabs")
+    base, extra = divmod(nz, world)
+    out, k = [], 0
+    for r in range(world):
+        n = base + (1 if r < extra else 0)
+        out.append((k, k + n))
+        k += n
+    return out
+
+
+def local_extent(rank, world, k0, k1):
+    """(first stored global plane, stored plane count, z_begin, z_end) of a rank's local array."""
+    lo = 1 if rank > 0 else 0
+    hi = 1 if rank < world - 1 else 0
+    return k0 - lo, (k1 - k0) + lo + hi, lo, lo + (k1 - k0)
+
+
+def exchange_planes(field, plane, z_begin, z_end, rank, world, group=None):
+    """Send the first / last owned plane of ``field`` (flat, x-fastest, local planes) to the lower /
+    upper neighbour's ghost plane and receive theirs.  Returns the list of Work handles."""
+    ops = []
+    if rank > 0:
+        ops.append(dist.P2POp(dist.isend, field[z_begin * plane:(z_begin + 1) * plane], rank - 1, group))
+        ops.append(dist.P2POp(dist.irecv, field[(z_begin - 1) * plane:z_begin * plane], rank - 1, group))
+    if rank < world - 1:
+        ops.append(dist.P2POp(dist.isend, field[(z_end - 1) * plane:z_end * plane], rank + 1, group))
+        ops.append(dist.P2POp(dist.irecv, field[z_end * plane:(z_end + 1) * plane], rank + 1, group))
+    return dist.batch_isend_irecv(ops) if ops else []
+
+
+class Level1Slab:
+    """One rank's slab of Level 1 in dwell mode (stepGOMELTDwellTime cF:2617-2664)."""
+
+    def __init__(self, gm, props, nodes, h, rank, world, bc5, nz_active=None, n_substrate=0, device=None):
+        self.gm, self.ops, self.props = gm, gm.ops, props
+        self.rank, self.world = rank, world
+        nx, ny, nz = (int(v) for v in nodes)
+        self.nodes_global = (nx, ny, nz)
+        self.plane = nx * ny
+        self.k0, self.k1 = partition_planes(nz, world)[rank]
+        self.g0, self.nzl, self.zb, self.ze = local_extent(rank, world, self.k0, self.k1)
+        self.grid = gm._lib.make_grid((nx, ny, self.nzl), h)
+        nza = nz if nz_active is None else int(nz_active)
+        self.nz_active_global = nza
+        self.nz_active = min(max(nza - self.g0, 0), self.nzl)
+        self.n_substrate = max(int(n_substrate) - self.g0 * self.plane, 0)
+        self.owns_top = self.k0 <= nza - 1 < self.k1
+        self.bc5 = list(bc5)
+        self.device = device
+        n = self.plane * self.nzl
+        self.T = torch.empty(n, dtype=torch.float32, device=device)
+        self.Tn = torch.empty(n, dtype=torch.float32, device=device)
+        self.S1 = torch.empty(n, dtype=torch.float32, device=device)
+        self.top = torch.zeros(self.plane, dtype=torch.float32, device=device)
+        self.comm = torch.cuda.Stream(device=device) if (device is not None and world > 1) else None
+        self.sweeps = 0
+
+    # ---- state ---------------------------------------------------------------------------
+    def owned(self, field):
+        return field[self.zb * self.plane:self.ze * self.plane]
+
+    def set_owned(self, T_owned, S1_owned):
+        self.owned(self.T).copy_(T_owned)
+        self.owned(self.S1).copy_(S1_owned)
+        self.fill_ghosts()
+
+    def fill_ghosts(self):
+        """Initial ghost planes of T and S1 (S1 never changes in dwell mode)."""
+        if self.world == 1:
+            return
+        for f in (self.T, self.S1):
+            for w in exchange_planes(f, self.plane, self.zb, self.ze, self.rank, self.world):
+                w.wait()
+        if self.device is not None:
+            torch.cuda.synchronize(self.device)
+
+    # ---- one sweep -----------------------------------------------------------------------
+    def _k1(self, dt, z0, z1, topflux):
+        if z1 <= z0:
+            return
+        self.ops.level_step(self.props, self.grid, self.T, self.S1, self.Tn, dt, topflux=topflux,
+                            nz_active=self.nz_active, n_substrate=self.n_substrate,
+                            flags=self.ops.STEP_BC_CONST, bc5=self.bc5, z_range=(z0, z1))
+
+    def dwell_sweep(self, dt):
+        ops = self.ops
+        top = None
+        if self.owns_top and self.nz_active >= 2:
+            ops.surface_flux(self.props, self.grid, self.T, self.top, nz_active=self.nz_active)
+            top = self.top
+        zb, ze = self.zb, self.ze
+        if self.world == 1:
+            self._k1(dt, zb, ze, top)
+        else:
+            lo = zb + 1 if self.rank > 0 else zb
+            hi = ze - 1 if self.rank < self.world - 1 else ze
+            hi = max(hi, lo)
+            self._k1(dt, zb, lo, top)            # first owned plane (needed by the rank below)
+            self._k1(dt, hi, ze, top)            # last owned plane (needed by the rank above)
+            main = torch.cuda.current_stream(self.device)
+            self.comm.wait_stream(main)
+            with torch.cuda.stream(self.comm):
+                works = exchange_planes(self.Tn, self.plane, zb, ze, self.rank, self.world)
+            self._k1(dt, lo, hi, top)            # interior overlaps the halo transfer
+            with torch.cuda.stream(self.comm):
+                for w in works:
+                    w.wait()
+            main.wait_stream(self.comm)
+        self.T, self.Tn = self.Tn, self.T
+        self.sweeps += 1
+        return self.T

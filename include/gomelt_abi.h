@@ -79,7 +79,7 @@ typedef struct gomelt_step_args {
     float         src_coef;    /* F[n] += src_coef * src_x[ix]*src_y[iy]*src_z[iz]              */
     const float  *topflux;     /* [nx*ny] or NULL: surface load added on plane nz_active-1      */
     float         dt;
-    int32_t       nz_active;   /* planes [0,nz_active) are active (tmp_ne_nn, cF:495-517)       */
+    int32_t       nz_active;   /* planes [0,nz_active) are active (tmp_ne_nn, cF:495-517); 0..nz */
     int64_t       n_substrate; /* S1 := 1 for node ids < n_substrate (cF:2592)                  */
     int32_t       flags;       /* GOMELT_STEP_*                                                 */
     float         bc5[5];      /* y-, y+, x-, x+, z- values for GOMELT_STEP_BC_CONST            */
@@ -90,6 +90,10 @@ typedef struct gomelt_step_args {
     float        *accum;       /* [nn] accumulated melt time, updated in place (ACCUM)          */
     float        *max_accum;   /* [nn] max accumulated melt time, updated in place (ACCUM)      */
     int32_t       z_chunk;     /* planes per z-chunk, 0 = library default                       */
+    int32_t       z_begin, z_end; /* finalise planes [z_begin, z_end) only; 0,0 = all planes.  A
+                                * z-slab rank passes its local array (ghost planes included) and
+                                * the owned range: planes z_begin-1 and z_end are read as ghosts;
+                                * nz_active / n_substrate are then in local planes / node ids.   */
 } gomelt_step_args_t;
 
 int gomelt_level_step_f32(const gomelt_props_t *props, const gomelt_step_args_t *args, void *stream);

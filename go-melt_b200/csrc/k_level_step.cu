@@ -20,36 +20,13 @@
 // plane (forward and backward exchanges are double-buffered and skewed by one plane).
 #include <stdarg.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "k_level_step_v2.cuh"
 
 namespace gomelt {
 
-struct StepParams {
-    int nx, ny, nz, nzl;   // nzl = active planes
-    long long nsub;
-    float lam[8];          // lambda'[sx + 2 sy + 4 sz] (already /64: two 1/8 factors folded)
-    float cdt;             // 64 dt / V
-    float dt;
-    PropK pk;
-    const float* T0;
-    const float* S1;
-    const float* rhs;
-    const float* srcx;
-    const float* srcy;
-    const float* srcz;
-    float scoef;
-    const float* topflux;
-    float* Tout;
-    float* S1out;
-    uint8_t* S2out;
-    const uint8_t* S2prev;
-    float* accum;
-    float* maxacc;
-    float bc[5];
-    int flags;
-    int zchunk;
-    int zbeg, zend;      // planes to finalise
-};
 
 template <int BY>
 __global__ void __launch_bounds__(32 * BY) level_step_kernel(const __grid_constant__ StepParams p) {
@@ -207,12 +184,48 @@ __global__ void __launch_bounds__(32 * BY) level_step_kernel(const __grid_consta
     }
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+template <int RY, int WPB, int FEAT>
+static void launch_v2(const StepParams& sp, int nch, cudaStream_t st) {
+    dim3 block(32, WPB);
+    const int strips = (sp.ny + RY - 1) / RY;
+    dim3 grid((sp.nx + 2 * K1_TX - 1) / (2 * K1_TX), (strips + WPB - 1) / WPB, nch);
+    level_step_v2<RY, WPB, FEAT><<<grid, block, 0, st>>>(sp);
+}
+
+// exact-feature instances for the hot call shapes; anything else runs the generic instance
+constexpr int F_L3_BENCH = K1F_SRC | K1F_TOP | K1F_S1OUT | K1F_CLAMP;
+constexpr int F_L3_SUB = F_L3_BENCH | K1F_SKIP;
+constexpr int F_L3_SUB2 = F_L3_SUB | K1F_S2OUT | K1F_ACCUM;
+constexpr int F_L1_DWELL = K1F_TOP | K1F_BCCONST;
+constexpr int F_L1_DWELL_SUB = F_L1_DWELL | K1F_NSUB;
+
 static int launch_step(const StepParams& sp, cudaStream_t st) {
-    constexpr int BY = 8;
-    dim3 block(32, BY);
     const int nch = (sp.zend - sp.zbeg + sp.zchunk - 1) / sp.zchunk;
-    dim3 grid((sp.nx + 29) / 30, (sp.ny + BY - 3) / (BY - 2), nch);
-    level_step_kernel<BY><<<grid, block, 0, st>>>(sp);
+    static const int variant = env_int("GOMELT_K1_VARIANT", 2);  // 1 = v1 (smem, 1 column / thread); dev A/B only
+    static const int generic_only = env_int("GOMELT_K1_GENERIC", 0);
+    constexpr int RY = 4, WPB = 2;
+    if (variant == 1) {
+        constexpr int BY = 8;
+        dim3 block(32, BY);
+        dim3 grid((sp.nx + 29) / 30, (sp.ny + BY - 3) / (BY - 2), nch);
+        level_step_kernel<BY><<<grid, block, 0, st>>>(sp);
+    } else if (generic_only) {
+        launch_v2<RY, WPB, K1F_ALL | K1F_GENERIC>(sp, nch, st);
+    } else {
+        switch (sp.feat) {
+            case F_L3_BENCH: launch_v2<RY, WPB, F_L3_BENCH>(sp, nch, st); break;
+            case F_L3_SUB: launch_v2<RY, WPB, F_L3_SUB>(sp, nch, st); break;
+            case F_L3_SUB2: launch_v2<RY, WPB, F_L3_SUB2>(sp, nch, st); break;
+            case F_L1_DWELL: launch_v2<RY, WPB, F_L1_DWELL>(sp, nch, st); break;
+            case F_L1_DWELL_SUB: launch_v2<RY, WPB, F_L1_DWELL_SUB>(sp, nch, st); break;
+            default: launch_v2<RY, WPB, K1F_ALL | K1F_GENERIC>(sp, nch, st); break;
+        }
+    }
     return check_launch("gomelt_level_step_f32");
 }
 
@@ -278,6 +291,24 @@ extern "C" int gomelt_level_step_f32(const gomelt_props_t* props, const gomelt_s
     for (int q = 0; q < 5; ++q) sp.bc[q] = a->bc5[q];
     sp.flags = a->flags;
     sp.zbeg = zbeg; sp.zend = zend;
+    {
+        const long long Pn = (long long)g.nx * g.ny;
+        const long long ns = a->n_substrate < 0 ? 0 : a->n_substrate;
+        sp.nsub_planes = (int)(ns / Pn < g.nz ? ns / Pn : g.nz);
+        sp.nsub_rem = sp.nsub_planes < g.nz ? (int)(ns - (long long)sp.nsub_planes * Pn) : 0;
+        int f = 0;
+        if (a->rhs) f |= K1F_RHS;
+        if (any_src) f |= K1F_SRC;
+        if (a->topflux) f |= K1F_TOP;
+        if (a->flags & GOMELT_STEP_WRITE_S1) f |= K1F_S1OUT;
+        if (a->flags & GOMELT_STEP_WRITE_S2) f |= K1F_S2OUT;
+        if (a->flags & GOMELT_STEP_ACCUM) f |= K1F_ACCUM;
+        if (a->flags & GOMELT_STEP_BC_CONST) f |= K1F_BCCONST;
+        if (a->flags & GOMELT_STEP_SKIP_FACES) f |= K1F_SKIP;
+        if (a->flags & GOMELT_STEP_CLAMP) f |= K1F_CLAMP;
+        if (ns > 0) f |= K1F_NSUB;
+        sp.feat = f;
+    }
     sp.zchunk = a->z_chunk > 0 ? a->z_chunk : (zend - zbeg);
     return launch_step(sp, (cudaStream_t)stream);
 }

@@ -1,0 +1,441 @@
+// K1 v2 — fused level step, register-tiled and packed (sm_100a).  See DESIGN.md "K1".
+//
+// Same mathematics as v1 (k_level_step.cu header): Haar-diagonalised hex8 stiffness, lumped mass,
+// forward Euler, no (ne,8)/(ne,8,8) arrays.  What changed is the mapping:
+//
+//  * one WARP owns a 60 x RY patch of node columns (+1 halo ring) and marches in z; no shared
+//    memory, no barriers: the halo ring is recomputed from (L1/L2-resident) redundant loads;
+//  * every thread carries TWO node columns 30 apart in x as the two halves of a float2 and all
+//    arithmetic is issued as packed FADD2 / FMUL2 / FFMA2 (Blackwell f32x2): the kernel is
+//    issue-bound, not FP32-throughput-bound, and packing halves the FP issue slots;
+//  * RY rows per thread: the y stage of the analysis / synthesis runs in registers; only the
+//    x stage crosses lanes (3 + 2 shuffles per node);
+//  * stage order  x -> z -> y  (analysis) and  y -> z -> x  (synthesis) keeps the state carried
+//    from plane to plane at 4 + 4 values per column; the plane loop is unrolled by two so the
+//    carried state ping-pongs between two register sets instead of being moved;
+//  * loads are unpredicated: out-of-domain columns / rows read a clamped (valid) address and are
+//    neutralised downstream - element columns by the mask xm, element rows by a warp-uniform test;
+//  * analysis, element layer and explicit update are fused row by row, so the only arrays that
+//    live across the row loop are the carried state and the prefetched next plane.
+#pragma once
+#include "common.cuh"
+
+namespace gomelt {
+
+struct StepParams {
+    int nx, ny, nz, nzl;   // nzl = active planes
+    long long nsub;
+    float lam[8];          // lambda'[sx + 2 sy + 4 sz] (already /64: two 1/8 factors folded)
+    float cdt;             // 64 dt / V
+    float dt;
+    PropK pk;
+    const float* T0;
+    const float* S1;
+    const float* rhs;
+    const float* srcx;
+    const float* srcy;
+    const float* srcz;
+    float scoef;
+    const float* topflux;
+    float* Tout;
+    float* S1out;
+    uint8_t* S2out;
+    const uint8_t* S2prev;
+    float* accum;
+    float* maxacc;
+    float bc[5];
+    int flags;
+    int zchunk;
+    int zbeg, zend;        // planes to finalise
+    int feat;              // K1F_* bits of this call (v2)
+    int nsub_planes, nsub_rem;  // n_substrate = nsub_planes * nx*ny + nsub_rem
+};
+
+#define GM_DI __device__ __forceinline__
+
+struct f2 {
+    float2 v;
+};
+GM_DI f2 mk2(float a, float b) { return f2{make_float2(a, b)}; }
+GM_DI f2 splat(float a) { return f2{make_float2(a, a)}; }
+GM_DI f2 operator+(f2 a, f2 b) { return f2{__fadd2_rn(a.v, b.v)}; }
+GM_DI f2 operator-(f2 a, f2 b) { return f2{__ffma2_rn(b.v, make_float2(-1.f, -1.f), a.v)}; }
+GM_DI f2 operator*(f2 a, f2 b) { return f2{__fmul2_rn(a.v, b.v)}; }
+GM_DI f2 fma2(f2 a, f2 b, f2 c) { return f2{__ffma2_rn(a.v, b.v, c.v)}; }
+GM_DI f2 neg(f2 a) { return mk2(-a.v.x, -a.v.y); }
+GM_DI f2 shdn(f2 a) {
+    return mk2(__shfl_down_sync(0xffffffffu, a.v.x, 1), __shfl_down_sync(0xffffffffu, a.v.y, 1));
+}
+GM_DI f2 shup(f2 a) {
+    return mk2(__shfl_up_sync(0xffffffffu, a.v.x, 1), __shfl_up_sync(0xffffffffu, a.v.y, 1));
+}
+
+GM_DI float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// computeStateProperties cF:2567-2614 for one node as straight-line selects (the compiler turns the
+// equivalent nested ternaries into divergent branches).  kb / cs = bulk conductivity / solid rho*cp
+// already evaluated (packed) by the caller; sub = 1 forces S1 (substrate).  Returns S1' (0/1) and S2.
+GM_DI void props_sel(const PropK& q, float T, float S1in, int sub, float kb, float cs, float& k, float& m,
+                     float& s1f, int& s2) {
+    asm("{\n\t.reg .pred p1, p2, p3;\n\t"
+        "setp.ge.f32 p2, %4, %6;\n\t"          // S2 = T >= T_liquidus
+        "setp.gt.f32 p3, %4, %7;\n\t"          // T > T_solidus (mushy when also !S2)
+        "setp.gt.f32 p1, %5, 0f3EFF7CEE;\n\t"  // S1 > 0.499
+        "setp.ne.or.s32 p1, %8, 0, p1;\n\t"    // | substrate
+        "selp.f32 %0, %9, %10, p1;\n\t"        // bulk : powder
+        "selp.f32 %0, %11, %0, p2;\n\t"        // fluid
+        "selp.f32 %1, %12, %13, p3;\n\t"       // mushy : solid
+        "selp.f32 %1, %14, %1, p2;\n\t"        // fluid
+        "or.pred p1, p1, p2;\n\t"
+        "selp.f32 %2, 0f3F800000, 0f00000000, p1;\n\t"
+        "selp.s32 %3, 1, 0, p2;\n\t}"
+        : "=&f"(k), "=&f"(m), "=f"(s1f), "=r"(s2)
+        : "f"(T), "f"(S1in), "f"(q.T_liq), "f"(q.T_sol), "r"(sub), "f"(kb), "f"(q.k_powder), "f"(q.k_fluid),
+          "f"(q.c_mushy), "f"(cs), "f"(q.c_fluid));
+}
+
+// Same without the state outputs (halo rows, calls that do not write S1 / S2).
+GM_DI void props_sel_km(const PropK& q, float T, float S1in, int sub, float kb, float cs, float& k, float& m) {
+    asm("{\n\t.reg .pred p1, p2, p3;\n\t"
+        "setp.ge.f32 p2, %2, %4;\n\t"
+        "setp.gt.f32 p3, %2, %5;\n\t"
+        "setp.gt.f32 p1, %3, 0f3EFF7CEE;\n\t"
+        "setp.ne.or.s32 p1, %6, 0, p1;\n\t"
+        "selp.f32 %0, %7, %8, p1;\n\t"
+        "selp.f32 %0, %9, %0, p2;\n\t"
+        "selp.f32 %1, %10, %11, p3;\n\t"
+        "selp.f32 %1, %12, %1, p2;\n\t}"
+        : "=&f"(k), "=&f"(m)
+        : "f"(T), "f"(S1in), "f"(q.T_liq), "f"(q.T_sol), "r"(sub), "f"(kb), "f"(q.k_powder), "f"(q.k_fluid),
+          "f"(q.c_mushy), "f"(cs), "f"(q.c_fluid));
+}
+
+// Plane base pointers are made opaque so that every access is base + 4 * (32-bit offset) =
+// one IMAD.WIDE, instead of a re-associated 64-bit index per access.
+template <typename T>
+GM_DI T* opaque(T* q) {
+    asm volatile("" : "+l"(q));
+    return q;
+}
+
+GM_DI void stg(float* q, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(q), "f"(v) : "memory"); }
+
+constexpr int K1_TX = 30;  // owned columns per half-warp tile (32 lanes - 2 halo)
+
+// Compile-time feature mask: a kernel instance carries code only for the features in FEAT.
+// K1F_GENERIC additionally tests the run-time flags / pointers, so one instance serves any call.
+enum : int {
+    K1F_RHS = 1 << 0,      // rhs array
+    K1F_SRC = 1 << 1,      // rank-1 source tables
+    K1F_TOP = 1 << 2,      // top-plane flux load
+    K1F_S1OUT = 1 << 3,
+    K1F_S2OUT = 1 << 4,
+    K1F_ACCUM = 1 << 5,
+    K1F_BCCONST = 1 << 6,
+    K1F_SKIP = 1 << 7,
+    K1F_CLAMP = 1 << 8,
+    K1F_NSUB = 1 << 9,     // substrate override present (n_substrate > 0)
+    K1F_ALL = (1 << 10) - 1,
+    K1F_GENERIC = 1 << 30,
+};
+
+template <int RY>
+struct K1State {           // x-staged fields of one plane (loaded rows) + T of the owned rows
+    f2 Xs[RY + 2], Xd[RY + 2], kx[RY + 2], mx[RY + 2], T[RY];
+};
+struct FinalPtrs {         // plane base pointers of the plane being finalised
+    float* out;
+    const float* rhs;
+};
+template <int RY>
+struct K1Raw {             // prefetched raw plane
+    f2 T[RY + 2], S[RY + 2];
+};
+
+template <int RY, int WPB, int FEAT>
+__global__ void __launch_bounds__(32 * WPB) level_step_v2(const __grid_constant__ StepParams p) {
+    constexpr int NR = RY + 2;  // loaded rows
+    constexpr bool GEN = (FEAT & K1F_GENERIC) != 0;
+    const int rtf = p.feat;     // run-time feature bits, set by the launcher
+#define K1_HAS(bit) (((FEAT & (bit)) != 0) && (!GEN || (rtf & (bit)) != 0))
+    const int lane = threadIdx.x;
+    const int nx = p.nx, ny = p.ny, nz = p.nz, nzl = p.nzl;
+    const int j0 = (blockIdx.y * WPB + threadIdx.y) * RY;  // first owned row
+    if (j0 >= ny) return;                                   // whole warp; no barriers in this kernel
+    const int ia = blockIdx.x * (2 * K1_TX) + lane - 1;     // column of half .x ; half .y is 30 further
+    const int ib = ia + K1_TX;
+    const bool lown = (lane >= 1) && (lane <= K1_TX);
+    const bool owna = lown && (ia < nx), ownb = lown && (ib < nx);
+    const f2 xm = mk2((ia >= 0 && ia + 1 < nx) ? 1.f : 0.f, (ib >= 0 && ib + 1 < nx) ? 1.f : 0.f);
+    const int P = nx * ny;  // nn < 2^31 is validated by the launcher
+    const int za = p.zbeg + blockIdx.z * p.zchunk;
+    const int zb = min(p.zend, za + p.zchunk);  // this warp finalises node planes [za, zb)
+    const int lfirst = max(za - 1, 0);
+    const int llast = min(min(zb, nz - 1), nzl - 1);  // last plane that carries data
+    // clamped column / row offsets: every load address is valid, no predicates
+    const int cola = min(max(ia, 0), nx - 1), colb = min(max(ib, 0), nx - 1);
+    unsigned offa[NR], offb[NR];  // in-plane element offsets of the loaded rows, per half
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int ro = min(max(j0 - 1 + r, 0), ny - 1) * nx;
+        offa[r] = (unsigned)(ro + cola);
+        offb[r] = (unsigned)(ro + colb);
+    }
+    const bool edge_lo = (j0 == 0), edge_hi = (j0 + RY >= ny);
+    const int nsub_planes = p.nsub_planes, nsub_rem = p.nsub_rem;  // substrate: whole planes (cF:575-578) + rest
+
+    f2 sfx = splat(0.f);
+    float sfy[RY];
+#pragma unroll
+    for (int r = 0; r < RY; ++r) sfy[r] = 0.f;
+    if (K1_HAS(K1F_SRC)) {
+        sfx = mk2(__ldg(p.srcx + cola) * p.scoef, __ldg(p.srcx + colb) * p.scoef);
+#pragma unroll
+        for (int r = 0; r < RY; ++r) sfy[r] = __ldg(p.srcy + min(j0 + r, ny - 1));
+    }
+
+    f2 Tt0[RY], Tt1[RY], myp[RY];  // top contributions (stiffness sx = 0 / 1, mass) of the previous layer
+#pragma unroll
+    for (int r = 0; r < RY; ++r) Tt0[r] = Tt1[r] = myp[r] = splat(0.f);
+
+    auto load_plane = [&](int l, K1Raw<RY>& raw) {
+        const float* __restrict__ Tl = opaque(p.T0 + (size_t)l * P);
+        const float* __restrict__ Sl = opaque(p.S1 + (size_t)l * P);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            raw.T[r] = mk2(__ldg(Tl + offa[r]), __ldg(Tl + offb[r]));
+            raw.S[r] = mk2(__ldg(Sl + offa[r]), __ldg(Sl + offb[r]));
+        }
+    };
+
+    // ---- node state of loaded row r of plane l (+ S1 / S2 / melt-time outputs) and its x stage -----
+    auto row_a = [&](size_t pl, float* so, int r, bool wr, int subrow, f2 T, f2 S, f2& xs, f2& xd, f2& kxr, f2& mxr) {
+        const f2 kb = fma2(splat(p.pk.k_a1), T, splat(p.pk.k_a0)), cs = fma2(splat(p.pk.c_a1), T, splat(p.pk.c_a0));
+        int suba = 0, subb = 0;
+        if (K1_HAS(K1F_NSUB)) {
+            suba = offa[r] < (unsigned)subrow;
+            subb = offb[r] < (unsigned)subrow;
+        }
+        f2 kn, mn, s1f = splat(0.f);
+        int s2a = 0, s2b = 0;
+        const bool outs = (r >= 1 && r <= RY) && (K1_HAS(K1F_S1OUT) || K1_HAS(K1F_S2OUT) || K1_HAS(K1F_ACCUM));
+        if (outs) {
+            props_sel(p.pk, T.v.x, S.v.x, suba, kb.v.x, cs.v.x, kn.v.x, mn.v.x, s1f.v.x, s2a);
+            props_sel(p.pk, T.v.y, S.v.y, subb, kb.v.y, cs.v.y, kn.v.y, mn.v.y, s1f.v.y, s2b);
+        } else {
+            props_sel_km(p.pk, T.v.x, S.v.x, suba, kb.v.x, cs.v.x, kn.v.x, mn.v.x);
+            props_sel_km(p.pk, T.v.y, S.v.y, subb, kb.v.y, cs.v.y, kn.v.y, mn.v.y);
+        }
+        if (outs) {
+            if (wr && (j0 + r - 1 < ny)) {
+                if (K1_HAS(K1F_S1OUT)) {
+                    if (owna) stg(so + offa[r], s1f.v.x);
+                    if (ownb) stg(so + offb[r], s1f.v.y);
+                }
+                if (K1_HAS(K1F_ACCUM)) {  // cF:3568-3578
+                    if (owna) {
+                        const size_t n = pl + offa[r];
+                        const bool prev = p.S2prev[n] != 0;
+                        const float ac = p.accum[n];
+                        const float reset = (!prev && s2a) ? ac : 0.f;
+                        p.maxacc[n] = fmaxf(reset, p.maxacc[n]);
+                        p.accum[n] = ac + (s2a ? p.dt : 0.f) - reset;
+                    }
+                    if (ownb) {
+                        const size_t n = pl + offb[r];
+                        const bool prev = p.S2prev[n] != 0;
+                        const float ac = p.accum[n];
+                        const float reset = (!prev && s2b) ? ac : 0.f;
+                        p.maxacc[n] = fmaxf(reset, p.maxacc[n]);
+                        p.accum[n] = ac + (s2b ? p.dt : 0.f) - reset;
+                    }
+                }
+                if (K1_HAS(K1F_S2OUT)) {
+                    if (owna) p.S2out[pl + offa[r]] = (uint8_t)s2a;
+                    if (ownb) p.S2out[pl + offb[r]] = (uint8_t)s2b;
+                }
+            }
+        }
+        const f2 Tr = shdn(T), kr = shdn(kn), mr = shdn(mn);
+        xs = Tr + T;
+        xd = Tr - T;
+        kxr = (kr + kn) * xm;
+        mxr = (mr + mn) * xm;
+    };
+
+    // ---- first plane of a chunk: x stage only -----------------------------------------------------
+    auto first_plane = [&](int l, const K1Raw<RY>& raw, K1State<RY>& st) {
+        const bool wr = (l >= za) && (l < zb);
+        const int subrow = (l < nsub_planes) ? (1 << 30) : ((l == nsub_planes) ? nsub_rem : 0);
+        const size_t pl = (size_t)l * P;
+        float* so = K1_HAS(K1F_S1OUT) ? opaque(p.S1out + pl) : nullptr;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            row_a(pl, so, r, wr, subrow, raw.T[r], raw.S[r], st.Xs[r], st.Xd[r], st.kx[r], st.mx[r]);
+            if (r >= 1 && r <= RY) st.T[r - 1] = raw.T[r];
+        }
+    };
+
+    // ---- write one finalised owned row of plane f ---------------------------------------------------
+    auto store_row = [&](int f, const FinalPtrs& fp, int r, f2 Tn) {
+        const int j = j0 + r;
+        bool ska = false, skb = false;
+        if (K1_HAS(K1F_BCCONST)) {  // assignBCs order: y-, y+, x-, x+, z-
+            if (j == 0) Tn = splat(p.bc[0]);
+            if (j == ny - 1) Tn = splat(p.bc[1]);
+            if (ia == 0) Tn.v.x = p.bc[2];
+            if (ib == 0) Tn.v.y = p.bc[2];
+            if (ia == nx - 1) Tn.v.x = p.bc[3];
+            if (ib == nx - 1) Tn.v.y = p.bc[3];
+            if (f == 0) Tn = splat(p.bc[4]);
+        } else if (K1_HAS(K1F_SKIP)) {
+            const bool fy = (j == 0) || (j == ny - 1) || (f == 0);
+            ska = fy || (ia == 0) || (ia == nx - 1);
+            skb = fy || (ib == 0) || (ib == nx - 1);
+        }
+        if (K1_HAS(K1F_CLAMP)) Tn = mk2(fmaxf(p.pk.T_amb, Tn.v.x), fmaxf(p.pk.T_amb, Tn.v.y));
+        float* __restrict__ out = fp.out;
+        if (owna && !ska) stg(out + offa[r + 1], Tn.v.x);
+        if (ownb && !skb) stg(out + offb[r + 1], Tn.v.y);
+    };
+
+    // ---- explicit update of owned row r of plane f from its assembled action (z0, z1, mz) ---------
+    auto final_row = [&](int f, const FinalPtrs& fp, int r, f2 sz, bool topf, f2 Tf, f2 z0, f2 z1, f2 mz) {
+        // x stage of the synthesis (shuffles are executed by the whole warp)
+        const f2 KT = (z0 - z1) + shup(z0 + z1);
+        const f2 mnode = mz + shup(mz);
+        if (j0 + r < ny) {
+            f2 rr = splat(0.f);
+            if (K1_HAS(K1F_RHS)) {
+                const float* __restrict__ rp = fp.rhs;
+                rr = mk2(__ldg(rp + offa[r + 1]), __ldg(rp + offb[r + 1]));
+            }
+            if (K1_HAS(K1F_SRC)) rr = fma2(sz, splat(sfy[r]), rr);
+            if (topf) rr = rr + mk2(__ldg(p.topflux + offa[r + 1]), __ldg(p.topflux + offb[r + 1]));
+            const f2 w = splat(p.cdt) * mk2(rcp_approx(mnode.v.x), rcp_approx(mnode.v.y));
+            store_row(f, fp, r, fma2(rr - KT, w, Tf));
+        }
+    };
+
+    // ---- plane l: node state, x stage, then the element layer (l-1, l) row by row; finalises
+    //      plane l-1 when do_final.  pv = state of plane l-1, cu <- state of plane l.
+    auto step_plane = [&](int l, const K1Raw<RY>& raw, const K1State<RY>& pv, K1State<RY>& cu, bool do_final) {
+        const bool wr = (l >= za) && (l < zb);
+        const int subrow = (l < nsub_planes) ? (1 << 30) : ((l == nsub_planes) ? nsub_rem : 0);
+        const int f = l - 1;
+        const size_t pl = (size_t)l * P;
+        float* so = K1_HAS(K1F_S1OUT) ? opaque(p.S1out + pl) : nullptr;
+        FinalPtrs fp;
+        fp.out = opaque(p.Tout + (pl - P));
+        fp.rhs = K1_HAS(K1F_RHS) ? opaque(p.rhs + (pl - P)) : nullptr;
+        f2 sz = splat(0.f);
+        if (K1_HAS(K1F_SRC)) sz = sfx * splat(__ldg(p.srcz + max(f, 0)));
+        const bool topf = K1_HAS(K1F_TOP) && (f == nzl - 1);
+        const f2 l1 = splat(p.lam[1]), l2 = splat(p.lam[2]), l3 = splat(p.lam[3]), l4 = splat(p.lam[4]),
+                 l5 = splat(p.lam[5]), l6 = splat(p.lam[6]), l7 = splat(p.lam[7]);
+        f2 c00, c01, c10, c11, cm;            // carries of the previous element row
+        f2 zl00, zl01, zl10, zl11, kzl, mzl;  // z-staged fields of the lower loaded row
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            f2 xs, xd, kxr, mxr;
+            row_a(pl, so, r, wr, subrow, raw.T[r], raw.S[r], xs, xd, kxr, mxr);
+            cu.Xs[r] = xs; cu.Xd[r] = xd; cu.kx[r] = kxr; cu.mx[r] = mxr;
+            if (r >= 1 && r <= RY) cu.T[r - 1] = raw.T[r];
+            // z stage of the analysis
+            const f2 zu00 = xs + pv.Xs[r], zu01 = xs - pv.Xs[r];
+            const f2 zu10 = xd + pv.Xd[r], zu11 = xd - pv.Xd[r];
+            const f2 kzu = kxr + pv.kx[r], mzu = mxr + pv.mx[r];
+            if (r >= 1) {
+                const int e = r - 1;  // element row between loaded rows e and e+1
+                f2 k8 = kzu + kzl;
+                f2 m8 = mzu + mzl;
+                // element rows that touch an out-of-domain node row do not exist
+                if ((e == 0 && edge_lo) || (edge_hi && j0 + e >= ny)) k8 = m8 = splat(0.f);
+                // y stage: sums (sy = 0) and differences (sy = 1); H000 is never needed (lambda = 0)
+                const f2 Hd00 = zu00 - zl00;
+                const f2 Hs01 = zu01 + zl01, Hd01 = zu01 - zl01;
+                const f2 Hs10 = zu10 + zl10, Hd10 = zu10 - zl10;
+                const f2 Hs11 = zu11 + zl11, Hd11 = zu11 - zl11;
+                // scaled by lambda'[sx + 2 sy + 4 sz]
+                const f2 q00 = (l2 * Hd00) * k8;  // (sx,sz) = (0,0): only the sy = 1 mode acts
+                const f2 g01 = l4 * Hs01, g10 = l1 * Hs10, g11 = l5 * Hs11;
+                const f2 d01 = l6 * Hd01, d10 = l3 * Hd10, d11 = l7 * Hd11;
+                if (e >= 1) {  // lower node row of this element row = loaded row e = owned row e-1
+                    const f2 R00 = c00 - q00;
+                    const f2 R01 = fma2(k8, g01 - d01, c01);
+                    const f2 R10 = fma2(k8, g10 - d10, c10);
+                    const f2 R11 = fma2(k8, g11 - d11, c11);
+                    // z stage of the synthesis: bottom (plane l-1) and top (plane l) parts
+                    const f2 z0 = Tt0[e - 1] + (R00 - R01);
+                    const f2 z1 = Tt1[e - 1] + (R10 - R11);
+                    Tt0[e - 1] = R00 + R01;
+                    Tt1[e - 1] = R10 + R11;
+                    const f2 my = cm + m8;
+                    const f2 mz = myp[e - 1] + my;
+                    myp[e - 1] = my;
+                    if (do_final) final_row(f, fp, e - 1, sz, topf, pv.T[e - 1], z0, z1, mz);
+                }
+                if (e < RY) {
+                    c00 = q00;
+                    c01 = (g01 + d01) * k8;
+                    c10 = (g10 + d10) * k8;
+                    c11 = (g11 + d11) * k8;
+                    cm = m8;
+                }
+            }
+            zl00 = zu00; zl01 = zu01; zl10 = zu10; zl11 = zu11; kzl = kzu; mzl = mzu;
+        }
+    };
+
+    // ---- last data plane of a chunk top: no layer above, its action is (Tt0, Tt1, myp) --------------
+    auto last_plane = [&](int f, const f2* Tf) {
+        f2 sz = splat(0.f);
+        if (K1_HAS(K1F_SRC)) sz = sfx * splat(__ldg(p.srcz + f));
+        const bool topf = K1_HAS(K1F_TOP) && (f == nzl - 1);
+        FinalPtrs fp;
+        fp.out = opaque(p.Tout + (size_t)f * P);
+        fp.rhs = K1_HAS(K1F_RHS) ? opaque(p.rhs + (size_t)f * P) : nullptr;
+#pragma unroll
+        for (int r = 0; r < RY; ++r) final_row(f, fp, r, sz, topf, Tf[r], Tt0[r], Tt1[r], myp[r]);
+    };
+
+    // ---- inactive planes (substitute_Tbar cF:2183) with the Dirichlet faces applied -------------
+    auto fill_inactive = [&](int f) {
+        FinalPtrs fp;
+        fp.out = opaque(p.Tout + (size_t)f * P);
+        fp.rhs = nullptr;
+#pragma unroll
+        for (int r = 0; r < RY; ++r)
+            if (j0 + r < ny) store_row(f, fp, r, splat(p.pk.T_amb));
+    };
+
+    int fdone = za;  // planes [za, fdone) are finalised
+    if (lfirst <= llast) {
+        K1Raw<RY> rawA, rawB;
+        K1State<RY> stA, stB;
+        load_plane(lfirst, rawA);
+        if (lfirst + 1 <= llast) load_plane(lfirst + 1, rawB);
+        first_plane(lfirst, rawA, stA);
+        // main loop, unrolled by two so the carried state ping-pongs: (stA, rawB) -> stB, (stB, rawA) -> stA
+        for (int l = lfirst + 1; l <= llast; l += 2) {
+            if (l + 1 <= llast) load_plane(l + 1, rawA);
+            step_plane(l, rawB, stA, stB, l - 1 >= za);
+            if (l + 1 > llast) break;
+            if (l + 2 <= llast) load_plane(l + 2, rawB);
+            step_plane(l + 1, rawA, stB, stA, l >= za);
+        }
+        if (llast >= za && llast < zb) {
+            if (((llast - lfirst) & 1) != 0) last_plane(llast, stB.T);  // parity of the plane held in stB
+            else last_plane(llast, stA.T);
+        }
+        fdone = max(za, llast + 1);
+    }
+    for (int f = fdone; f < zb; ++f) fill_inactive(f);  // planes >= nz_active
+#undef K1_HAS
+}
+
+}  // namespace gomelt

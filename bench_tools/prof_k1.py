@@ -3,10 +3,9 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import gomelt_b200 as gm
-from oracle import computeFunctions as cF
-P = cF.SetupProperties({"laser_radius": 0.1, "laser_depth": 0.1, "laser_absorptivity": 0.45, "T_amb": 298.15,
-                        "T_solidus": 1533, "T_liquidus": 1609, "h_conv": 1.5e-05, "emissivity": 0.3,
-                        "latent_heat_evap": 6457000.0})
+P = gm.schema.SetupProperties({"laser_radius": 0.1, "laser_depth": 0.1, "laser_absorptivity": 0.45, "T_amb": 298.15,
+                               "T_solidus": 1533, "T_liquidus": 1609, "h_conv": 1.5e-05, "emissivity": 0.3,
+                               "latent_heat_evap": 6457000.0})
 ops = gm.ops
 props = gm._lib.make_props(P)
 nx, ny, nz = 513, 513, 39

@@ -208,7 +208,7 @@ static int launch_step(const StepParams& sp, cudaStream_t st) {
     const int nch = (sp.zend - sp.zbeg + sp.zchunk - 1) / sp.zchunk;
     static const int variant = env_int("GOMELT_K1_VARIANT", 2);  // 1 = v1 (smem, 1 column / thread); dev A/B only
     static const int generic_only = env_int("GOMELT_K1_GENERIC", 0);
-    constexpr int RY = 4, WPB = 2;
+    constexpr int RY = 4, WPB = 1;  // one warp per CTA: warps are independent, finest SM balance
     if (variant == 1) {
         constexpr int BY = 8;
         dim3 block(32, BY);
@@ -218,7 +218,13 @@ static int launch_step(const StepParams& sp, cudaStream_t st) {
         launch_v2<RY, WPB, K1F_ALL | K1F_GENERIC>(sp, nch, st);
     } else {
         switch (sp.feat) {
-            case F_L3_BENCH: launch_v2<RY, WPB, F_L3_BENCH>(sp, nch, st); break;
+            case F_L3_BENCH: {
+                static const int wpb = env_int("GOMELT_K1_WPB", WPB);  // dev tuning knob
+                if (wpb == 2) launch_v2<RY, 2, F_L3_BENCH>(sp, nch, st);
+                else if (wpb == 4) launch_v2<RY, 4, F_L3_BENCH>(sp, nch, st);
+                else launch_v2<RY, WPB, F_L3_BENCH>(sp, nch, st);
+                break;
+            }
             case F_L3_SUB: launch_v2<RY, WPB, F_L3_SUB>(sp, nch, st); break;
             case F_L3_SUB2: launch_v2<RY, WPB, F_L3_SUB2>(sp, nch, st); break;
             case F_L1_DWELL: launch_v2<RY, WPB, F_L1_DWELL>(sp, nch, st); break;

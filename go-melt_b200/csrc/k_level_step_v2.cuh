@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(32 * WPB) level_step_v2(const __grid_constant_
 
     // ---- plane l: node state, x stage, then the element layer (l-1, l) row by row; finalises
     //      plane l-1 when do_final.  pv = state of plane l-1, cu <- state of plane l.
-    auto step_plane = [&](int l, const K1Raw<RY>& raw, const K1State<RY>& pv, K1State<RY>& cu, bool do_final) {
+    auto step_plane = [&](int l, const K1Raw<RY>& raw, const K1State<RY>& pv, K1State<RY>& cu, bool do_final, f2 sz) {
         const bool wr = (l >= za) && (l < zb);
         const int subrow = (l < nsub_planes) ? (1 << 30) : ((l == nsub_planes) ? nsub_rem : 0);
         const int f = l - 1;
@@ -332,9 +332,8 @@ __global__ void __launch_bounds__(32 * WPB) level_step_v2(const __grid_constant_
         FinalPtrs fp;
         fp.out = opaque(p.Tout + (pl - P));
         fp.rhs = K1_HAS(K1F_RHS) ? opaque(p.rhs + (pl - P)) : nullptr;
-        f2 sz = splat(0.f);
-        if (K1_HAS(K1F_SRC)) sz = sfx * splat(__ldg(p.srcz + max(f, 0)));
-        const bool topf = K1_HAS(K1F_TOP) && (f == nzl - 1);
+        // the top-flux plane nzl-1 is always the last data plane of its chunk: finalised by last_plane
+        constexpr bool topf = false;
         const f2 l1 = splat(p.lam[1]), l2 = splat(p.lam[2]), l3 = splat(p.lam[3]), l4 = splat(p.lam[4]),
                  l5 = splat(p.lam[5]), l6 = splat(p.lam[6]), l7 = splat(p.lam[7]);
         f2 c00, c01, c10, c11, cm;            // carries of the previous element row
@@ -421,12 +420,19 @@ __global__ void __launch_bounds__(32 * WPB) level_step_v2(const __grid_constant_
         if (lfirst + 1 <= llast) load_plane(lfirst + 1, rawB);
         first_plane(lfirst, rawA, stA);
         // main loop, unrolled by two so the carried state ping-pongs: (stA, rawB) -> stB, (stB, rawA) -> stA
+        // source z-factor of the plane finalised next, fetched one plane ahead
+        auto srcz_of = [&](int f) { return K1_HAS(K1F_SRC) ? __ldg(p.srcz + min(max(f, 0), nz - 1)) : 0.f; };
+        float szn = srcz_of(lfirst);
         for (int l = lfirst + 1; l <= llast; l += 2) {
             if (l + 1 <= llast) load_plane(l + 1, rawA);
-            step_plane(l, rawB, stA, stB, l - 1 >= za);
+            float szc = szn;
+            szn = srcz_of(l);
+            step_plane(l, rawB, stA, stB, l - 1 >= za, sfx * splat(szc));
             if (l + 1 > llast) break;
             if (l + 2 <= llast) load_plane(l + 2, rawB);
-            step_plane(l + 1, rawA, stB, stA, l >= za);
+            szc = szn;
+            szn = srcz_of(l + 1);
+            step_plane(l + 1, rawA, stB, stA, l >= za, sfx * splat(szc));
         }
         if (llast >= za && llast < zb) {
             if (((llast - lfirst) & 1) != 0) last_plane(llast, stB.T);  // parity of the plane held in stB

@@ -1,0 +1,33 @@
+"""Generate tests/golden/*.npz by executing the reference's own, unmodified source
+(/root/reference/go_melt/computeFunctions.py) through the NumPy ``jax`` shim.
+
+    python tests/golden/make_golden.py            (needs /root/reference; run in the build container)
+
+The fixtures travel with the repo; the reference and the shim are not needed to run the tests.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import jax_numpy_shim as shim  # noqa: E402
+import scenario  # noqa: E402
+
+
+def main():
+    cF = shim.load_reference()
+    t0 = time.time()
+    out = scenario.run(cF, wrap=shim._wrap)
+    flat = {}
+    for phase, d in out.items():
+        for k, v in d.items():
+            flat[f"{phase}/{k}"] = np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, "small_run_reference.npz"), **flat)
+    print(f"small_run_reference.npz: {len(flat)} arrays, {time.time() - t0:.1f} s")
+
+
+if __name__ == "__main__":
+    main()

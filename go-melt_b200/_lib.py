@@ -46,6 +46,36 @@ class StepArgs(C.Structure):
     ]
 
 
+class Axis(C.Structure):
+    _fields_ = [("coords", C.c_void_p), ("n", C.c_int32)]
+
+
+class InterpArgs(C.Structure):
+    _fields_ = [
+        ("src", Axis * 3),
+        ("u", C.c_void_p), ("u2", C.c_void_p), ("alpha", C.c_float), ("beta", C.c_float),
+        ("tx", C.c_void_p), ("ty", C.c_void_p), ("tz", C.c_void_p),
+        ("ntx", C.c_int32), ("nty", C.c_int32), ("ntz", C.c_int32),
+        ("mode", C.c_int32), ("faces_only", C.c_int32), ("has_clamp", C.c_int32), ("clamp_min", C.c_float),
+        ("map_x", C.c_void_p), ("map_y", C.c_void_p), ("map_z", C.c_void_p),
+        ("map_nx", C.c_int32), ("map_ny", C.c_int32),
+        ("base", C.c_void_p), ("out", C.c_void_p),
+    ]
+
+
+class ProjectArgs(C.Structure):
+    _fields_ = [
+        ("fine", Axis * 3), ("parent", Axis * 3),
+        ("A", C.c_void_p), ("A2", C.c_void_p), ("coef", C.c_void_p),
+        ("mode", C.c_int32), ("scale", C.c_float),
+        ("cell0", C.c_int32 * 3), ("ncell", C.c_int32 * 3),
+        ("first_x", C.c_void_p), ("first_y", C.c_void_p), ("first_z", C.c_void_p),
+        ("elems_per_cell_hint", C.c_int32),
+        ("cellsum", C.c_void_p), ("V", C.c_void_p), ("accumulate", C.c_int32),
+    ]
+
+
+INTERP_SET, INTERP_ADD, INTERP_RSUB = 0, 1, 2
 STEP_CLAMP, STEP_WRITE_S1, STEP_WRITE_S2 = 0x01, 0x02, 0x04
 STEP_BC_CONST, STEP_SKIP_FACES, STEP_ACCUM = 0x08, 0x10, 0x20
 
@@ -61,6 +91,15 @@ SIGNATURES = {
     "gomelt_source_tables_f32": (C.c_int, [C.POINTER(Props), C.POINTER(Grid), C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.POINTER(C.c_float * 3), C.c_float, C.c_void_p,
                                            C.c_void_p, C.c_void_p, c_float_p, C.c_void_p]),
+    "gomelt_interp_f32": (C.c_int, [C.POINTER(InterpArgs), C.c_void_p]),
+    "gomelt_box_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                  C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "gomelt_rank1_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_float, C.c_int32, C.c_void_p]),
+    "gomelt_coarse_source_tables_f32": (C.c_int, [C.POINTER(Props), C.POINTER(Axis * 3), C.POINTER(Axis * 3),
+                                                  C.POINTER(C.c_float * 3), C.c_float, C.c_void_p, C.c_void_p,
+                                                  C.c_void_p, c_float_p, C.c_void_p]),
+    "gomelt_project_f32": (C.c_int, [C.POINTER(ProjectArgs), C.c_void_p]),
     "gomelt_diag_fp32_rate": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                         C.POINTER(C.c_double), C.c_void_p]),
 }

@@ -96,6 +96,91 @@ def source_tables(props, grid, coords, laser_xyz, laserP, tx, ty, tz):
     return coef.value
 
 
+def _axes(coords):
+    ax = (_lib.Axis * 3)()
+    for d in range(3):
+        ax[d].coords = coords[d].data_ptr()
+        ax[d].n = int(coords[d].numel())
+    return ax
+
+
+def interp(src_coords, u, tgt_coords, out, *, mode=_lib.INTERP_SET, u2=None, alpha=1.0, beta=0.0, faces_only=False,
+           clamp_min=None, index_map=None, base=None):
+    """gomelt_interp_f32: trilinear interpolation of ``u`` (on the level with device coordinate arrays
+    ``src_coords``) at the tensor-product target grid ``tgt_coords`` -> ``out`` (see gomelt_abi.h).
+    ``index_map`` = (mx, my, mz, big_nx, big_ny) scatters the result through a tensor-product index set."""
+    lib = _lib.load()
+    a = _lib.InterpArgs()
+    a.src = _axes(src_coords)
+    a.u, a.u2 = u.data_ptr(), (u2.data_ptr() if u2 is not None else None)
+    a.alpha, a.beta = float(alpha), float(beta)
+    a.tx, a.ty, a.tz = (t.data_ptr() for t in tgt_coords)
+    a.ntx, a.nty, a.ntz = (int(t.numel()) for t in tgt_coords)
+    a.mode, a.faces_only = int(mode), int(bool(faces_only))
+    a.has_clamp, a.clamp_min = (0, 0.0) if clamp_min is None else (1, float(clamp_min))
+    if index_map is not None:
+        mx, my, mz, bnx, bny = index_map
+        a.map_x, a.map_y, a.map_z, a.map_nx, a.map_ny = mx.data_ptr(), my.data_ptr(), mz.data_ptr(), int(bnx), int(bny)
+    a.base = base.data_ptr() if base is not None else None
+    a.out = out.data_ptr()
+    _lib.check(lib.gomelt_interp_f32(C.byref(a), _lib.stream_ptr()), "gomelt_interp_f32")
+    _count()
+    return out
+
+
+def box_copy(src, dst, idx3, big_nx, big_ny, scatter):
+    """gomelt_box_copy: window <-> big grid through the tensor-product index vectors ``idx3`` (int32)."""
+    lib = _lib.load()
+    es = src.element_size()
+    if es != dst.element_size() or es not in (1, 4):
+        raise _lib.GomeltError("box_copy: float32 or uint8/bool tensors of the same width")
+    nx, ny, nz = (int(t.numel()) for t in idx3)
+    _lib.check(lib.gomelt_box_copy(_lib.ptr(src), _lib.ptr(dst), es, _lib.ptr(idx3[0]), _lib.ptr(idx3[1]),
+                                   _lib.ptr(idx3[2]), nx, ny, nz, int(big_nx), int(big_ny), int(bool(scatter)),
+                                   _lib.stream_ptr()), "gomelt_box_copy")
+    _count()
+    return dst
+
+
+def rank1(F, tx, ty, tz, coef, accumulate=True):
+    lib = _lib.load()
+    _lib.check(lib.gomelt_rank1_f32(_lib.ptr(F), _lib.ptr(tx), _lib.ptr(ty), _lib.ptr(tz), int(tx.numel()),
+                                    int(ty.numel()), int(tz.numel()), float(coef), int(bool(accumulate)),
+                                    _lib.stream_ptr()), "gomelt_rank1_f32")
+    _count()
+    return F
+
+
+def coarse_source_tables(props, fine_coords, parent_coords, laser_xyz, laserP, tx, ty, tz):
+    """gomelt_coarse_source_tables_f32 -> 6 sqrt(3) P eta (multiply by the fine wq and use with rank1)."""
+    lib = _lib.load()
+    v = (C.c_float * 3)(float(laser_xyz[0]), float(laser_xyz[1]), float(laser_xyz[2]))
+    coef = C.c_float(0.0)
+    fa, pa = _axes(fine_coords), _axes(parent_coords)
+    _lib.check(lib.gomelt_coarse_source_tables_f32(C.byref(props), C.byref(fa), C.byref(pa), C.byref(v), float(laserP),
+                                                   _lib.ptr(tx), _lib.ptr(ty), _lib.ptr(tz), C.byref(coef),
+                                                   _lib.stream_ptr()), "gomelt_coarse_source_tables_f32")
+    _count(3)
+    return coef.value
+
+
+def project(fine_coords, parent_coords, A, coef, V, cells, *, mode, scale=1.0, A2=None, accumulate=True):
+    """gomelt_project_f32.  ``cells`` = dict(cell0, ncell, first (3 int32 device arrays), cellsum, hint)."""
+    lib = _lib.load()
+    a = _lib.ProjectArgs()
+    a.fine, a.parent = _axes(fine_coords), _axes(parent_coords)
+    a.A, a.A2, a.coef = A.data_ptr(), (A2.data_ptr() if A2 is not None else None), coef.data_ptr()
+    a.mode, a.scale = int(mode), float(scale)
+    a.cell0 = (C.c_int32 * 3)(*[int(v) for v in cells["cell0"]])
+    a.ncell = (C.c_int32 * 3)(*[int(v) for v in cells["ncell"]])
+    a.first_x, a.first_y, a.first_z = (t.data_ptr() for t in cells["first"])
+    a.elems_per_cell_hint = int(cells["hint"])
+    a.cellsum, a.V, a.accumulate = cells["cellsum"].data_ptr(), V.data_ptr(), int(bool(accumulate))
+    _lib.check(lib.gomelt_project_f32(C.byref(a), _lib.stream_ptr()), "gomelt_project_f32")
+    _count(2)
+    return V
+
+
 def diag_fp32_rate(kind, iters=4096, blocks=148 * 8, threads=256):
     """FP32 issue-rate micro-benchmark; returns lane-ops per second (timed with CUDA events)."""
     torch = _lib.require_cuda()

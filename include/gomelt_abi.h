@@ -117,6 +117,86 @@ int gomelt_source_tables_f32(const gomelt_props_t *props, const gomelt_grid_t *g
                              const float *y, const float *z, const float laser_xyz[3], float laserP,
                              float *tx, float *ty, float *tz, float *coef, void *stream);
 
+/* ---- inter-level transfers (no materialised operators; see DESIGN.md "Transfers") ---------------------
+ * A level is seen through its three 1-D node-coordinate arrays (Level["node_coords"], cF:32-64). */
+typedef struct gomelt_axis {
+    const float *coords;   /* [n] device array of node coordinates along the axis */
+    int32_t      n;        /* nodes (= elements + 1)                              */
+} gomelt_axis_t;
+
+#define GOMELT_INTERP_SET  0   /* out[o] = I                 */
+#define GOMELT_INTERP_ADD  1   /* out[o] += I                */
+#define GOMELT_INTERP_RSUB 2   /* out[o] = base[o] - I       */
+
+/* K2 / K4 / K5 - trilinear interpolation of a source-level field at the nodes of a tensor-product
+ * target grid.  Replaces interpolatePoints cF:1131-1210, interpolatePointsMatrix cF:1028-1107 +
+ * interpolate_w_matrix cF:1110-1128 (weights are recomputed, never stored), the face-only use in
+ * assignBCsFine cF:1598-1620 (faces_only: targets on the y-,y+,x-,x+,z- faces), the time blend
+ * alpha*new + beta*old of cF:3349/3389 (u2), the scatter into the parent's overlap nodes of
+ * getNewTprime cF:2086-2090 (map_*), T' = T - I(parent) cF:2094-2097 (RSUB) and the
+ * max(I(T0), T_amb) of the layer change gm:215-218 (clamp).  Points outside the source grid by
+ * more than the reference's 1e-2 weight window contribute 0 (cF:1101-1102). */
+typedef struct gomelt_interp_args {
+    gomelt_axis_t src[3];
+    const float  *u;              /* source field [src nn]                                   */
+    const float  *u2;             /* NULL, or second source field: value = alpha*u + beta*u2 */
+    float         alpha, beta;
+    const float  *tx, *ty, *tz;   /* target coordinates                                      */
+    int32_t       ntx, nty, ntz;
+    int32_t       mode;           /* GOMELT_INTERP_*                                         */
+    int32_t       faces_only;
+    int32_t       has_clamp;
+    float         clamp_min;      /* result = max(result, clamp_min) when has_clamp          */
+    const int32_t *map_x, *map_y, *map_z; /* NULL, or index vectors: o = mx[i] + my[j]*map_nx + mz[k]*map_nx*map_ny */
+    int32_t       map_nx, map_ny;
+    const float  *base;           /* RSUB                                                    */
+    float        *out;
+} gomelt_interp_args_t;
+
+int gomelt_interp_f32(const gomelt_interp_args_t *args, void *stream);
+
+/* Window <-> big-grid copies through a tensor-product index set (getOverlapRegion cF:1642-1669):
+ * scatter = 0: dst[t] = src[idx(t)]   (S1/S2 regather from Level 0, cF:2500-2502)
+ * scatter = 1: dst[idx(t)] = src[t]   (Level-3 state back to Level 0, cF:2390-2392)
+ * elem_size 4 (float) or 1 (uint8). */
+int gomelt_box_copy(const void *src, void *dst, int32_t elem_size, const int32_t *ix, const int32_t *iy,
+                    const int32_t *iz, int32_t nx, int32_t ny, int32_t nz, int32_t big_nx, int32_t big_ny,
+                    int32_t scatter, void *stream);
+
+/* F[n] (+)= coef * tx[ix]*ty[iy]*tz[iz]: a projected source term added to a parent load vector. */
+int gomelt_rank1_f32(float *F, const float *tx, const float *ty, const float *tz, int32_t nx, int32_t ny,
+                     int32_t nz, float coef, int32_t accumulate, void *stream);
+
+/* K6 for the parents: computeSources cF:928-988 / computeLevelSource cF:2667-2730.  The laser source
+ * integrated at the FINE level's Gauss points and projected with the PARENT's shape functions is
+ * rank-1: Fc[n] = coef * wq_fine * tx[ix]*ty[iy]*tz[iz] (*coef returns 6 sqrt3 P eta). */
+int gomelt_coarse_source_tables_f32(const gomelt_props_t *props, const gomelt_axis_t fine[3],
+                                    const gomelt_axis_t parent[3], const float laser_xyz[3], float laserP,
+                                    float *tx, float *ty, float *tz, float *coef, void *stream);
+
+/* K3 - fine -> parent correction vectors, integrated at the fine Gauss points:
+ *   mode 0: V[c] (+)= - sum wq * grad Nc . (kbar grad A)          computeCoarseTprimeTerm_jax cF:1477-1565,
+ *                                                                  computeL1/L2TprimeTerms_Part1 cF:2733-2914
+ *   mode 1: V[c] (+)= - scale * sum wq * Nc * (rcbar * A)          computeCoarseTprimeMassTerm_jax cF:1396-1474,
+ *                                                                  ..._Part2 cF:3057-3221 (A = A - A2, scale = 1/dt)
+ * The fine elements are grouped by parent cell: cell0 / ncell = box of parent cells that contain fine
+ * elements, first_d[i] = first fine element (axis d) of parent cell cell0[d] + i (length ncell[d] + 1).
+ * cellsum is scratch [ncell_x*ncell_y*ncell_z*8].  Deterministic (no float atomics). */
+typedef struct gomelt_project_args {
+    gomelt_axis_t fine[3], parent[3];
+    const float  *A, *A2, *coef;
+    int32_t       mode;
+    float         scale;
+    int32_t       cell0[3], ncell[3];
+    const int32_t *first_x, *first_y, *first_z;
+    int32_t       elems_per_cell_hint;
+    float        *cellsum;
+    float        *V;
+    int32_t       accumulate;
+} gomelt_project_args_t;
+
+int gomelt_project_f32(const gomelt_project_args_t *args, void *stream);
+
 const char *gomelt_last_error(void);
 int gomelt_abi_version(void);
 

@@ -27,6 +27,24 @@ def main():
             flat[f"{phase}/{k}"] = np.asarray(v)
     np.savez_compressed(os.path.join(HERE, "small_run_reference.npz"), **flat)
     print(f"small_run_reference.npz: {len(flat)} arrays, {time.time() - t0:.1f} s")
+    toolpath_golden(cF)
+
+
+def toolpath_golden(cF):
+    """The reference's own G-code parser (createPath.parsingGcode cP:6-188, unmodified) on its own example."""
+    import importlib
+    import json
+    import shutil
+    import tempfile
+
+    cP = importlib.import_module("createPath")
+    inp = json.load(open("/root/reference/examples/example.json"))
+    tmp = tempfile.mkdtemp() + "/"
+    nm = dict(inp["nonmesh"], save_path=tmp, toolpath=tmp + "toolpath.txt",
+              gcode="/root/reference/examples/gcodefiles/example.gcode")
+    n = cP.parsingGcode(cF.SetupNonmesh(nm), cF.SetupProperties(inp["properties"]), [0.04, 0.04, 0.04])
+    shutil.copy(tmp + "toolpath.txt", os.path.join(HERE, "toolpath_example.txt"))
+    print(f"toolpath_example.txt: {n} rows")
 
 
 if __name__ == "__main__":

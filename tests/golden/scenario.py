@@ -51,6 +51,8 @@ def toolpath_rows():
 
 
 def _np(x):
+    if hasattr(x, "detach"):  # torch tensor (CUDA product)
+        return x.detach().cpu().numpy()
     return np.asarray(x)
 
 

@@ -1,0 +1,37 @@
+"""G-code -> toolpath text: the product's and the oracle's parsers against the byte-exact output of the
+reference's own parser on its own example (tests/golden/toolpath_example.txt, written by
+tests/golden/make_golden.py running createPath.parsingGcode cP:6-188 unmodified)."""
+import importlib
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GCODE = "G0 X2.0 Y2.000 Z0.04\nG1 X8.0 Y2.000 Z0.04\n"   # examples/gcodefiles/example.gcode
+NONMESH = {"timestep_L3": 1e-05, "dwell_time": 1.0, "wait_time": 200, "output_files": 1, "record_step": 25,
+           "Level1_record_step": 1, "laser_velocity": 1000, "layer_num": 0, "subcycle_num_L2": 5,
+           "subcycle_num_L3": 5, "info_T": 1, "dwell_time_multiplier": 8, "use_txt": 0}   # ex:117-133
+
+
+def _run(parse, setup_nonmesh, tmp_path, tag):
+    g = tmp_path / "example.gcode"
+    g.write_text(GCODE)
+    nm = dict(NONMESH, save_path=str(tmp_path) + "/", gcode=str(g), toolpath=str(tmp_path / f"{tag}.txt"))
+    n = parse(setup_nonmesh(nm), {"laser_power": 285.0})
+    return n, (tmp_path / f"{tag}.txt").read_bytes()
+
+
+def test_product_toolpath_is_byte_identical_to_the_reference(tmp_path):
+    tp = importlib.import_module("go-melt_b200.toolpath")
+    sc = importlib.import_module("go-melt_b200.schema")
+    golden = open(os.path.join(HERE, "golden", "toolpath_example.txt"), "rb").read()
+    n, text = _run(tp.parsingGcode, sc.SetupNonmesh, tmp_path, "product")
+    assert n == 1299 and text == golden
+    assert len({len(line) for line in text.splitlines()}) == 1   # fixed-width rows (gm:125-126 seeks by row)
+    assert tp.count_lines(str(tmp_path / "product.txt")) == 1299
+
+
+def test_oracle_toolpath_is_byte_identical_to_the_reference(tmp_path):
+    from oracle import computeFunctions as cF
+
+    golden = open(os.path.join(HERE, "golden", "toolpath_example.txt"), "rb").read()
+    n, text = _run(cF.parsingGcode, cF.SetupNonmesh, tmp_path, "oracle")
+    assert n == 1299 and text == golden

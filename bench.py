@@ -219,7 +219,7 @@ def run_gomelt_single(args):
     clocks = sampler.stop(t_wall0, time.time())
     peaks = read_peaks()
     achieved = B_ALG_L3 * nn / k1_avg_s / 1e9
-    traffic = read_traffic("level_step_kernel")
+    traffic = read_traffic("level_step_v2")
     line = {
         "metric": "Level-3 DOF-updates/s", "value": value, "unit": "DOF-updates/s", "n_gpus": 1,
         "steps": K, "warmup": W, "ms_per_step": 1e3 * total_s / K, "higher_is_better": True,
@@ -232,7 +232,7 @@ def run_gomelt_single(args):
                          "events summed", "state": "device-resident (value) / host buffers (e2e)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
-                     "kernel": "level_step_kernel", "bytes_per_dof": B_ALG_L3,
+                     "kernel": "level_step_v2", "bytes_per_dof": B_ALG_L3,
                      "kernel_us": k1_avg_s * 1e6, "peak_source": peaks["source"]},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
     }

@@ -83,6 +83,7 @@ STEP_BC_CONST, STEP_SKIP_FACES, STEP_ACCUM = 0x08, 0x10, 0x20
 SIGNATURES = {
     "gomelt_abi_version": (C.c_int, []),
     "gomelt_last_error": (C.c_char_p, []),
+    "gomelt_xla_ffi_available": (C.c_int, []),
     "gomelt_level_step_f32": (C.c_int, [C.POINTER(Props), C.POINTER(StepArgs), C.c_void_p]),
     "gomelt_state_props_f32": (C.c_int, [C.POINTER(Props), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

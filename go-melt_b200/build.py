@@ -18,12 +18,32 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
 def sources():
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+    """Every .cu (sm_100a kernels + C ABI) and .cc (the compile-guarded XLA-FFI shim)."""
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cc")))
+
+
+def xla_include_dirs():
+    """jaxlib's header tree (xla/ffi/api/ffi.h) when a jaxlib exists; [] in this image."""
+    inc = os.environ.get("GOMELT_XLA_INCLUDE")
+    if inc:
+        return [inc]
+    try:
+        import importlib.util
+
+        spec = importlib.util.find_spec("jaxlib")
+        if spec and spec.submodule_search_locations:
+            d = os.path.join(list(spec.submodule_search_locations)[0], "include")
+            if os.path.exists(os.path.join(d, "xla", "ffi", "api", "ffi.h")):
+                return [d]
+    except Exception:
+        pass
+    return []
 
 
 def _digest():
     h = hashlib.sha256()
     files = sources() + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cuh")]
+    h.update(repr(xla_include_dirs()).encode())
     files.append(os.path.join(ROOT, "include", "gomelt_abi.h"))
     for f in files:
         with open(f, "rb") as fh:
@@ -47,7 +67,8 @@ def build_library(force=False, verbose=False, ptxas_v=False):
             if fh.read().strip() == dig:
                 return out
     cmd = [NVCC, "-shared", "-Xcompiler", "-fPIC", "-O3", "-std=c++17", "-lineinfo", *ARCH,
-           "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", out, *sources()]
+           "-I", os.path.join(ROOT, "include"), "-I", CSRC, *[a for d in xla_include_dirs() for a in ("-I", d)],
+           "-o", out, *sources()]
     if ptxas_v:
         cmd.insert(1, "-Xptxas=-v")
     if verbose or ptxas_v:

@@ -200,6 +200,10 @@ int gomelt_project_f32(const gomelt_project_args_t *args, void *stream);
 const char *gomelt_last_error(void);
 int gomelt_abi_version(void);
 
+/* 1 when the library was built with jaxlib's xla/ffi/api/ffi.h and exports the XLA FFI handler symbols
+ * (GomeltLevelStepFfi, ...: csrc/xla_ffi_shim.cc), 0 otherwise (this image: no jaxlib). */
+int gomelt_xla_ffi_available(void);
+
 /* Diagnostics: FP32 issue-rate micro-benchmark.  kind: 0 = FFMA (3-reg),
  * 1 = FADD, 2 = packed FFMA2 (fma.rn.f32x2).  Returns lane-ops executed in *ops. */
 int gomelt_diag_fp32_rate(int32_t kind, int32_t iters, int32_t blocks, int32_t threads, float *sink,

@@ -189,12 +189,12 @@ static int env_int(const char* name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
-template <int RY, int WPB, int FEAT>
+template <int RY, int WPB, int FEAT, int MINB = 1>
 static void launch_v2(const StepParams& sp, int nch, cudaStream_t st) {
     dim3 block(32, WPB);
     const int strips = (sp.ny + RY - 1) / RY;
     dim3 grid((sp.nx + 2 * K1_TX - 1) / (2 * K1_TX), (strips + WPB - 1) / WPB, nch);
-    level_step_v2<RY, WPB, FEAT><<<grid, block, 0, st>>>(sp);
+    level_step_v2<RY, WPB, FEAT, MINB><<<grid, block, 0, st>>>(sp);
 }
 
 // exact-feature instances for the hot call shapes; anything else runs the generic instance
@@ -220,7 +220,14 @@ static int launch_step(const StepParams& sp, cudaStream_t st) {
         switch (sp.feat) {
             case F_L3_BENCH: {
                 static const int wpb = env_int("GOMELT_K1_WPB", WPB);  // dev tuning knob
-                if (wpb == 2) launch_v2<RY, 2, F_L3_BENCH>(sp, nch, st);
+                static const int exp = env_int("GOMELT_K1_EXP", 0);    // dev A/B of tile shape / register cap
+                if (exp == 1) launch_v2<4, 1, F_L3_BENCH, 12>(sp, nch, st);
+                else if (exp == 2) launch_v2<3, 1, F_L3_BENCH, 1>(sp, nch, st);
+                else if (exp == 3) launch_v2<3, 1, F_L3_BENCH, 12>(sp, nch, st);
+                else if (exp == 4) launch_v2<2, 1, F_L3_BENCH, 1>(sp, nch, st);
+                else if (exp == 5) launch_v2<2, 1, F_L3_BENCH, 16>(sp, nch, st);
+                else if (exp == 6) launch_v2<4, 1, F_L3_BENCH, 10>(sp, nch, st);
+                else if (wpb == 2) launch_v2<RY, 2, F_L3_BENCH>(sp, nch, st);
                 else if (wpb == 4) launch_v2<RY, 4, F_L3_BENCH>(sp, nch, st);
                 else launch_v2<RY, WPB, F_L3_BENCH>(sp, nch, st);
                 break;

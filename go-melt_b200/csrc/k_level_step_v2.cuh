@@ -122,9 +122,38 @@ GM_DI T* opaque(T* q) {
     return q;
 }
 
-GM_DI void stg(float* q, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(q), "f"(v) : "memory"); }
-
 constexpr int K1_TX = 30;  // owned columns per half-warp tile (32 lanes - 2 halo)
+
+// Both halves of a packed pair through ONE address: q points at the column of half .y (always >= 0), half
+// .x is K1_TX columns (120 bytes) below it as an immediate offset, so a pair costs one 64-bit add instead of
+// two widened index computations.  fa / fb guard the two accesses (columns outside the grid are never
+// touched; a guarded-off load keeps the old - finite - register value, which is neutralised downstream).
+GM_DI void ld2(const char* q, int fa, int fb, f2& v) {
+    asm("{\n\t.reg .pred pa, pb;\n\t"
+        "setp.ne.s32 pa, %3, 0;\n\t"
+        "setp.ne.s32 pb, %4, 0;\n\t"
+        "@pa ld.global.nc.f32 %0, [%2+-120];\n\t"
+        "@pb ld.global.nc.f32 %1, [%2];\n\t}"
+        : "+f"(v.v.x), "+f"(v.v.y)
+        : "l"(q), "r"(fa), "r"(fb));
+}
+GM_DI void st2(char* q, int fa, int fb, f2 v) {
+    asm volatile("{\n\t.reg .pred pa, pb;\n\t"
+                 "setp.ne.s32 pa, %3, 0;\n\t"
+                 "setp.ne.s32 pb, %4, 0;\n\t"
+                 "@pa st.global.f32 [%0+-120], %1;\n\t"
+                 "@pb st.global.f32 [%0], %2;\n\t}"
+                 ::"l"(q), "f"(v.v.x), "f"(v.v.y), "r"(fa), "r"(fb)
+                 : "memory");
+}
+// A load pinned in program order (volatile asm is not moved across the volatile stores): used for the
+// one-plane-ahead fetch of the source z-factor, which the scheduler otherwise sinks next to its use.
+GM_DI float ldg_pinned(const float* q) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(q));
+    return v;
+}
+static_assert(K1_TX * 4 == 120, "ld2 / st2 hard-code the half distance");
 
 // Compile-time feature mask: a kernel instance carries code only for the features in FEAT.
 // K1F_GENERIC additionally tests the run-time flags / pointers, so one instance serves any call.
@@ -147,17 +176,17 @@ template <int RY>
 struct K1State {           // x-staged fields of one plane (loaded rows) + T of the owned rows
     f2 Xs[RY + 2], Xd[RY + 2], kx[RY + 2], mx[RY + 2], T[RY];
 };
-struct FinalPtrs {         // plane base pointers of the plane being finalised
-    float* out;
-    const float* rhs;
+struct FinalPtrs {         // plane base pointers (bytes) of the plane being finalised
+    char* out;
+    const char* rhs;
 };
 template <int RY>
 struct K1Raw {             // prefetched raw plane
     f2 T[RY + 2], S[RY + 2];
 };
 
-template <int RY, int WPB, int FEAT>
-__global__ void __launch_bounds__(32 * WPB) level_step_v2(const __grid_constant__ StepParams p) {
+template <int RY, int WPB, int FEAT, int MINB = 1>
+__global__ void __launch_bounds__(32 * WPB, MINB) level_step_v2(const __grid_constant__ StepParams p) {
     constexpr int NR = RY + 2;  // loaded rows
     constexpr bool GEN = (FEAT & K1F_GENERIC) != 0;
     const int rtf = p.feat;     // run-time feature bits, set by the launcher
@@ -170,24 +199,27 @@ __global__ void __launch_bounds__(32 * WPB) level_step_v2(const __grid_constant_
     const int ib = ia + K1_TX;
     const bool lown = (lane >= 1) && (lane <= K1_TX);
     const bool owna = lown && (ia < nx), ownb = lown && (ib < nx);
+    const int la = (ia >= 0 && ia < nx) ? 1 : 0, lb = (ib < nx) ? 1 : 0;  // load guards
+    const int oa = owna ? 1 : 0, ob = ownb ? 1 : 0;                      // store guards
     const f2 xm = mk2((ia >= 0 && ia + 1 < nx) ? 1.f : 0.f, (ib >= 0 && ib + 1 < nx) ? 1.f : 0.f);
     const int P = nx * ny;  // nn < 2^31 is validated by the launcher
     const int za = p.zbeg + blockIdx.z * p.zchunk;
     const int zb = min(p.zend, za + p.zchunk);  // this warp finalises node planes [za, zb)
     const int lfirst = max(za - 1, 0);
     const int llast = min(min(zb, nz - 1), nzl - 1);  // last plane that carries data
-    // clamped column / row offsets: every load address is valid, no predicates
+    // rows are clamped (warp-uniform), columns are guarded: in-plane BYTE offset of half .y per loaded row
     const int cola = min(max(ia, 0), nx - 1), colb = min(max(ib, 0), nx - 1);
-    unsigned offa[NR], offb[NR];  // in-plane element offsets of the loaded rows, per half
+    unsigned offb[NR];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-        const int ro = min(max(j0 - 1 + r, 0), ny - 1) * nx;
-        offa[r] = (unsigned)(ro + cola);
-        offb[r] = (unsigned)(ro + colb);
-    }
+    for (int r = 0; r < NR; ++r) offb[r] = 4u * (unsigned)(min(max(j0 - 1 + r, 0), ny - 1) * nx + ib);
     const bool edge_lo = (j0 == 0), edge_hi = (j0 + RY >= ny);
     const int nsub_planes = p.nsub_planes, nsub_rem = p.nsub_rem;  // substrate: whole planes (cF:575-578) + rest
 
+    // A value loaded outside the plane loop is passed through one real ALU op right away (xor with an
+    // opaque zero), so that its scoreboard wait happens here and not at its first use inside the loop,
+    // where the same scoreboard also tracks the next plane's prefetch (measured: 1.4 stall cycles / issue).
+    const int opaque_zero = nx >> 31;
+    auto settle = [&](float x) { return __int_as_float(__float_as_int(x) ^ opaque_zero); };
     f2 sfx = splat(0.f);
     float sfy[RY];
 #pragma unroll
@@ -195,7 +227,7 @@ __global__ void __launch_bounds__(32 * WPB) level_step_v2(const __grid_constant_
     if (K1_HAS(K1F_SRC)) {
         sfx = mk2(__ldg(p.srcx + cola) * p.scoef, __ldg(p.srcx + colb) * p.scoef);
 #pragma unroll
-        for (int r = 0; r < RY; ++r) sfy[r] = __ldg(p.srcy + min(j0 + r, ny - 1));
+        for (int r = 0; r < RY; ++r) sfy[r] = settle(__ldg(p.srcy + min(j0 + r, ny - 1)));
     }
 
     f2 Tt0[RY], Tt1[RY], myp[RY];  // top contributions (stiffness sx = 0 / 1, mass) of the previous layer
@@ -203,22 +235,23 @@ __global__ void __launch_bounds__(32 * WPB) level_step_v2(const __grid_constant_
     for (int r = 0; r < RY; ++r) Tt0[r] = Tt1[r] = myp[r] = splat(0.f);
 
     auto load_plane = [&](int l, K1Raw<RY>& raw) {
-        const float* __restrict__ Tl = opaque(p.T0 + (size_t)l * P);
-        const float* __restrict__ Sl = opaque(p.S1 + (size_t)l * P);
+        const char* Tl = (const char*)(p.T0 + (size_t)l * P);
+        const char* Sl = (const char*)(p.S1 + (size_t)l * P);
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-            raw.T[r] = mk2(__ldg(Tl + offa[r]), __ldg(Tl + offb[r]));
-            raw.S[r] = mk2(__ldg(Sl + offa[r]), __ldg(Sl + offb[r]));
+            ld2(Tl + offb[r], la, lb, raw.T[r]);
+            ld2(Sl + offb[r], la, lb, raw.S[r]);
         }
     };
 
     // ---- node state of loaded row r of plane l (+ S1 / S2 / melt-time outputs) and its x stage -----
-    auto row_a = [&](size_t pl, float* so, int r, bool wr, int subrow, f2 T, f2 S, f2& xs, f2& xd, f2& kxr, f2& mxr) {
+    auto row_a = [&](size_t pl, char* so, int r, bool wr, int subrow, f2 T, f2 S, f2& xs, f2& xd, f2& kxr, f2& mxr) {
         const f2 kb = fma2(splat(p.pk.k_a1), T, splat(p.pk.k_a0)), cs = fma2(splat(p.pk.c_a1), T, splat(p.pk.c_a0));
         int suba = 0, subb = 0;
+        const int eb = (int)(offb[r] >> 2), ea = eb - K1_TX;  // in-plane node ids of the two halves
         if (K1_HAS(K1F_NSUB)) {
-            suba = offa[r] < (unsigned)subrow;
-            subb = offb[r] < (unsigned)subrow;
+            suba = ea < subrow;
+            subb = eb < subrow;
         }
         f2 kn, mn, s1f = splat(0.f);
         int s2a = 0, s2b = 0;
@@ -232,13 +265,10 @@ __global__ void __launch_bounds__(32 * WPB) level_step_v2(const __grid_constant_
         }
         if (outs) {
             if (wr && (j0 + r - 1 < ny)) {
-                if (K1_HAS(K1F_S1OUT)) {
-                    if (owna) stg(so + offa[r], s1f.v.x);
-                    if (ownb) stg(so + offb[r], s1f.v.y);
-                }
+                if (K1_HAS(K1F_S1OUT)) st2(so + offb[r], oa, ob, s1f);
                 if (K1_HAS(K1F_ACCUM)) {  // cF:3568-3578
                     if (owna) {
-                        const size_t n = pl + offa[r];
+                        const size_t n = pl + ea;
                         const bool prev = p.S2prev[n] != 0;
                         const float ac = p.accum[n];
                         const float reset = (!prev && s2a) ? ac : 0.f;
@@ -246,7 +276,7 @@ __global__ void __launch_bounds__(32 * WPB) level_step_v2(const __grid_constant_
                         p.accum[n] = ac + (s2a ? p.dt : 0.f) - reset;
                     }
                     if (ownb) {
-                        const size_t n = pl + offb[r];
+                        const size_t n = pl + eb;
                         const bool prev = p.S2prev[n] != 0;
                         const float ac = p.accum[n];
                         const float reset = (!prev && s2b) ? ac : 0.f;
@@ -255,8 +285,8 @@ __global__ void __launch_bounds__(32 * WPB) level_step_v2(const __grid_constant_
                     }
                 }
                 if (K1_HAS(K1F_S2OUT)) {
-                    if (owna) p.S2out[pl + offa[r]] = (uint8_t)s2a;
-                    if (ownb) p.S2out[pl + offb[r]] = (uint8_t)s2b;
+                    if (owna) p.S2out[pl + ea] = (uint8_t)s2a;
+                    if (ownb) p.S2out[pl + eb] = (uint8_t)s2b;
                 }
             }
         }
@@ -272,7 +302,7 @@ __global__ void __launch_bounds__(32 * WPB) level_step_v2(const __grid_constant_
         const bool wr = (l >= za) && (l < zb);
         const int subrow = (l < nsub_planes) ? (1 << 30) : ((l == nsub_planes) ? nsub_rem : 0);
         const size_t pl = (size_t)l * P;
-        float* so = K1_HAS(K1F_S1OUT) ? opaque(p.S1out + pl) : nullptr;
+        char* so = K1_HAS(K1F_S1OUT) ? (char*)(p.S1out + pl) : nullptr;
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
             row_a(pl, so, r, wr, subrow, raw.T[r], raw.S[r], st.Xs[r], st.Xd[r], st.kx[r], st.mx[r]);
@@ -298,9 +328,7 @@ __global__ void __launch_bounds__(32 * WPB) level_step_v2(const __grid_constant_
             skb = fy || (ib == 0) || (ib == nx - 1);
         }
         if (K1_HAS(K1F_CLAMP)) Tn = mk2(fmaxf(p.pk.T_amb, Tn.v.x), fmaxf(p.pk.T_amb, Tn.v.y));
-        float* __restrict__ out = fp.out;
-        if (owna && !ska) stg(out + offa[r + 1], Tn.v.x);
-        if (ownb && !skb) stg(out + offb[r + 1], Tn.v.y);
+        st2(fp.out + offb[r + 1], (owna && !ska) ? 1 : 0, (ownb && !skb) ? 1 : 0, Tn);
     };
 
     // ---- explicit update of owned row r of plane f from its assembled action (z0, z1, mz) ---------
@@ -310,12 +338,13 @@ __global__ void __launch_bounds__(32 * WPB) level_step_v2(const __grid_constant_
         const f2 mnode = mz + shup(mz);
         if (j0 + r < ny) {
             f2 rr = splat(0.f);
-            if (K1_HAS(K1F_RHS)) {
-                const float* __restrict__ rp = fp.rhs;
-                rr = mk2(__ldg(rp + offa[r + 1]), __ldg(rp + offb[r + 1]));
-            }
+            if (K1_HAS(K1F_RHS)) ld2(fp.rhs + offb[r + 1], la, lb, rr);
             if (K1_HAS(K1F_SRC)) rr = fma2(sz, splat(sfy[r]), rr);
-            if (topf) rr = rr + mk2(__ldg(p.topflux + offa[r + 1]), __ldg(p.topflux + offb[r + 1]));
+            if (topf) {
+                f2 tf = splat(0.f);
+                ld2((const char*)p.topflux + offb[r + 1], la, lb, tf);
+                rr = rr + tf;
+            }
             const f2 w = splat(p.cdt) * mk2(rcp_approx(mnode.v.x), rcp_approx(mnode.v.y));
             store_row(f, fp, r, fma2(rr - KT, w, Tf));
         }
@@ -328,10 +357,10 @@ __global__ void __launch_bounds__(32 * WPB) level_step_v2(const __grid_constant_
         const int subrow = (l < nsub_planes) ? (1 << 30) : ((l == nsub_planes) ? nsub_rem : 0);
         const int f = l - 1;
         const size_t pl = (size_t)l * P;
-        float* so = K1_HAS(K1F_S1OUT) ? opaque(p.S1out + pl) : nullptr;
+        char* so = K1_HAS(K1F_S1OUT) ? (char*)(p.S1out + pl) : nullptr;
         FinalPtrs fp;
-        fp.out = opaque(p.Tout + (pl - P));
-        fp.rhs = K1_HAS(K1F_RHS) ? opaque(p.rhs + (pl - P)) : nullptr;
+        fp.out = (char*)(p.Tout + (pl - P));
+        fp.rhs = K1_HAS(K1F_RHS) ? (const char*)(p.rhs + (pl - P)) : nullptr;
         // the top-flux plane nzl-1 is always the last data plane of its chunk: finalised by last_plane
         constexpr bool topf = false;
         const f2 l1 = splat(p.lam[1]), l2 = splat(p.lam[2]), l3 = splat(p.lam[3]), l4 = splat(p.lam[4]),
@@ -390,14 +419,27 @@ __global__ void __launch_bounds__(32 * WPB) level_step_v2(const __grid_constant_
         }
     };
 
+    // ---- source z-factor of plane f: 32 consecutive factors live one per lane and are broadcast by
+    //      shuffle (a per-plane uniform global load sat on the critical path: long-scoreboard stalls)
+    float szwin = 0.f;
+    int szbase = -(1 << 30);
+    auto srcz_at = [&](int f) -> float {
+        if (!K1_HAS(K1F_SRC)) return 0.f;
+        if (f - szbase >= 32 || f < szbase) {  // warp-uniform
+            szbase = f;
+            szwin = settle(__ldg(p.srcz + min(f + lane, nz - 1)));
+        }
+        return __shfl_sync(0xffffffffu, szwin, f - szbase);
+    };
+
     // ---- last data plane of a chunk top: no layer above, its action is (Tt0, Tt1, myp) --------------
     auto last_plane = [&](int f, const f2* Tf) {
         f2 sz = splat(0.f);
-        if (K1_HAS(K1F_SRC)) sz = sfx * splat(__ldg(p.srcz + f));
+        if (K1_HAS(K1F_SRC)) sz = sfx * splat(srcz_at(f));
         const bool topf = K1_HAS(K1F_TOP) && (f == nzl - 1);
         FinalPtrs fp;
-        fp.out = opaque(p.Tout + (size_t)f * P);
-        fp.rhs = K1_HAS(K1F_RHS) ? opaque(p.rhs + (size_t)f * P) : nullptr;
+        fp.out = (char*)(p.Tout + (size_t)f * P);
+        fp.rhs = K1_HAS(K1F_RHS) ? (const char*)(p.rhs + (size_t)f * P) : nullptr;
 #pragma unroll
         for (int r = 0; r < RY; ++r) final_row(f, fp, r, sz, topf, Tf[r], Tt0[r], Tt1[r], myp[r]);
     };
@@ -405,7 +447,7 @@ __global__ void __launch_bounds__(32 * WPB) level_step_v2(const __grid_constant_
     // ---- inactive planes (substitute_Tbar cF:2183) with the Dirichlet faces applied -------------
     auto fill_inactive = [&](int f) {
         FinalPtrs fp;
-        fp.out = opaque(p.Tout + (size_t)f * P);
+        fp.out = (char*)(p.Tout + (size_t)f * P);
         fp.rhs = nullptr;
 #pragma unroll
         for (int r = 0; r < RY; ++r)
@@ -414,25 +456,21 @@ __global__ void __launch_bounds__(32 * WPB) level_step_v2(const __grid_constant_
 
     int fdone = za;  // planes [za, fdone) are finalised
     if (lfirst <= llast) {
-        K1Raw<RY> rawA, rawB;
+        K1Raw<RY> rawA, rawB;  // zero-initialised: guarded-off loads keep these (finite) values
+#pragma unroll
+        for (int r = 0; r < NR; ++r) rawA.T[r] = rawA.S[r] = rawB.T[r] = rawB.S[r] = splat(0.f);
         K1State<RY> stA, stB;
         load_plane(lfirst, rawA);
         if (lfirst + 1 <= llast) load_plane(lfirst + 1, rawB);
         first_plane(lfirst, rawA, stA);
         // main loop, unrolled by two so the carried state ping-pongs: (stA, rawB) -> stB, (stB, rawA) -> stA
         // source z-factor of the plane finalised next, fetched one plane ahead
-        auto srcz_of = [&](int f) { return K1_HAS(K1F_SRC) ? __ldg(p.srcz + min(max(f, 0), nz - 1)) : 0.f; };
-        float szn = srcz_of(lfirst);
         for (int l = lfirst + 1; l <= llast; l += 2) {
             if (l + 1 <= llast) load_plane(l + 1, rawA);
-            float szc = szn;
-            szn = srcz_of(l);
-            step_plane(l, rawB, stA, stB, l - 1 >= za, sfx * splat(szc));
+            step_plane(l, rawB, stA, stB, l - 1 >= za, sfx * splat(srcz_at(l - 1)));
             if (l + 1 > llast) break;
             if (l + 2 <= llast) load_plane(l + 2, rawB);
-            szc = szn;
-            szn = srcz_of(l + 1);
-            step_plane(l + 1, rawA, stB, stA, l >= za, sfx * splat(szc));
+            step_plane(l + 1, rawA, stB, stA, l >= za, sfx * splat(srcz_at(l)));
         }
         if (llast >= za && llast < zb) {
             if (((llast - lfirst) & 1) != 0) last_plane(llast, stB.T);  // parity of the plane held in stB

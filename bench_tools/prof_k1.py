@@ -19,6 +19,6 @@ Tout = torch.empty_like(T0); S1o = torch.empty_like(T0)
 tx = torch.rand(nx, device="cuda"); ty = torch.rand(ny, device="cuda"); tz = torch.rand(nz, device="cuda")
 top = torch.zeros(nx * ny, device="cuda")
 for it in range(4):
-    ops.level_step(props, grid, T0, S1, Tout, 1e-5, src=(tx, ty, tz, 1e-3), topflux=top, n_substrate=0,
-                   flags=ops.STEP_CLAMP | ops.STEP_WRITE_S1, S1_out=S1o, z_chunk=zc)
+    ops.level_step(props, grid, T0, S1, Tout, 1e-5, src=(tx, ty, tz, 1e-3), n_substrate=0,
+                   flags=ops.STEP_CLAMP | ops.STEP_WRITE_S1 | ops.STEP_FUSED_FLUX, S1_out=S1o, z_chunk=zc)
 torch.cuda.synchronize()

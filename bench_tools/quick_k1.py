@@ -26,8 +26,8 @@ for zc in [int(a) for a in sys.argv[1:]] or (0, 20, 13, 10):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.level_step(props, grid, T0, S1, Tout, 1e-5, src=(tx, ty, tz, 1e-3), topflux=top, n_substrate=0,
-                       flags=ops.STEP_CLAMP | ops.STEP_WRITE_S1, S1_out=S1o, z_chunk=zc)
+        ops.level_step(props, grid, T0, S1, Tout, 1e-5, src=(tx, ty, tz, 1e-3), n_substrate=0,
+                       flags=ops.STEP_CLAMP | ops.STEP_WRITE_S1 | ops.STEP_FUSED_FLUX, S1_out=S1o, z_chunk=zc)
         e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     t = np.median(ts[3:]) * 1e-3

@@ -75,9 +75,29 @@ class ProjectArgs(C.Structure):
     ]
 
 
+class SubstepsArgs(C.Structure):
+    _fields_ = [
+        ("grid", Grid),
+        ("x", C.c_void_p), ("y", C.c_void_p), ("z", C.c_void_p),
+        ("n", C.c_int32),
+        ("rows", C.c_void_p),
+        ("T_in", C.c_void_p), ("T_a", C.c_void_p), ("T_b", C.c_void_p),
+        ("S1_in", C.c_void_p), ("S1", C.c_void_p),
+        ("n_substrate", C.c_int64),
+        ("flags", C.c_int32),
+        ("tables", C.c_void_p),
+        ("S2", C.c_void_p), ("accum", C.c_void_p), ("max_accum", C.c_void_p),
+        ("faces", C.POINTER(InterpArgs)),
+        ("faces_n", C.c_float),
+        ("T_last", C.POINTER(C.c_void_p)),
+    ]
+
+
+MAX_SUBSTEPS = 64
 INTERP_SET, INTERP_ADD, INTERP_RSUB = 0, 1, 2
 STEP_CLAMP, STEP_WRITE_S1, STEP_WRITE_S2 = 0x01, 0x02, 0x04
 STEP_BC_CONST, STEP_SKIP_FACES, STEP_ACCUM = 0x08, 0x10, 0x20
+STEP_FUSED_FLUX = 0x40
 
 # name -> (restype, argtypes); kept in one table so tests can check every header symbol loads
 SIGNATURES = {
@@ -92,6 +112,10 @@ SIGNATURES = {
     "gomelt_source_tables_f32": (C.c_int, [C.POINTER(Props), C.POINTER(Grid), C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.POINTER(C.c_float * 3), C.c_float, C.c_void_p,
                                            C.c_void_p, C.c_void_p, c_float_p, C.c_void_p]),
+    "gomelt_source_tables_batch_f32": (C.c_int, [C.POINTER(Props), C.POINTER(Grid), C.c_void_p, C.c_void_p,
+                                                 C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, c_float_p,
+                                                 C.c_void_p]),
+    "gomelt_l3_substeps_f32": (C.c_int, [C.POINTER(Props), C.POINTER(SubstepsArgs), C.c_void_p]),
     "gomelt_interp_f32": (C.c_int, [C.POINTER(InterpArgs), C.c_void_p]),
     "gomelt_box_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                   C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),

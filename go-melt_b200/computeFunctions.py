@@ -251,21 +251,24 @@ def _bc5(L1):
     return [c["y"][0], c["y"][1], c["x"][0], c["x"][1], c["z"][0]]
 
 
-def _solve_L1(Levels, T0, S1, rhs, top, tmp_ne_nn, dt, properties, n_sub, clamp=True):
-    """solveMatrixFreeFE + substitute_Tbar + assignBCs (+ clamp) on Level 1 (cF:2172-2185, 2813-2854)."""
+def _solve_L1(Levels, T0, S1, rhs, tmp_ne_nn, dt, properties, n_sub, clamp=True):
+    """computeConvRadBC + solveMatrixFreeFE + substitute_Tbar + assignBCs (+ clamp) on Level 1
+    (cF:2207-2301, 2172-2185, 2813-2854); the surface load of the top active plane is evaluated inside K1."""
     L1 = Levels[1]
     out = _torch().empty_like(T0)
-    flags = ops.STEP_BC_CONST | (ops.STEP_CLAMP if clamp else 0)
-    return ops.level_step(_props(properties), _grid(L1), T0, S1, out, float(dt), rhs=rhs, topflux=top,
+    flags = ops.STEP_BC_CONST | ops.STEP_FUSED_FLUX | (ops.STEP_CLAMP if clamp else 0)
+    return ops.level_step(_props(properties), _grid(L1), T0, S1, out, float(dt), rhs=rhs,
                           nz_active=_nz_active(L1, tmp_ne_nn[1]), n_substrate=int(n_sub), flags=flags,
                           bc5=_bc5(L1))
 
 
-def _solve_child(L, T0, S1, rhs, src, top, dt, properties, n_sub, **kw):
-    """solveMatrixFreeFE on a window level; the 5 Dirichlet faces are left for _faces_from_parent."""
+def _solve_child(L, T0, S1, rhs, src, dt, properties, n_sub, **kw):
+    """computeConvRadBC + solveMatrixFreeFE on a window level (surface load fused into K1); the 5 Dirichlet
+    faces are left for _faces_from_parent."""
     out = _torch().empty_like(T0)
-    return ops.level_step(_props(properties), _grid(L), T0, S1, out, float(dt), rhs=rhs, src=src, topflux=top,
-                          n_substrate=int(n_sub), flags=ops.STEP_SKIP_FACES | ops.STEP_CLAMP | kw.pop("flags", 0), **kw)
+    flags = ops.STEP_SKIP_FACES | ops.STEP_CLAMP | ops.STEP_FUSED_FLUX | kw.pop("flags", 0)
+    return ops.level_step(_props(properties), _grid(L), T0, S1, out, float(dt), rhs=rhs, src=src,
+                          n_substrate=int(n_sub), flags=flags, **kw)
 
 
 def getNewTprime(Fine, FineT0, CoarseT, Coarse, C2F=None):
@@ -332,13 +335,11 @@ def stepGOMELT(Levels, ne_nn, tmp_ne_nn, Shapes, LInterp, v, properties, dt, las
     L3["S1"], L3["S2"], k3, rc3 = computeStateProperties(L3["T0"], L3["S1"], properties, substrate[3])
     L2["S1"], _, k2, rc2 = computeStateProperties(L2["T0"], L2["S1"], properties, substrate[2])
     _push_S1_to_L1(Levels, substrate)
-    # loads: laser source on Level 3 (rank-1 tables), its projections on Levels 1-2, surface fluxes
+    # loads: laser source on Level 3 (rank-1 tables) and its projections on Levels 1-2; the surface fluxes
+    # (computeConvRadBC cF:2348-2350) are evaluated inside each level step from that level's T0
     src3 = _l3_source(L3, v, properties, laserP)
     F1 = _projected_source(L3, L1, [v], [laserP], properties)
     F2 = _projected_source(L3, L2, [v], [laserP], properties)
-    top1 = _surface_flux(L1, L1["T0"], _nz_active(L1, tmp_ne_nn[1]), properties)
-    top2 = _surface_flux(L2, L2["T0"], L2["nodes"][2], properties)
-    top3 = _surface_flux(L3, L3["T0"], L3["nodes"][2], properties)
     # computeCoarseTprimeTerm_jax cF:1477-1565
     Vcu, Vmu = _zeros_like_level(L1), _zeros_like_level(L2)
     _project(Shapes["L3L1"], L3["Tprime0"], k3, Vcu, mode=0)
@@ -346,11 +347,11 @@ def stepGOMELT(Levels, ne_nn, tmp_ne_nn, Shapes, LInterp, v, properties, dt, las
     _project(Shapes["L3L2"], L3["Tprime0"], k3, Vmu, mode=0)
 
     def solutions(Vc, Vm, L3_interior=None):
-        T1 = _solve_L1(Levels, L1["T0"], L1["S1"], F1 + Vc, top1, tmp_ne_nn, dt, properties, substrate[1])
-        T2 = _solve_child(L2, L2["T0"], L2["S1"], F2 + Vm, None, top2, dt, properties, substrate[2])
+        T1 = _solve_L1(Levels, L1["T0"], L1["S1"], F1 + Vc, tmp_ne_nn, dt, properties, substrate[1])
+        T2 = _solve_child(L2, L2["T0"], L2["S1"], F2 + Vm, None, dt, properties, substrate[2])
         _faces_from_parent(L1, T1, L2, T2, T_amb)
         if L3_interior is None:
-            T3 = _solve_child(L3, L3["T0"], L3["S1"], None, src3, top3, dt, properties, substrate[3])
+            T3 = _solve_child(L3, L3["T0"], L3["S1"], None, src3, dt, properties, substrate[3])
         else:
             T3 = L3_interior  # same T0, F, k, rho*cp, Corr = 0: only the faces change (cF:2199-2201)
         _faces_from_parent(L2, T2, L3, T3, T_amb)
@@ -374,8 +375,7 @@ def stepGOMELTDwellTime(Levels, tmp_ne_nn, ne_nn, properties, dt, substrate):
     """cF:2617-2664: Level 1 only, no clamp."""
     L1 = Levels[1]
     L1["T0"], L1["S1"] = _f(L1["T0"]), _f(L1["S1"])
-    top = _surface_flux(L1, L1["T0"], _nz_active(L1, tmp_ne_nn[1]), properties)
-    L1["T0"] = _solve_L1(Levels, L1["T0"], L1["S1"], None, top, tmp_ne_nn, float(_host(dt)), properties,
+    L1["T0"] = _solve_L1(Levels, L1["T0"], L1["S1"], None, tmp_ne_nn, float(_host(dt)), properties,
                          substrate[1], clamp=False)
     return Levels
 
@@ -391,18 +391,16 @@ def subcycleGOMELT(Levels, ne_nn, Shapes, substrate, LInterp, tmp_ne_nn, laser_p
     P = np.asarray(_host(laserP), F32)
     N2, N3 = int(subcycle[0]), int(subcycle[1])
     fN2, fN3 = F32(subcycle[3]), F32(subcycle[4])
-    nz1 = _nz_active(L1, tmp_ne_nn[1])
 
     _, _, k3_L1, rc3_L1 = computeStateProperties(L3["T0"], L3["S1"], properties, substrate[3])
     _, _, k2_L1, rc2_L1 = computeStateProperties(L2["T0"], L2["S1"], properties, substrate[2])
     _push_S1_to_L1(Levels, substrate)
     dt_all = float(rows[:, 5].sum(dtype=F32))
     F1 = _projected_source(L3, L1, rows, P, properties)
-    top1 = _surface_flux(L1, L1["T0"], nz1, properties)
     V1 = _zeros_like_level(L1)
     _project(Shapes["L3L1"], L3["Tprime0"], k3_L1, V1, mode=0)
     _project(Shapes["L2L1"], L2["Tprime0"], k2_L1, V1, mode=0)
-    L1T = _solve_L1(Levels, L1["T0"], L1["S1"], F1 + V1, top1, tmp_ne_nn, dt_all, properties, substrate[1])
+    L1T = _solve_L1(Levels, L1["T0"], L1["S1"], F1 + V1, tmp_ne_nn, dt_all, properties, substrate[1])
 
     def L2_common(T2, S12, T3, Tp3, S13, isub):
         a2 = F32(isub + 1) / fN2
@@ -411,43 +409,45 @@ def subcycleGOMELT(Levels, ne_nn, Shapes, substrate, LInterp, tmp_ne_nn, laser_p
         _, _, k3, rc3 = computeStateProperties(T3, S13, properties, substrate[3])
         S12n, _, k2, rc2 = computeStateProperties(T2, S12, properties, substrate[2])
         F2 = _projected_source(L3, L2, rows[sl], P[sl], properties)
-        top2 = _surface_flux(L2, T2, L2["nodes"][2], properties)
         V2 = _zeros_like_level(L2)
         _project(Shapes["L3L2"], Tp3, k3, V2, mode=0)
         dt2 = float(rows[sl, 5].sum(dtype=F32))
-        return float(a2), float(b2), rc3, S12n, F2, top2, V2, dt2
+        return float(a2), float(b2), rc3, S12n, F2, V2, dt2
 
-    def solve_L2(T2, S12, F2, V2, top2, dt2, a2, b2, L1new):
-        T2n = _solve_child(L2, T2, S12, F2 + V2, None, top2, dt2, properties, substrate[2])
+    def solve_L2(T2, S12, F2, V2, dt2, a2, b2, L1new):
+        T2n = _solve_child(L2, T2, S12, F2 + V2, None, dt2, properties, substrate[2])
         _faces_from_parent(L1, L1new, L2, T2n, T_amb, blend=(a2, b2, L1["T0"]))
         return T2n
 
-    def L3_substep(T3, S13, i3, i2, L2new, L2prev, accum=None):
-        ll = i3 + i2 * N3
-        src3 = _l3_source(L3, rows[ll], properties, P[ll])
-        top3 = _surface_flux(L3, T3, L3["nodes"][2], properties)
-        a3 = F32(i3 + 1) / fN3
-        b3 = F32(1) - a3
-        S13n = torch.empty_like(S13)
-        kw = dict(S1_out=S13n)
-        flags = ops.STEP_WRITE_S1
+    # the inner scan (subcycleL3_Part1 / _Part2, cF:3367-3412 / 3530-3590) is one C-ABI call per Level-2 substep:
+    # all N3 source tables in one launch, then N3 x (fused level step + face prolongation from Level 2)
+    rowsP = rows.copy()
+    rowsP[:, 6] = P
+    nx3, ny3, nz3 = L3["nodes"]
+    scratch = {"T": [torch.empty_like(L3["T0"]) for _ in range(2)], "S1": torch.empty_like(L3["S1"]),
+               "tables": torch.empty(N3 * (nx3 + ny3 + nz3), device="cuda", dtype=torch.float32)}
+    c3, c2 = _coords(L3["node_coords"]), _coords(L2["node_coords"])
+
+    def L3_block(T3, S13, i2, L2new, L2prev, accum=None):
+        A, B = scratch["T"]
+        Ta, Tb = (B, A) if T3 is A else (A, B)  # T_a != T_in; T_in may be T_b
+        kw, flags = {}, ops.STEP_SKIP_FACES | ops.STEP_CLAMP
         if accum is not None:
-            S2prev, mx, ac = accum
-            S2n = torch.empty_like(S2prev)
-            kw.update(S2_out=S2n, S2_prev=S2prev, accum=ac, max_accum=mx)
+            S2w, mx_, ac_ = accum
+            kw = dict(S2=S2w, accum=ac_, max_accum=mx_)
             flags |= ops.STEP_WRITE_S2 | ops.STEP_ACCUM
-        T3n = _solve_child(L3, T3, S13, None, src3, top3, float(rows[ll, 5]), properties, substrate[3], flags=flags, **kw)
-        _faces_from_parent(L2, L2new, L3, T3n, T_amb, blend=(float(a3), float(b3), L2prev))
-        return (T3n, S13n) if accum is None else (T3n, S13n, S2n)
+        T3n = ops.l3_substeps(_props(properties), _grid(L3), c3, rowsP[i2 * N3:(i2 + 1) * N3], T3, Ta, Tb,
+                              scratch["S1"], scratch["tables"], S1_in=S13, n_substrate=int(substrate[3]),
+                              flags=flags, faces=(c2, L2new, L2prev, fN3, T_amb), **kw)
+        return T3n, scratch["S1"]
 
     # ---- predictor pass cF:3308-3430 ----
     T2, S12, T3, Tp3, S13 = L2["T0"], L2["S1"], L3["T0"], L3["Tprime0"], L3["S1"]
     Tp3_hist = []
     for i2 in range(N2):
-        a2, b2, _, S12n, F2, top2, V2, dt2 = L2_common(T2, S12, T3, Tp3, S13, i2)
-        T2n = solve_L2(T2, S12, F2, V2, top2, dt2, a2, b2, L1T)
-        for i3 in range(N3):
-            T3, S13 = L3_substep(T3, S13, i3, i2, T2n, T2)
+        a2, b2, _, S12n, F2, V2, dt2 = L2_common(T2, S12, T3, Tp3, S13, i2)
+        T2n = solve_L2(T2, S12, F2, V2, dt2, a2, b2, L1T)
+        T3, S13 = L3_block(T3, S13, i2, T2n, T2)
         Tp3, T2n = getNewTprime(L3, T3, T2n, L2)
         T2, S12 = T2n, S12n
         Tp3_hist.append(Tp3)
@@ -455,18 +455,17 @@ def subcycleGOMELT(Levels, ne_nn, Shapes, substrate, LInterp, tmp_ne_nn, laser_p
     Tp2, L1T = getNewTprime(L2, T2, L1T, L1)
     _project(Shapes["L3L1"], Tp3, rc3_L1, V1, mode=1, scale=1.0 / F32(dt_all), A2=L3["Tprime0"])
     _project(Shapes["L2L1"], Tp2, rc2_L1, V1, mode=1, scale=1.0 / F32(dt_all), A2=L2["Tprime0"])
-    L1T = _solve_L1(Levels, L1["T0"], L1["S1"], F1 + V1, top1, tmp_ne_nn, dt_all, properties, substrate[1])
+    L1T = _solve_L1(Levels, L1["T0"], L1["S1"], F1 + V1, tmp_ne_nn, dt_all, properties, substrate[1])
     # ---- corrector pass cF:3458-3622 ----
     T2, S12, T3, Tp3, S13 = L2["T0"], L2["S1"], L3["T0"], L3["Tprime0"], L3["S1"]
-    S23 = L3["S2"]
+    S23 = L3["S2"].clone()  # updated in place by the corrector substeps
     mx = _f(max_accum_L3).clone()
     ac = _f(accum_L3).clone()
     for i2 in range(N2):
-        a2, b2, rc3, S12n, F2, top2, V2, dt2 = L2_common(T2, S12, T3, Tp3, S13, i2)
+        a2, b2, rc3, S12n, F2, V2, dt2 = L2_common(T2, S12, T3, Tp3, S13, i2)
         _project(Shapes["L3L2"], Tp3_hist[i2], rc3, V2, mode=1, scale=1.0 / F32(dt2), A2=Tp3)
-        T2n = solve_L2(T2, S12, F2, V2, top2, dt2, a2, b2, L1T)
-        for i3 in range(N3):
-            T3, S13, S23 = L3_substep(T3, S13, i3, i2, T2n, T2, accum=(S23, mx, ac))
+        T2n = solve_L2(T2, S12, F2, V2, dt2, a2, b2, L1T)
+        T3, S13 = L3_block(T3, S13, i2, T2n, T2, accum=(S23, mx, ac))
         Tp3, T2n = getNewTprime(L3, T3, T2n, L2)
         T2, S12 = T2n, S12n
     L2["T0"], L2["S1"], L3["T0"], L3["Tprime0"], L3["S1"], L3["S2"] = T2, S12, T3, Tp3, S13, S23

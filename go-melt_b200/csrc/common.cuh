@@ -47,6 +47,42 @@ inline PropK fold_props(const gomelt_props_t& p) {
     return q;
 }
 
+// computeConvRadBC cF:2207-2301: constants of the top-surface flux, folded once on the host.
+struct FluxK {
+    float T_amb, T_cap, invT_b, Lev, cp_fluid, CM, CT, evcCP, h_conv, sig_eps, Tamb4;
+    float wq;  // hx*hy/4
+};
+
+inline FluxK fold_flux(const gomelt_props_t& p, const gomelt_grid_t& g) {
+    FluxK fk;
+    fk.T_amb = p.T_amb;
+    fk.T_cap = p.T_boiling + 1000.f;
+    fk.invT_b = 1.0f / p.T_boiling;
+    fk.Lev = p.Lev;
+    fk.cp_fluid = p.cp_fluid;
+    fk.CM = p.CM_coeff;
+    fk.CT = p.CT_coeff;
+    fk.evcCP = p.evc * p.CP_coeff;
+    fk.h_conv = p.h_conv;
+    fk.sig_eps = p.sigma_sb * p.vareps;
+    const float Ta2 = p.T_amb * p.T_amb;
+    fk.Tamb4 = Ta2 * Ta2;
+    fk.wq = (g.hx * g.hy) * 0.25f;
+    return fk;
+}
+
+// convection + radiation + evaporation flux at one surface Gauss point (cF:2270-2293)
+__device__ __forceinline__ float flux_at(const FluxK& f, float Tq) {
+    Tq = fminf(Tq, f.T_cap);
+    const float invT = 1.0f / Tq;
+    const float E_pv = f.Lev + f.cp_fluid * (Tq - f.T_amb);
+    const float MolMot = sqrtf(f.CM * invT);
+    const float S = f.evcCP * expf(-f.CT * (invT - f.invT_b)) * MolMot * E_pv;
+    const float T2 = Tq * Tq;
+    float q = f.h_conv * (f.T_amb - Tq) + f.sig_eps * (f.Tamb4 - T2 * T2) - S;
+    return q * 1e-6f;
+}
+
 // State + properties of one node.  S1 in: float (thresholded at 0.499), forced to 1 on substrate.
 __device__ __forceinline__ void node_props(const PropK& q, float T, float S1in, bool substrate,
                                            float& k, float& rhocp, bool& s1, bool& s2) {

@@ -34,22 +34,6 @@ __global__ void state_props_kernel(PropK pk, const float* __restrict__ T, const 
 }
 
 // ---- computeConvRadBC cF:2207-2301 -------------------------------------------------------
-struct FluxK {
-    float T_amb, T_cap, invT_b, Lev, cp_fluid, CM, CT, evcCP, h_conv, sig_eps, Tamb4;
-    float wq;  // hx*hy/4
-};
-
-__device__ __forceinline__ float flux_at(const FluxK& f, float Tq) {
-    Tq = fminf(Tq, f.T_cap);
-    const float invT = 1.0f / Tq;
-    const float E_pv = f.Lev + f.cp_fluid * (Tq - f.T_amb);
-    const float MolMot = sqrtf(f.CM * invT);
-    const float S = f.evcCP * expf(-f.CT * (invT - f.invT_b)) * MolMot * E_pv;
-    const float T2 = Tq * Tq;
-    float q = f.h_conv * (f.T_amb - Tq) + f.sig_eps * (f.Tamb4 - T2 * T2) - S;
-    return q * 1e-6f;
-}
-
 // One thread per top-plane node; gathers its <= 4 adjacent top elements in increasing element
 // id (the order the reference's scatter-add applies them), recomputing each element's 4 Gauss
 // fluxes: deterministic, no atomics; the top plane is 1/nz of the level.
@@ -89,10 +73,8 @@ __global__ void surface_flux_kernel(FluxK fk, int nx, int ny, const float* __res
 // ---- K6: separable source tables ----------------------------------------------------------
 // t[i] = sum_{e in {i-1,i}} sum_{q in {0,1}} N1[q][a] * c * exp(-3 (x_q - v)^2 / s^2),
 // x_q = N1[q][0] x_e + N1[q][1] x_{e+1}  (getQuadratureCoords cF:3151-3166), N1[q][a] = (1 +- 1/sqrt3)/2.
-__global__ void source_table_kernel(const float* __restrict__ x, int n, float v, float inv_s2_3, float c,
-                                    float* __restrict__ t) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__device__ __forceinline__ float source_table_value(const float* __restrict__ x, int n, int i, float v,
+                                                    float inv_s2_3, float c) {
     const float g = 0.57735026918962576f;
     const float Nlo = 0.5f * (1.f + g), Nhi = 0.5f * (1.f - g);  // weight of the near / far node
     float acc = 0.f;
@@ -106,7 +88,25 @@ __global__ void source_table_kernel(const float* __restrict__ x, int n, float v,
         // node i is local corner 1 of element i-1, corner 0 of element i
         acc += (e == i) ? (Nlo * Q0 + Nhi * Q1) : (Nhi * Q0 + Nlo * Q1);
     }
-    t[i] = acc;
+    return acc;
+}
+
+// All three axes of up to GOMELT_MAX_SUBSTEPS laser positions in ONE launch: blockIdx.y = axis,
+// blockIdx.z = laser row; tables of row s live at tables + s * (nx + ny + nz) as [tx | ty | tz].
+struct TableBatch {
+    float v[GOMELT_MAX_SUBSTEPS][3];
+};
+__global__ void source_table_batch_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                          const float* __restrict__ z, int nx, int ny, int nz,
+                                          const __grid_constant__ TableBatch tb, float inv_r2, float inv_d2, float rc,
+                                          float dc, float* __restrict__ tables) {
+    const int axis = blockIdx.y, s = blockIdx.z;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float* c = axis == 0 ? x : (axis == 1 ? y : z);
+    const int n = axis == 0 ? nx : (axis == 1 ? ny : nz);
+    if (i >= n) return;
+    float* out = tables + (size_t)s * (nx + ny + nz) + (axis == 0 ? 0 : (axis == 1 ? nx : nx + ny));
+    out[i] = source_table_value(c, n, i, tb.v[s][axis], axis == 2 ? inv_d2 : inv_r2, axis == 2 ? dc : rc);
 }
 
 // ---- FP32 issue-rate diagnostic -----------------------------------------------------------
@@ -180,20 +180,7 @@ extern "C" int gomelt_surface_flux_f32(const gomelt_props_t* p, const gomelt_gri
         set_error("gomelt_surface_flux_f32: bad grid / nz_active %d", nz_active);
         return GOMELT_E_SIZE;
     }
-    FluxK fk;
-    fk.T_amb = p->T_amb;
-    fk.T_cap = p->T_boiling + 1000.f;
-    fk.invT_b = 1.0f / p->T_boiling;
-    fk.Lev = p->Lev;
-    fk.cp_fluid = p->cp_fluid;
-    fk.CM = p->CM_coeff;
-    fk.CT = p->CT_coeff;
-    fk.evcCP = p->evc * p->CP_coeff;
-    fk.h_conv = p->h_conv;
-    fk.sig_eps = p->sigma_sb * p->vareps;
-    const float Ta2 = p->T_amb * p->T_amb;
-    fk.Tamb4 = Ta2 * Ta2;
-    fk.wq = (g->hx * g->hy) * 0.25f;
+    const FluxK fk = fold_flux(*p, *g);
     dim3 block(32, 8), grid((g->nx + 31) / 32, (g->ny + 7) / 8);
     const float* plane = T0 + (long long)(nz_active - 1) * g->nx * g->ny;
     surface_flux_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(fk, g->nx, g->ny, plane, flux, add);
@@ -214,11 +201,54 @@ extern "C" int gomelt_source_tables_f32(const gomelt_props_t* p, const gomelt_gr
     const float rsq = p->laser_radius * p->laser_radius, dsq = p->laser_depth * p->laser_depth;
     const float wq = (g->hx * g->hy * g->hz) * 0.125f;
     *coef = pcoeff * wq;
-    cudaStream_t st = (cudaStream_t)stream;
-    source_table_kernel<<<(g->nx + 127) / 128, 128, 0, st>>>(x, g->nx, laser_xyz[0], 1.f / rsq, rcoeff, tx);
-    source_table_kernel<<<(g->ny + 127) / 128, 128, 0, st>>>(y, g->ny, laser_xyz[1], 1.f / rsq, rcoeff, ty);
-    source_table_kernel<<<(g->nz + 127) / 128, 128, 0, st>>>(z, g->nz, laser_xyz[2], 1.f / dsq, dcoeff, tz);
+    // one launch: the three tables are one "batch" of a single laser row writing to tx / ty / tz
+    TableBatch tb;
+    tb.v[0][0] = laser_xyz[0]; tb.v[0][1] = laser_xyz[1]; tb.v[0][2] = laser_xyz[2];
+    const int nmax = g->nx > g->ny ? (g->nx > g->nz ? g->nx : g->nz) : (g->ny > g->nz ? g->ny : g->nz);
+    if (ty == tx + g->nx && tz == ty + g->ny) {
+        source_table_batch_kernel<<<dim3((nmax + 127) / 128, 3, 1), 128, 0, (cudaStream_t)stream>>>(
+            x, y, z, g->nx, g->ny, g->nz, tb, 1.f / rsq, 1.f / dsq, rcoeff, dcoeff, tx);
+    } else {  // separately allocated tables: one axis per launch
+        const float* cs[3] = {x, y, z};
+        float* ts[3] = {tx, ty, tz};
+        const int ns[3] = {g->nx, g->ny, g->nz};
+        for (int d = 0; d < 3; ++d) {
+            TableBatch t1;
+            t1.v[0][0] = t1.v[0][1] = t1.v[0][2] = laser_xyz[d];
+            // a 1-axis launch: present axis d as "x" of a grid with ny = nz = 0 blocks
+            source_table_batch_kernel<<<dim3((ns[d] + 127) / 128, 1, 1), 128, 0, (cudaStream_t)stream>>>(
+                cs[d], cs[d], cs[d], ns[d], 0, 0, t1, d == 2 ? 1.f / dsq : 1.f / rsq, 1.f / dsq,
+                d == 2 ? dcoeff : rcoeff, dcoeff, ts[d]);
+        }
+    }
     return check_launch("gomelt_source_tables_f32");
+}
+
+extern "C" int gomelt_source_tables_batch_f32(const gomelt_props_t* p, const gomelt_grid_t* g, const float* x,
+                                              const float* y, const float* z, const float* rows, int32_t n,
+                                              float* tables, float* coef, void* stream) {
+    if (!p || !g || !x || !y || !z || !rows || !tables || !coef) {
+        set_error("gomelt_source_tables_batch_f32: NULL argument");
+        return GOMELT_E_NULL;
+    }
+    if (n < 1 || n > GOMELT_MAX_SUBSTEPS) {
+        set_error("gomelt_source_tables_batch_f32: n = %d outside 1..%d", n, GOMELT_MAX_SUBSTEPS);
+        return GOMELT_E_SIZE;
+    }
+    const float rcoeff = 1.f / (p->laser_radius * sqrtf((float)M_PI));
+    const float dcoeff = 1.f / (p->laser_depth * sqrtf((float)M_PI));
+    const float rsq = p->laser_radius * p->laser_radius, dsq = p->laser_depth * p->laser_depth;
+    const float wq = (g->hx * g->hy * g->hz) * 0.125f;
+    TableBatch tb;
+    for (int s = 0; s < n; ++s) {
+        const float* row = rows + 7 * (size_t)s;
+        tb.v[s][0] = row[0]; tb.v[s][1] = row[1]; tb.v[s][2] = row[2];
+        coef[s] = (6.f * sqrtf(3.f) * row[6] * p->laser_eta) * wq;  // computeSourceFunction_jax cF:1014
+    }
+    const int nmax = g->nx > g->ny ? (g->nx > g->nz ? g->nx : g->nz) : (g->ny > g->nz ? g->ny : g->nz);
+    source_table_batch_kernel<<<dim3((nmax + 127) / 128, 3, n), 128, 0, (cudaStream_t)stream>>>(
+        x, y, z, g->nx, g->ny, g->nz, tb, 1.f / rsq, 1.f / dsq, rcoeff, dcoeff, tables);
+    return check_launch("gomelt_source_tables_batch_f32");
 }
 
 extern "C" int gomelt_diag_fp32_rate(int32_t kind, int32_t iters, int32_t blocks, int32_t threads, float* sink,

@@ -198,10 +198,10 @@ static void launch_v2(const StepParams& sp, int nch, cudaStream_t st) {
 }
 
 // exact-feature instances for the hot call shapes; anything else runs the generic instance
-constexpr int F_L3_BENCH = K1F_SRC | K1F_TOP | K1F_S1OUT | K1F_CLAMP;
+constexpr int F_L3_BENCH = K1F_SRC | K1F_FLUX | K1F_S1OUT | K1F_CLAMP;
 constexpr int F_L3_SUB = F_L3_BENCH | K1F_SKIP;
 constexpr int F_L3_SUB2 = F_L3_SUB | K1F_S2OUT | K1F_ACCUM;
-constexpr int F_L1_DWELL = K1F_TOP | K1F_BCCONST;
+constexpr int F_L1_DWELL = K1F_FLUX | K1F_BCCONST;
 constexpr int F_L1_DWELL_SUB = F_L1_DWELL | K1F_NSUB;
 
 static int launch_step(const StepParams& sp, cudaStream_t st) {
@@ -296,6 +296,7 @@ extern "C" int gomelt_level_step_f32(const gomelt_props_t* props, const gomelt_s
     sp.cdt = (float)(64.0 * (double)a->dt / V);
     sp.dt = a->dt;
     sp.pk = fold_props(*props);
+    sp.fk = fold_flux(*props, g);
     sp.T0 = a->T0; sp.S1 = a->S1; sp.rhs = a->rhs;
     sp.srcx = a->src_x; sp.srcy = a->src_y; sp.srcz = a->src_z; sp.scoef = a->src_coef;
     sp.topflux = a->topflux;
@@ -313,6 +314,7 @@ extern "C" int gomelt_level_step_f32(const gomelt_props_t* props, const gomelt_s
         if (a->rhs) f |= K1F_RHS;
         if (any_src) f |= K1F_SRC;
         if (a->topflux) f |= K1F_TOP;
+        if (a->flags & GOMELT_STEP_FUSED_FLUX) f |= K1F_FLUX;
         if (a->flags & GOMELT_STEP_WRITE_S1) f |= K1F_S1OUT;
         if (a->flags & GOMELT_STEP_WRITE_S2) f |= K1F_S2OUT;
         if (a->flags & GOMELT_STEP_ACCUM) f |= K1F_ACCUM;

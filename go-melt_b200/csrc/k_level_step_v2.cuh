@@ -49,6 +49,7 @@ struct StepParams {
     int zbeg, zend;        // planes to finalise
     int feat;              // K1F_* bits of this call (v2)
     int nsub_planes, nsub_rem;  // n_substrate = nsub_planes * nx*ny + nsub_rem
+    FluxK fk;              // top-surface flux constants (K1F_FLUX)
 };
 
 #define GM_DI __device__ __forceinline__
@@ -168,9 +169,27 @@ enum : int {
     K1F_SKIP = 1 << 7,
     K1F_CLAMP = 1 << 8,
     K1F_NSUB = 1 << 9,     // substrate override present (n_substrate > 0)
-    K1F_ALL = (1 << 10) - 1,
+    K1F_FLUX = 1 << 10,    // top-surface flux (computeConvRadBC) evaluated in the step from T0's top plane
+    K1F_ALL = (1 << 11) - 1,
     K1F_GENERIC = 1 << 30,
 };
+
+// computeConvRadBC cF:2270-2293 with the hardware approximations (rcp / sqrt / ex2, <= 2 ulp each): used
+// by the fused top-plane epilogue, where 8 (RY + 1) flux evaluations per thread sit on every warp's tail.
+// The surface load is a small part of a node's update, so T stays well inside the 1e-5 parity tolerance
+// (tests/test_level_step_gpu.py checks it against the exact-libm stand-alone kernel and the oracle).
+GM_DI float flux_fast(const FluxK& f, float Tq) {
+    Tq = fminf(Tq, f.T_cap);
+    const float invT = rcp_approx(Tq);
+    const float E_pv = fmaf(f.cp_fluid, Tq - f.T_amb, f.Lev);
+    float root, ex;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(root) : "f"(f.CM * invT));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"((-1.4426950408889634f * f.CT) * (invT - f.invT_b)));
+    const float S = f.evcCP * ex * root * E_pv;
+    const float T2 = Tq * Tq;
+    const float q = f.h_conv * (f.T_amb - Tq) + f.sig_eps * (f.Tamb4 - T2 * T2) - S;
+    return q * 1e-6f;
+}
 
 template <int RY>
 struct K1State {           // x-staged fields of one plane (loaded rows) + T of the owned rows
@@ -332,7 +351,8 @@ __global__ void __launch_bounds__(32 * WPB, MINB) level_step_v2(const __grid_con
     };
 
     // ---- explicit update of owned row r of plane f from its assembled action (z0, z1, mz) ---------
-    auto final_row = [&](int f, const FinalPtrs& fp, int r, f2 sz, bool topf, f2 Tf, f2 z0, f2 z1, f2 mz) {
+    auto final_row = [&](int f, const FinalPtrs& fp, int r, f2 sz, bool topf, f2 Tf, f2 z0, f2 z1, f2 mz,
+                         f2 fl = f2{make_float2(0.f, 0.f)}) {
         // x stage of the synthesis (shuffles are executed by the whole warp)
         const f2 KT = (z0 - z1) + shup(z0 + z1);
         const f2 mnode = mz + shup(mz);
@@ -340,6 +360,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) level_step_v2(const __grid_con
             f2 rr = splat(0.f);
             if (K1_HAS(K1F_RHS)) ld2(fp.rhs + offb[r + 1], la, lb, rr);
             if (K1_HAS(K1F_SRC)) rr = fma2(sz, splat(sfy[r]), rr);
+            if (K1_HAS(K1F_FLUX)) rr = rr + fl;
             if (topf) {
                 f2 tf = splat(0.f);
                 ld2((const char*)p.topflux + offb[r + 1], la, lb, tf);
@@ -432,16 +453,65 @@ __global__ void __launch_bounds__(32 * WPB, MINB) level_step_v2(const __grid_con
         return __shfl_sync(0xffffffffu, szwin, f - szbase);
     };
 
+    // ---- computeConvRadBC cF:2207-2301 fused: load of the top face of element layer nzl-2 on the owned
+    //      nodes of plane nzl-1, from that plane's T0 (still in the prefetch registers).  This lane's
+    //      element column spans its node column and the right neighbour's; per element 2x2 Gauss points,
+    //      N2^T (q wq); a node sums its <= 4 elements in increasing element id like the reference's
+    //      scatter-add: (i-1,j-1) a=2, (i,j-1) a=3, (i-1,j) a=1, (i,j) a=0.
+    auto fused_top_flux = [&](const K1Raw<RY>& raw, f2* fl) {
+        // The plane loop's registers are dead here; the element loop is kept rolled (one code copy: an
+        // unrolled version evicts the plane loop from the instruction cache) by staging through shared memory.
+        __shared__ float2 sT[WPB][NR][32];
+        __shared__ float2 sA[WPB][RY + 1][4][32];
+        const int wy = threadIdx.y;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) sT[wy][r][lane] = raw.T[r].v;
+        __syncwarp();
+        const float* sTf = reinterpret_cast<const float*>(&sT[wy][0][0]);
+        float* sAf = reinterpret_cast<float*>(&sA[wy][0][0][0]);
+        const int lane1 = min(lane + 1, 31);
+        const float g = 0.57735026918962576f;
+        const float NA = 0.25f * (1.f + g) * (1.f + g), NB = 0.25f * (1.f + g) * (1.f - g),
+                    NC = 0.25f * (1.f - g) * (1.f - g);
+        const float wq = p.fk.wq;
+#pragma unroll 1
+        for (int it = 0; it < 2 * (RY + 1); ++it) {
+            const int e = it >> 1, h = it & 1;  // element row between loaded rows e, e + 1; half of the pair
+            const float T0n = sTf[(e * 32 + lane) * 2 + h], T1n = sTf[(e * 32 + lane1) * 2 + h];
+            const float T2n = sTf[((e + 1) * 32 + lane1) * 2 + h], T3n = sTf[((e + 1) * 32 + lane) * 2 + h];
+            const int ic = h ? ib : ia;
+            const bool exists = (ic >= 0) && (ic + 1 < nx) && !((e == 0 && edge_lo) || (edge_hi && j0 + e >= ny));
+            const float q0 = flux_fast(p.fk, fmaf(NB, T3n, fmaf(NC, T2n, fmaf(NB, T1n, NA * T0n)))) * wq;
+            const float q1 = flux_fast(p.fk, fmaf(NC, T3n, fmaf(NB, T2n, fmaf(NA, T1n, NB * T0n)))) * wq;
+            const float q2 = flux_fast(p.fk, fmaf(NB, T3n, fmaf(NA, T2n, fmaf(NB, T1n, NC * T0n)))) * wq;
+            const float q3 = flux_fast(p.fk, fmaf(NA, T3n, fmaf(NB, T2n, fmaf(NC, T1n, NB * T0n)))) * wq;
+            sAf[((e * 4 + 0) * 32 + lane) * 2 + h] = exists ? fmaf(NB, q3, fmaf(NC, q2, fmaf(NB, q1, NA * q0))) : 0.f;
+            sAf[((e * 4 + 1) * 32 + lane) * 2 + h] = exists ? fmaf(NC, q3, fmaf(NB, q2, fmaf(NA, q1, NB * q0))) : 0.f;
+            sAf[((e * 4 + 2) * 32 + lane) * 2 + h] = exists ? fmaf(NB, q3, fmaf(NA, q2, fmaf(NB, q1, NC * q0))) : 0.f;
+            sAf[((e * 4 + 3) * 32 + lane) * 2 + h] = exists ? fmaf(NA, q3, fmaf(NB, q2, fmaf(NC, q1, NB * q0))) : 0.f;
+        }
+        __syncwarp();
+        const int lm = max(lane - 1, 0);
+#pragma unroll
+        for (int r = 0; r < RY; ++r)  // owned row r = loaded row r + 1: upper node of element row r, lower of r + 1
+            fl[r] = ((f2{sA[wy][r][2][lm]} + f2{sA[wy][r][3][lane]}) + f2{sA[wy][r + 1][1][lm]}) +
+                    f2{sA[wy][r + 1][0][lane]};
+    };
+
     // ---- last data plane of a chunk top: no layer above, its action is (Tt0, Tt1, myp) --------------
-    auto last_plane = [&](int f, const f2* Tf) {
+    auto last_plane = [&](int f, const f2* Tf, const K1Raw<RY>& raw) {
         f2 sz = splat(0.f);
         if (K1_HAS(K1F_SRC)) sz = sfx * splat(srcz_at(f));
         const bool topf = K1_HAS(K1F_TOP) && (f == nzl - 1);
+        f2 fl[RY];
+#pragma unroll
+        for (int r = 0; r < RY; ++r) fl[r] = splat(0.f);
+        if (K1_HAS(K1F_FLUX) && f == nzl - 1 && nzl >= 2) fused_top_flux(raw, fl);  // warp-uniform
         FinalPtrs fp;
         fp.out = (char*)(p.Tout + (size_t)f * P);
         fp.rhs = K1_HAS(K1F_RHS) ? (const char*)(p.rhs + (size_t)f * P) : nullptr;
 #pragma unroll
-        for (int r = 0; r < RY; ++r) final_row(f, fp, r, sz, topf, Tf[r], Tt0[r], Tt1[r], myp[r]);
+        for (int r = 0; r < RY; ++r) final_row(f, fp, r, sz, topf, Tf[r], Tt0[r], Tt1[r], myp[r], fl[r]);
     };
 
     // ---- inactive planes (substitute_Tbar cF:2183) with the Dirichlet faces applied -------------
@@ -473,8 +543,8 @@ __global__ void __launch_bounds__(32 * WPB, MINB) level_step_v2(const __grid_con
             step_plane(l + 1, rawA, stB, stA, l >= za, sfx * splat(srcz_at(l)));
         }
         if (llast >= za && llast < zb) {
-            if (((llast - lfirst) & 1) != 0) last_plane(llast, stB.T);  // parity of the plane held in stB
-            else last_plane(llast, stA.T);
+            if (((llast - lfirst) & 1) != 0) last_plane(llast, stB.T, rawB);  // parity of the plane held in stB
+            else last_plane(llast, stA.T, rawA);
         }
         fdone = max(za, llast + 1);
     }

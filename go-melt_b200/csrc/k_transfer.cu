@@ -53,12 +53,36 @@ __global__ void interp_kernel(const InterpParams p) {
                 hz = __fsub_rn(p.sz.c[1], p.sz.c[0]);
     const float inv_vol = __fdiv_rn(1.0f, __fmul_rn(__fmul_rn(hx, hy), hz));
     const int nnx = p.sx.n, nnxy = p.sx.n * p.sy.n;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-         t += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(t % p.ntx);
-        const int j = (int)((t / p.ntx) % p.nty);
-        const int k = (int)(t / ((long long)p.ntx * p.nty));
-        if (p.faces_only && !(i == 0 || i == p.ntx - 1 || j == 0 || j == p.nty - 1 || k == 0)) continue;
+    // faces_only: enumerate the nodes of the 5 Dirichlet faces directly (z- plane, then the y and x faces of
+    // the planes above it) instead of visiting every node of the level
+    const long long fA = (long long)p.ntx * p.nty, fB = 2LL * p.ntx * (p.ntz - 1),
+                    fC = 2LL * (p.nty - 2) * (p.ntz - 1);
+    const long long count = p.faces_only ? fA + fB + fC : total;
+    for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < count;
+         w += (long long)gridDim.x * blockDim.x) {
+        int i, j, k;
+        if (!p.faces_only) {
+            i = (int)(w % p.ntx);
+            j = (int)((w / p.ntx) % p.nty);
+            k = (int)(w / ((long long)p.ntx * p.nty));
+        } else if (w < fA) {
+            k = 0;
+            j = (int)(w / p.ntx);
+            i = (int)(w % p.ntx);
+        } else if (w < fA + fB) {
+            const long long u = w - fA;
+            const int r = (int)(u % (2 * p.ntx));
+            k = 1 + (int)(u / (2 * p.ntx));
+            j = r < p.ntx ? 0 : p.nty - 1;
+            i = r % p.ntx;
+        } else {
+            const long long u = w - fA - fB;
+            const int r = (int)(u % (2 * (p.nty - 2)));
+            k = 1 + (int)(u / (2 * (p.nty - 2)));
+            i = (r & 1) ? p.ntx - 1 : 0;
+            j = 1 + (r >> 1);
+        }
+        const long long t = i + (long long)j * p.ntx + (long long)k * p.ntx * p.nty;
         const float x = p.tx[i], y = p.ty[j], z = p.tz[k];
         const int ex = cell_of(x, p.sx.c[0], hx, p.sx.n - 1);
         const int ey = cell_of(y, p.sy.c[0], hy, p.sy.n - 1);
@@ -366,7 +390,9 @@ extern "C" int gomelt_interp_f32(const gomelt_interp_args_t* a, void* stream) {
     p.mode = a->mode; p.faces_only = a->faces_only; p.clamp_min = a->clamp_min; p.has_clamp = a->has_clamp;
     p.mx = a->map_x; p.my = a->map_y; p.mz = a->map_z; p.map_nx = a->map_nx; p.map_ny = a->map_ny;
     p.base = a->base; p.out = a->out;
-    const long long total = (long long)a->ntx * a->nty * a->ntz;
+    long long total = (long long)a->ntx * a->nty * a->ntz;
+    if (a->faces_only)
+        total = (long long)a->ntx * a->nty + 2LL * a->ntx * (a->ntz - 1) + 2LL * (a->nty - 2) * (a->ntz - 1);
     interp_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("gomelt_interp_f32");
 }

@@ -4,7 +4,7 @@ torch's current stream.  One function per ``extern "C"`` entry point of include/
 import ctypes as C
 
 from . import _lib
-from ._lib import (STEP_ACCUM, STEP_BC_CONST, STEP_CLAMP, STEP_SKIP_FACES,  # noqa: F401
+from ._lib import (STEP_ACCUM, STEP_BC_CONST, STEP_CLAMP, STEP_FUSED_FLUX, STEP_SKIP_FACES,  # noqa: F401
                    STEP_WRITE_S1, STEP_WRITE_S2)
 
 LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
@@ -84,7 +84,8 @@ def surface_flux(props, grid, T0, flux, nz_active=None, add=False):
 
 
 def source_tables(props, grid, coords, laser_xyz, laserP, tx, ty, tz):
-    """computeSourcesL3 cF:2960-3012 as rank-1 tables (gomelt_source_tables_f32) -> coef."""
+    """computeSourcesL3 cF:2960-3012 as rank-1 tables (gomelt_source_tables_f32) -> coef.  One launch when
+    tx, ty, tz are consecutive slices of one buffer, else three."""
     lib = _lib.load()
     v = (C.c_float * 3)(float(laser_xyz[0]), float(laser_xyz[1]), float(laser_xyz[2]))
     coef = C.c_float(0.0)
@@ -92,7 +93,9 @@ def source_tables(props, grid, coords, laser_xyz, laserP, tx, ty, tz):
                                             _lib.ptr(coords[1]), _lib.ptr(coords[2]), C.byref(v),
                                             float(laserP), _lib.ptr(tx), _lib.ptr(ty), _lib.ptr(tz),
                                             C.byref(coef), _lib.stream_ptr()), "gomelt_source_tables_f32")
-    _count(3)
+    es = tx.element_size()
+    _count(1 if (ty.data_ptr() == tx.data_ptr() + es * tx.numel() and tz.data_ptr() == ty.data_ptr() + es * ty.numel())
+           else 3)
     return coef.value
 
 
@@ -126,6 +129,62 @@ def interp(src_coords, u, tgt_coords, out, *, mode=_lib.INTERP_SET, u2=None, alp
     _lib.check(lib.gomelt_interp_f32(C.byref(a), _lib.stream_ptr()), "gomelt_interp_f32")
     _count()
     return out
+
+
+def _interp_args(src_coords, u, tgt_coords, out, *, mode=_lib.INTERP_SET, u2=None, alpha=1.0, beta=0.0,
+                 faces_only=False, clamp_min=None):
+    a = _lib.InterpArgs()
+    a.src = _axes(src_coords)
+    a.u, a.u2 = u.data_ptr(), (u2.data_ptr() if u2 is not None else None)
+    a.alpha, a.beta = float(alpha), float(beta)
+    a.tx, a.ty, a.tz = (t.data_ptr() for t in tgt_coords)
+    a.ntx, a.nty, a.ntz = (int(t.numel()) for t in tgt_coords)
+    a.mode, a.faces_only = int(mode), int(bool(faces_only))
+    a.has_clamp, a.clamp_min = (0, 0.0) if clamp_min is None else (1, float(clamp_min))
+    a.out = out.data_ptr() if out is not None else None
+    return a
+
+
+def l3_substeps(props, grid, coords, rows, T_in, T_a, T_b, S1, tables, *, S1_in=None, n_substrate=0, flags=0,
+                S2=None, accum=None, max_accum=None, faces=None):
+    """gomelt_l3_substeps_f32: the inner scan of subcycleGOMELT (cF:3367-3412 / 3530-3590) as one call.
+    ``rows`` = host float32 array [n, 7] of toolpath rows; ``faces`` = None or
+    (parent_coords, parent_new, parent_old, fN3, clamp_min).  Returns the tensor (T_a or T_b) that holds the
+    newest temperature.  Substep i writes T_a (i even) / T_b (i odd); substep 0 reads T_in (may be T_b) and
+    S1_in (default S1); S1 / S2 / accum / max_accum are updated in place."""
+    import numpy as np
+
+    lib = _lib.load()
+    rows = np.ascontiguousarray(rows, dtype=np.float32)
+    n = int(rows.shape[0])
+    nn = grid.nx * grid.ny * grid.nz
+    for t, name in ((T_in, "T_in"), (T_a, "T_a"), (T_b, "T_b"), (S1, "S1"), (S1_in, "S1_in"), (accum, "accum"),
+                    (max_accum, "max_accum")):
+        _chk_f32(t, nn, name)
+    _chk_f32(tables, n * (grid.nx + grid.ny + grid.nz), "tables")
+    a = _lib.SubstepsArgs()
+    a.grid = grid
+    a.x, a.y, a.z = (c.data_ptr() for c in coords)
+    a.n = n
+    a.rows = rows.ctypes.data
+    a.T_in, a.T_a, a.T_b, a.S1 = T_in.data_ptr(), T_a.data_ptr(), T_b.data_ptr(), S1.data_ptr()
+    a.S1_in = S1_in.data_ptr() if S1_in is not None else None
+    a.n_substrate, a.flags = int(n_substrate), int(flags)
+    a.tables = tables.data_ptr()
+    a.S2 = S2.data_ptr() if S2 is not None else None
+    a.accum = accum.data_ptr() if accum is not None else None
+    a.max_accum = max_accum.data_ptr() if max_accum is not None else None
+    fa = None
+    if faces is not None:
+        pc, pnew, pold, fN, clamp_min = faces
+        fa = _interp_args(pc, pnew, coords, None, u2=pold, faces_only=True, clamp_min=clamp_min)
+        a.faces = C.pointer(fa)
+        a.faces_n = float(fN)
+    last = C.c_void_p(0)
+    a.T_last = C.pointer(last)
+    _lib.check(lib.gomelt_l3_substeps_f32(C.byref(props), C.byref(a), _lib.stream_ptr()), "gomelt_l3_substeps_f32")
+    _count(1 + n * (2 if faces is not None else 1))
+    return T_a if last.value == T_a.data_ptr() else T_b
 
 
 def box_copy(src, dst, idx3, big_nx, big_ny, scatter):

@@ -103,16 +103,16 @@ class Level1Slab:
     def _k1(self, dt, z0, z1, topflux):
         if z1 <= z0:
             return
+        # the surface load of the top active plane (computeConvRadBC) is evaluated inside K1 by the launch
+        # that finalises that plane; `topflux` is kept for callers that pre-computed it
+        flags = self.ops.STEP_BC_CONST | (self.ops.STEP_FUSED_FLUX if topflux is None else 0)
         self.ops.level_step(self.props, self.grid, self.T, self.S1, self.Tn, dt, topflux=topflux,
                             nz_active=self.nz_active, n_substrate=self.n_substrate,
-                            flags=self.ops.STEP_BC_CONST, bc5=self.bc5, z_range=(z0, z1))
+                            flags=flags, bc5=self.bc5, z_range=(z0, z1))
 
     def dwell_sweep(self, dt):
         ops = self.ops
         top = None
-        if self.owns_top and self.nz_active >= 2:
-            ops.surface_flux(self.props, self.grid, self.T, self.top, nz_active=self.nz_active)
-            top = self.top
         zb, ze = self.zb, self.ze
         if self.world == 1:
             self._k1(dt, zb, ze, top)

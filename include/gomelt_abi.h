@@ -69,6 +69,8 @@ typedef struct gomelt_props {
 #define GOMELT_STEP_BC_CONST   0x08  /* Level-1 Dirichlet constants on 5 faces (all planes)    */
 #define GOMELT_STEP_SKIP_FACES 0x10  /* do not write the 5 Dirichlet faces (child levels)      */
 #define GOMELT_STEP_ACCUM      0x20  /* update accum / max_accum with S2_prev -> S2 transition */
+#define GOMELT_STEP_FUSED_FLUX 0x40  /* computeConvRadBC cF:2207-2301 evaluated inside the step from T0 on plane
+                                        nz_active-1 and added to that plane's load (instead of `topflux`)   */
 
 typedef struct gomelt_step_args {
     gomelt_grid_t grid;
@@ -116,6 +118,14 @@ int gomelt_surface_flux_f32(const gomelt_props_t *props, const gomelt_grid_t *gr
 int gomelt_source_tables_f32(const gomelt_props_t *props, const gomelt_grid_t *grid, const float *x,
                              const float *y, const float *z, const float laser_xyz[3], float laserP,
                              float *tx, float *ty, float *tz, float *coef, void *stream);
+
+/* Batched K6: the tables of n laser rows in ONE launch.  rows = HOST array [n][7] of toolpath rows
+ * (x, y, z, Ljump, Ldwell, dt, P - cP:71-74); tables = device [n][nx + ny + nz] laid out [tx | ty | tz] per
+ * row; coef = HOST [n] out.  n <= GOMELT_MAX_SUBSTEPS. */
+#define GOMELT_MAX_SUBSTEPS 64
+int gomelt_source_tables_batch_f32(const gomelt_props_t *props, const gomelt_grid_t *grid, const float *x,
+                                   const float *y, const float *z, const float *rows, int32_t n, float *tables,
+                                   float *coef, void *stream);
 
 /* ---- inter-level transfers (no materialised operators; see DESIGN.md "Transfers") ---------------------
  * A level is seen through its three 1-D node-coordinate arrays (Level["node_coords"], cF:32-64). */
@@ -196,6 +206,40 @@ typedef struct gomelt_project_args {
 } gomelt_project_args_t;
 
 int gomelt_project_f32(const gomelt_project_args_t *args, void *stream);
+
+/* ---- the Level-3 inner scan as ONE call ------------------------------------------------------------------
+ * subcycleL3_Part1 / subcycleL3_Part2 of subcycleGOMELT (the inner jax.lax.scan, cF:3367-3412 / 3530-3590): n
+ * substeps of   computeSourcesL3 cF:2960 -> computeConvRadBC cF:2207 -> computeSolutions_L3 cF:3015 (explicit
+ * solve, Dirichlet faces <- alpha*parent_new + beta*parent_old with alpha = (i+1)/faces_n (cF:3386-3389),
+ * max(T_amb, .)), state update, and - with GOMELT_STEP_ACCUM - the melt-time bookkeeping cF:3568-3578.
+ * Launches: 1 (all source tables) + n (fused level steps) + n (face prolongation, when `faces` is given).
+ * Substep i writes W_i = T_a (i even) / T_b (i odd) and reads W_(i-1), substep 0 reads T_in, which is never
+ * written unless it is T_b (so a caller can keep its initial field, or ping-pong by passing T_in = T_b).  The
+ * buffer holding the newest field is returned in *T_last.  S1_in likewise is read by substep 0 only (NULL = S1).
+ * flags: GOMELT_STEP_CLAMP | GOMELT_STEP_SKIP_FACES | GOMELT_STEP_WRITE_S2 | GOMELT_STEP_ACCUM are honoured;
+ * WRITE_S1 (in place) and FUSED_FLUX are always on. */
+typedef struct gomelt_substeps_args {
+    gomelt_grid_t grid;
+    const float  *x, *y, *z;      /* device node-coordinate arrays of the level                               */
+    int32_t       n;              /* substeps, 1..GOMELT_MAX_SUBSTEPS                                         */
+    const float  *rows;           /* HOST [n][7] toolpath rows: x, y, z, Ljump, Ldwell, dt, P                 */
+    const float  *T_in;           /* [nn] temperature at the start of the block                               */
+    float        *T_a, *T_b;      /* ping-pong temperature buffers [nn]; T_a != T_in                          */
+    const float  *S1_in;          /* [nn] state at the start of the block, or NULL = S1                       */
+    float        *S1;             /* [nn] written by every substep, read from substep 1 on                    */
+    int64_t       n_substrate;
+    int32_t       flags;
+    float        *tables;         /* device scratch [n * (nx + ny + nz)]                                      */
+    uint8_t      *S2;             /* [nn] in place (WRITE_S2 / ACCUM) or NULL                                 */
+    float        *accum, *max_accum; /* [nn] in place (ACCUM) or NULL                                         */
+    const gomelt_interp_args_t *faces; /* NULL, or the face prolongation from the parent: u = parent_new, u2 =
+                                     parent_old, tx/ty/tz = this level's coordinates; out / alpha / beta /
+                                     faces_only are set per substep by the call                                */
+    float         faces_n;        /* fN3 (float, as the reference divides: alpha = (i+1)/fN3, beta = 1-alpha) */
+    float       **T_last;         /* HOST out: buffer holding the newest temperature (may be NULL)            */
+} gomelt_substeps_args_t;
+
+int gomelt_l3_substeps_f32(const gomelt_props_t *props, const gomelt_substeps_args_t *args, void *stream);
 
 const char *gomelt_last_error(void);
 int gomelt_abi_version(void);

@@ -46,7 +46,7 @@ def _oracle_step(P, lv, T0, S1, nsub, dt, v, laserP, rhs=None, ne=None, flux=Tru
 
 
 def _gpu_step(gm, P, lv, T0, S1, nsub, dt, v, laserP, rhs=None, nz_active=None, flags=0, bc5=None,
-              z_chunk=0, flux=True, extra=None):
+              z_chunk=0, flux=True, extra=None, fused=False):
     import torch
 
     ops = gm.ops
@@ -61,7 +61,9 @@ def _gpu_step(gm, P, lv, T0, S1, nsub, dt, v, laserP, rhs=None, nz_active=None, 
         coef = ops.source_tables(props, grid, coords, v, laserP, tx, ty, tz)
         src = (tx, ty, tz, coef)
     top = None
-    if flux:
+    if flux and fused:  # computeConvRadBC evaluated inside K1 (GOMELT_STEP_FUSED_FLUX)
+        flags |= ops.STEP_FUSED_FLUX
+    elif flux:
         top = torch.empty(nx * ny, device="cuda")
         ops.surface_flux(props, grid, dT0, top, nz_active=nz_active)
     Tout = torch.full((nn,), -7.0, device="cuda")
@@ -88,6 +90,48 @@ def test_level3_substep_matches_oracle(gm, example_props, elements, seed):
     assert _rel(T, Tref) <= RTOL, _rel(T, Tref)
     assert np.array_equal(S1g, S1ref)
     assert np.array_equal(S2g, S2ref)  # S2 is a pure function of the (identical) input T0: bit-exact
+
+
+@pytest.mark.parametrize("elements,seed,hot", [((36, 28, 12), 0, 1.0), ((61, 17, 5), 1, 1.3), ((7, 9, 3), 2, 1.0),
+                                               ((1, 1, 1), 6, 1.0), ((59, 4, 2), 7, 1.3), ((60, 5, 2), 8, 1.0),
+                                               ((123, 41, 3), 9, 1.0)])
+def test_fused_surface_flux_matches_oracle_and_separate_kernel(gm, example_props, elements, seed, hot):
+    """GOMELT_STEP_FUSED_FLUX: computeConvRadBC cF:2207-2301 inside K1's top plane (ragged tiles, tile
+    seams at 60 columns / 4 rows, temperatures past the T_boiling + 1000 cap)."""
+    bounds = ((1.0, 1.0 + 0.02 * elements[0]), (1.0, 1.0 + 0.02 * elements[1]), (-0.02 * elements[2], 0.0))
+    P, lv, T0, S1, nsub = _setup(gm, example_props, elements, bounds, seed, nsub_planes=1)
+    T0 = (T0 * hot).astype(np.float32)
+    v = np.array([0.5 * (bounds[0][0] + bounds[0][1]), 0.5 * (bounds[1][0] + bounds[1][1]), 0.0], np.float32)
+    Tref, _, _ = _oracle_step(P, lv, T0, S1, nsub, 1e-5, v, 285.0)
+    Tsep, _, _ = _gpu_step(gm, P, lv, T0, S1, nsub, 1e-5, v, 285.0)
+    Tfus, _, _ = _gpu_step(gm, P, lv, T0, S1, nsub, 1e-5, v, 285.0, fused=True)
+    Tnone, _, _ = _gpu_step(gm, P, lv, T0, S1, nsub, 1e-5, v, 285.0, flux=False)
+    assert np.isfinite(Tfus).all()
+    assert _rel(Tfus, Tref) <= RTOL, _rel(Tfus, Tref)
+    assert _rel(Tfus, Tsep) <= 2e-6
+    nxy = lv["nodes"][0] * lv["nodes"][1]
+    assert np.array_equal(Tfus[:-nxy], Tnone[:-nxy])       # only the top plane carries the surface load
+    assert np.abs(Tfus[-nxy:] - Tnone[-nxy:]).max() > 0    # ... and it does carry it
+    for zc in (1, 2):
+        Tz, _, _ = _gpu_step(gm, P, lv, T0, S1, nsub, 1e-5, v, 285.0, fused=True, z_chunk=zc)
+        assert np.array_equal(Tz, Tfus), zc
+
+
+def test_fused_surface_flux_on_the_active_layer(gm, example_props):
+    """Level 1: the surface load sits on plane nz_active-1, inactive planes above are T_amb."""
+    elements = (25, 10, 12)
+    bounds = ((0.0, 10.0), (0.0, 4.0), (-2.0, 0.4))
+    P, lv, T0, S1, _ = _setup(gm, example_props, elements, bounds, 9)
+    nx, ny, nz = lv["nodes"]
+    cond = {"x": [301.0, 302.0], "y": [303.0, 304.0], "z": [305.0, 306.0]}
+    bc5 = [cond["y"][0], cond["y"][1], cond["x"][0], cond["x"][1], cond["z"][0]]
+    for nz_active in (2, 9, nz):
+        tmp_ne, tmp_nn = elements[0] * elements[1] * (nz_active - 1), nx * ny * nz_active
+        Levels = [None, dict(lv, T0=T0, S1=S1, conditions=cond)]
+        Tref = cF.stepGOMELTDwellTime(Levels, (tmp_ne, tmp_nn), (0, 0, lv["nn"]), P, 2e-3, (0, 4 * nx * ny))[1]["T0"]
+        T, _, _ = _gpu_step(gm, P, lv, T0, S1, 4 * nx * ny, 2e-3, None, 0.0, nz_active=nz_active,
+                            flags=gm.ops.STEP_BC_CONST, bc5=bc5, fused=True)
+        assert _rel(T, Tref) <= RTOL, (nz_active, _rel(T, Tref))
 
 
 def test_z_chunking_is_bit_identical(gm, example_props):
@@ -222,3 +266,54 @@ def test_surface_flux_and_source_tables(gm, example_props):
     coef = gm.ops.source_tables(props, grid, coords, v, 285.0, tx, ty, tz)
     F = coef * np.einsum("k,j,i->kji", tz.cpu().numpy(), ty.cpu().numpy(), tx.cpu().numpy()).reshape(-1)
     assert np.max(np.abs(F - Fref)) <= 3e-6 * np.max(np.abs(Fref))
+
+
+def test_l3_substeps_one_call_equals_single_launches(gm, example_props):
+    """gomelt_l3_substeps_f32 (the inner scan of subcycleGOMELT as one call) against the same substeps
+    launched one by one, and against the oracle's substep sequence."""
+    import torch
+
+    ops = gm.ops
+    elements = (47, 21, 6)
+    bounds = ((0.0, 0.94), (0.0, 0.42), (-0.12, 0.0))
+    P, lv, T0, S1, nsub = _setup(gm, example_props, elements, bounds, 31, nsub_planes=2)
+    props = gm._lib.make_props(P)
+    grid = gm._lib.make_grid(lv["nodes"], lv["h"])
+    nx, ny, nz = lv["nodes"]
+    n = 5
+    rows = np.zeros((n, 7), np.float32)
+    for i in range(n):
+        rows[i] = (0.40 + 0.013 * i, 0.2 + 0.004 * i, 0.0, 1, 1, 1e-5 * (1 + 0.1 * i), 285.0 - 10 * i)
+    coords = [_dev(c) for c in lv["node_coords"]]
+    # one call
+    Tin, S1w = _dev(T0), _dev(S1)
+    A, B = torch.empty_like(Tin), torch.empty_like(Tin)
+    tables = torch.empty(n * (nx + ny + nz), device="cuda")
+    S2 = torch.zeros(lv["nn"], device="cuda", dtype=torch.uint8)
+    last = ops.l3_substeps(props, grid, coords, rows, Tin, A, B, S1w.clone(), tables, n_substrate=nsub,
+                           flags=ops.STEP_CLAMP | ops.STEP_WRITE_S2, S2=S2)
+    assert last is A  # n odd: the last substep wrote T_a
+    assert torch.equal(Tin, _dev(T0))  # T_in is preserved
+    # one by one
+    cur, S1c = _dev(T0), _dev(S1)
+    S2c = torch.zeros(lv["nn"], device="cuda", dtype=torch.uint8)
+    tx, ty, tz = (torch.empty(m, device="cuda") for m in (nx, ny, nz))
+    Tref, S1ref = T0.copy(), S1.copy()
+    ne_nn = (0, lv["ne"], 0, 0, lv["nn"])
+    for i in range(n):
+        coef = ops.source_tables(props, grid, coords, rows[i, :3], float(rows[i, 6]), tx, ty, tz)
+        nxt = torch.empty_like(cur)
+        ops.level_step(props, grid, cur, S1c, nxt, float(rows[i, 5]), src=(tx, ty, tz, coef), n_substrate=nsub,
+                       flags=ops.STEP_CLAMP | ops.STEP_WRITE_S1 | ops.STEP_WRITE_S2 | ops.STEP_FUSED_FLUX,
+                       S1_out=S1c, S2_out=S2c)
+        cur = nxt
+        S1ref, S2ref, k, rc = cF.computeStateProperties(Tref, S1ref, P, nsub)
+        F = cF.computeSourcesL3(lv, rows[i, :3], ne_nn, P, rows[i, 6])
+        F = cF.computeConvRadBC(lv, Tref, lv["ne"], lv["nn"], P, F)
+        Tref = np.maximum(np.float32(P["T_amb"]),
+                          cF.solveMatrixFreeFE(lv, lv["nn"], lv["ne"], k, rc, np.float32(rows[i, 5]), Tref, F, 0))
+    torch.cuda.synchronize()
+    assert torch.equal(last, cur)
+    assert torch.equal(S2, S2c)
+    assert _rel(last.cpu().numpy(), Tref) <= RTOL
+    assert np.array_equal(S2.cpu().numpy().astype(bool), S2ref)

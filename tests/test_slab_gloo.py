@@ -37,6 +37,7 @@ def _free_port():
 class _OracleOps:
     """Test double for go-melt_b200.ops on CPU tensors: the oracle's dwell step on the local slab."""
     STEP_BC_CONST = 0x08
+    STEP_FUSED_FLUX = 0x40
     LAUNCHES = 0
 
     def __init__(self, cF, P, make_level, h):
@@ -67,6 +68,8 @@ class _OracleOps:
         if topflux is not None:
             F[(nz_active - 1) * P_:nz_active * P_] = topflux.numpy()
         ne = (nx - 1) * (ny - 1) * max(nz_active - 1, 0)
+        if (flags & self.STEP_FUSED_FLUX) and nz_active >= 2:  # computeConvRadBC inside the step
+            F = cF.computeConvRadBC(lv, T, ne, nn, self.P, F)
         Tn = cF.solveMatrixFreeFE(lv, nn, ne, k, rc, dt, T, F, 0)
         Tn[nz_active * P_:] = np.float32(self.P["T_amb"])
         T3 = Tn.reshape(nz, ny, nx)
@@ -123,10 +126,7 @@ def _worker(rank, world, port, out):
 def _cpu_sweep(sl, dt):
     """Level1Slab.dwell_sweep without CUDA streams (same call sequence)."""
     slab_mod = sys.modules[type(sl).__module__]
-    top = None
-    if sl.owns_top and sl.nz_active >= 2:
-        sl.ops.surface_flux(sl.props, sl.grid, sl.T, sl.top, nz_active=sl.nz_active)
-        top = sl.top
+    top = None  # the surface load is evaluated inside the level step (GOMELT_STEP_FUSED_FLUX)
     zb, ze = sl.zb, sl.ze
     lo = zb + 1 if sl.rank > 0 else zb
     hi = max(ze - 1 if sl.rank < sl.world - 1 else ze, lo)

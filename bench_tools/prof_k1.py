@@ -16,7 +16,7 @@ g = torch.Generator(device="cuda").manual_seed(0)
 T0 = 300 + 2000 * torch.rand(nn, device="cuda", generator=g)
 S1 = (torch.rand(nn, device="cuda", generator=g) > 0.5).float()
 Tout = torch.empty_like(T0); S1o = torch.empty_like(T0)
-tx = torch.rand(nx, device="cuda"); ty = torch.rand(ny, device="cuda"); tz = torch.rand(nz, device="cuda")
+tx = torch.rand(nx, device="cuda", generator=g); ty = torch.rand(ny, device="cuda", generator=g); tz = torch.rand(nz, device="cuda", generator=g)
 top = torch.zeros(nx * ny, device="cuda")
 for it in range(4):
     ops.level_step(props, grid, T0, S1, Tout, 1e-5, src=(tx, ty, tz, 1e-3), n_substrate=0,

@@ -1,0 +1,83 @@
+"""BASELINE.json configs[0]: examples/example.json (the reference's default single-track three-level run, 1299
+toolpath rows, 1.006 simulated seconds) through the drop-in driver on cuda:0 -> wall-s per sim-s, and the
+oracle (NumPy restatement of the reference) on the first ORACLE_ROWS rows on the host for the CPU figure.
+
+    python bench_tools/run_example.py [--oracle-rows N] [--skip-gpu]
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def load_input(tmp, rows=None):
+    inp = json.load(open(os.path.join(ROOT, "examples", "example.json")))
+    inp["nonmesh"].update(save_path=tmp + "/", toolpath=os.path.join(tmp, "toolpath.txt"),
+                          gcode=os.path.join(ROOT, "examples", "gcodefiles", "example.gcode"), info_T=0)
+    if rows is not None:  # truncated toolpath: generate it, keep the first rows, switch to use_txt
+        tp = importlib.import_module("go-melt_b200.toolpath")
+        sc = importlib.import_module("go-melt_b200.schema")
+        tp.parsingGcode(sc.SetupNonmesh(inp["nonmesh"]), sc.SetupProperties(inp["properties"]))
+        lines = open(inp["nonmesh"]["toolpath"]).readlines()[:rows]
+        open(inp["nonmesh"]["toolpath"], "w").writelines(lines)
+        inp["nonmesh"]["use_txt"] = 1
+    return inp
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--oracle-rows", type=int, default=75)
+    ap.add_argument("--skip-gpu", action="store_true")
+    args = ap.parse_args()
+    drv = importlib.import_module("go-melt_b200.driver")
+    out = {}
+    if not args.skip_gpu:
+        import torch
+
+        import gomelt_b200 as gm
+
+        for rep in range(2):  # first pass warms up allocator / module loading
+            l0 = gm.ops.LAUNCHES
+            res = drv.go_melt(load_input(tempfile.mkdtemp()), write_final=False)
+        torch.cuda.synchronize()
+        out["gpu"] = {"wall_s": res["wall_seconds"], "sim_s": res["sim_seconds"],
+                      "wall_s_per_sim_s": res["wall_seconds"] / res["sim_seconds"], "steps": res["time_inc"],
+                      "counts": res["counts"], "kernel_launches": gm.ops.LAUNCHES - l0}
+    if args.oracle_rows > 0:
+        import numpy as np
+
+        from driver_support import NumpyArrays
+        from oracle import computeFunctions as cF
+
+        t0 = time.time()
+        ref = drv.go_melt(load_input(tempfile.mkdtemp(), args.oracle_rows), cf=cF, xp=NumpyArrays(), write_final=False)
+        dt = time.time() - t0
+        out["oracle_cpu"] = {"rows": args.oracle_rows, "wall_s": dt, "sim_s": ref["sim_seconds"],
+                             "wall_s_per_sim_s": dt / ref["sim_seconds"], "counts": ref["counts"],
+                             "cores": 1, "kind": "NumPy float32 restatement of the reference (not JAX/XLA)"}
+        if not args.skip_gpu:
+            t0 = time.time()
+            got = drv.go_melt(load_input(tempfile.mkdtemp(), args.oracle_rows), write_final=False)
+            out["gpu_first_rows_wall_s"] = time.time() - t0
+            par = {}
+            for lvl in (1, 2, 3):
+                a = got["Levels"][lvl]["T0"].cpu().numpy()
+                b = np.asarray(ref["Levels"][lvl]["T0"])
+                par[f"L{lvl}_T_max_rel_err"] = float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0)))
+            par["L3_S2_equal"] = bool(np.array_equal(got["Levels"][3]["S2"].cpu().numpy().astype(bool),
+                                                     np.asarray(ref["Levels"][3]["S2"]).astype(bool)))
+            par["L3_S2_count"] = int(np.asarray(ref["Levels"][3]["S2"]).sum())
+            par["L3_T_max"] = float(np.asarray(ref["Levels"][3]["T0"]).max())
+            out["parity_first_rows"] = par
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -199,14 +199,38 @@ struct FinalPtrs {         // plane base pointers (bytes) of the plane being fin
     char* out;
     const char* rhs;
 };
+template <int RY, bool STAGE>
+struct K1Raw;              // prefetched raw plane (T0 and S1 of the RY + 2 loaded rows, both halves)
 template <int RY>
-struct K1Raw {             // prefetched raw plane
-    f2 T[RY + 2], S[RY + 2];
+struct K1Raw<RY, false> {  // held in registers
+    f2 Tr[RY + 2], Sr[RY + 2];
+    GM_DI f2 T(int r) const { return Tr[r]; }
+    GM_DI f2 S(int r) const { return Sr[r]; }
+};
+template <int RY>
+struct K1Raw<RY, true> {   // staged in shared memory by cp.async: [field][row][lane] float2, b = this lane's slot
+    const float2* b;
+    GM_DI f2 T(int r) const { return f2{b[r * 32]}; }
+    GM_DI f2 S(int r) const { return f2{b[(RY + 2 + r) * 32]}; }
 };
 
-template <int RY, int WPB, int FEAT, int MINB = 1>
+GM_DI unsigned smem_u32(const void* q) { return (unsigned)__cvta_generic_to_shared(q); }
+// 4-byte cp.async of both halves of a pair (half .x 120 bytes below the address of half .y); a guarded-off
+// half is zero-filled (src-size 0: nothing is read).
+GM_DI void cp_async_pair(unsigned dst, const char* q, int fa, int fb) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1+-120], 4, %2;\n\t"
+                 "cp.async.ca.shared.global [%0+4], [%1], 4, %3;" ::"r"(dst), "l"(q), "r"(fa * 4), "r"(fb * 4)
+                 : "memory");
+}
+GM_DI void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+GM_DI void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int RY, int WPB, int FEAT, int MINB = 1, bool STAGE = false>
 __global__ void __launch_bounds__(32 * WPB, MINB) level_step_v2(const __grid_constant__ StepParams p) {
     constexpr int NR = RY + 2;  // loaded rows
+    using Raw = K1Raw<RY, STAGE>;
+    __shared__ float2 s_stage[STAGE ? WPB : 1][2][2][STAGE ? NR : 1][STAGE ? 32 : 1];  // [warp][buffer][T|S][row][lane]
     constexpr bool GEN = (FEAT & K1F_GENERIC) != 0;
     const int rtf = p.feat;     // run-time feature bits, set by the launcher
 #define K1_HAS(bit) (((FEAT & (bit)) != 0) && (!GEN || (rtf & (bit)) != 0))
@@ -253,13 +277,30 @@ __global__ void __launch_bounds__(32 * WPB, MINB) level_step_v2(const __grid_con
 #pragma unroll
     for (int r = 0; r < RY; ++r) Tt0[r] = Tt1[r] = myp[r] = splat(0.f);
 
-    auto load_plane = [&](int l, K1Raw<RY>& raw) {
+    auto load_plane = [&](int l, Raw& raw) {
         const char* Tl = (const char*)(p.T0 + (size_t)l * P);
         const char* Sl = (const char*)(p.S1 + (size_t)l * P);
+        if constexpr (STAGE) {
+            const unsigned d = smem_u32(raw.b);
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            ld2(Tl + offb[r], la, lb, raw.T[r]);
-            ld2(Sl + offb[r], la, lb, raw.S[r]);
+            for (int r = 0; r < NR; ++r) {
+                cp_async_pair(d + (unsigned)(r * 32 * sizeof(float2)), Tl + offb[r], la, lb);
+                cp_async_pair(d + (unsigned)((NR + r) * 32 * sizeof(float2)), Sl + offb[r], la, lb);
+            }
+            cp_async_commit();
+        } else {
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                ld2(Tl + offb[r], la, lb, raw.Tr[r]);
+                ld2(Sl + offb[r], la, lb, raw.Sr[r]);
+            }
+        }
+    };
+    // plane data of the older of (at most) two groups in flight has landed
+    auto landed = [&](bool newer_in_flight) {
+        if constexpr (STAGE) {
+            if (newer_in_flight) cp_async_wait<1>();
+            else cp_async_wait<0>();
         }
     };
 
@@ -317,15 +358,16 @@ __global__ void __launch_bounds__(32 * WPB, MINB) level_step_v2(const __grid_con
     };
 
     // ---- first plane of a chunk: x stage only -----------------------------------------------------
-    auto first_plane = [&](int l, const K1Raw<RY>& raw, K1State<RY>& st) {
+    auto first_plane = [&](int l, const Raw& raw, K1State<RY>& st) {
         const bool wr = (l >= za) && (l < zb);
         const int subrow = (l < nsub_planes) ? (1 << 30) : ((l == nsub_planes) ? nsub_rem : 0);
         const size_t pl = (size_t)l * P;
         char* so = K1_HAS(K1F_S1OUT) ? (char*)(p.S1out + pl) : nullptr;
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-            row_a(pl, so, r, wr, subrow, raw.T[r], raw.S[r], st.Xs[r], st.Xd[r], st.kx[r], st.mx[r]);
-            if (r >= 1 && r <= RY) st.T[r - 1] = raw.T[r];
+            const f2 Tr_ = raw.T(r);
+            row_a(pl, so, r, wr, subrow, Tr_, raw.S(r), st.Xs[r], st.Xd[r], st.kx[r], st.mx[r]);
+            if (r >= 1 && r <= RY) st.T[r - 1] = Tr_;
         }
     };
 
@@ -373,7 +415,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) level_step_v2(const __grid_con
 
     // ---- plane l: node state, x stage, then the element layer (l-1, l) row by row; finalises
     //      plane l-1 when do_final.  pv = state of plane l-1, cu <- state of plane l.
-    auto step_plane = [&](int l, const K1Raw<RY>& raw, const K1State<RY>& pv, K1State<RY>& cu, bool do_final, f2 sz) {
+    auto step_plane = [&](int l, const Raw& raw, const K1State<RY>& pv, K1State<RY>& cu, bool do_final, f2 sz) {
         const bool wr = (l >= za) && (l < zb);
         const int subrow = (l < nsub_planes) ? (1 << 30) : ((l == nsub_planes) ? nsub_rem : 0);
         const int f = l - 1;
@@ -391,9 +433,10 @@ __global__ void __launch_bounds__(32 * WPB, MINB) level_step_v2(const __grid_con
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
             f2 xs, xd, kxr, mxr;
-            row_a(pl, so, r, wr, subrow, raw.T[r], raw.S[r], xs, xd, kxr, mxr);
+            const f2 Tr_ = raw.T(r);
+            row_a(pl, so, r, wr, subrow, Tr_, raw.S(r), xs, xd, kxr, mxr);
             cu.Xs[r] = xs; cu.Xd[r] = xd; cu.kx[r] = kxr; cu.mx[r] = mxr;
-            if (r >= 1 && r <= RY) cu.T[r - 1] = raw.T[r];
+            if (r >= 1 && r <= RY) cu.T[r - 1] = Tr_;
             // z stage of the analysis
             const f2 zu00 = xs + pv.Xs[r], zu01 = xs - pv.Xs[r];
             const f2 zu10 = xd + pv.Xd[r], zu11 = xd - pv.Xd[r];
@@ -458,14 +501,14 @@ __global__ void __launch_bounds__(32 * WPB, MINB) level_step_v2(const __grid_con
     //      element column spans its node column and the right neighbour's; per element 2x2 Gauss points,
     //      N2^T (q wq); a node sums its <= 4 elements in increasing element id like the reference's
     //      scatter-add: (i-1,j-1) a=2, (i,j-1) a=3, (i-1,j) a=1, (i,j) a=0.
-    auto fused_top_flux = [&](const K1Raw<RY>& raw, f2* fl) {
+    auto fused_top_flux = [&](const Raw& raw, f2* fl) {
         // The plane loop's registers are dead here; the element loop is kept rolled (one code copy: an
         // unrolled version evicts the plane loop from the instruction cache) by staging through shared memory.
         __shared__ float2 sT[WPB][NR][32];
         __shared__ float2 sA[WPB][RY + 1][4][32];
         const int wy = threadIdx.y;
 #pragma unroll
-        for (int r = 0; r < NR; ++r) sT[wy][r][lane] = raw.T[r].v;
+        for (int r = 0; r < NR; ++r) sT[wy][r][lane] = raw.T(r).v;
         __syncwarp();
         const float* sTf = reinterpret_cast<const float*>(&sT[wy][0][0]);
         float* sAf = reinterpret_cast<float*>(&sA[wy][0][0][0]);
@@ -499,7 +542,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) level_step_v2(const __grid_con
     };
 
     // ---- last data plane of a chunk top: no layer above, its action is (Tt0, Tt1, myp) --------------
-    auto last_plane = [&](int f, const f2* Tf, const K1Raw<RY>& raw) {
+    auto last_plane = [&](int f, const f2* Tf, const Raw& raw) {
         f2 sz = splat(0.f);
         if (K1_HAS(K1F_SRC)) sz = sfx * splat(srcz_at(f));
         const bool topf = K1_HAS(K1F_TOP) && (f == nzl - 1);
@@ -526,20 +569,28 @@ __global__ void __launch_bounds__(32 * WPB, MINB) level_step_v2(const __grid_con
 
     int fdone = za;  // planes [za, fdone) are finalised
     if (lfirst <= llast) {
-        K1Raw<RY> rawA, rawB;  // zero-initialised: guarded-off loads keep these (finite) values
+        Raw rawA, rawB;
+        if constexpr (STAGE) {
+            rawA.b = &s_stage[threadIdx.y][0][0][0][lane];
+            rawB.b = &s_stage[threadIdx.y][1][0][0][lane];
+        } else {  // zero-initialised: guarded-off loads keep these (finite) values
 #pragma unroll
-        for (int r = 0; r < NR; ++r) rawA.T[r] = rawA.S[r] = rawB.T[r] = rawB.S[r] = splat(0.f);
+            for (int r = 0; r < NR; ++r) rawA.Tr[r] = rawA.Sr[r] = rawB.Tr[r] = rawB.Sr[r] = splat(0.f);
+        }
         K1State<RY> stA, stB;
         load_plane(lfirst, rawA);
         if (lfirst + 1 <= llast) load_plane(lfirst + 1, rawB);
+        landed(lfirst + 1 <= llast);
         first_plane(lfirst, rawA, stA);
         // main loop, unrolled by two so the carried state ping-pongs: (stA, rawB) -> stB, (stB, rawA) -> stA
         // source z-factor of the plane finalised next, fetched one plane ahead
         for (int l = lfirst + 1; l <= llast; l += 2) {
             if (l + 1 <= llast) load_plane(l + 1, rawA);
+            landed(l + 1 <= llast);
             step_plane(l, rawB, stA, stB, l - 1 >= za, sfx * splat(srcz_at(l - 1)));
             if (l + 1 > llast) break;
             if (l + 2 <= llast) load_plane(l + 2, rawB);
+            landed(l + 2 <= llast);
             step_plane(l + 1, rawA, stB, stA, l >= za, sfx * splat(srcz_at(l)));
         }
         if (llast >= za && llast < zb) {

@@ -1,0 +1,67 @@
+"""go-melt_b200/driver.py: (CPU) the loop's control flow on the reference's own example toolpath, and (GPU)
+the whole drop-in run against the oracle driven through the same loop."""
+import importlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from driver_support import NumpyArrays, RecordingStub, small_two_layer_input
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_mode_sequence_on_the_example_toolpath(tmp_path):
+    """the default example is 25 single-step rows (layer start), 30 subcycle blocks, 25
+    single-step rows (wait counter near wait_time), 499 Level-1 dwell rows; moveEverything runs on every
+    single-step / dwell row and once per subcycle block (gm:292, 422)."""
+    drv = importlib.import_module("go-melt_b200.driver")
+    sc = importlib.import_module("go-melt_b200.schema")
+    tp = importlib.import_module("go-melt_b200.toolpath")
+
+    class Real:
+        SetupProperties, SetupNonmesh, getStaticSubcycle = sc.SetupProperties, sc.SetupNonmesh, sc.getStaticSubcycle
+        count_lines, parsingGcode = tp.count_lines, tp.parsingGcode
+
+    inp = json.load(open(os.path.join(ROOT, "examples", "example.json")))
+    inp["nonmesh"].update(save_path=str(tmp_path) + "/", toolpath=str(tmp_path / "toolpath.txt"),
+                          gcode=os.path.join(ROOT, "examples", "gcodefiles", "example.gcode"))
+    stub = RecordingStub(Real)
+    out = drv.go_melt(inp, cf=stub, xp=NumpyArrays(), write_final=False)
+    assert out["total_t_inc"] == 1299 and out["time_inc"] == 1299
+    assert abs(out["sim_seconds"] - 1.006) < 1e-4
+    c = out["counts"]
+    assert (c["stepGOMELT"], c["subcycleGOMELT"], c["stepGOMELTDwellTime"], c["moveEverything"]) == (50, 30, 499, 579)
+    calls = [x for x in stub.calls if x != "move"]
+    assert calls[:25] == ["step"] * 25 and calls[25:55] == ["subcycle"] * 30
+    assert calls[55:80] == ["step"] * 25 and calls[80:] == ["dwell"] * 499
+
+
+@pytest.mark.gpu
+def test_whole_run_matches_oracle(tmp_path):
+    """Two layers from G-code through go_melt(): product (CUDA) vs oracle (NumPy), same driver loop.
+    Temperatures within 1e-5 relative, states / melt flags / melt-time bookkeeping exact or to rounding."""
+    from oracle import computeFunctions as cF
+
+    drv = importlib.import_module("go-melt_b200.driver")
+    (tmp_path / "gpu").mkdir()
+    (tmp_path / "cpu").mkdir()
+    got = drv.go_melt(small_two_layer_input(str(tmp_path / "gpu")), write_final=True)
+    ref = drv.go_melt(small_two_layer_input(str(tmp_path / "cpu")), cf=cF, xp=NumpyArrays(), write_final=False)
+    assert got["counts"] == ref["counts"] and got["time_inc"] == ref["time_inc"]
+    c = got["counts"]
+    assert c["layers"] == 2 and c["stepGOMELT"] > 0 and c["subcycleGOMELT"] > 0 and c["stepGOMELTDwellTime"] > 0
+    host = lambda a: a.detach().cpu().numpy() if hasattr(a, "detach") else np.asarray(a)
+    for lvl in (1, 2, 3):
+        a, b = host(got["Levels"][lvl]["T0"]), host(ref["Levels"][lvl]["T0"])
+        err = float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0)))
+        assert err <= 1e-5, (lvl, err)
+        assert np.array_equal(host(got["Levels"][lvl]["S1"]), host(ref["Levels"][lvl]["S1"])), lvl
+    assert np.array_equal(host(got["Levels"][3]["S2"]).astype(bool), host(ref["Levels"][3]["S2"]).astype(bool))
+    assert np.array_equal(host(got["Levels"][0]["S1"]), host(ref["Levels"][0]["S1"]))
+    acc_g, acc_r = host(got["accum_time"]), host(ref["accum_time"])
+    assert acc_r.max() > 0  # the run melts
+    assert np.allclose(acc_g, acc_r, rtol=1e-5, atol=1e-9)
+    final = np.load(tmp_path / "gpu" / "FinalTemperatureFields.npz")
+    assert np.array_equal(final["L3T"], host(got["Levels"][3]["T0"]))

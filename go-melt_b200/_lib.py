@@ -43,6 +43,7 @@ class StepArgs(C.Structure):
         ("S2_prev", C.c_void_p), ("accum", C.c_void_p), ("max_accum", C.c_void_p),
         ("z_chunk", C.c_int32),
         ("z_begin", C.c_int32), ("z_end", C.c_int32),
+        ("peer_lo", C.c_void_p), ("peer_hi", C.c_void_p),
     ]
 
 

@@ -44,6 +44,8 @@ constexpr int F_L3_SUB = F_L3_BENCH | K1F_SKIP;
 constexpr int F_L3_SUB2 = F_L3_SUB | K1F_S2OUT | K1F_ACCUM;
 constexpr int F_L1_DWELL = K1F_FLUX | K1F_BCCONST;
 constexpr int F_L1_DWELL_SUB = F_L1_DWELL | K1F_NSUB;
+constexpr int F_L1_DWELL_PEER = F_L1_DWELL | K1F_PEER;
+constexpr int F_L1_DWELL_SUB_PEER = F_L1_DWELL_SUB | K1F_PEER;
 
 static int launch_step(const StepParams& sp, cudaStream_t st) {
     const int nch = (sp.zend - sp.zbeg + sp.zchunk - 1) / sp.zchunk;
@@ -71,6 +73,8 @@ static int launch_step(const StepParams& sp, cudaStream_t st) {
             case F_L3_SUB2: launch_v2<RY, WPB, F_L3_SUB2>(sp, nch, st); break;
             case F_L1_DWELL: launch_v2<RY, WPB, F_L1_DWELL>(sp, nch, st); break;
             case F_L1_DWELL_SUB: launch_v2<RY, WPB, F_L1_DWELL_SUB>(sp, nch, st); break;
+            case F_L1_DWELL_PEER: launch_v2<RY, WPB, F_L1_DWELL_PEER>(sp, nch, st); break;
+            case F_L1_DWELL_SUB_PEER: launch_v2<RY, WPB, F_L1_DWELL_SUB_PEER>(sp, nch, st); break;
             default: launch_v2<RY, WPB, K1F_ALL | K1F_GENERIC>(sp, nch, st); break;
         }
     }
@@ -140,6 +144,7 @@ extern "C" int gomelt_level_step_f32(const gomelt_props_t* props, const gomelt_s
     for (int q = 0; q < 5; ++q) sp.bc[q] = a->bc5[q];
     sp.flags = a->flags;
     sp.zbeg = zbeg; sp.zend = zend;
+    sp.peer_lo = a->peer_lo; sp.peer_hi = a->peer_hi;
     {
         const long long Pn = (long long)g.nx * g.ny;
         const long long ns = a->n_substrate < 0 ? 0 : a->n_substrate;
@@ -157,6 +162,7 @@ extern "C" int gomelt_level_step_f32(const gomelt_props_t* props, const gomelt_s
         if (a->flags & GOMELT_STEP_SKIP_FACES) f |= K1F_SKIP;
         if (a->flags & GOMELT_STEP_CLAMP) f |= K1F_CLAMP;
         if (ns > 0) f |= K1F_NSUB;
+        if (a->peer_lo || a->peer_hi) f |= K1F_PEER;
         sp.feat = f;
     }
     sp.zchunk = a->z_chunk > 0 ? a->z_chunk : (zend - zbeg);

@@ -50,6 +50,8 @@ struct StepParams {
     int feat;              // K1F_* bits of this call (v2)
     int nsub_planes, nsub_rem;  // n_substrate = nsub_planes * nx*ny + nsub_rem
     FluxK fk;              // top-surface flux constants (K1F_FLUX)
+    float* peer_lo;        // neighbour ghost planes in peer memory (K1F_PEER), or nullptr
+    float* peer_hi;
 };
 
 #define GM_DI __device__ __forceinline__
@@ -170,7 +172,8 @@ enum : int {
     K1F_CLAMP = 1 << 8,
     K1F_NSUB = 1 << 9,     // substrate override present (n_substrate > 0)
     K1F_FLUX = 1 << 10,    // top-surface flux (computeConvRadBC) evaluated in the step from T0's top plane
-    K1F_ALL = (1 << 11) - 1,
+    K1F_PEER = 1 << 11,    // boundary planes of T_out are also stored to the z-neighbours' ghost planes (NVLink)
+    K1F_ALL = (1 << 12) - 1,
     K1F_GENERIC = 1 << 30,
 };
 
@@ -390,6 +393,10 @@ __global__ void __launch_bounds__(32 * WPB, MINB) level_step_v2(const __grid_con
         }
         if (K1_HAS(K1F_CLAMP)) Tn = mk2(fmaxf(p.pk.T_amb, Tn.v.x), fmaxf(p.pk.T_amb, Tn.v.y));
         st2(fp.out + offb[r + 1], (owna && !ska) ? 1 : 0, (ownb && !skb) ? 1 : 0, Tn);
+        if (K1_HAS(K1F_PEER)) {  // halo exchange fused into the step: plain stores to peer-mapped memory
+            if (f == p.zbeg && p.peer_lo) st2((char*)p.peer_lo + offb[r + 1], (owna && !ska) ? 1 : 0, (ownb && !skb) ? 1 : 0, Tn);
+            if (f == p.zend - 1 && p.peer_hi) st2((char*)p.peer_hi + offb[r + 1], (owna && !ska) ? 1 : 0, (ownb && !skb) ? 1 : 0, Tn);
+        }
     };
 
     // ---- explicit update of owned row r of plane f from its assembled action (z0, z1, mz) ---------

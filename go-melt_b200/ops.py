@@ -25,8 +25,10 @@ def _chk_f32(t, n, name):
 
 def level_step(props, grid, T0, S1, T_out, dt, *, rhs=None, src=None, topflux=None, nz_active=None,
                n_substrate=0, flags=0, bc5=None, S1_out=None, S2_out=None, S2_prev=None, accum=None,
-               max_accum=None, z_chunk=0, z_range=None):
-    """K1 (gomelt_level_step_f32): one explicit sweep of one level.  ``src`` = (tx, ty, tz, coef)."""
+               max_accum=None, z_chunk=0, z_range=None, peer_lo=None, peer_hi=None):
+    """K1 (gomelt_level_step_f32): one explicit sweep of one level.  ``src`` = (tx, ty, tz, coef).
+    ``peer_lo`` / ``peer_hi`` = raw device addresses (int) of the z-neighbours' ghost planes in peer-mapped
+    memory: the boundary planes of ``T_out`` are stored there by the same kernel."""
     lib = _lib.load()
     nn = grid.nx * grid.ny * grid.nz
     for t, name in ((T0, "T0"), (S1, "S1"), (T_out, "T_out"), (rhs, "rhs"), (S1_out, "S1_out"),
@@ -54,6 +56,7 @@ def level_step(props, grid, T0, S1, T_out, dt, *, rhs=None, src=None, topflux=No
     a.z_chunk = int(z_chunk)
     if z_range is not None:
         a.z_begin, a.z_end = int(z_range[0]), int(z_range[1])
+    a.peer_lo, a.peer_hi = (int(peer_lo) if peer_lo else None), (int(peer_hi) if peer_hi else None)
     _lib.check(lib.gomelt_level_step_f32(C.byref(props), C.byref(a), _lib.stream_ptr()), "gomelt_level_step_f32")
     _count()
     return T_out

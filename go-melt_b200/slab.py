@@ -6,8 +6,16 @@ contiguous floats and a halo is a zero-copy slice.  Each rank stores its owned p
 plus one ghost plane per neighbour; an explicit sweep (stepGOMELTDwellTime cF:2617-2664) needs the
 neighbour's boundary plane of T (27-point stencil, radius 1) and - once - of S1.
 
-Per sweep (``Level1Slab.dwell_sweep``):
-  1. fused level step (K1) on the two boundary planes of the owned range,
+Per sweep, fused path (``symmetric=True``, the default on GPUs): the temperature buffers live in
+peer-mapped symmetric memory (torch.distributed._symmetric_memory: CUDA VMM handles exchanged once), and
+ONE launch of K1 over the owned planes also stores its two boundary planes straight into the
+neighbours' ghost planes with plain st.global over NVLink (gomelt_step_args_t.peer_lo / peer_hi) - the
+halo exchange is fused into the step.  A device-side barrier on the stream then orders sweep s+1 after
+every rank's sweep s (it protects both the ghost planes just written and the buffers about to be
+overwritten).  No NCCL call, no pack / copy kernel, no boundary / interior split.
+
+Fallback path (``symmetric=False``; CPU tensors in the gloo tests, or GOMELT_SLAB_NCCL=1 for A/B):
+  1. K1 on the two boundary planes of the owned range,
   2. those planes go to the neighbours' ghost planes (NCCL send/recv over NVLink, side stream),
   3. K1 on the interior planes overlaps the transfer,
   4. the main stream joins the transfer; buffers swap.
@@ -56,7 +64,8 @@ def exchange_planes(field, plane, z_begin, z_end, rank, world, group=None):
 class Level1Slab:
     """One rank's slab of Level 1 in dwell mode (stepGOMELTDwellTime cF:2617-2664)."""
 
-    def __init__(self, gm, props, nodes, h, rank, world, bc5, nz_active=None, n_substrate=0, device=None):
+    def __init__(self, gm, props, nodes, h, rank, world, bc5, nz_active=None, n_substrate=0, device=None,
+                 symmetric=False):
         self.gm, self.ops, self.props = gm, gm.ops, props
         self.rank, self.world = rank, world
         nx, ny, nz = (int(v) for v in nodes)
@@ -73,11 +82,29 @@ class Level1Slab:
         self.bc5 = list(bc5)
         self.device = device
         n = self.plane * self.nzl
-        self.T = torch.empty(n, dtype=torch.float32, device=device)
-        self.Tn = torch.empty(n, dtype=torch.float32, device=device)
+        self.symmetric = bool(symmetric) and world > 1 and device is not None
+        if self.symmetric:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            # one symmetric allocation of two halves (T and T_next), sized for the largest slab so that
+            # every rank's layout is the same; half h of rank q starts at ptrs[q] + 4 * h * nmax
+            parts = partition_planes(nz, world)
+            self._nmax = self.plane * (max(b - a for a, b in parts) + 2)
+            self._buf = symm_mem.empty(2 * self._nmax, dtype=torch.float32, device=device)
+            self._hdl = symm_mem.rendezvous(self._buf, dist.group.WORLD.group_name)
+            self._ptrs = [int(q) for q in self._hdl.buffer_ptrs]
+            self._halves = [self._buf[:n], self._buf[self._nmax:self._nmax + n]]
+            self._cur = 0
+            self.T, self.Tn = self._halves
+            # local index of the plane of each neighbour that mirrors my boundary plane
+            self._ghost_lo = None if rank == 0 else local_extent(rank - 1, world, *parts[rank - 1])[3]  # its z_end
+            self._ghost_hi = None if rank == world - 1 else 0                                            # its plane 0
+        else:
+            self.T = torch.empty(n, dtype=torch.float32, device=device)
+            self.Tn = torch.empty(n, dtype=torch.float32, device=device)
         self.S1 = torch.empty(n, dtype=torch.float32, device=device)
         self.top = torch.zeros(self.plane, dtype=torch.float32, device=device)
-        self.comm = torch.cuda.Stream(device=device) if (device is not None and world > 1) else None
+        self.comm = torch.cuda.Stream(device=device) if (device is not None and world > 1 and not self.symmetric) else None
         self.sweeps = 0
 
     # ---- state ---------------------------------------------------------------------------
@@ -110,8 +137,28 @@ class Level1Slab:
                             nz_active=self.nz_active, n_substrate=self.n_substrate,
                             flags=flags, bc5=self.bc5, z_range=(z0, z1))
 
+    def _peer(self, q, half, ghost_plane):
+        return self._ptrs[q] + 4 * (half * self._nmax + ghost_plane * self.plane)
+
+    def dwell_sweep_fused(self, dt):
+        """One launch: K1 over the owned planes, boundary planes also stored into the neighbours' ghost planes
+        of their next-temperature buffer; then a device-side barrier on the stream."""
+        nxt = 1 - self._cur
+        lo = self._peer(self.rank - 1, nxt, self._ghost_lo) if self.rank > 0 else None
+        hi = self._peer(self.rank + 1, nxt, self._ghost_hi) if self.rank < self.world - 1 else None
+        self.ops.level_step(self.props, self.grid, self._halves[self._cur], self.S1, self._halves[nxt], dt,
+                            nz_active=self.nz_active, n_substrate=self.n_substrate,
+                            flags=self.ops.STEP_BC_CONST | self.ops.STEP_FUSED_FLUX, bc5=self.bc5,
+                            z_range=(self.zb, self.ze), peer_lo=lo, peer_hi=hi)
+        self._hdl.barrier(channel=0)
+        self._cur = nxt
+        self.T, self.Tn = self._halves[nxt], self._halves[1 - nxt]
+        self.sweeps += 1
+        return self.T
+
     def dwell_sweep(self, dt):
-        ops = self.ops
+        if self.symmetric:
+            return self.dwell_sweep_fused(dt)
         top = None
         zb, ze = self.zb, self.ze
         if self.world == 1:

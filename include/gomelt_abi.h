@@ -96,6 +96,11 @@ typedef struct gomelt_step_args {
                                 * z-slab rank passes its local array (ghost planes included) and
                                 * the owned range: planes z_begin-1 and z_end are read as ghosts;
                                 * nz_active / n_substrate are then in local planes / node ids.   */
+    float        *peer_lo;     /* NULL, or [nx*ny] in a z-neighbour GPU's memory (peer-mapped, NVLink): the
+                                * finalised plane z_begin of T_out is ALSO stored there - the lower
+                                * neighbour's upper ghost plane - by the same kernel (halo exchange fused
+                                * into the step; no separate copy / collective).                         */
+    float        *peer_hi;     /* likewise plane z_end-1 -> the upper neighbour's lower ghost plane      */
 } gomelt_step_args_t;
 
 int gomelt_level_step_f32(const gomelt_props_t *props, const gomelt_step_args_t *args, void *stream);

@@ -166,5 +166,6 @@ extern "C" int gomelt_level_step_f32(const gomelt_props_t* props, const gomelt_s
         sp.feat = f;
     }
     sp.zchunk = a->z_chunk > 0 ? a->z_chunk : (zend - zbeg);
+    if (any_src && sp.zchunk > K1_SRCZ_MAX) sp.zchunk = K1_SRCZ_MAX;  // the chunk's z-factors live in shared memory
     return launch_step(sp, (cudaStream_t)stream);
 }

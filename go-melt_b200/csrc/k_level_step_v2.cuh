@@ -126,6 +126,7 @@ GM_DI T* opaque(T* q) {
 }
 
 constexpr int K1_TX = 30;  // owned columns per half-warp tile (32 lanes - 2 halo)
+constexpr int K1_SRCZ_MAX = 254;  // planes per z-chunk when the call carries source tables
 
 // Both halves of a packed pair through ONE address: q points at the column of half .y (always >= 0), half
 // .x is K1_TX columns (120 bytes) below it as an immediate offset, so a pair costs one 64-bit add instead of
@@ -327,8 +328,13 @@ __global__ void __launch_bounds__(32 * WPB, MINB) level_step_v2(const __grid_con
             props_sel_km(p.pk, T.v.y, S.v.y, subb, kb.v.y, cs.v.y, kn.v.y, mn.v.y);
         }
         if (outs) {
-            if (wr && (j0 + r - 1 < ny)) {
-                if (K1_HAS(K1F_S1OUT)) st2(so + offb[r], oa, ob, s1f);
+            // warp-uniform conditions are folded into the store guards, not branched on: branches split the
+            // unrolled plane body into per-row basic blocks and stop the scheduler from interleaving rows
+            // S1' is a node-local function of (T0, S1): the halo planes of a chunk (wr false) may be written
+            // too - their owner writes the same value - so only the row guard remains (plane-invariant)
+            const int gw = (j0 + r - 1 < ny) ? 1 : 0;
+            if (K1_HAS(K1F_S1OUT)) st2(so + offb[r], oa & gw, ob & gw, s1f);
+            if ((K1_HAS(K1F_ACCUM) || K1_HAS(K1F_S2OUT)) && gw && wr) {
                 if (K1_HAS(K1F_ACCUM)) {  // cF:3568-3578
                     if (owna) {
                         const size_t n = pl + ea;
@@ -375,7 +381,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) level_step_v2(const __grid_con
     };
 
     // ---- write one finalised owned row of plane f ---------------------------------------------------
-    auto store_row = [&](int f, const FinalPtrs& fp, int r, f2 Tn) {
+    auto store_row = [&](int f, const FinalPtrs& fp, int r, f2 Tn, int g = 1) {
         const int j = j0 + r;
         bool ska = false, skb = false;
         if (K1_HAS(K1F_BCCONST)) {  // assignBCs order: y-, y+, x-, x+, z-
@@ -392,10 +398,11 @@ __global__ void __launch_bounds__(32 * WPB, MINB) level_step_v2(const __grid_con
             skb = fy || (ib == 0) || (ib == nx - 1);
         }
         if (K1_HAS(K1F_CLAMP)) Tn = mk2(fmaxf(p.pk.T_amb, Tn.v.x), fmaxf(p.pk.T_amb, Tn.v.y));
-        st2(fp.out + offb[r + 1], (owna && !ska) ? 1 : 0, (ownb && !skb) ? 1 : 0, Tn);
+        const int ga = (owna && !ska) ? g : 0, gb = (ownb && !skb) ? g : 0;
+        st2(fp.out + offb[r + 1], ga, gb, Tn);
         if (K1_HAS(K1F_PEER)) {  // halo exchange fused into the step: plain stores to peer-mapped memory
-            if (f == p.zbeg && p.peer_lo) st2((char*)p.peer_lo + offb[r + 1], (owna && !ska) ? 1 : 0, (ownb && !skb) ? 1 : 0, Tn);
-            if (f == p.zend - 1 && p.peer_hi) st2((char*)p.peer_hi + offb[r + 1], (owna && !ska) ? 1 : 0, (ownb && !skb) ? 1 : 0, Tn);
+            if (f == p.zbeg && p.peer_lo) st2((char*)p.peer_lo + offb[r + 1], ga, gb, Tn);
+            if (f == p.zend - 1 && p.peer_hi) st2((char*)p.peer_hi + offb[r + 1], ga, gb, Tn);
         }
     };
 
@@ -405,7 +412,8 @@ __global__ void __launch_bounds__(32 * WPB, MINB) level_step_v2(const __grid_con
         // x stage of the synthesis (shuffles are executed by the whole warp)
         const f2 KT = (z0 - z1) + shup(z0 + z1);
         const f2 mnode = mz + shup(mz);
-        if (j0 + r < ny) {
+        {   // rows past the grid are computed and guarded off (no branch)
+            const int g = (j0 + r < ny) ? 1 : 0;
             f2 rr = splat(0.f);
             if (K1_HAS(K1F_RHS)) ld2(fp.rhs + offb[r + 1], la, lb, rr);
             if (K1_HAS(K1F_SRC)) rr = fma2(sz, splat(sfy[r]), rr);
@@ -416,7 +424,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) level_step_v2(const __grid_con
                 rr = rr + tf;
             }
             const f2 w = splat(p.cdt) * mk2(rcp_approx(mnode.v.x), rcp_approx(mnode.v.y));
-            store_row(f, fp, r, fma2(rr - KT, w, Tf));
+            store_row(f, fp, r, fma2(rr - KT, w, Tf), g);
         }
     };
 
@@ -428,8 +436,11 @@ __global__ void __launch_bounds__(32 * WPB, MINB) level_step_v2(const __grid_con
         const int f = l - 1;
         const size_t pl = (size_t)l * P;
         char* so = K1_HAS(K1F_S1OUT) ? (char*)(p.S1out + pl) : nullptr;
+        // A chunk's lower halo plane (f < za, once per chunk) is not finalised here: its rows are computed like
+        // any other and stored to plane za instead, where the next step overwrites them (same thread, same
+        // addresses, program order) - no per-plane guard in the loop.
         FinalPtrs fp;
-        fp.out = (char*)(p.Tout + (pl - P));
+        fp.out = (char*)(p.Tout + (do_final ? pl - P : pl));
         fp.rhs = K1_HAS(K1F_RHS) ? (const char*)(p.rhs + (pl - P)) : nullptr;
         // the top-flux plane nzl-1 is always the last data plane of its chunk: finalised by last_plane
         constexpr bool topf = false;
@@ -476,7 +487,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) level_step_v2(const __grid_con
                     const f2 my = cm + m8;
                     const f2 mz = myp[e - 1] + my;
                     myp[e - 1] = my;
-                    if (do_final) final_row(f, fp, e - 1, sz, topf, pv.T[e - 1], z0, z1, mz);
+                    final_row(do_final ? f : -1, fp, e - 1, sz, topf, pv.T[e - 1], z0, z1, mz);
                 }
                 if (e < RY) {
                     c00 = q00;
@@ -490,18 +501,16 @@ __global__ void __launch_bounds__(32 * WPB, MINB) level_step_v2(const __grid_con
         }
     };
 
-    // ---- source z-factor of plane f: 32 consecutive factors live one per lane and are broadcast by
-    //      shuffle (a per-plane uniform global load sat on the critical path: long-scoreboard stalls)
-    float szwin = 0.f;
-    int szbase = -(1 << 30);
-    auto srcz_at = [&](int f) -> float {
-        if (!K1_HAS(K1F_SRC)) return 0.f;
-        if (f - szbase >= 32 || f < szbase) {  // warp-uniform
-            szbase = f;
-            szwin = settle(__ldg(p.srcz + min(f + lane, nz - 1)));
-        }
-        return __shfl_sync(0xffffffffu, szwin, f - szbase);
-    };
+    // ---- source z-factor of plane f: the chunk's factors are copied to shared memory once (a per-plane
+    //      uniform global load - even a predicated-off refill - makes the consumer wait on the scoreboard it
+    //      shares with the next plane's prefetch: measured 0.9 stall cycles / issue).  The launcher keeps
+    //      chunks of source-carrying calls within K1_SRCZ_MAX planes.
+    __shared__ float s_srcz[(FEAT & K1F_SRC) ? WPB : 1][(FEAT & K1F_SRC) ? K1_SRCZ_MAX + 2 : 1];
+    if (K1_HAS(K1F_SRC)) {
+        for (int i = lane; i <= llast - lfirst; i += 32) s_srcz[threadIdx.y][i] = __ldg(p.srcz + lfirst + i);
+        __syncwarp();
+    }
+    auto srcz_at = [&](int f) -> float { return K1_HAS(K1F_SRC) ? s_srcz[threadIdx.y][f - lfirst] : 0.f; };
 
     // ---- computeConvRadBC cF:2207-2301 fused: load of the top face of element layer nzl-2 on the owned
     //      nodes of plane nzl-1, from that plane's T0 (still in the prefetch registers).  This lane's

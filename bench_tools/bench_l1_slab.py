@@ -105,6 +105,25 @@ def run_gomelt_multi(args, read_peaks, ClockSampler, host_properties, single_gpu
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
     clocks = sampler.stop(t0, t1) if sampler is not None else None
+    # same-workload single-GPU reference (one slab of the same size, no neighbours), timed on rank 0 outside
+    # the timed region, so that a weak-scaling efficiency can be read off this one line
+    one_gpu = None
+    if world > 1:
+        if rank == 0:
+            s1 = gm.slab.Level1Slab(gm, props, (L1_NX, L1_NY, SLAB_PLANES), L1_H, 0, 1, [P["T_amb"]] * 5, device=device)
+            s1.set_owned(sl.owned(sl.T)[: s1.plane * SLAB_PLANES].clone(), torch.ones(s1.plane * SLAB_PLANES, device=device))
+            for _ in range(W):
+                s1.dwell_sweep(DT_DWELL)
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(K):
+                s1.dwell_sweep(DT_DWELL)
+            f1.record()
+            torch.cuda.synchronize()
+            one_gpu = f0.elapsed_time(f1) * 1e-3 / K
+            del s1
+        dist.barrier()
     if rank == 0:
         peaks = read_peaks()
         value = K * nn_total / total_s
@@ -130,6 +149,10 @@ def run_gomelt_multi(args, read_peaks, ClockSampler, host_properties, single_gpu
                     "h2d_bytes_per_step": 4 * nown * world, "d2h_bytes_per_step": 4 * nown * world,
                     "api": "host-buffer sweep: upload owned T planes, halo fill, one dwell sweep, download"},
             "gpu_launches": launches, "clocks": clocks,
+            "same_workload_1gpu": None if one_gpu is None else {
+                "ms_per_step": 1e3 * one_gpu, "value": L1_NX * L1_NY * SLAB_PLANES / one_gpu,
+                "weak_scaling_efficiency": one_gpu / (total_s / K),
+                "note": "one 25-plane slab on rank 0, no neighbours, timed right after the N-GPU region"},
             "halo_bytes_per_step_per_gpu": 4 * sl.plane * ((1 if rank > 0 else 0) + (1 if rank < world - 1 else 0)),
             "halo": ("in-kernel peer stores (symmetric memory)" if sl.symmetric else "NCCL send/recv") if world > 1
                     else "none",

@@ -38,42 +38,44 @@ static void launch_v2(const StepParams& sp, int nch, cudaStream_t st) {
     level_step_v2<RY, WPB, FEAT, MINB, STAGE><<<grid, block, 0, st>>>(sp);
 }
 
-// exact-feature instances for the hot call shapes; anything else runs the generic instance
-constexpr int F_L3_BENCH = K1F_SRC | K1F_FLUX | K1F_S1OUT | K1F_CLAMP;
-constexpr int F_L3_SUB = F_L3_BENCH | K1F_SKIP;
-constexpr int F_L3_SUB2 = F_L3_SUB | K1F_S2OUT | K1F_ACCUM;
-constexpr int F_L1_DWELL = K1F_FLUX | K1F_BCCONST;
+// Exact-feature instances for the call shapes the steppers issue; anything else runs the generic instance.
+// Except for the two benchmark shapes the substrate override is compiled in (its test is two integer
+// compares per row and n_substrate = 0 switches it off), so a shape is looked up with K1F_NSUB set.
+constexpr int F_L3_BENCH = K1F_SRC | K1F_FLUX | K1F_S1OUT | K1F_CLAMP;       // bench.py L3-10M window
+constexpr int F_L3_SUB = F_L3_BENCH | K1F_SKIP | K1F_NSUB;                     // subcycleL3_Part1 cF:3367-3412
+constexpr int F_L3_SUB2 = F_L3_SUB | K1F_S2OUT | K1F_ACCUM;                    // subcycleL3_Part2 cF:3530-3590
+constexpr int F_L3_STEP = K1F_SRC | K1F_FLUX | K1F_CLAMP | K1F_SKIP | K1F_NSUB;  // stepGOMELT Level 3
+constexpr int F_L2 = K1F_RHS | K1F_FLUX | K1F_CLAMP | K1F_SKIP | K1F_NSUB;     // Level 2 (step / subcycle)
+constexpr int F_L1 = K1F_RHS | K1F_FLUX | K1F_CLAMP | K1F_BCCONST | K1F_NSUB;  // Level 1 (step / subcycle)
+constexpr int F_L1_DWELL = K1F_FLUX | K1F_BCCONST;                             // stepGOMELTDwellTime / slab bench
 constexpr int F_L1_DWELL_SUB = F_L1_DWELL | K1F_NSUB;
-constexpr int F_L1_DWELL_PEER = F_L1_DWELL | K1F_PEER;
+constexpr int F_L1_DWELL_PEER = F_L1_DWELL | K1F_PEER;                         // ... with the fused halo stores
 constexpr int F_L1_DWELL_SUB_PEER = F_L1_DWELL_SUB | K1F_PEER;
 
 static int launch_step(const StepParams& sp, cudaStream_t st) {
     const int nch = (sp.zend - sp.zbeg + sp.zchunk - 1) / sp.zchunk;
     static const int generic_only = env_int("GOMELT_K1_GENERIC", 0);
+    static const int exp = env_int("GOMELT_K1_EXP", 0);  // dev A/B of the benchmark shape
     constexpr int RY = 4, WPB = 1;  // one warp per CTA: warps are independent, finest SM balance
+    const int f = sp.feat;
     if (generic_only) {
         launch_v2<RY, WPB, K1F_ALL | K1F_GENERIC>(sp, nch, st);
+    } else if (f == F_L3_BENCH) {
+        if (exp == 1) launch_v2<4, 1, F_L3_BENCH, 1, true>(sp, nch, st);        // cp.async-staged prefetch
+        else if (exp == 2) launch_v2<3, 1, F_L3_BENCH, 12, true>(sp, nch, st);  // ... RY = 3, 12 warps / SM
+        else launch_v2<RY, WPB, F_L3_BENCH>(sp, nch, st);
+    } else if (f == F_L1_DWELL) {
+        launch_v2<RY, WPB, F_L1_DWELL>(sp, nch, st);
+    } else if (f == F_L1_DWELL_PEER) {
+        launch_v2<RY, WPB, F_L1_DWELL_PEER>(sp, nch, st);
     } else {
-        switch (sp.feat) {
-            case F_L3_BENCH: {
-                static const int wpb = env_int("GOMELT_K1_WPB", WPB);  // dev tuning knob
-                static const int exp = env_int("GOMELT_K1_EXP", 0);    // dev A/B of tile shape / register cap
-                if (exp == 1) launch_v2<4, 1, F_L3_BENCH, 1, true>(sp, nch, st);
-                else if (exp == 2) launch_v2<3, 1, F_L3_BENCH, 12, true>(sp, nch, st);
-                else if (exp == 3) launch_v2<3, 1, F_L3_BENCH, 1, true>(sp, nch, st);
-                else if (exp == 4) launch_v2<2, 1, F_L3_BENCH, 16, true>(sp, nch, st);
-                else if (exp == 5) launch_v2<4, 1, F_L3_BENCH, 10, true>(sp, nch, st);
-                else if (exp == 6) launch_v2<3, 1, F_L3_BENCH, 12, false>(sp, nch, st);
-                else if (wpb == 2) launch_v2<RY, 2, F_L3_BENCH>(sp, nch, st);
-                else if (wpb == 4) launch_v2<RY, 4, F_L3_BENCH>(sp, nch, st);
-                else launch_v2<RY, WPB, F_L3_BENCH>(sp, nch, st);
-                break;
-            }
+        switch (f | K1F_NSUB) {
             case F_L3_SUB: launch_v2<RY, WPB, F_L3_SUB>(sp, nch, st); break;
             case F_L3_SUB2: launch_v2<RY, WPB, F_L3_SUB2>(sp, nch, st); break;
-            case F_L1_DWELL: launch_v2<RY, WPB, F_L1_DWELL>(sp, nch, st); break;
+            case F_L3_STEP: launch_v2<RY, WPB, F_L3_STEP>(sp, nch, st); break;
+            case F_L2: launch_v2<RY, WPB, F_L2>(sp, nch, st); break;
+            case F_L1: launch_v2<RY, WPB, F_L1>(sp, nch, st); break;
             case F_L1_DWELL_SUB: launch_v2<RY, WPB, F_L1_DWELL_SUB>(sp, nch, st); break;
-            case F_L1_DWELL_PEER: launch_v2<RY, WPB, F_L1_DWELL_PEER>(sp, nch, st); break;
             case F_L1_DWELL_SUB_PEER: launch_v2<RY, WPB, F_L1_DWELL_SUB_PEER>(sp, nch, st); break;
             default: launch_v2<RY, WPB, K1F_ALL | K1F_GENERIC>(sp, nch, st); break;
         }

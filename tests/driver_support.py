@@ -131,3 +131,22 @@ def small_two_layer_input(tmp):
                           wait_time=6, dwell_time=2e-4, dwell_time_multiplier=1, subcycle_num_L2=2,
                           subcycle_num_L3=2, record_step=4, info_T=0, laser_velocity=500)
     return inp
+
+
+def serpentine_input(tmp):
+    """BASELINE.json configs[2] in miniature: one layer, three serpentine tracks joined by rapid (G0) moves, so
+    that jump rows and the faster-than-100x-velocity single-step trigger (gm:168-171) are exercised."""
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import scenario
+
+    inp = copy.deepcopy(scenario.SMALL_INPUT)
+    g = os.path.join(tmp, "serpentine.gcode")
+    with open(g, "w") as fh:
+        fh.write("G0 X0.40 Y0.36 Z0.0\nG1 X0.48 Y0.36 Z0.0\nG0 X0.48 Y0.40 Z0.0\nG1 X0.40 Y0.40 Z0.0\n"
+                 "G0 X0.40 Y0.44 Z0.0\nG1 X0.48 Y0.44 Z0.0\n")
+    inp["nonmesh"].update(save_path=tmp + "/", toolpath=os.path.join(tmp, "toolpath.txt"), gcode=g, use_txt=0,
+                          wait_time=4, dwell_time=8e-5, dwell_time_multiplier=1, subcycle_num_L2=2,
+                          subcycle_num_L3=2, record_step=4, info_T=0, laser_velocity=500)
+    return inp

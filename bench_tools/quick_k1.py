@@ -1,4 +1,9 @@
-"""Scratch timing of K1 at the 10 M-node Level-3 size (not the bench contract; see bench.py)."""
+"""Scratch timing of K1 at the 10 M-node Level-3 size (not the bench contract; see bench.py).
+
+    python bench_tools/quick_k1.py [shape ...]     shapes: nat (natural-boundary bench shape, general kernel),
+        sub (subcycle L3 substep shape: SKIP_FACES, fast kernel), subg (same call on the general kernel),
+        l2 (rhs shape), dwell (Level-1 dwell shape on a 1001 x 1001 x 25 slab)
+"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -9,31 +14,49 @@ P = gm.schema.SetupProperties({"laser_radius": 0.1, "laser_depth": 0.1, "laser_a
                                "latent_heat_evap": 6457000.0})
 ops = gm.ops
 props = gm._lib.make_props(P)
-nx, ny, nz = 513, 513, 39
-grid = gm._lib.make_grid((nx, ny, nz), (0.02, 0.02, 0.02))
-nn = nx * ny * nz
-g = torch.Generator(device="cuda").manual_seed(0)
-T0 = 300 + 2000 * torch.rand(nn, device="cuda", generator=g)
-S1 = (torch.rand(nn, device="cuda", generator=g) > 0.5).float()
-Tout = torch.empty_like(T0); S1o = torch.empty_like(T0)
+PEAK = 6542.1e9
 flush = torch.empty(64 * 1024 * 1024, device="cuda")
-tx = torch.rand(nx, device="cuda", generator=g); ty = torch.rand(ny, device="cuda", generator=g); tz = torch.rand(nz, device="cuda", generator=g)
-top = torch.zeros(nx * ny, device="cuda")
-print("variant", os.environ.get("GOMELT_K1_VARIANT", "2"), "generic", os.environ.get("GOMELT_K1_GENERIC", "0"))
-for zc in [int(a) for a in sys.argv[1:]] or (0, 20, 13, 10):
+
+
+def run(shape, zc=0):
+    nx, ny, nz = (1001, 1001, 25) if shape.startswith("dwell") else (513, 513, 39)
+    grid = gm._lib.make_grid((nx, ny, nz), (0.02, 0.02, 0.02))
+    nn = nx * ny * nz
+    g = torch.Generator(device="cuda").manual_seed(0)
+    hot = os.environ.get("GOMELT_QUICK_HOT", "1") == "1"
+    T0 = (300 + 2000 * torch.rand(nn, device="cuda", generator=g)) if hot else (300 + 900 * torch.rand(nn, device="cuda", generator=g))
+    S1 = (torch.rand(nn, device="cuda", generator=g) > 0.5).float()
+    Tout = torch.empty_like(T0); S1o = torch.empty_like(T0)
+    tx = torch.rand(nx, device="cuda", generator=g); ty = torch.rand(ny, device="cuda", generator=g); tz = torch.rand(nz, device="cuda", generator=g)
+    rhs = 1e-4 * torch.randn(nn, device="cuda", generator=g)
+    kw, bpd = {}, 16
+    if shape == "nat":
+        kw = dict(src=(tx, ty, tz, 1e-3), flags=ops.STEP_CLAMP | ops.STEP_WRITE_S1 | ops.STEP_FUSED_FLUX, S1_out=S1o)
+    elif shape in ("sub", "subg"):
+        kw = dict(src=(tx, ty, tz, 1e-3), S1_out=S1o, n_substrate=2 * nx * ny,
+                  flags=ops.STEP_CLAMP | ops.STEP_WRITE_S1 | ops.STEP_FUSED_FLUX | ops.STEP_SKIP_FACES |
+                  (ops.STEP_GENERAL_KERNEL if shape == "subg" else 0))
+    elif shape in ("l2", "l2g"):
+        kw = dict(rhs=rhs, n_substrate=2 * nx * ny, flags=ops.STEP_CLAMP | ops.STEP_FUSED_FLUX | ops.STEP_SKIP_FACES |
+                  (ops.STEP_GENERAL_KERNEL if shape == "l2g" else 0))
+        bpd = 16
+    elif shape in ("dwell", "dwellg"):
+        kw = dict(flags=ops.STEP_BC_CONST | ops.STEP_FUSED_FLUX | (ops.STEP_GENERAL_KERNEL if shape == "dwellg" else 0),
+                  bc5=[298.15] * 5)
+        bpd = 12
     ts = []
-    for it in range(8):
+    for it in range(9):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.level_step(props, grid, T0, S1, Tout, 1e-5, src=(tx, ty, tz, 1e-3), n_substrate=0,
-                       flags=ops.STEP_CLAMP | ops.STEP_WRITE_S1 | ops.STEP_FUSED_FLUX, S1_out=S1o, z_chunk=zc)
+        ops.level_step(props, grid, T0, S1, Tout, 1e-5, z_chunk=zc, **kw)
         e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     t = np.median(ts[3:]) * 1e-3
-    print(f"z_chunk={zc:3d}: {t*1e6:8.1f} us  {nn/t/1e9:7.2f} G DOF/s  {nn*16/t/1e9:7.1f} GB/s algorithmic ({nn*16/t/6542.1e9*100:.1f}% of measured HBM peak)")
-import hashlib
-torch.cuda.synchronize()
-print("out sha1", hashlib.sha1(Tout.cpu().numpy().tobytes()).hexdigest()[:16], hashlib.sha1(S1o.cpu().numpy().tobytes()).hexdigest()[:16])
-if os.environ.get("GOMELT_K1_DUMP"):
-    np.save(os.environ["GOMELT_K1_DUMP"], Tout.cpu().numpy())
+    print(f"{shape:6s} z_chunk={zc:3d}: {t*1e6:8.1f} us  {nn/t/1e9:7.2f} G DOF/s  {nn*bpd/t/1e9:7.1f} GB/s algorithmic "
+          f"({nn*bpd/t/PEAK*100:.1f}% of measured HBM peak)", flush=True)
+
+
+for a in sys.argv[1:] or ["nat", "sub", "subg"]:
+    shape, _, zc = a.partition(":")
+    run(shape, int(zc or 0))

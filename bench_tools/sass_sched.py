@@ -1,0 +1,96 @@
+"""Static schedule of a kernel's hottest loop from its SASS (runs here, no GPU):
+
+    python bench_tools/sass_sched.py <lib.so> <mangled-name-substring> [--all]
+
+Finds the largest backward-branch region of the function, counts opcodes in it and sums the stall
+fields of the control words (bits [105:109) of each 128-bit instruction, B300_MICROARCH.md "Per-warp
+issue scheduler"): the sum is the minimum number of cycles ONE warp needs per loop trip when nothing
+waits on a scoreboard, i.e. the static single-warp issue model.
+"""
+import collections
+import re
+import subprocess
+import sys
+
+
+def parse(lib, name):
+    txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+    funcs, cur = {}, None
+    for ln in txt.splitlines():
+        m = re.search(r"Function : (\S+)", ln)
+        if m:
+            cur = m.group(1)
+            funcs[cur] = []
+            continue
+        if cur is not None:
+            funcs[cur].append(ln)
+    hits = [f for f in funcs if name in f]
+    if not hits:
+        raise SystemExit(f"no function matching {name}; have: " + "\n".join(funcs))
+    fn = hits[0]
+    ins = []  # (addr, text, lo, hi)
+    lines = funcs[fn]
+    i = 0
+    while i < len(lines):
+        m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);\s+/\* (0x[0-9a-f]{16}) \*/", lines[i])
+        if m and i + 1 < len(lines):
+            m2 = re.match(r"\s+/\* (0x[0-9a-f]{16}) \*/", lines[i + 1])
+            if m2:
+                ins.append((int(m.group(1), 16), m.group(2).strip(), int(m.group(3), 16), int(m2.group(1), 16)))
+                i += 2
+                continue
+        i += 1
+    return fn, ins
+
+
+def ctrl(hi):
+    stall = (hi >> (105 - 64)) & 0xF
+    yld = (hi >> (109 - 64)) & 1
+    wbar = (hi >> (110 - 64)) & 7
+    rbar = (hi >> (113 - 64)) & 7
+    wait = (hi >> (116 - 64)) & 0x3F
+    return stall, yld, wbar, rbar, wait
+
+
+def opname(text):
+    p = text.split()
+    b = p[1] if p[0].startswith("@") else p[0]
+    return b.split(".")[0]
+
+
+FMA = {"FFMA", "FMUL", "FADD", "FFMA2", "FMUL2", "FADD2", "IMAD", "HFMA2", "IMAD.WIDE"}
+
+
+def main():
+    lib, name = sys.argv[1], sys.argv[2]
+    fn, ins = parse(lib, name)
+    print(fn, len(ins), "instructions")
+    addr_idx = {a: k for k, (a, *_r) in enumerate(ins)}
+    loops = []
+    for k, (a, t, lo, hi) in enumerate(ins):
+        m = re.search(r"BRA\S*\s+(?:\S+,\s*)?`\(\.L_x_\d+\)|BRA\S*.*0x([0-9a-f]+)", t)
+        if "BRA" in t:
+            m = re.search(r"0x([0-9a-f]+)", t)
+            if m:
+                tgt = int(m.group(1), 16)
+                if tgt <= a and tgt in addr_idx:
+                    loops.append((k - addr_idx[tgt] + 1, addr_idx[tgt], k))
+    loops.sort(reverse=True)
+    for n, s, e in loops[: (len(loops) if "--all" in sys.argv else 1)]:
+        ops = collections.Counter()
+        stall_sum = 0
+        waits = 0
+        for a, t, lo, hi in ins[s : e + 1]:
+            st, yld, wbar, rbar, wait = ctrl(hi)
+            ops[opname(t)] += 1
+            stall_sum += max(st, 1)
+            waits += 1 if wait else 0
+        print(f"loop [{ins[s][0]:#x}, {ins[e][0]:#x}] {n} instr, sum(stall) = {stall_sum} cycles, "
+              f"{waits} instr wait on a scoreboard")
+        print("  " + "  ".join(f"{k}={v}" for k, v in ops.most_common(30)))
+        hist = collections.Counter(max(ctrl(hi)[0], 1) for *_x, hi in ins[s : e + 1])
+        print("  stall histogram:", dict(sorted(hist.items())))
+
+
+if __name__ == "__main__":
+    main()

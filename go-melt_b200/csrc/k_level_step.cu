@@ -21,6 +21,7 @@
 
 #include "common.cuh"
 #include "k_level_step_v2.cuh"
+#include "k_level_step_v3.cuh"
 
 namespace gomelt {
 
@@ -52,8 +53,53 @@ constexpr int F_L1_DWELL_SUB = F_L1_DWELL | K1F_NSUB;
 constexpr int F_L1_DWELL_PEER = F_L1_DWELL | K1F_PEER;                         // ... with the fused halo stores
 constexpr int F_L1_DWELL_SUB_PEER = F_L1_DWELL_SUB | K1F_PEER;
 
+template <int RY, int FEAT, int MINB = 1>
+static void launch_v3(const StepParams& sp, int nch, cudaStream_t st) {
+    dim3 grid((sp.nx - 2 + 2 * K1_TX - 1) / (2 * K1_TX), (sp.ny - 2 + RY - 1) / RY, nch);
+    level_step_v3<RY, FEAT, MINB><<<grid, 32, 0, st>>>(sp);
+}
+
+// v3 (k_level_step_v3.cuh) serves the Dirichlet-side-face shapes of the steppers on grids that hold a full tile.
+// Returns false when the call is not one of them (v2 takes it).  GOMELT_STEP_BC_CONST calls get their five
+// constant faces from face_const_kernel (the step itself never stores a face node).
+static bool try_launch_v3(const StepParams& sp, int nch, cudaStream_t st) {
+    static const int off = env_int("GOMELT_K1_V2", 0);  // dev A/B: force the v2 path
+    constexpr int RY = 4;
+    const int f = sp.feat;
+    if (off || (sp.flags & GOMELT_STEP_GENERAL_KERNEL) || !(f & (K1F_SKIP | K1F_BCCONST)) ||
+        (f & (K1F_S2OUT | K1F_ACCUM | K1F_TOP)))
+        return false;
+    if (sp.nx < 2 * K1_TX + 2 || sp.ny < RY + 2 || sp.nzl < 2 || sp.nsub_rem != 0) return false;
+    // plane 0 is never finalised: its row stores are redirected to plane 1, which the same warp must overwrite
+    if (sp.zbeg == 0 && (sp.zchunk < 2 || sp.zend < 2)) return false;
+    constexpr int V3_L3_SUB = K1F_SRC | K1F_FLUX | K1F_S1OUT | K1F_CLAMP | K1F_NSUB;  // subcycleL3_Part1
+    constexpr int V3_L3_STEP = K1F_SRC | K1F_FLUX | K1F_CLAMP | K1F_NSUB;             // stepGOMELT Level 3
+    constexpr int V3_RHS = K1F_RHS | K1F_FLUX | K1F_CLAMP | K1F_NSUB;                 // Level 2 and Level 1 (step / subcycle)
+    constexpr int V3_DWELL = K1F_FLUX | K1F_NSUB;                                     // stepGOMELTDwellTime (no clamp)
+    constexpr int V3_DWELL_PEER = V3_DWELL | K1F_PEER;                                // ... with the fused halo stores
+    switch ((f & ~(K1F_SKIP | K1F_BCCONST)) | K1F_NSUB) {
+        case V3_L3_SUB:
+            if (sp.exp & 4) launch_v3<RY, V3_L3_SUB, 12>(sp, nch, st);  // dev experiment: 168-register cap
+            else launch_v3<RY, V3_L3_SUB>(sp, nch, st);
+            break;
+        case V3_L3_STEP: launch_v3<RY, V3_L3_STEP>(sp, nch, st); break;
+        case V3_RHS: launch_v3<RY, V3_RHS>(sp, nch, st); break;
+        case V3_DWELL: launch_v3<RY, V3_DWELL>(sp, nch, st); break;
+        case V3_DWELL_PEER: launch_v3<RY, V3_DWELL_PEER>(sp, nch, st); break;
+        default: return false;
+    }
+    if (f & K1F_BCCONST) {
+        const long long n = (long long)(2 * sp.nx + 2 * sp.ny) * (sp.zend - sp.zbeg) + (sp.zbeg == 0 ? (long long)sp.nx * sp.ny : 0);
+        const int blocks = (int)((n + 255) / 256 < 4 * GOMELT_SM_COUNT ? (n + 255) / 256 : 4 * GOMELT_SM_COUNT);
+        face_const_kernel<<<blocks, 256, 0, st>>>(sp.Tout, sp.nx, sp.ny, sp.nz, sp.zbeg, sp.zend, sp.bc[0], sp.bc[1], sp.bc[2],
+                                                  sp.bc[3], sp.bc[4], sp.peer_lo, sp.peer_hi);
+    }
+    return true;
+}
+
 static int launch_step(const StepParams& sp, cudaStream_t st) {
     const int nch = (sp.zend - sp.zbeg + sp.zchunk - 1) / sp.zchunk;
+    if (try_launch_v3(sp, nch, st)) return check_launch("gomelt_level_step_f32");
     static const int generic_only = env_int("GOMELT_K1_GENERIC", 0);
     static const int exp = env_int("GOMELT_K1_EXP", 0);  // dev A/B of the benchmark shape
     constexpr int RY = 4, WPB = 1;  // one warp per CTA: warps are independent, finest SM balance
@@ -123,6 +169,7 @@ extern "C" int gomelt_level_step_f32(const gomelt_props_t* props, const gomelt_s
     const double hx = g.hx, hy = g.hy, hz = g.hz, V = hx * hy * hz;
     const double c[3] = {V / (hx * hx), V / (hy * hy), V / (hz * hz)};
     const double muD[2] = {0.0, 2.0}, muM[2] = {0.5, 1.0 / 6.0};
+    double lam_d[8];
     for (int s = 0; s < 8; ++s) {
         const int sd[3] = {s & 1, (s >> 1) & 1, (s >> 2) & 1};
         double lam = 0.0;
@@ -133,6 +180,13 @@ extern "C" int gomelt_level_step_f32(const gomelt_props_t* props, const gomelt_s
             lam += t;
         }
         sp.lam[s] = (float)(lam / 64.0);  // 1/8 (Haar inverse) * 1/8 (kbar = k8/8)
+        lam_d[s] = lam / 64.0;
+    }
+    // v3: mode pairs (sx,sz) = (0,1), (1,0), (1,1); l_s = lambda'[sy = 0], l_d = lambda'[sy = 1]
+    const int pair_s[3] = {4, 1, 5}, pair_d[3] = {6, 3, 7};
+    for (int q = 0; q < 3; ++q) {
+        sp.lamA[q] = (float)(lam_d[pair_s[q]] + lam_d[pair_d[q]]);
+        sp.lamB[q] = (float)(lam_d[pair_s[q]] - lam_d[pair_d[q]]);
     }
     sp.cdt = (float)(64.0 * (double)a->dt / V);
     sp.dt = a->dt;
@@ -147,6 +201,10 @@ extern "C" int gomelt_level_step_f32(const gomelt_props_t* props, const gomelt_s
     sp.flags = a->flags;
     sp.zbeg = zbeg; sp.zend = zend;
     sp.peer_lo = a->peer_lo; sp.peer_hi = a->peer_hi;
+    {
+        static const int exp_env = env_int("GOMELT_K1_EXP", 0);
+        sp.exp = exp_env;
+    }
     {
         const long long Pn = (long long)g.nx * g.ny;
         const long long ns = a->n_substrate < 0 ? 0 : a->n_substrate;

@@ -26,6 +26,7 @@ struct StepParams {
     int nx, ny, nz, nzl;   // nzl = active planes
     long long nsub;
     float lam[8];          // lambda'[sx + 2 sy + 4 sz] (already /64: two 1/8 factors folded)
+    float lamA[3], lamB[3];  // v3: l_s + l_d and l_s - l_d of the (sx,sz) = (0,1), (1,0), (1,1) mode pairs
     float cdt;             // 64 dt / V
     float dt;
     PropK pk;
@@ -52,6 +53,7 @@ struct StepParams {
     FluxK fk;              // top-surface flux constants (K1F_FLUX)
     float* peer_lo;        // neighbour ghost planes in peer memory (K1F_PEER), or nullptr
     float* peer_hi;
+    int exp;               // dev experiments (GOMELT_K1_EXP), 0 in production
 };
 
 #define GM_DI __device__ __forceinline__

@@ -1,0 +1,383 @@
+// K1 v3 — fused level step for the call shapes whose four side faces (x-, x+, y-, y+) and bottom face are
+// Dirichlet (GOMELT_STEP_SKIP_FACES: child levels, faces come from the parent, assignBCsFine cF:1598-1620;
+// GOMELT_STEP_BC_CONST: Level 1, assignBCs cF:1568-1595).  That is every call the steppers issue
+// (stepGOMELT, subcycleGOMELT, stepGOMELTDwellTime); the natural-boundary form stays on v2.
+//
+// Same mathematics, mapping and plane pipeline as v2 (k_level_step_v2.cuh: one warp per 60 x RY column patch
+// marching in z, packed f32x2, no shared memory in the plane loop).  What v3 removes is everything that
+// exists only because a v2 tile may hang over the grid edge:
+//
+//  * tiles cover the OWNED region [1, nx-2] x [1, ny-2] only (face nodes are never stored by the step) and
+//    the last tile / strip is shifted inwards so that all 64 x (RY+2) loaded columns / rows are inside the
+//    grid: the overlap is computed twice with bit-identical results (same operations on the same data), so
+//    the duplicate stores are benign.  No load guards, no element-column mask, no edge-row selects, one
+//    store predicate (the 30 owned lanes);
+//  * the substrate override (cF:2589-2590) is whole planes in every reference call (getSubstrateNodes
+//    cF:562-579), so it becomes a per-plane threshold (S1 > -1) instead of a per-node compare;
+//  * the y stage of the analysis and the lambda scaling are folded:  with A = l_s + l_d, B = l_s - l_d,
+//      l_s (zu + zl) - l_d (zu - zl) = B zu + A zl,     l_s (zu + zl) + l_d (zu - zl) = A zu + B zl,
+//    and B z is formed once per loaded row: 42 instead of 84 packed instructions per warp-plane.
+//
+// Measured on B200 the packed-FP instruction stream is bound by register-file read bandwidth (FADD2 / FFMA2
+// with register operands occupy the scheduler for 2 / 3 cycles and nothing co-issues in their shadow:
+// bench_tools/ubench_pipes.cu), i.e. by the instruction count itself - hence this variant.
+#pragma once
+#include "k_level_step_v2.cuh"
+
+namespace gomelt {
+
+// computeStateProperties cF:2567-2614 as selects; thr = 0.499, or -1 on substrate planes (forces S1).
+GM_DI void props3(const PropK& q, float T, float S1in, float thr, float kb, float cs, float& k, float& m, float& s1f) {
+    asm("{\n\t.reg .pred p1, p2, p3;\n\t"
+        "setp.ge.f32 p2, %3, %6;\n\t"
+        "setp.gt.f32 p3, %3, %7;\n\t"
+        "setp.gt.f32 p1, %4, %5;\n\t"
+        "selp.f32 %0, %8, %9, p1;\n\t"
+        "selp.f32 %0, %10, %0, p2;\n\t"
+        "selp.f32 %1, %11, %12, p3;\n\t"
+        "selp.f32 %1, %13, %1, p2;\n\t"
+        "or.pred p1, p1, p2;\n\t"
+        "selp.f32 %2, 0f3F800000, 0f00000000, p1;\n\t}"
+        : "=&f"(k), "=&f"(m), "=f"(s1f)
+        : "f"(T), "f"(S1in), "f"(thr), "f"(q.T_liq), "f"(q.T_sol), "f"(kb), "f"(q.k_powder), "f"(q.k_fluid),
+          "f"(q.c_mushy), "f"(cs), "f"(q.c_fluid));
+}
+GM_DI void props3_km(const PropK& q, float T, float S1in, float thr, float kb, float cs, float& k, float& m) {
+    asm("{\n\t.reg .pred p1, p2, p3;\n\t"
+        "setp.ge.f32 p2, %2, %5;\n\t"
+        "setp.gt.f32 p3, %2, %6;\n\t"
+        "setp.gt.f32 p1, %3, %4;\n\t"
+        "selp.f32 %0, %7, %8, p1;\n\t"
+        "selp.f32 %0, %9, %0, p2;\n\t"
+        "selp.f32 %1, %10, %11, p3;\n\t"
+        "selp.f32 %1, %12, %1, p2;\n\t}"
+        : "=&f"(k), "=&f"(m)
+        : "f"(T), "f"(S1in), "f"(thr), "f"(q.T_liq), "f"(q.T_sol), "f"(kb), "f"(q.k_powder), "f"(q.k_fluid),
+          "f"(q.c_mushy), "f"(cs), "f"(q.c_fluid));
+}
+
+// Unguarded pair load: half .y at q, half .x 30 columns (120 bytes) below it.
+GM_DI f2 ld2u(const char* q) {
+    const float* f = reinterpret_cast<const float*>(q);
+    return mk2(__ldg(f - K1_TX), __ldg(f));
+}
+
+template <int RY>
+struct K3State {  // x-staged fields of one plane (loaded rows) + T of the owned rows
+    f2 Xs[RY + 2], Xd[RY + 2], kx[RY + 2], mx[RY + 2], T[RY];
+};
+template <int RY>
+struct K3Raw {    // prefetched raw plane
+    f2 Tr[RY + 2], Sr[RY + 2];
+};
+
+// FEAT: K1F_RHS, K1F_SRC, K1F_FLUX, K1F_S1OUT, K1F_CLAMP, K1F_NSUB (whole planes), K1F_BCCONST, K1F_PEER;
+// K1F_SKIP is implied when K1F_BCCONST is absent.  Requires nx >= 62, ny >= RY + 2, nz_active >= 2.
+template <int RY, int FEAT, int MINB = 1>
+__global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant__ StepParams p) {
+    constexpr int NR = RY + 2;
+    constexpr bool F_RHS = (FEAT & K1F_RHS) != 0, F_SRC = (FEAT & K1F_SRC) != 0, F_FLUX = (FEAT & K1F_FLUX) != 0;
+    constexpr bool F_S1 = (FEAT & K1F_S1OUT) != 0, F_CLAMP = (FEAT & K1F_CLAMP) != 0, F_NSUB = (FEAT & K1F_NSUB) != 0;
+    constexpr bool F_BC = (FEAT & K1F_BCCONST) != 0, F_PEER = (FEAT & K1F_PEER) != 0;
+    const int lane = threadIdx.x;
+    const int nx = p.nx, ny = p.ny, nz = p.nz, nzl = p.nzl;
+    const int c0 = min((int)blockIdx.x * (2 * K1_TX), nx - (2 * K1_TX + 2));  // column of lane 0, half .x
+    const int j0 = min(1 + (int)blockIdx.y * RY, ny - 1 - RY);                  // first owned row
+    const int ia = c0 + lane, ib = ia + K1_TX;
+    const int own = (lane >= 1 && lane <= K1_TX) ? 1 : 0;
+    // the same flag through two expressions ptxas does not identify: with one predicate on both stores of a pair
+    // it turns the predication into a divergent branch around the row's tail (BSSY / BSYNC per row)
+    const int owna = ((unsigned)(lane - 1) < (unsigned)K1_TX) ? 1 : 0, ownb = (int)((0x7FFFFFFEu >> lane) & 1u);
+    const int sa = own | (ia == 0 ? 1 : 0), sb = own | (ib == nx - 1 ? 1 : 0);  // lanes that store S1 (faces too)
+    const int P = nx * ny;
+    const int za = p.zbeg + blockIdx.z * p.zchunk;
+    const int zb = min(p.zend, za + p.zchunk);  // this warp finalises node planes [za, zb)
+    const int lfirst = max(za - 1, 0);
+    const int llast = min(min(zb, nz - 1), nzl - 1);  // last plane that carries data
+    unsigned off[NR];                                  // in-plane byte offset of half .y per loaded row
+#pragma unroll
+    for (int r = 0; r < NR; ++r) off[r] = 4u * (unsigned)((j0 - 1 + r) * nx + ib);
+    const int nsub_planes = p.nsub_planes;
+
+    const int opaque_zero = nx >> 31;
+    auto settle = [&](float x) { return __int_as_float(__float_as_int(x) ^ opaque_zero); };
+    f2 sfx = splat(0.f);
+    float sfy[RY];
+#pragma unroll
+    for (int r = 0; r < RY; ++r) sfy[r] = 0.f;
+    if (F_SRC) {
+        sfx = mk2(__ldg(p.srcx + ia) * p.scoef, __ldg(p.srcx + ib) * p.scoef);
+#pragma unroll
+        for (int r = 0; r < RY; ++r) sfy[r] = settle(__ldg(p.srcy + j0 + r));
+    }
+    // Level-1 Dirichlet constants on the side faces (assignBCs order y-, y+, x-, x+: later wins on edges):
+    // the face nodes are the halo lanes / rows of the outermost tiles; they are written once per plane.
+    f2 Tt0[RY], Tt1[RY], myp[RY];
+#pragma unroll
+    for (int r = 0; r < RY; ++r) Tt0[r] = Tt1[r] = myp[r] = splat(0.f);
+
+    auto load_plane = [&](int l, K3Raw<RY>& raw) {
+        const char* Tl = (const char*)(p.T0 + (size_t)l * P);
+        const char* Sl = (const char*)(p.S1 + (size_t)l * P);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            raw.Tr[r] = ld2u(Tl + off[r]);
+            raw.Sr[r] = ld2u(Sl + off[r]);
+        }
+    };
+
+    // ---- node state of loaded row r (+ S1 output) and its x stage ------------------------------------
+    auto row_a = [&](char* so, int r, float thr, f2 T, f2 S, f2& xs, f2& xd, f2& kxr, f2& mxr) {
+        const f2 kb = fma2(splat(p.pk.k_a1), T, splat(p.pk.k_a0)), cs = fma2(splat(p.pk.c_a1), T, splat(p.pk.c_a0));
+        f2 kn, mn;
+        if (F_S1) {
+            // S1' is node-local, so every loaded node (halo rows, halo planes of a chunk, face lanes) may be
+            // written: its owner writes the same value.  This is what covers the face nodes without a guard.
+            f2 s1f;
+            props3(p.pk, T.v.x, S.v.x, thr, kb.v.x, cs.v.x, kn.v.x, mn.v.x, s1f.v.x);
+            props3(p.pk, T.v.y, S.v.y, thr, kb.v.y, cs.v.y, kn.v.y, mn.v.y, s1f.v.y);
+            st2(so + off[r], sa, sb, s1f);
+        } else {
+            props3_km(p.pk, T.v.x, S.v.x, thr, kb.v.x, cs.v.x, kn.v.x, mn.v.x);
+            props3_km(p.pk, T.v.y, S.v.y, thr, kb.v.y, cs.v.y, kn.v.y, mn.v.y);
+        }
+        const f2 Tr = shdn(T), kr = shdn(kn), mr = shdn(mn);
+        xs = Tr + T;
+        xd = Tr - T;
+        kxr = kr + kn;
+        mxr = mr + mn;
+    };
+    auto plane_thr = [&](int l) -> float { return (F_NSUB && l < nsub_planes) ? -1.0f : 0.499f; };
+
+    auto first_plane = [&](int l, const K3Raw<RY>& raw, K3State<RY>& st) {
+        char* so = F_S1 ? (char*)(p.S1out + (size_t)l * P) : nullptr;
+        const float thr = plane_thr(l);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            row_a(so, r, thr, raw.Tr[r], raw.Sr[r], st.Xs[r], st.Xd[r], st.kx[r], st.mx[r]);
+            if (r >= 1 && r <= RY) st.T[r - 1] = raw.Tr[r];
+        }
+    };
+
+    // ---- write one finalised owned row of plane f (side faces are not owned; see the header) ---------
+    auto store_row = [&](int f, char* out, int r, f2 Tn) {
+        if (F_CLAMP) Tn = mk2(fmaxf(p.pk.T_amb, Tn.v.x), fmaxf(p.pk.T_amb, Tn.v.y));
+        st2(out + off[r + 1], owna, ownb, Tn);
+        if (F_PEER) {  // halo exchange fused into the step: plain stores to peer-mapped memory
+            if (f == p.zbeg && p.peer_lo) st2((char*)p.peer_lo + off[r + 1], owna, ownb, Tn);
+            if (f == p.zend - 1 && p.peer_hi) st2((char*)p.peer_hi + off[r + 1], owna, ownb, Tn);
+        }
+    };
+
+    // use_fl is a literal at every call site (the lambdas are inlined): only the top plane carries a flux
+    auto final_row = [&](int f, char* out, const char* rhs, int r, f2 sz, f2 Tf, f2 z0, f2 z1, f2 mz, bool use_fl,
+                         f2 fl) {
+        const f2 KT = (z0 - z1) + shup(z0 + z1);
+        const f2 mnode = mz + shup(mz);
+        const f2 rc = mk2(rcp_approx(mnode.v.x), rcp_approx(mnode.v.y));
+        if (F_RHS || F_SRC || (F_FLUX && use_fl)) {
+            f2 rr = splat(0.f);
+            if (F_RHS) rr = ld2u(rhs + off[r + 1]);
+            if (F_SRC) rr = fma2(sz, splat(sfy[r]), rr);
+            if (F_FLUX && use_fl) rr = rr + fl;
+            store_row(f, out, r, fma2(rr - KT, splat(p.cdt) * rc, Tf));
+        } else {
+            store_row(f, out, r, fma2(KT, splat(-p.cdt) * rc, Tf));
+        }
+    };
+
+    const f2 l2 = splat(p.lam[2]);
+    const f2 A01 = splat(p.lamA[0]), A10 = splat(p.lamA[1]), A11 = splat(p.lamA[2]);
+    const f2 B01 = splat(p.lamB[0]), B10 = splat(p.lamB[1]), B11 = splat(p.lamB[2]);
+
+    // ---- plane l: node state, x stage, then the element layer (l-1, l) row by row; finalises plane l-1
+    //      when do_final.  pv = state of plane l-1, cu <- state of plane l.
+    auto step_plane = [&](int l, const K3Raw<RY>& raw, const K3State<RY>& pv, K3State<RY>& cu, bool do_final, f2 sz) {
+        const int f = l - 1;
+        const size_t pl = (size_t)l * P;
+        char* so = F_S1 ? (char*)(p.S1out + pl) : nullptr;
+        const float thr = plane_thr(l);
+        // A plane that must not be finalised here (a chunk's lower halo plane; the Dirichlet bottom plane 0) is
+        // computed like any other and stored to plane l instead, where the next step overwrites it (same
+        // thread, same addresses, program order) - no per-plane guard in the loop.
+        char* out = (char*)(p.Tout + (do_final ? pl - P : pl));
+        const char* rhs = F_RHS ? (const char*)(p.rhs + (pl - P)) : nullptr;
+        f2 c00, c01, c10, c11, cm;                            // carries of the previous element row
+        f2 zl00, zl01, zl10, zl11, kzl, mzl, bl01, bl10, bl11;  // z-staged fields of the lower loaded row
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            f2 xs, xd, kxr, mxr;
+            row_a(so, r, thr, raw.Tr[r], raw.Sr[r], xs, xd, kxr, mxr);
+            cu.Xs[r] = xs; cu.Xd[r] = xd; cu.kx[r] = kxr; cu.mx[r] = mxr;
+            if (r >= 1 && r <= RY) cu.T[r - 1] = raw.Tr[r];
+            // z stage of the analysis
+            const f2 zu00 = xs + pv.Xs[r], zu01 = xs - pv.Xs[r];
+            const f2 zu10 = xd + pv.Xd[r], zu11 = xd - pv.Xd[r];
+            const f2 kzu = kxr + pv.kx[r], mzu = mxr + pv.mx[r];
+            const f2 bu01 = B01 * zu01, bu10 = B10 * zu10, bu11 = B11 * zu11;
+            if (r >= 1) {
+                const int e = r - 1;  // element row between loaded rows e and e+1
+                const f2 k8 = kzu + kzl;
+                const f2 m8 = mzu + mzl;
+                const f2 q00 = (l2 * (zu00 - zl00)) * k8;  // (sx,sz) = (0,0): only the sy = 1 mode acts
+                if (e >= 1) {  // lower node row of this element row = loaded row e = owned row e-1
+                    const f2 R00 = c00 - q00;
+                    const f2 R01 = fma2(k8, fma2(A01, zl01, bu01), c01);
+                    const f2 R10 = fma2(k8, fma2(A10, zl10, bu10), c10);
+                    const f2 R11 = fma2(k8, fma2(A11, zl11, bu11), c11);
+                    // z stage of the synthesis: bottom (plane l-1) and top (plane l) parts
+                    const f2 z0 = Tt0[e - 1] + (R00 - R01);
+                    const f2 z1 = Tt1[e - 1] + (R10 - R11);
+                    Tt0[e - 1] = R00 + R01;
+                    Tt1[e - 1] = R10 + R11;
+                    const f2 my = cm + m8;
+                    const f2 mz = myp[e - 1] + my;
+                    myp[e - 1] = my;
+                    final_row(f, out, rhs, e - 1, sz, pv.T[e - 1], z0, z1, mz, false, splat(0.f));
+                }
+                if (e < RY) {
+                    c00 = q00;
+                    c01 = fma2(A01, zu01, bl01) * k8;
+                    c10 = fma2(A10, zu10, bl10) * k8;
+                    c11 = fma2(A11, zu11, bl11) * k8;
+                    cm = m8;
+                }
+            }
+            zl00 = zu00; zl01 = zu01; zl10 = zu10; zl11 = zu11; kzl = kzu; mzl = mzu;
+            bl01 = bu01; bl10 = bu10; bl11 = bu11;
+        }
+    };
+
+    // ---- the chunk's source z-factors live in shared memory (see v2) ---------------------------------
+    __shared__ float s_srcz[F_SRC ? K1_SRCZ_MAX + 2 : 1];
+    if (F_SRC) {
+        for (int i = lane; i <= llast - lfirst; i += 32) s_srcz[i] = __ldg(p.srcz + lfirst + i);
+        __syncwarp();
+    }
+    auto srcz_at = [&](int f) -> float { return F_SRC ? s_srcz[f - lfirst] : 0.f; };
+
+    // ---- computeConvRadBC cF:2207-2301 fused (see v2): every element of the tile exists here ----------
+    auto fused_top_flux = [&](const K3Raw<RY>& raw, f2* fl) {
+        __shared__ float2 sT[NR][32];
+        __shared__ float2 sA[RY + 1][4][32];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) sT[r][lane] = raw.Tr[r].v;
+        __syncwarp();
+        const float* sTf = reinterpret_cast<const float*>(&sT[0][0]);
+        float* sAf = reinterpret_cast<float*>(&sA[0][0][0]);
+        const int lane1 = min(lane + 1, 31);
+        const float g = 0.57735026918962576f;
+        const float NA = 0.25f * (1.f + g) * (1.f + g), NB = 0.25f * (1.f + g) * (1.f - g),
+                    NC = 0.25f * (1.f - g) * (1.f - g);
+        const float wq = p.fk.wq;
+#pragma unroll 1
+        for (int it = 0; it < 2 * (RY + 1); ++it) {
+            const int e = it >> 1, h = it & 1;  // element row between loaded rows e, e + 1; half of the pair
+            const float T0n = sTf[(e * 32 + lane) * 2 + h], T1n = sTf[(e * 32 + lane1) * 2 + h];
+            const float T2n = sTf[((e + 1) * 32 + lane1) * 2 + h], T3n = sTf[((e + 1) * 32 + lane) * 2 + h];
+            const float q0 = flux_fast(p.fk, fmaf(NB, T3n, fmaf(NC, T2n, fmaf(NB, T1n, NA * T0n)))) * wq;
+            const float q1 = flux_fast(p.fk, fmaf(NC, T3n, fmaf(NB, T2n, fmaf(NA, T1n, NB * T0n)))) * wq;
+            const float q2 = flux_fast(p.fk, fmaf(NB, T3n, fmaf(NA, T2n, fmaf(NB, T1n, NC * T0n)))) * wq;
+            const float q3 = flux_fast(p.fk, fmaf(NA, T3n, fmaf(NB, T2n, fmaf(NC, T1n, NB * T0n)))) * wq;
+            sAf[((e * 4 + 0) * 32 + lane) * 2 + h] = fmaf(NB, q3, fmaf(NC, q2, fmaf(NB, q1, NA * q0)));
+            sAf[((e * 4 + 1) * 32 + lane) * 2 + h] = fmaf(NC, q3, fmaf(NB, q2, fmaf(NA, q1, NB * q0)));
+            sAf[((e * 4 + 2) * 32 + lane) * 2 + h] = fmaf(NB, q3, fmaf(NA, q2, fmaf(NB, q1, NC * q0)));
+            sAf[((e * 4 + 3) * 32 + lane) * 2 + h] = fmaf(NA, q3, fmaf(NB, q2, fmaf(NC, q1, NB * q0)));
+        }
+        __syncwarp();
+        const int lm = max(lane - 1, 0);
+#pragma unroll
+        for (int r = 0; r < RY; ++r)  // owned row r = loaded row r + 1: upper node of element row r, lower of r + 1
+            fl[r] = ((f2{sA[r][2][lm]} + f2{sA[r][3][lane]}) + f2{sA[r + 1][1][lm]}) + f2{sA[r + 1][0][lane]};
+    };
+
+    // ---- last data plane of a chunk top: no layer above, its action is (Tt0, Tt1, myp) --------------
+    auto last_plane = [&](int f, const f2* Tf, const K3Raw<RY>& raw) {
+        f2 sz = splat(0.f);
+        if (F_SRC) sz = sfx * splat(srcz_at(f));
+        f2 fl[RY];
+#pragma unroll
+        for (int r = 0; r < RY; ++r) fl[r] = splat(0.f);
+        if (F_FLUX && f == nzl - 1) fused_top_flux(raw, fl);  // warp-uniform
+        char* out = (char*)(p.Tout + (size_t)f * P);
+        const char* rhs = F_RHS ? (const char*)(p.rhs + (size_t)f * P) : nullptr;
+#pragma unroll
+        for (int r = 0; r < RY; ++r) final_row(f, out, rhs, r, sz, Tf[r], Tt0[r], Tt1[r], myp[r], true, fl[r]);
+    };
+
+    int fdone = za;  // planes [za, fdone) are finalised
+    if (p.exp & 1) {  // dev experiment: phase-shift the second resident warp of a scheduler
+        const int lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        if ((lin / 592) & 1) __nanosleep(p.exp >> 8);
+    }
+    auto l2_prefetch = [&](int l) {  // dev experiment: pull a plane into L2 ahead of the register prefetch
+        const char* Tl = (const char*)(p.T0 + (size_t)l * P);
+        const char* Sl = (const char*)(p.S1 + (size_t)l * P);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Tl + off[r]));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Sl + off[r]));
+        }
+    };
+    if (lfirst <= llast) {
+        K3Raw<RY> rawA, rawB;
+        K3State<RY> stA, stB;
+        load_plane(lfirst, rawA);
+        if (lfirst + 1 <= llast) load_plane(lfirst + 1, rawB);
+        first_plane(lfirst, rawA, stA);
+        // main loop, unrolled by two so the carried state ping-pongs: (stA, rawB) -> stB, (stB, rawA) -> stA
+        // plane 0 is the Dirichlet bottom face: never finalised (l - 1 >= 1)
+        for (int l = lfirst + 1; l <= llast; l += 2) {
+            if (l + 1 <= llast) load_plane(l + 1, rawA);
+            if ((p.exp & 2) && l + 3 <= llast) { l2_prefetch(l + 2); l2_prefetch(l + 3); }
+            step_plane(l, rawB, stA, stB, l - 1 >= max(za, 1), sfx * splat(srcz_at(l - 1)));
+            if (l + 1 > llast) break;
+            if (l + 2 <= llast) load_plane(l + 2, rawB);
+            step_plane(l + 1, rawA, stB, stA, l >= max(za, 1), sfx * splat(srcz_at(l)));
+        }
+        if (llast >= za && llast < zb) {
+            if (((llast - lfirst) & 1) != 0) last_plane(llast, stB.T, rawB);  // parity of the plane held in stB
+            else last_plane(llast, stA.T, rawA);
+        }
+        fdone = max(za, llast + 1);
+    }
+    // planes >= nz_active (substitute_Tbar cF:2183); the side faces belong to the face pass
+    for (int f = max(fdone, 1); f < zb; ++f) {
+        char* out = (char*)(p.Tout + (size_t)f * P);
+#pragma unroll
+        for (int r = 0; r < RY; ++r) st2(out + off[r + 1], owna, ownb, splat(p.pk.T_amb));
+    }
+}
+
+// Level-1 Dirichlet constants on the five faces of T_out (assignBCs cF:1568-1595, order y-, y+, x-, x+, z-:
+// the later face wins on shared edges), planes [zbeg, zend), and - for a z-slab rank - on the same nodes of the
+// neighbours' ghost planes (peer_lo <- plane zbeg, peer_hi <- plane zend-1).  One thread per face node:
+// ~2 (nx + ny) nz + nx ny nodes, a fraction of a percent of a sweep.
+__global__ void face_const_kernel(float* __restrict__ T, int nx, int ny, int nz, int zbeg, int zend, float b0, float b1,
+                                  float b2, float b3, float b4, float* __restrict__ peer_lo, float* __restrict__ peer_hi) {
+    const int per_plane = 2 * nx + 2 * ny;  // y- row, y+ row, x- column, x+ column
+    const long long nside = (long long)per_plane * (zend - zbeg);
+    const long long nbot = (zbeg == 0) ? (long long)nx * ny : 0;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nside + nbot;
+         t += (long long)gridDim.x * blockDim.x) {
+        if (t < nside) {
+            const int z = zbeg + (int)(t / per_plane), q = (int)(t % per_plane);
+            if (z == 0) continue;  // the bottom plane is written whole below
+            int i, j;
+            float v;
+            if (q < nx) { i = q; j = 0; v = (i == 0) ? b2 : (i == nx - 1) ? b3 : b0; }
+            else if (q < 2 * nx) { i = q - nx; j = ny - 1; v = (i == 0) ? b2 : (i == nx - 1) ? b3 : b1; }
+            else if (q < 2 * nx + ny) { i = 0; j = q - 2 * nx; v = b2; }
+            else { i = nx - 1; j = q - 2 * nx - ny; v = b3; }
+            const size_t in_plane = (size_t)j * nx + i;
+            T[(size_t)z * nx * ny + in_plane] = v;
+            if (z == zbeg && peer_lo) peer_lo[in_plane] = v;
+            if (z == zend - 1 && peer_hi) peer_hi[in_plane] = v;
+        } else {
+            T[t - nside] = b4;
+            if (zend == 1 && peer_hi) peer_hi[t - nside] = b4;
+        }
+    }
+}
+
+}  // namespace gomelt

@@ -4,7 +4,8 @@ torch's current stream.  One function per ``extern "C"`` entry point of include/
 import ctypes as C
 
 from . import _lib
-from ._lib import (STEP_ACCUM, STEP_BC_CONST, STEP_CLAMP, STEP_FUSED_FLUX, STEP_SKIP_FACES,  # noqa: F401
+from ._lib import (STEP_ACCUM, STEP_BC_CONST, STEP_CLAMP, STEP_FUSED_FLUX, STEP_GENERAL_KERNEL,  # noqa: F401
+                   STEP_SKIP_FACES,
                    STEP_WRITE_S1, STEP_WRITE_S2)
 
 LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)

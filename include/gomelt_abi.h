@@ -71,6 +71,9 @@ typedef struct gomelt_props {
 #define GOMELT_STEP_ACCUM      0x20  /* update accum / max_accum with S2_prev -> S2 transition */
 #define GOMELT_STEP_FUSED_FLUX 0x40  /* computeConvRadBC cF:2207-2301 evaluated inside the step from T0 on plane
                                         nz_active-1 and added to that plane's load (instead of `topflux`)   */
+#define GOMELT_STEP_GENERAL_KERNEL 0x80 /* run the general (natural-boundary capable) kernel even when the call
+                                        qualifies for the Dirichlet-side-face fast kernel; results agree to f32
+                                        rounding (tests A/B the two kernels through this bit)               */
 
 typedef struct gomelt_step_args {
     gomelt_grid_t grid;

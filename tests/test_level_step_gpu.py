@@ -317,3 +317,124 @@ def test_l3_substeps_one_call_equals_single_launches(gm, example_props):
     assert torch.equal(S2, S2c)
     assert _rel(last.cpu().numpy(), Tref) <= RTOL
     assert np.array_equal(S2.cpu().numpy().astype(bool), S2ref)
+
+
+def _faces_mask(nx, ny, nz):
+    face = np.zeros((nz, ny, nx), bool)
+    face[0] = True
+    face[:, 0] = face[:, -1] = True
+    face[:, :, 0] = face[:, :, -1] = True
+    return face
+
+
+@pytest.mark.parametrize("elements,nsub_planes,shape", [
+    ((100, 100, 10), 0, "l3_sub"), ((129, 37, 9), 3, "l3_sub"), ((61, 5, 4), 2, "l3_step"),
+    ((140, 66, 12), 4, "l2"), ((75, 23, 7), 0, "l2")])
+def test_dirichlet_side_face_kernel_matches_general_kernel_and_oracle(gm, example_props, elements, nsub_planes, shape):
+    """The fast kernel for the steppers' Dirichlet-side-face call shapes (k_level_step_v3.cuh: inward-shifted
+    overlapping tiles, folded y stage) against the general kernel on the same call and against the oracle:
+    interior T within 1e-5, S1' bit-exact on EVERY node (faces included), the five Dirichlet faces untouched."""
+    import torch
+
+    ops = gm.ops
+    ex, ey, ez = elements
+    bounds = ((0.0, 0.02 * ex), (0.0, 0.02 * ey), (-0.02 * ez, 0.0))
+    P, lv, T0, S1, nsub = _setup(gm, example_props, elements, bounds, 11, nsub_planes=nsub_planes)
+    T0 = (T0 * 1.2).astype(np.float32)
+    nx, ny, nz = lv["nodes"]
+    v = np.array([0.01 * ex, 0.01 * ey, 0.0], np.float32)
+    dt = 1e-5
+    rng = np.random.default_rng(5)
+    rhs = (rng.standard_normal(lv["nn"]) * 1e-4).astype(np.float32) if shape == "l2" else None
+    laserP = 0.0 if shape == "l2" else 285.0
+    flags = ops.STEP_SKIP_FACES | ops.STEP_CLAMP
+    props = gm._lib.make_props(P)
+    grid = gm._lib.make_grid(lv["nodes"], lv["h"])
+    dT0, dS1 = _dev(T0), _dev(S1)
+    src = None
+    if laserP:
+        coords = [_dev(c) for c in lv["node_coords"]]
+        tx, ty, tz = (torch.empty(n, device="cuda") for n in (nx, ny, nz))
+        src = (tx, ty, tz, ops.source_tables(props, grid, coords, v, laserP, tx, ty, tz))
+    outs = []
+    for extra in (0, ops.STEP_GENERAL_KERNEL):
+        Tout = torch.full((lv["nn"],), -7.0, device="cuda")
+        S1o = torch.full((lv["nn"],), -3.0, device="cuda")
+        kw = dict(S1_out=S1o) if shape == "l3_sub" else {}
+        f = flags | ops.STEP_FUSED_FLUX | extra | (ops.STEP_WRITE_S1 if shape == "l3_sub" else 0)
+        ops.level_step(props, grid, dT0, dS1, Tout, dt, rhs=None if rhs is None else _dev(rhs), src=src,
+                       n_substrate=nsub, flags=f, **kw)
+        torch.cuda.synchronize()
+        outs.append((Tout.cpu().numpy(), S1o.cpu().numpy()))
+    (Tf, S1f), (Tg, S1g) = outs
+    face = _faces_mask(nx, ny, nz).ravel()
+    assert (Tf[face] == -7.0).all() and (Tg[face] == -7.0).all()
+    assert _rel(Tf[~face], Tg[~face]) <= 2e-6, _rel(Tf[~face], Tg[~face])
+    if shape == "l3_sub":
+        assert np.array_equal(S1f, S1g)
+    Tref, S1ref, _ = _oracle_step(P, lv, T0, S1, nsub, dt, v, laserP, rhs=rhs)
+    Tref = np.maximum(np.float32(P["T_amb"]), Tref)
+    assert _rel(Tf[~face], Tref[~face]) <= RTOL, _rel(Tf[~face], Tref[~face])
+    if shape == "l3_sub":
+        assert np.array_equal(S1f, S1ref)
+
+
+def test_dirichlet_side_face_kernel_z_chunks_and_inactive_planes(gm, example_props):
+    """z-chunked launches of the fast kernel are bit-identical to the single-chunk launch, and planes above
+    nz_active are filled with T_amb on the owned nodes only."""
+    import torch
+
+    ops = gm.ops
+    elements = (90, 30, 11)
+    bounds = ((0.0, 1.8), (0.0, 0.6), (-0.22, 0.0))
+    P, lv, T0, S1, nsub = _setup(gm, example_props, elements, bounds, 3, nsub_planes=2)
+    nx, ny, nz = lv["nodes"]
+    props = gm._lib.make_props(P)
+    grid = gm._lib.make_grid(lv["nodes"], lv["h"])
+    dT0, dS1 = _dev(T0), _dev(S1)
+    rhs = _dev((np.random.default_rng(1).standard_normal(lv["nn"]) * 1e-4).astype(np.float32))
+    res = []
+    for zc, extra in ((0, 0), (3, 0), (2, 0), (0, ops.STEP_GENERAL_KERNEL)):
+        Tout = torch.full((lv["nn"],), -7.0, device="cuda")
+        ops.level_step(props, grid, dT0, dS1, Tout, 1e-5, rhs=rhs, n_substrate=nsub, nz_active=nz - 3,
+                       flags=ops.STEP_SKIP_FACES | ops.STEP_CLAMP | ops.STEP_FUSED_FLUX | extra, z_chunk=zc)
+        torch.cuda.synchronize()
+        res.append(Tout.cpu().numpy())
+    assert np.array_equal(res[0], res[1]) and np.array_equal(res[0], res[2])
+    face = _faces_mask(nx, ny, nz).ravel()
+    assert (res[0][face] == -7.0).all()
+    assert _rel(res[0][~face], res[3][~face]) <= 2e-6
+    top = res[0].reshape(nz, ny, nx)[nz - 3:, 1:-1, 1:-1]
+    assert (top == np.float32(P["T_amb"])).all()
+
+
+@pytest.mark.parametrize("z_range", [None, (0, 5), (3, 8), (4, 5)])
+def test_dirichlet_side_face_kernel_level1_constants(gm, example_props, z_range):
+    """GOMELT_STEP_BC_CONST on the fast kernel (owned interior by the step, the five constant faces by
+    face_const_kernel) against the general kernel: interior within f32 rounding, faces exactly the constants in
+    assignBCs order (cF:1568-1595), planes outside z_range untouched, inactive planes T_amb + faces."""
+    import torch
+
+    ops = gm.ops
+    elements = (70, 21, 9)
+    bounds = ((0.0, 14.0), (0.0, 4.2), (-1.8, 0.0))
+    P, lv, T0, S1, nsub = _setup(gm, example_props, elements, bounds, 8, nsub_planes=3)
+    nx, ny, nz = lv["nodes"]
+    props = gm._lib.make_props(P)
+    grid = gm._lib.make_grid(lv["nodes"], lv["h"])
+    dT0, dS1 = _dev(T0), _dev(S1)
+    bc5 = [301.0, 302.0, 303.0, 304.0, 305.0]
+    res = []
+    for extra in (0, ops.STEP_GENERAL_KERNEL):
+        Tout = torch.full((lv["nn"],), -7.0, device="cuda")
+        ops.level_step(props, grid, dT0, dS1, Tout, 2e-3, n_substrate=nsub, nz_active=nz - 2, bc5=bc5,
+                       flags=ops.STEP_BC_CONST | ops.STEP_FUSED_FLUX | extra, z_range=z_range)
+        torch.cuda.synchronize()
+        res.append(Tout.cpu().numpy().reshape(nz, ny, nx))
+    fast, gen = res
+    face = _faces_mask(nx, ny, nz)
+    assert np.array_equal(fast[face], gen[face])
+    assert _rel(fast[~face], gen[~face]) <= 2e-6, _rel(fast[~face], gen[~face])
+    z0, z1 = z_range or (0, nz)
+    assert (fast[:z0] == -7.0).all() and (fast[z1:] == -7.0).all()
+    assert fast[max(z0, 1), 0, 0] == np.float32(303.0) and fast[max(z0, 1), -1, -1] == np.float32(304.0)

@@ -142,7 +142,7 @@ def run_gomelt_multi(args, read_peaks, ClockSampler, host_properties, single_gpu
                        "nodes": nn_total, "parallelism": f"z-slab x{world}",
                        "l2": "working set per GPU 300 MB > 126 MB L2 (inputs larger than L2)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": "level_step_v2",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": "level_step_v3",
                          "bytes_per_dof": B_ALG_L1, "peak_source": peaks["source"],
                          "note": "per GPU, whole sweep (halo exchange included)"},
             "e2e": {"value": Ke * nn_total / e2e_s, "unit": "DOF-updates/s",

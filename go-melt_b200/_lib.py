@@ -91,6 +91,7 @@ class SubstepsArgs(C.Structure):
         ("faces", C.POINTER(InterpArgs)),
         ("faces_n", C.c_float),
         ("T_last", C.POINTER(C.c_void_p)),
+        ("faces_scratch", C.c_void_p),
     ]
 
 
@@ -119,6 +120,10 @@ SIGNATURES = {
                                                  C.c_void_p]),
     "gomelt_l3_substeps_f32": (C.c_int, [C.POINTER(Props), C.POINTER(SubstepsArgs), C.c_void_p]),
     "gomelt_interp_f32": (C.c_int, [C.POINTER(InterpArgs), C.c_void_p]),
+    "gomelt_faces_count": (C.c_longlong, [C.c_int32, C.c_int32, C.c_int32]),
+    "gomelt_faces_gather_f32": (C.c_int, [C.POINTER(InterpArgs), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gomelt_faces_blend_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float,
+                                         C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
     "gomelt_box_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                   C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "gomelt_rank1_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,

@@ -79,8 +79,7 @@ static bool try_launch_v3(const StepParams& sp, int nch, cudaStream_t st) {
     constexpr int V3_DWELL_PEER = V3_DWELL | K1F_PEER;                                // ... with the fused halo stores
     switch ((f & ~(K1F_SKIP | K1F_BCCONST)) | K1F_NSUB) {
         case V3_L3_SUB:
-            if (sp.exp & 4) launch_v3<RY, V3_L3_SUB, 12>(sp, nch, st);  // dev experiment: 168-register cap
-            else launch_v3<RY, V3_L3_SUB>(sp, nch, st);
+            launch_v3<RY, V3_L3_SUB>(sp, nch, st);
             break;
         case V3_L3_STEP: launch_v3<RY, V3_L3_STEP>(sp, nch, st); break;
         case V3_RHS: launch_v3<RY, V3_RHS>(sp, nch, st); break;
@@ -182,16 +181,27 @@ extern "C" int gomelt_level_step_f32(const gomelt_props_t* props, const gomelt_s
         sp.lam[s] = (float)(lam / 64.0);  // 1/8 (Haar inverse) * 1/8 (kbar = k8/8)
         lam_d[s] = lam / 64.0;
     }
-    // v3: mode pairs (sx,sz) = (0,1), (1,0), (1,1); l_s = lambda'[sy = 0], l_d = lambda'[sy = 1]
+    // v3: mode pairs (sx,sz) = (0,1), (1,0), (1,1); l_s = lambda'[sy = 0], l_d = lambda'[sy = 1]; everything
+    // relative to s = lambda'[2] (see StepParams)
     const int pair_s[3] = {4, 1, 5}, pair_d[3] = {6, 3, 7};
+    const double s_norm = lam_d[2];
     for (int q = 0; q < 3; ++q) {
-        sp.lamA[q] = (float)(lam_d[pair_s[q]] + lam_d[pair_d[q]]);
-        sp.lamB[q] = (float)(lam_d[pair_s[q]] - lam_d[pair_d[q]]);
+        sp.lamA[q] = (float)((lam_d[pair_s[q]] + lam_d[pair_d[q]]) / s_norm);
+        sp.lamB[q] = (float)((lam_d[pair_s[q]] - lam_d[pair_d[q]]) / s_norm);
     }
     sp.cdt = (float)(64.0 * (double)a->dt / V);
     sp.dt = a->dt;
     sp.pk = fold_props(*props);
     sp.fk = fold_flux(*props, g);
+    {
+        const double mscale = 1.0 / ((64.0 * (double)a->dt / V) * s_norm);
+        sp.n_ca0 = (float)((double)props->rho * (double)props->cp_solid_a0 * mscale);
+        sp.n_ca1 = (float)((double)props->rho * (double)props->cp_solid_a1 * mscale);
+        sp.n_cmushy = (float)((double)props->rho * (double)props->cp_mushy * mscale);
+        sp.n_cfluid = (float)((double)props->rho * (double)props->cp_fluid * mscale);
+        sp.n_inv_s = (float)(1.0 / s_norm);
+        sp.n_wq = (float)((double)sp.fk.wq / s_norm);
+    }
     sp.T0 = a->T0; sp.S1 = a->S1; sp.rhs = a->rhs;
     sp.srcx = a->src_x; sp.srcy = a->src_y; sp.srcz = a->src_z; sp.scoef = a->src_coef;
     sp.topflux = a->topflux;

@@ -54,6 +54,9 @@ struct StepParams {
     float* peer_lo;        // neighbour ghost planes in peer memory (K1F_PEER), or nullptr
     float* peer_hi;
     int exp;               // dev experiments (GOMELT_K1_EXP), 0 in production
+    // v3 normalisation: stiffness modes divided by s = lambda'[2], masses by cdt * s, loads by s (so that
+    // T_new = T + (rr/s - KT/s) / (mnode/(cdt s)) needs neither the lambda'[2] nor the cdt multiply)
+    float n_ca0, n_ca1, n_cmushy, n_cfluid, n_inv_s, n_wq;
 };
 
 #define GM_DI __device__ __forceinline__

@@ -27,7 +27,8 @@
 namespace gomelt {
 
 // computeStateProperties cF:2567-2614 as selects; thr = 0.499, or -1 on substrate planes (forces S1).
-GM_DI void props3(const PropK& q, float T, float S1in, float thr, float kb, float cs, float& k, float& m, float& s1f) {
+GM_DI void props3(const PropK& q, float c_mushy, float c_fluid, float T, float S1in, float thr, float kb, float cs, float& k,
+                  float& m, float& s1f) {
     asm("{\n\t.reg .pred p1, p2, p3;\n\t"
         "setp.ge.f32 p2, %3, %6;\n\t"
         "setp.gt.f32 p3, %3, %7;\n\t"
@@ -40,9 +41,10 @@ GM_DI void props3(const PropK& q, float T, float S1in, float thr, float kb, floa
         "selp.f32 %2, 0f3F800000, 0f00000000, p1;\n\t}"
         : "=&f"(k), "=&f"(m), "=f"(s1f)
         : "f"(T), "f"(S1in), "f"(thr), "f"(q.T_liq), "f"(q.T_sol), "f"(kb), "f"(q.k_powder), "f"(q.k_fluid),
-          "f"(q.c_mushy), "f"(cs), "f"(q.c_fluid));
+          "f"(c_mushy), "f"(cs), "f"(c_fluid));
 }
-GM_DI void props3_km(const PropK& q, float T, float S1in, float thr, float kb, float cs, float& k, float& m) {
+GM_DI void props3_km(const PropK& q, float c_mushy, float c_fluid, float T, float S1in, float thr, float kb, float cs,
+                     float& k, float& m) {
     asm("{\n\t.reg .pred p1, p2, p3;\n\t"
         "setp.ge.f32 p2, %2, %5;\n\t"
         "setp.gt.f32 p3, %2, %6;\n\t"
@@ -53,7 +55,7 @@ GM_DI void props3_km(const PropK& q, float T, float S1in, float thr, float kb, f
         "selp.f32 %1, %12, %1, p2;\n\t}"
         : "=&f"(k), "=&f"(m)
         : "f"(T), "f"(S1in), "f"(thr), "f"(q.T_liq), "f"(q.T_sol), "f"(kb), "f"(q.k_powder), "f"(q.k_fluid),
-          "f"(q.c_mushy), "f"(cs), "f"(q.c_fluid));
+          "f"(c_mushy), "f"(cs), "f"(c_fluid));
 }
 
 // Unguarded pair load: half .y at q, half .x 30 columns (120 bytes) below it.
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     constexpr int NR = RY + 2;
     constexpr bool F_RHS = (FEAT & K1F_RHS) != 0, F_SRC = (FEAT & K1F_SRC) != 0, F_FLUX = (FEAT & K1F_FLUX) != 0;
     constexpr bool F_S1 = (FEAT & K1F_S1OUT) != 0, F_CLAMP = (FEAT & K1F_CLAMP) != 0, F_NSUB = (FEAT & K1F_NSUB) != 0;
-    constexpr bool F_BC = (FEAT & K1F_BCCONST) != 0, F_PEER = (FEAT & K1F_PEER) != 0;
+    constexpr bool F_PEER = (FEAT & K1F_PEER) != 0;
     const int lane = threadIdx.x;
     const int nx = p.nx, ny = p.ny, nz = p.nz, nzl = p.nzl;
     const int c0 = min((int)blockIdx.x * (2 * K1_TX), nx - (2 * K1_TX + 2));  // column of lane 0, half .x
@@ -87,8 +89,14 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     const int own = (lane >= 1 && lane <= K1_TX) ? 1 : 0;
     // the same flag through two expressions ptxas does not identify: with one predicate on both stores of a pair
     // it turns the predication into a divergent branch around the row's tail (BSSY / BSYNC per row)
-    const int owna = ((unsigned)(lane - 1) < (unsigned)K1_TX) ? 1 : 0, ownb = (int)((0x7FFFFFFEu >> lane) & 1u);
-    const int sa = own | (ia == 0 ? 1 : 0), sb = own | (ib == nx - 1 ? 1 : 0);  // lanes that store S1 (faces too)
+    int owna = ((unsigned)(lane - 1) < (unsigned)K1_TX) ? 1 : 0, ownb = (int)((0x7FFFFFFEu >> lane) & 1u);
+#ifdef GOMELT_K1_ABLATE  // timing-only ablations: GOMELT_K1_EXP bit 16 = no T stores, 32 = no S1 stores,
+    if (p.exp & 16) owna = ownb = 0;  // 64 = every load hits two cached planes
+#endif
+    int sa = own | (ia == 0 ? 1 : 0), sb = own | (ib == nx - 1 ? 1 : 0);  // lanes that store S1 (faces too)
+#ifdef GOMELT_K1_ABLATE
+    if (p.exp & 32) sa = sb = 0;
+#endif
     const int P = nx * ny;
     const int za = p.zbeg + blockIdx.z * p.zchunk;
     const int zb = min(p.zend, za + p.zchunk);  // this warp finalises node planes [za, zb)
@@ -106,7 +114,7 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
 #pragma unroll
     for (int r = 0; r < RY; ++r) sfy[r] = 0.f;
     if (F_SRC) {
-        sfx = mk2(__ldg(p.srcx + ia) * p.scoef, __ldg(p.srcx + ib) * p.scoef);
+        sfx = mk2(__ldg(p.srcx + ia) * (p.scoef * p.n_inv_s), __ldg(p.srcx + ib) * (p.scoef * p.n_inv_s));
 #pragma unroll
         for (int r = 0; r < RY; ++r) sfy[r] = settle(__ldg(p.srcy + j0 + r));
     }
@@ -117,6 +125,9 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     for (int r = 0; r < RY; ++r) Tt0[r] = Tt1[r] = myp[r] = splat(0.f);
 
     auto load_plane = [&](int l, K3Raw<RY>& raw) {
+#ifdef GOMELT_K1_ABLATE
+        if (p.exp & 64) l = l & 1;
+#endif
         const char* Tl = (const char*)(p.T0 + (size_t)l * P);
         const char* Sl = (const char*)(p.S1 + (size_t)l * P);
 #pragma unroll
@@ -128,18 +139,19 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
 
     // ---- node state of loaded row r (+ S1 output) and its x stage ------------------------------------
     auto row_a = [&](char* so, int r, float thr, f2 T, f2 S, f2& xs, f2& xd, f2& kxr, f2& mxr) {
-        const f2 kb = fma2(splat(p.pk.k_a1), T, splat(p.pk.k_a0)), cs = fma2(splat(p.pk.c_a1), T, splat(p.pk.c_a0));
+        // masses carry the 1 / (cdt * lambda'[2]) normalisation (StepParams)
+        const f2 kb = fma2(splat(p.pk.k_a1), T, splat(p.pk.k_a0)), cs = fma2(splat(p.n_ca1), T, splat(p.n_ca0));
         f2 kn, mn;
         if (F_S1) {
             // S1' is node-local, so every loaded node (halo rows, halo planes of a chunk, face lanes) may be
             // written: its owner writes the same value.  This is what covers the face nodes without a guard.
             f2 s1f;
-            props3(p.pk, T.v.x, S.v.x, thr, kb.v.x, cs.v.x, kn.v.x, mn.v.x, s1f.v.x);
-            props3(p.pk, T.v.y, S.v.y, thr, kb.v.y, cs.v.y, kn.v.y, mn.v.y, s1f.v.y);
+            props3(p.pk, p.n_cmushy, p.n_cfluid, T.v.x, S.v.x, thr, kb.v.x, cs.v.x, kn.v.x, mn.v.x, s1f.v.x);
+            props3(p.pk, p.n_cmushy, p.n_cfluid, T.v.y, S.v.y, thr, kb.v.y, cs.v.y, kn.v.y, mn.v.y, s1f.v.y);
             st2(so + off[r], sa, sb, s1f);
         } else {
-            props3_km(p.pk, T.v.x, S.v.x, thr, kb.v.x, cs.v.x, kn.v.x, mn.v.x);
-            props3_km(p.pk, T.v.y, S.v.y, thr, kb.v.y, cs.v.y, kn.v.y, mn.v.y);
+            props3_km(p.pk, p.n_cmushy, p.n_cfluid, T.v.x, S.v.x, thr, kb.v.x, cs.v.x, kn.v.x, mn.v.x);
+            props3_km(p.pk, p.n_cmushy, p.n_cfluid, T.v.y, S.v.y, thr, kb.v.y, cs.v.y, kn.v.y, mn.v.y);
         }
         const f2 Tr = shdn(T), kr = shdn(kn), mr = shdn(mn);
         xs = Tr + T;
@@ -172,21 +184,21 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     // use_fl is a literal at every call site (the lambdas are inlined): only the top plane carries a flux
     auto final_row = [&](int f, char* out, const char* rhs, int r, f2 sz, f2 Tf, f2 z0, f2 z1, f2 mz, bool use_fl,
                          f2 fl) {
-        const f2 KT = (z0 - z1) + shup(z0 + z1);
+        const f2 nKT = (z1 - z0) - shup(z0 + z1);  // minus the stiffness action on this node
         const f2 mnode = mz + shup(mz);
         const f2 rc = mk2(rcp_approx(mnode.v.x), rcp_approx(mnode.v.y));
+        // normalised form: T_new = T + (rr / s - KT / s) / (mnode / (cdt s)); rc is the reciprocal of the latter
         if (F_RHS || F_SRC || (F_FLUX && use_fl)) {
-            f2 rr = splat(0.f);
-            if (F_RHS) rr = ld2u(rhs + off[r + 1]);
+            f2 rr = nKT;
+            if (F_RHS) rr = fma2(ld2u(rhs + off[r + 1]), splat(p.n_inv_s), rr);
             if (F_SRC) rr = fma2(sz, splat(sfy[r]), rr);
             if (F_FLUX && use_fl) rr = rr + fl;
-            store_row(f, out, r, fma2(rr - KT, splat(p.cdt) * rc, Tf));
+            store_row(f, out, r, fma2(rr, rc, Tf));
         } else {
-            store_row(f, out, r, fma2(KT, splat(-p.cdt) * rc, Tf));
+            store_row(f, out, r, fma2(nKT, rc, Tf));
         }
     };
 
-    const f2 l2 = splat(p.lam[2]);
     const f2 A01 = splat(p.lamA[0]), A10 = splat(p.lamA[1]), A11 = splat(p.lamA[2]);
     const f2 B01 = splat(p.lamB[0]), B10 = splat(p.lamB[1]), B11 = splat(p.lamB[2]);
 
@@ -219,7 +231,7 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
                 const int e = r - 1;  // element row between loaded rows e and e+1
                 const f2 k8 = kzu + kzl;
                 const f2 m8 = mzu + mzl;
-                const f2 q00 = (l2 * (zu00 - zl00)) * k8;  // (sx,sz) = (0,0): only the sy = 1 mode acts
+                const f2 q00 = (zu00 - zl00) * k8;  // (sx,sz) = (0,0): only the sy = 1 mode acts (lambda = 1 after normalisation)
                 if (e >= 1) {  // lower node row of this element row = loaded row e = owned row e-1
                     const f2 R00 = c00 - q00;
                     const f2 R01 = fma2(k8, fma2(A01, zl01, bu01), c01);
@@ -269,7 +281,7 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
         const float g = 0.57735026918962576f;
         const float NA = 0.25f * (1.f + g) * (1.f + g), NB = 0.25f * (1.f + g) * (1.f - g),
                     NC = 0.25f * (1.f - g) * (1.f - g);
-        const float wq = p.fk.wq;
+        const float wq = p.n_wq;  // hx hy / 4 with the load normalisation
 #pragma unroll 1
         for (int it = 0; it < 2 * (RY + 1); ++it) {
             const int e = it >> 1, h = it & 1;  // element row between loaded rows e, e + 1; half of the pair
@@ -306,19 +318,6 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     };
 
     int fdone = za;  // planes [za, fdone) are finalised
-    if (p.exp & 1) {  // dev experiment: phase-shift the second resident warp of a scheduler
-        const int lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-        if ((lin / 592) & 1) __nanosleep(p.exp >> 8);
-    }
-    auto l2_prefetch = [&](int l) {  // dev experiment: pull a plane into L2 ahead of the register prefetch
-        const char* Tl = (const char*)(p.T0 + (size_t)l * P);
-        const char* Sl = (const char*)(p.S1 + (size_t)l * P);
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(Tl + off[r]));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(Sl + off[r]));
-        }
-    };
     if (lfirst <= llast) {
         K3Raw<RY> rawA, rawB;
         K3State<RY> stA, stB;
@@ -329,7 +328,6 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
         // plane 0 is the Dirichlet bottom face: never finalised (l - 1 >= 1)
         for (int l = lfirst + 1; l <= llast; l += 2) {
             if (l + 1 <= llast) load_plane(l + 1, rawA);
-            if ((p.exp & 2) && l + 3 <= llast) { l2_prefetch(l + 2); l2_prefetch(l + 3); }
             step_plane(l, rawB, stA, stB, l - 1 >= max(za, 1), sfx * splat(srcz_at(l - 1)));
             if (l + 1 > llast) break;
             if (l + 2 <= llast) load_plane(l + 2, rawB);

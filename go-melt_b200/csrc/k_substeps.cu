@@ -29,6 +29,16 @@ extern "C" int gomelt_l3_substeps_f32(const gomelt_props_t* props, const gomelt_
     float coef[GOMELT_MAX_SUBSTEPS];
     int rc = gomelt_source_tables_batch_f32(props, &g, a->x, a->y, a->z, a->rows, a->n, a->tables, coef, stream);
     if (rc) return rc;
+    const long long nface = gomelt_faces_count(g.nx, g.ny, g.nz);
+    const bool compact_faces = a->faces && a->faces_scratch;
+    if (compact_faces) {  // both parent interpolants at the face nodes, once for the whole block
+        if (!a->faces->u2) {
+            set_error("gomelt_l3_substeps_f32: faces_scratch needs faces->u2 (parent_old)");
+            return GOMELT_E_NULL;
+        }
+        rc = gomelt_faces_gather_f32(a->faces, a->faces_scratch, a->faces_scratch + nface, stream);
+        if (rc) return rc;
+    }
     const size_t stride = (size_t)g.nx + g.ny + g.nz;
     const float* Tin = a->T_in;
     for (int i = 0; i < a->n; ++i) {
@@ -56,7 +66,12 @@ extern "C" int gomelt_l3_substeps_f32(const gomelt_props_t* props, const gomelt_
         s.max_accum = a->max_accum;
         rc = gomelt_level_step_f32(props, &s, stream);
         if (rc) return rc;
-        if (a->faces) {
+        if (compact_faces) {
+            const float alpha = (float)(i + 1) / a->faces_n;  // cF:3386-3387, float32 like the traced scalars
+            rc = gomelt_faces_blend_f32(a->faces_scratch, a->faces_scratch + nface, g.nx, g.ny, g.nz, alpha, 1.0f - alpha,
+                                        a->faces->has_clamp, a->faces->clamp_min, Tout, stream);
+            if (rc) return rc;
+        } else if (a->faces) {
             gomelt_interp_args_t f = *a->faces;
             f.alpha = (float)(i + 1) / a->faces_n;  // cF:3386-3387, float32 like the traced scalars
             f.beta = 1.0f - f.alpha;

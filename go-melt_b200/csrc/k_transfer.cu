@@ -130,6 +130,89 @@ __global__ void interp_kernel(const InterpParams p) {
     }
 }
 
+// ---- face prolongation split for the Level-3 inner scan --------------------------------------------------
+// The N3 substeps of a subcycle block prolong the SAME two parent fields with different blend factors
+// (alpha_i = (i+1)/N3, cF:3386-3389).  I(alpha u + beta u2) = alpha I(u) + beta I(u2), so both interpolants
+// are gathered once per block into compact face arrays (the 16 scattered parent reads per face node happen
+// once instead of N3 times) and every substep only blends and scatters them.
+__device__ __forceinline__ void face_node(int w, int ntx, int nty, int ntz, int& i, int& j, int& k) {
+    // same enumeration as interp_kernel's faces_only: z- plane, then the y faces and the x faces of the planes above
+    const int fA = ntx * nty, fB = 2 * ntx * (ntz - 1);
+    if (w < fA) {
+        k = 0;
+        j = w / ntx;
+        i = w - j * ntx;
+    } else if (w < fA + fB) {
+        const int u = w - fA;
+        const int q = u / (2 * ntx), r = u - q * (2 * ntx);
+        k = 1 + q;
+        j = r < ntx ? 0 : nty - 1;
+        i = r < ntx ? r : r - ntx;
+    } else {
+        const int u = w - fA - fB;
+        const int q = u / (2 * (nty - 2)), r = u - q * (2 * (nty - 2));
+        k = 1 + q;
+        i = (r & 1) ? ntx - 1 : 0;
+        j = 1 + (r >> 1);
+    }
+}
+
+__global__ void faces_gather_kernel(const InterpParams p, float* __restrict__ fa, float* __restrict__ fb, int nface) {
+    const float hx = __fsub_rn(p.sx.c[1], p.sx.c[0]), hy = __fsub_rn(p.sy.c[1], p.sy.c[0]),
+                hz = __fsub_rn(p.sz.c[1], p.sz.c[0]);
+    const float inv_vol = __fdiv_rn(1.0f, __fmul_rn(__fmul_rn(hx, hy), hz));
+    const int nnx = p.sx.n, nnxy = p.sx.n * p.sy.n;
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < nface; w += gridDim.x * blockDim.x) {
+        int i, j, k;
+        face_node(w, p.ntx, p.nty, p.ntz, i, j, k);
+        const float x = p.tx[i], y = p.ty[j], z = p.tz[k];
+        const int ex = cell_of(x, p.sx.c[0], hx, p.sx.n - 1);
+        const int ey = cell_of(y, p.sy.c[0], hy, p.sy.n - 1);
+        const int ez = cell_of(z, p.sz.c[0], hz, p.sz.n - 1);
+        const float ax0 = __fsub_rn(p.sx.c[ex + 1], x), ax1 = __fsub_rn(x, p.sx.c[ex]);
+        const float ay0 = __fsub_rn(p.sy.c[ey + 1], y), ay1 = __fsub_rn(y, p.sy.c[ey]);
+        const float az0 = __fsub_rn(p.sz.c[ez + 1], z), az1 = __fsub_rn(z, p.sz.c[ez]);
+        float N[8];  // compute3DN cF:1375-1391, hex8 local order
+        N[0] = __fmul_rn(__fmul_rn(__fmul_rn(ax0, ay0), az0), inv_vol);
+        N[1] = __fmul_rn(__fmul_rn(__fmul_rn(ax1, ay0), az0), inv_vol);
+        N[2] = __fmul_rn(__fmul_rn(__fmul_rn(ax1, ay1), az0), inv_vol);
+        N[3] = __fmul_rn(__fmul_rn(__fmul_rn(ax0, ay1), az0), inv_vol);
+        N[4] = __fmul_rn(__fmul_rn(__fmul_rn(ax0, ay0), az1), inv_vol);
+        N[5] = __fmul_rn(__fmul_rn(__fmul_rn(ax1, ay0), az1), inv_vol);
+        N[6] = __fmul_rn(__fmul_rn(__fmul_rn(ax1, ay1), az1), inv_vol);
+        N[7] = __fmul_rn(__fmul_rn(__fmul_rn(ax0, ay1), az1), inv_vol);
+        bool valid = true;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) valid = valid && (N[a] >= -1e-2f) && (N[a] <= 1.0f + 1e-2f);
+        const long long b = ex + (long long)ey * nnx + (long long)ez * nnxy;
+        const long long nd[8] = {b, b + 1, b + 1 + nnx, b + nnx, b + nnxy, b + 1 + nnxy, b + 1 + nnx + nnxy,
+                                 b + nnx + nnxy};
+        float accA = 0.f, accB = 0.f;
+        if (valid) {
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                const float wt = fminf(fmaxf(N[a], 0.f), 1.f);
+                accA = __fadd_rn(accA, __fmul_rn(wt, p.u[nd[a]]));
+                accB = __fadd_rn(accB, __fmul_rn(wt, p.u2[nd[a]]));
+            }
+        }
+        fa[w] = accA;
+        fb[w] = accB;
+    }
+}
+
+__global__ void faces_blend_kernel(const float* __restrict__ fa, const float* __restrict__ fb, int nface, int ntx, int nty,
+                                   int ntz, float alpha, float beta, int has_clamp, float clamp_min,
+                                   float* __restrict__ out) {
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < nface; w += gridDim.x * blockDim.x) {
+        int i, j, k;
+        face_node(w, ntx, nty, ntz, i, j, k);
+        float r = __fadd_rn(__fmul_rn(alpha, fa[w]), __fmul_rn(beta, fb[w]));
+        if (has_clamp) r = fmaxf(r, clamp_min);
+        out[(size_t)i + (size_t)j * ntx + (size_t)k * ntx * nty] = r;
+    }
+}
+
 // ---- box gather / scatter between a window and a larger grid ----------------------------------
 template <typename T>
 __global__ void box_copy_kernel(const T* __restrict__ src, T* __restrict__ dst, const int* __restrict__ ix,
@@ -395,6 +478,48 @@ extern "C" int gomelt_interp_f32(const gomelt_interp_args_t* a, void* stream) {
         total = (long long)a->ntx * a->nty + 2LL * a->ntx * (a->ntz - 1) + 2LL * (a->nty - 2) * (a->ntz - 1);
     interp_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("gomelt_interp_f32");
+}
+
+extern "C" long long gomelt_faces_count(int32_t ntx, int32_t nty, int32_t ntz) {
+    return (long long)ntx * nty + 2LL * ntx * (ntz - 1) + 2LL * (nty - 2) * (ntz - 1);
+}
+
+extern "C" int gomelt_faces_gather_f32(const gomelt_interp_args_t* a, float* face_a, float* face_b, void* stream) {
+    if (!a || !a->u || !a->u2 || !face_a || !face_b || !a->tx || !a->ty || !a->tz || !axis_ok(a->src[0]) ||
+        !axis_ok(a->src[1]) || !axis_ok(a->src[2])) {
+        set_error("gomelt_faces_gather_f32: NULL argument / source axis with < 2 nodes (u and u2 are both required)");
+        return GOMELT_E_NULL;
+    }
+    const long long nface = gomelt_faces_count(a->ntx, a->nty, a->ntz);
+    if (a->ntx < 2 || a->nty < 2 || a->ntz < 2 || nface > 2000000000LL) {
+        set_error("gomelt_faces_gather_f32: bad target grid");
+        return GOMELT_E_SIZE;
+    }
+    InterpParams p = {};
+    p.sx = {a->src[0].coords, a->src[0].n};
+    p.sy = {a->src[1].coords, a->src[1].n};
+    p.sz = {a->src[2].coords, a->src[2].n};
+    p.u = a->u; p.u2 = a->u2;
+    p.tx = a->tx; p.ty = a->ty; p.tz = a->tz; p.ntx = a->ntx; p.nty = a->nty; p.ntz = a->ntz;
+    faces_gather_kernel<<<grid_for(nface, 128), 128, 0, (cudaStream_t)stream>>>(p, face_a, face_b, (int)nface);
+    return check_launch("gomelt_faces_gather_f32");
+}
+
+extern "C" int gomelt_faces_blend_f32(const float* face_a, const float* face_b, int32_t ntx, int32_t nty, int32_t ntz,
+                                      float alpha, float beta, int32_t has_clamp, float clamp_min, float* out,
+                                      void* stream) {
+    if (!face_a || !face_b || !out) {
+        set_error("gomelt_faces_blend_f32: NULL argument");
+        return GOMELT_E_NULL;
+    }
+    const long long nface = gomelt_faces_count(ntx, nty, ntz);
+    if (ntx < 2 || nty < 2 || ntz < 2 || nface > 2000000000LL) {
+        set_error("gomelt_faces_blend_f32: bad target grid");
+        return GOMELT_E_SIZE;
+    }
+    faces_blend_kernel<<<grid_for(nface, 256), 256, 0, (cudaStream_t)stream>>>(face_a, face_b, (int)nface, ntx, nty, ntz,
+                                                                              alpha, beta, has_clamp, clamp_min, out);
+    return check_launch("gomelt_faces_blend_f32");
 }
 
 extern "C" int gomelt_box_copy(const void* src, void* dst, int32_t elem_size, const int32_t* ix, const int32_t* iy,

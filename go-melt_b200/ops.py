@@ -149,8 +149,24 @@ def _interp_args(src_coords, u, tgt_coords, out, *, mode=_lib.INTERP_SET, u2=Non
     return a
 
 
+_FACE_SCRATCH = {}
+
+
+def faces_scratch(grid, device):
+    """Device scratch for the compact face interpolants of a subcycle block (2 x gomelt_faces_count floats),
+    cached per grid shape."""
+    import torch
+
+    lib = _lib.load()
+    n = int(lib.gomelt_faces_count(grid.nx, grid.ny, grid.nz))
+    key = (n, str(device))
+    if key not in _FACE_SCRATCH:
+        _FACE_SCRATCH[key] = torch.empty(2 * n, device=device, dtype=torch.float32)
+    return _FACE_SCRATCH[key]
+
+
 def l3_substeps(props, grid, coords, rows, T_in, T_a, T_b, S1, tables, *, S1_in=None, n_substrate=0, flags=0,
-                S2=None, accum=None, max_accum=None, faces=None):
+                S2=None, accum=None, max_accum=None, faces=None, compact_faces=True):
     """gomelt_l3_substeps_f32: the inner scan of subcycleGOMELT (cF:3367-3412 / 3530-3590) as one call.
     ``rows`` = host float32 array [n, 7] of toolpath rows; ``faces`` = None or
     (parent_coords, parent_new, parent_old, fN3, clamp_min).  Returns the tensor (T_a or T_b) that holds the
@@ -184,10 +200,12 @@ def l3_substeps(props, grid, coords, rows, T_in, T_a, T_b, S1, tables, *, S1_in=
         fa = _interp_args(pc, pnew, coords, None, u2=pold, faces_only=True, clamp_min=clamp_min)
         a.faces = C.pointer(fa)
         a.faces_n = float(fN)
+        if compact_faces and pold is not None and n > 1:  # parents interpolated once per block, blended per substep
+            a.faces_scratch = faces_scratch(grid, T_a.device).data_ptr()
     last = C.c_void_p(0)
     a.T_last = C.pointer(last)
     _lib.check(lib.gomelt_l3_substeps_f32(C.byref(props), C.byref(a), _lib.stream_ptr()), "gomelt_l3_substeps_f32")
-    _count(1 + n * (2 if faces is not None else 1))
+    _count(1 + n * (2 if faces is not None else 1) + (1 if a.faces_scratch else 0))
     return T_a if last.value == T_a.data_ptr() else T_b
 
 

@@ -173,6 +173,17 @@ typedef struct gomelt_interp_args {
 
 int gomelt_interp_f32(const gomelt_interp_args_t *args, void *stream);
 
+/* Face prolongation of a subcycle block in two parts (assignBCsFine cF:1598-1620 with the time blend of
+ * cF:3386-3389): the block's N3 substeps prolong the same two parent fields with different blend factors, and
+ * I(alpha u + beta u2) = alpha I(u) + beta I(u2).  gomelt_faces_gather_f32 interpolates u and u2 (both required)
+ * at the nodes of the five Dirichlet faces of the target grid once, into compact arrays of
+ * gomelt_faces_count(ntx, nty, ntz) floats each; gomelt_faces_blend_f32 writes
+ * out[face node] = max(clamp_min, alpha*face_a + beta*face_b) (the clamp when has_clamp). */
+long long gomelt_faces_count(int32_t ntx, int32_t nty, int32_t ntz);
+int gomelt_faces_gather_f32(const gomelt_interp_args_t *args, float *face_a, float *face_b, void *stream);
+int gomelt_faces_blend_f32(const float *face_a, const float *face_b, int32_t ntx, int32_t nty, int32_t ntz,
+                           float alpha, float beta, int32_t has_clamp, float clamp_min, float *out, void *stream);
+
 /* Window <-> big-grid copies through a tensor-product index set (getOverlapRegion cF:1642-1669):
  * scatter = 0: dst[t] = src[idx(t)]   (S1/S2 regather from Level 0, cF:2500-2502)
  * scatter = 1: dst[idx(t)] = src[t]   (Level-3 state back to Level 0, cF:2390-2392)
@@ -220,7 +231,8 @@ int gomelt_project_f32(const gomelt_project_args_t *args, void *stream);
  * substeps of   computeSourcesL3 cF:2960 -> computeConvRadBC cF:2207 -> computeSolutions_L3 cF:3015 (explicit
  * solve, Dirichlet faces <- alpha*parent_new + beta*parent_old with alpha = (i+1)/faces_n (cF:3386-3389),
  * max(T_amb, .)), state update, and - with GOMELT_STEP_ACCUM - the melt-time bookkeeping cF:3568-3578.
- * Launches: 1 (all source tables) + n (fused level steps) + n (face prolongation, when `faces` is given).
+ * Launches: 1 (all source tables) + n (fused level steps) + n (face prolongation, when `faces` is given; see
+ * faces_scratch).
  * Substep i writes W_i = T_a (i even) / T_b (i odd) and reads W_(i-1), substep 0 reads T_in, which is never
  * written unless it is T_b (so a caller can keep its initial field, or ping-pong by passing T_in = T_b).  The
  * buffer holding the newest field is returned in *T_last.  S1_in likewise is read by substep 0 only (NULL = S1).
@@ -245,6 +257,10 @@ typedef struct gomelt_substeps_args {
                                      faces_only are set per substep by the call                                */
     float         faces_n;        /* fN3 (float, as the reference divides: alpha = (i+1)/fN3, beta = 1-alpha) */
     float       **T_last;         /* HOST out: buffer holding the newest temperature (may be NULL)            */
+    float        *faces_scratch;  /* NULL, or device scratch [2 * gomelt_faces_count(nx, ny, nz)]: the two parent
+                                     fields are interpolated at the face nodes ONCE per call (gomelt_faces_gather_f32)
+                                     and every substep blends them (gomelt_faces_blend_f32) instead of
+                                     re-interpolating; launches 1 + 1 + 2n; agrees with the NULL path to rounding */
 } gomelt_substeps_args_t;
 
 int gomelt_l3_substeps_f32(const gomelt_props_t *props, const gomelt_substeps_args_t *args, void *stream);

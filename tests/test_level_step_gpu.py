@@ -438,3 +438,41 @@ def test_dirichlet_side_face_kernel_level1_constants(gm, example_props, z_range)
     z0, z1 = z_range or (0, nz)
     assert (fast[:z0] == -7.0).all() and (fast[z1:] == -7.0).all()
     assert fast[max(z0, 1), 0, 0] == np.float32(303.0) and fast[max(z0, 1), -1, -1] == np.float32(304.0)
+
+
+def test_l3_substeps_compact_faces_equal_per_substep_prolongation(gm, example_props):
+    """The block-level split of the face prolongation (parents interpolated once at the face nodes, blended per
+    substep: gomelt_faces_gather_f32 / gomelt_faces_blend_f32) against the per-substep interpolation."""
+    import torch
+
+    ops = gm.ops
+    elements = (64, 22, 6)
+    bounds = ((0.2, 0.2 + 64 * 0.02), (0.1, 0.1 + 22 * 0.02), (-0.12, 0.0))
+    P, lv, T0, S1, nsub = _setup(gm, example_props, elements, bounds, 13, nsub_planes=2)
+    par = make_level((40, 20, 5), ((0.0, 1.6), (0.0, 0.8), (-0.2, 0.0)))
+    rng = np.random.default_rng(2)
+    Pnew = smooth_field(par, rng)
+    Pold = (Pnew - 3.0 * rng.random(par["nn"])).astype(np.float32)
+    props = gm._lib.make_props(P)
+    grid = gm._lib.make_grid(lv["nodes"], lv["h"])
+    nx, ny, nz = lv["nodes"]
+    n = 5
+    rows = np.zeros((n, 7), np.float32)
+    for i in range(n):
+        rows[i] = (0.7 + 0.013 * i, 0.3, 0.0, 1, 1, 1e-5, 285.0)
+    coords = [_dev(c) for c in lv["node_coords"]]
+    pc = [_dev(c) for c in par["node_coords"]]
+    res = []
+    for compact in (True, False):
+        Tin, S1w = _dev(T0), _dev(S1)
+        A, B = torch.empty_like(Tin), torch.empty_like(Tin)
+        tables = torch.empty(n * (nx + ny + nz), device="cuda")
+        last = ops.l3_substeps(props, grid, coords, rows, Tin, A, B, S1w, tables, n_substrate=nsub,
+                               flags=ops.STEP_CLAMP | ops.STEP_SKIP_FACES,
+                               faces=(pc, _dev(Pnew), _dev(Pold), float(n), float(P["T_amb"])), compact_faces=compact)
+        torch.cuda.synchronize()
+        res.append((last.cpu().numpy(), S1w.cpu().numpy()))
+    assert _rel(res[0][0], res[1][0]) <= 1e-6, _rel(res[0][0], res[1][0])
+    assert np.array_equal(res[0][1], res[1][1])
+    face = _faces_mask(nx, ny, nz).ravel()
+    assert np.isfinite(res[0][0]).all() and (res[0][0][face] >= np.float32(P["T_amb"])).all()

@@ -105,6 +105,7 @@ STEP_GENERAL_KERNEL = 0x80
 # name -> (restype, argtypes); kept in one table so tests can check every header symbol loads
 SIGNATURES = {
     "gomelt_abi_version": (C.c_int, []),
+    "gomelt_launch_count": (C.c_longlong, []),
     "gomelt_last_error": (C.c_char_p, []),
     "gomelt_xla_ffi_available": (C.c_int, []),
     "gomelt_level_step_f32": (C.c_int, [C.POINTER(Props), C.POINTER(StepArgs), C.c_void_p]),
@@ -175,12 +176,20 @@ def check(rc, what=""):
         raise GomeltError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")
 
 
-def require_cuda():
-    import torch
+_TORCH_CUDA = None
 
-    if not torch.cuda.is_available():
-        raise GomeltError("CUDA device required: the GO-MELT step has no CPU path in this package")
-    return torch
+
+def require_cuda():
+    """torch, after checking ONCE that a CUDA device exists (torch.cuda.is_available() costs microseconds per
+    call and the steppers ask ~100 times per toolpath row)."""
+    global _TORCH_CUDA
+    if _TORCH_CUDA is None:
+        import torch
+
+        if not torch.cuda.is_available():
+            raise GomeltError("CUDA device required: the GO-MELT step has no CPU path in this package")
+        _TORCH_CUDA = torch
+    return _TORCH_CUDA
 
 
 def ptr(t):
@@ -189,8 +198,11 @@ def ptr(t):
 
 
 def stream_ptr():
-    import torch
-
+    """torch's current CUDA stream of the current device as a raw cudaStream_t."""
+    torch = require_cuda()
+    raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if raw is not None:
+        return C.c_void_p(raw(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

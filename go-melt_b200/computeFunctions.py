@@ -203,9 +203,23 @@ def _projected_source(L3, parent, rows, powers, properties, F=None):
     return F
 
 
+_PAIR_CACHE = {}
+
+
 def _pair_cells(fine, parent):
     """Group the fine elements by parent cell (the role of Shapes[.][2] / the node set of Gauss point 0,
-    cF:1351): per axis, parent cell of each fine element by the reference's floor rule."""
+    cF:1351): per axis, parent cell of each fine element by the reference's floor rule.  Memoised by the
+    content of the six coordinate arrays: the windows revisit the same integer shifts row after row."""
+    key = tuple(np.asarray(L["node_coords"][d], F32).tobytes() for L in (fine, parent) for d in range(3))
+    hit = _PAIR_CACHE.get(key)
+    if hit is None:
+        if len(_PAIR_CACHE) > 512:
+            _PAIR_CACHE.clear()
+        hit = _PAIR_CACHE[key] = _pair_cells_build(fine, parent)
+    return hit
+
+
+def _pair_cells_build(fine, parent):
     torch = _torch()
     g = F32(0.57735026918962576)
     lo, hi = F32(0.5) * (F32(1) + g), F32(0.5) * (F32(1) - g)

@@ -13,6 +13,7 @@
 namespace gomelt {
 
 void set_error(const char* fmt, ...);
+void count_launch(int n = 1);  // process-wide count of kernels launched by the library (gomelt_launch_count)
 
 inline int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();

@@ -2,6 +2,7 @@
 // separable source tables (K6 / a7-a9), error plumbing and an FP32 issue-rate diagnostic.
 #include <math.h>
 #include <stdarg.h>
+#include <atomic>
 #include <string.h>
 
 #include "common.cuh"
@@ -9,6 +10,10 @@
 namespace gomelt {
 
 static thread_local char g_err[512] = "";
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -150,6 +155,8 @@ using namespace gomelt;
 
 extern "C" const char* gomelt_last_error(void) { return g_err; }
 extern "C" int gomelt_abi_version(void) { return GOMELT_ABI_VERSION; }
+namespace gomelt { long long launches_so_far(); }
+extern "C" long long gomelt_launch_count(void) { return gomelt::launches_so_far(); }
 
 extern "C" int gomelt_state_props_f32(const gomelt_props_t* props, const float* T, const float* S1, int64_t nn,
                                       int64_t n_substrate, float* S1_out, uint8_t* S2_out, float* k_out,
@@ -166,7 +173,7 @@ extern "C" int gomelt_state_props_f32(const gomelt_props_t* props, const float* 
     const long long want = (nn + threads - 1) / threads;
     const int blocks = (int)(want < GOMELT_SM_COUNT * 8 ? want : GOMELT_SM_COUNT * 8);
     state_props_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(fold_props(*props), T, S1, nn, n_substrate,
-                                                                     S1_out, S2_out, k_out, rhocp_out);
+                                                                     S1_out, S2_out, k_out, rhocp_out), count_launch();
     return check_launch("gomelt_state_props_f32");
 }
 
@@ -183,7 +190,7 @@ extern "C" int gomelt_surface_flux_f32(const gomelt_props_t* p, const gomelt_gri
     const FluxK fk = fold_flux(*p, *g);
     dim3 block(32, 8), grid((g->nx + 31) / 32, (g->ny + 7) / 8);
     const float* plane = T0 + (long long)(nz_active - 1) * g->nx * g->ny;
-    surface_flux_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(fk, g->nx, g->ny, plane, flux, add);
+    surface_flux_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(fk, g->nx, g->ny, plane, flux, add), count_launch();
     return check_launch("gomelt_surface_flux_f32");
 }
 
@@ -207,7 +214,7 @@ extern "C" int gomelt_source_tables_f32(const gomelt_props_t* p, const gomelt_gr
     const int nmax = g->nx > g->ny ? (g->nx > g->nz ? g->nx : g->nz) : (g->ny > g->nz ? g->ny : g->nz);
     if (ty == tx + g->nx && tz == ty + g->ny) {
         source_table_batch_kernel<<<dim3((nmax + 127) / 128, 3, 1), 128, 0, (cudaStream_t)stream>>>(
-            x, y, z, g->nx, g->ny, g->nz, tb, 1.f / rsq, 1.f / dsq, rcoeff, dcoeff, tx);
+            x, y, z, g->nx, g->ny, g->nz, tb, 1.f / rsq, 1.f / dsq, rcoeff, dcoeff, tx), count_launch();
     } else {  // separately allocated tables: one axis per launch
         const float* cs[3] = {x, y, z};
         float* ts[3] = {tx, ty, tz};
@@ -218,7 +225,7 @@ extern "C" int gomelt_source_tables_f32(const gomelt_props_t* p, const gomelt_gr
             // a 1-axis launch: present axis d as "x" of a grid with ny = nz = 0 blocks
             source_table_batch_kernel<<<dim3((ns[d] + 127) / 128, 1, 1), 128, 0, (cudaStream_t)stream>>>(
                 cs[d], cs[d], cs[d], ns[d], 0, 0, t1, d == 2 ? 1.f / dsq : 1.f / rsq, 1.f / dsq,
-                d == 2 ? dcoeff : rcoeff, dcoeff, ts[d]);
+                d == 2 ? dcoeff : rcoeff, dcoeff, ts[d]), count_launch();
         }
     }
     return check_launch("gomelt_source_tables_f32");
@@ -247,7 +254,7 @@ extern "C" int gomelt_source_tables_batch_f32(const gomelt_props_t* p, const gom
     }
     const int nmax = g->nx > g->ny ? (g->nx > g->nz ? g->nx : g->nz) : (g->ny > g->nz ? g->ny : g->nz);
     source_table_batch_kernel<<<dim3((nmax + 127) / 128, 3, n), 128, 0, (cudaStream_t)stream>>>(
-        x, y, z, g->nx, g->ny, g->nz, tb, 1.f / rsq, 1.f / dsq, rcoeff, dcoeff, tables);
+        x, y, z, g->nx, g->ny, g->nz, tb, 1.f / rsq, 1.f / dsq, rcoeff, dcoeff, tables), count_launch();
     return check_launch("gomelt_source_tables_batch_f32");
 }
 
@@ -258,9 +265,9 @@ extern "C" int gomelt_diag_fp32_rate(int32_t kind, int32_t iters, int32_t blocks
         return GOMELT_E_NULL;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (kind == 0) fp32_rate_kernel<0><<<blocks, threads, 0, st>>>(iters, sink, 1.0000001f, 1e-7f);
-    else if (kind == 1) fp32_rate_kernel<1><<<blocks, threads, 0, st>>>(iters, sink, 1.0000001f, 1e-7f);
-    else fp32_rate_kernel<2><<<blocks, threads, 0, st>>>(iters, sink, 1.0000001f, 1e-7f);
+    if (kind == 0) fp32_rate_kernel<0><<<blocks, threads, 0, st>>>(iters, sink, 1.0000001f, 1e-7f), count_launch();
+    else if (kind == 1) fp32_rate_kernel<1><<<blocks, threads, 0, st>>>(iters, sink, 1.0000001f, 1e-7f), count_launch();
+    else fp32_rate_kernel<2><<<blocks, threads, 0, st>>>(iters, sink, 1.0000001f, 1e-7f), count_launch();
     *ops = (double)iters * 64.0 * (double)blocks * (double)threads;
     return check_launch("gomelt_diag_fp32_rate");
 }

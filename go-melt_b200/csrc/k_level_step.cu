@@ -36,7 +36,7 @@ static void launch_v2(const StepParams& sp, int nch, cudaStream_t st) {
     dim3 block(32, WPB);
     const int strips = (sp.ny + RY - 1) / RY;
     dim3 grid((sp.nx + 2 * K1_TX - 1) / (2 * K1_TX), (strips + WPB - 1) / WPB, nch);
-    level_step_v2<RY, WPB, FEAT, MINB, STAGE><<<grid, block, 0, st>>>(sp);
+    level_step_v2<RY, WPB, FEAT, MINB, STAGE><<<grid, block, 0, st>>>(sp), count_launch();
 }
 
 // Exact-feature instances for the call shapes the steppers issue; anything else runs the generic instance.
@@ -56,7 +56,7 @@ constexpr int F_L1_DWELL_SUB_PEER = F_L1_DWELL_SUB | K1F_PEER;
 template <int RY, int FEAT, int MINB = 1>
 static void launch_v3(const StepParams& sp, int nch, cudaStream_t st) {
     dim3 grid((sp.nx - 2 + 2 * K1_TX - 1) / (2 * K1_TX), (sp.ny - 2 + RY - 1) / RY, nch);
-    level_step_v3<RY, FEAT, MINB><<<grid, 32, 0, st>>>(sp);
+    level_step_v3<RY, FEAT, MINB><<<grid, 32, 0, st>>>(sp), count_launch();
 }
 
 // v3 (k_level_step_v3.cuh) serves the Dirichlet-side-face shapes of the steppers on grids that hold a full tile.
@@ -91,7 +91,7 @@ static bool try_launch_v3(const StepParams& sp, int nch, cudaStream_t st) {
         const long long n = (long long)(2 * sp.nx + 2 * sp.ny) * (sp.zend - sp.zbeg) + (sp.zbeg == 0 ? (long long)sp.nx * sp.ny : 0);
         const int blocks = (int)((n + 255) / 256 < 4 * GOMELT_SM_COUNT ? (n + 255) / 256 : 4 * GOMELT_SM_COUNT);
         face_const_kernel<<<blocks, 256, 0, st>>>(sp.Tout, sp.nx, sp.ny, sp.nz, sp.zbeg, sp.zend, sp.bc[0], sp.bc[1], sp.bc[2],
-                                                  sp.bc[3], sp.bc[4], sp.peer_lo, sp.peer_hi);
+                                                  sp.bc[3], sp.bc[4], sp.peer_lo, sp.peer_hi), count_launch();
     }
     return true;
 }

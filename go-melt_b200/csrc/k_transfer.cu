@@ -476,7 +476,7 @@ extern "C" int gomelt_interp_f32(const gomelt_interp_args_t* a, void* stream) {
     long long total = (long long)a->ntx * a->nty * a->ntz;
     if (a->faces_only)
         total = (long long)a->ntx * a->nty + 2LL * a->ntx * (a->ntz - 1) + 2LL * (a->nty - 2) * (a->ntz - 1);
-    interp_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    interp_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p), count_launch();
     return check_launch("gomelt_interp_f32");
 }
 
@@ -501,7 +501,7 @@ extern "C" int gomelt_faces_gather_f32(const gomelt_interp_args_t* a, float* fac
     p.sz = {a->src[2].coords, a->src[2].n};
     p.u = a->u; p.u2 = a->u2;
     p.tx = a->tx; p.ty = a->ty; p.tz = a->tz; p.ntx = a->ntx; p.nty = a->nty; p.ntz = a->ntz;
-    faces_gather_kernel<<<grid_for(nface, 128), 128, 0, (cudaStream_t)stream>>>(p, face_a, face_b, (int)nface);
+    faces_gather_kernel<<<grid_for(nface, 128), 128, 0, (cudaStream_t)stream>>>(p, face_a, face_b, (int)nface), count_launch();
     return check_launch("gomelt_faces_gather_f32");
 }
 
@@ -518,7 +518,7 @@ extern "C" int gomelt_faces_blend_f32(const float* face_a, const float* face_b, 
         return GOMELT_E_SIZE;
     }
     faces_blend_kernel<<<grid_for(nface, 256), 256, 0, (cudaStream_t)stream>>>(face_a, face_b, (int)nface, ntx, nty, ntz,
-                                                                              alpha, beta, has_clamp, clamp_min, out);
+                                                                              alpha, beta, has_clamp, clamp_min, out), count_launch();
     return check_launch("gomelt_faces_blend_f32");
 }
 
@@ -537,10 +537,10 @@ extern "C" int gomelt_box_copy(const void* src, void* dst, int32_t elem_size, co
     cudaStream_t st = (cudaStream_t)stream;
     if (elem_size == 4)
         box_copy_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)src, (float*)dst, ix, iy, iz, nx, ny,
-                                                                     nz, big_nx, big_ny, scatter);
+                                                                     nz, big_nx, big_ny, scatter), count_launch();
     else
         box_copy_kernel<uint8_t><<<grid_for(total, 256), 256, 0, st>>>((const uint8_t*)src, (uint8_t*)dst, ix, iy, iz,
-                                                                       nx, ny, nz, big_nx, big_ny, scatter);
+                                                                       nx, ny, nz, big_nx, big_ny, scatter), count_launch();
     return check_launch("gomelt_box_copy");
 }
 
@@ -551,7 +551,7 @@ extern "C" int gomelt_rank1_f32(float* F, const float* tx, const float* ty, cons
         return GOMELT_E_NULL;
     }
     const long long total = (long long)nx * ny * nz;
-    rank1_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(F, tx, ty, tz, nx, ny, nz, coef, accumulate);
+    rank1_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(F, tx, ty, tz, nx, ny, nz, coef, accumulate), count_launch();
     return check_launch("gomelt_rank1_f32");
 }
 
@@ -581,7 +581,7 @@ extern "C" int gomelt_coarse_source_tables_f32(const gomelt_props_t* p, const go
     for (int d = 0; d < 3; ++d)
         coarse_source_table_kernel<<<(parent[d].n + 63) / 64, 64, 0, st>>>(fine[d].coords, fine[d].n, parent[d].coords,
                                                                            parent[d].n, laser_xyz[d], is2[d], cc[d],
-                                                                           out[d]);
+                                                                           out[d]), count_launch();
     return check_launch("gomelt_coarse_source_tables_f32");
 }
 
@@ -613,15 +613,15 @@ extern "C" int gomelt_project_f32(const gomelt_project_args_t* a, void* stream) 
     cudaStream_t st = (cudaStream_t)stream;
     if (a->elems_per_cell_hint <= 16) {
         const long long threads = ncell * 8;
-        project_cells_kernel<8><<<(int)((threads + 127) / 128), 128, 0, st>>>(p);
+        project_cells_kernel<8><<<(int)((threads + 127) / 128), 128, 0, st>>>(p), count_launch();
     } else {
         const long long threads = ncell * 32;
-        project_cells_kernel<32><<<(int)((threads + 127) / 128), 128, 0, st>>>(p);
+        project_cells_kernel<32><<<(int)((threads + 127) / 128), 128, 0, st>>>(p), count_launch();
     }
     int rc = check_launch("gomelt_project_f32 (cells)");
     if (rc) return rc;
     const long long nnode = (long long)(p.ncx + 1) * (p.ncy + 1) * (p.ncz + 1);
     project_nodes_kernel<<<grid_for(nnode, 256), 256, 0, st>>>(a->cellsum, p.c0x, p.c0y, p.c0z, p.ncx, p.ncy, p.ncz,
-                                                               a->parent[0].n, a->parent[1].n, a->V, a->accumulate);
+                                                               a->parent[0].n, a->parent[1].n, a->V, a->accumulate), count_launch();
     return check_launch("gomelt_project_f32 (nodes)");
 }

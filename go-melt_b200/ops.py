@@ -8,12 +8,14 @@ from ._lib import (STEP_ACCUM, STEP_BC_CONST, STEP_CLAMP, STEP_FUSED_FLUX, STEP_
                    STEP_SKIP_FACES,
                    STEP_WRITE_S1, STEP_WRITE_S2)
 
-LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+LAUNCHES = 0  # kernels launched by the library in this process (bench.py reports the difference as gpu_launches)
 
 
 def _count(n=1):
+    """Refresh LAUNCHES from the library's own counter (gomelt_launch_count: every <<< >>> site counts itself, so
+    calls that issue several kernels - the one-call inner scan, a Level-1 step + its constant faces - are exact)."""
     global LAUNCHES
-    LAUNCHES += n
+    LAUNCHES = int(_lib.load().gomelt_launch_count())
 
 
 def _chk_f32(t, n, name):

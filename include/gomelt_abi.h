@@ -267,6 +267,8 @@ int gomelt_l3_substeps_f32(const gomelt_props_t *props, const gomelt_substeps_ar
 
 const char *gomelt_last_error(void);
 int gomelt_abi_version(void);
+/* Kernels launched by this library in this process so far (every <<< >>> site counts itself). */
+long long gomelt_launch_count(void);
 
 /* 1 when the library was built with jaxlib's xla/ffi/api/ffi.h and exports the XLA FFI handler symbols
  * (GomeltLevelStepFfi, ...: csrc/xla_ffi_shim.cc), 0 otherwise (this image: no jaxlib). */

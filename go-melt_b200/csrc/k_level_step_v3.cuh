@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     constexpr int NR = RY + 2;
     constexpr bool F_RHS = (FEAT & K1F_RHS) != 0, F_SRC = (FEAT & K1F_SRC) != 0, F_FLUX = (FEAT & K1F_FLUX) != 0;
     constexpr bool F_S1 = (FEAT & K1F_S1OUT) != 0, F_CLAMP = (FEAT & K1F_CLAMP) != 0, F_NSUB = (FEAT & K1F_NSUB) != 0;
-    constexpr bool F_PEER = (FEAT & K1F_PEER) != 0;
+    constexpr bool F_PEER = (FEAT & K1F_PEER) != 0, F_PF = (FEAT & K1F_PF) != 0;
     const int lane = threadIdx.x;
     const int nx = p.nx, ny = p.ny, nz = p.nz, nzl = p.nzl;
     const int c0 = min((int)blockIdx.x * (2 * K1_TX), nx - (2 * K1_TX + 2));  // column of lane 0, half .x
@@ -134,6 +134,19 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
         for (int r = 0; r < NR; ++r) {
             raw.Tr[r] = ld2u(Tl + off[r]);
             raw.Sr[r] = ld2u(Sl + off[r]);
+        }
+    };
+
+    // L2 prefetch of plane l: one instruction per loaded row and field, lane i touching 8 bytes further than lane
+    // i-1, so that the 32 lanes cover the 256 bytes both halves of the row segment span
+    const unsigned pf_lane = 8u * (unsigned)lane - 4u * (unsigned)K1_TX;
+    auto l2_prefetch = [&](int l) {
+        const char* Tl = (const char*)(p.T0 + (size_t)l * P);
+        const char* Sl = (const char*)(p.S1 + (size_t)l * P);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Tl + off[r] - 4u * (unsigned)lane + pf_lane));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Sl + off[r] - 4u * (unsigned)lane + pf_lane));
         }
     };
 
@@ -328,9 +341,11 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
         // plane 0 is the Dirichlet bottom face: never finalised (l - 1 >= 1)
         for (int l = lfirst + 1; l <= llast; l += 2) {
             if (l + 1 <= llast) load_plane(l + 1, rawA);
+            if (F_PF && l + 3 <= llast) l2_prefetch(l + 3);
             step_plane(l, rawB, stA, stB, l - 1 >= max(za, 1), sfx * splat(srcz_at(l - 1)));
             if (l + 1 > llast) break;
             if (l + 2 <= llast) load_plane(l + 2, rawB);
+            if (F_PF && l + 4 <= llast) l2_prefetch(l + 4);
             step_plane(l + 1, rawA, stB, stA, l >= max(za, 1), sfx * splat(srcz_at(l)));
         }
         if (llast >= za && llast < zb) {

@@ -106,6 +106,7 @@ STEP_GENERAL_KERNEL = 0x80
 SIGNATURES = {
     "gomelt_abi_version": (C.c_int, []),
     "gomelt_launch_count": (C.c_longlong, []),
+    "gomelt_minmax_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "gomelt_last_error": (C.c_char_p, []),
     "gomelt_xla_ffi_available": (C.c_int, []),
     "gomelt_level_step_f32": (C.c_int, [C.POINTER(Props), C.POINTER(StepArgs), C.c_void_p]),

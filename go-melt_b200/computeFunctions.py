@@ -25,6 +25,7 @@ import numpy as np
 from . import _lib, levels, ops, schema
 from .schema import SetupNonmesh, SetupProperties, getStaticSubcycle  # noqa: F401
 from .toolpath import count_lines, parsingGcode  # noqa: F401
+from .output import saveFinalResult, saveResult, saveResults, saveResultsFinal, saveState  # noqa: F401
 
 F32 = np.float32
 
@@ -585,6 +586,29 @@ def melting_temp(temps, delt_T, T_melt, accum_time, idx):
     above = (_f(temps) > float(F32(T_melt))).to(torch.float32) * float(F32(_host(delt_T)))
     acc.index_add_(0, idx_t, above)
     return acc
+
+
+def printLevelMaxMin(Ls, Lnames):
+    """cF:3635-3665: print min / max of every level's T0 and stop on invalid physics (non-finite, <= 0 or
+    > 1e5 K) like the reference (``sys.exit(1)``); one fused reduction per level instead of two host syncs."""
+    import sys
+
+    from . import output
+
+    for name, (lo, hi, bad) in zip(Lnames, output.level_minmax([None] + list(Ls))):
+        print(f"{name}: min T = {lo:.2f} K, max T = {hi:.2f} K")
+        if bad or not (0 < lo <= 1e5) or not (0 < hi <= 1e5):
+            print("Terminating program: temperature out of range")
+            sys.exit(1)
+
+
+def save_object(obj, filename):
+    """gm:398 / cF save_object: ``obj`` = [Levels, accum_time, max_accum_time, time_inc, record_inc]; written as a
+    raw-dump checkpoint directory next to where the reference writes its ``.pkl`` (output.save_checkpoint)."""
+    from . import output
+
+    path = str(filename)
+    return output.save_checkpoint(path[:-4] if path.endswith(".pkl") else path, *obj)
 
 
 def levelMaxMin(Ls):

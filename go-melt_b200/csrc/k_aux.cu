@@ -149,11 +149,65 @@ __global__ void fp32_rate_kernel(int iters, float* sink, float bin, float cin) {
     if (s == 12345.678f) sink[0] = s;
 }
 
+// ---- min / max monitor (printLevelMaxMin cF:3635-3665 as one reduction; N3 of SURVEY.md 8(f)) -----------
+__device__ __forceinline__ void atomic_min_f32(float* a, float v) {
+    if (v >= 0.f) atomicMin(reinterpret_cast<int*>(a), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f32(float* a, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(a), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
+}
+__global__ void minmax_init_kernel(float* out) {
+    out[0] = __int_as_float(0x7f800000);  // +inf
+    out[1] = __int_as_float(0xff800000);  // -inf
+    out[2] = 0.f;
+}
+__global__ void minmax_kernel(const float* __restrict__ x, long long n, float* out) {
+    float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);
+    int bad = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        if (isfinite(v)) {
+            lo = fminf(lo, v);
+            hi = fmaxf(hi, v);
+        } else {
+            ++bad;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (lo <= hi) {  // the warp saw at least one finite value
+            atomic_min_f32(out, lo);
+            atomic_max_f32(out + 1, hi);
+        }
+        if (bad) atomicAdd(out + 2, (float)bad);
+    }
+}
+
 }  // namespace gomelt
 
 using namespace gomelt;
 
 extern "C" const char* gomelt_last_error(void) { return g_err; }
+extern "C" int gomelt_minmax_f32(const float* x, int64_t n, float* out3, void* stream) {
+    if (!x || !out3 || n < 1) {
+        set_error("gomelt_minmax_f32: NULL argument / empty field");
+        return GOMELT_E_NULL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    minmax_init_kernel<<<1, 1, 0, st>>>(out3), count_launch();
+    long long blocks = (n + 4 * 256 - 1) / (4 * 256);
+    if (blocks > 8 * GOMELT_SM_COUNT) blocks = 8 * GOMELT_SM_COUNT;
+    minmax_kernel<<<(int)blocks, 256, 0, st>>>(x, n, out3), count_launch();
+    return check_launch("gomelt_minmax_f32");
+}
+
 extern "C" int gomelt_abi_version(void) { return GOMELT_ABI_VERSION; }
 namespace gomelt { long long launches_so_far(); }
 extern "C" long long gomelt_launch_count(void) { return gomelt::launches_so_far(); }

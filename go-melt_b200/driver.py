@@ -8,10 +8,11 @@ single-step / subcycle / dwell mode predicate (gm:162-172), layer change, wait c
 reference's.  The same function drives the NumPy oracle in the tests (``cf`` / ``xp`` arguments), which
 is how the loop itself is parity-checked.
 
-Not restated (host I/O outside the path, SURVEY.md 2 "OUT OF SCOPE"): VTK output (``saveResults*`` /
-``saveState``, pyevtk) and the dill checkpoint files - the ``on_record`` / ``on_checkpoint`` hooks are
-called where the reference writes them, and the checkpoint *flags* that influence the stepping mode
-(gm:179-193, 390-411) are kept.
+File output is behind hooks (``on_record`` / ``on_layer_state`` / ``on_checkpoint`` / ``on_info`` /
+``on_final``), called where the reference writes its files; ``output.driver_hooks()`` supplies the
+dependency-free implementations (``.vtr`` files with the reference's names, raw-dump checkpoints, fused
+min / max monitor) and the CLI installs them.  The checkpoint *flags* that influence the stepping mode
+(gm:179-193, 390-411) are kept in the loop itself.
 
 CLI (gm:533-580):  python go-melt_b200/driver.py [DEVICE_ID] [input.json]
 """
@@ -283,6 +284,8 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
     if hasattr(xp, "sync"):
         xp.sync()
     wall = time.time() - tstart
+    if "on_final" in hooks:  # saveState(Level 0) + saveResultsFinal gm:501-502
+        hooks["on_final"](Levels, Nonmesh)
     if write_final:  # gm:504-516
         np.savez(f"{Nonmesh['save_path']}FinalTemperatureFields", L1T=xp.host(Levels[1]["T0"]),
                  L2T=xp.host(Levels[2]["T0"]), L3T=xp.host(Levels[3]["T0"]))
@@ -304,7 +307,9 @@ def main(argv):
     except FileNotFoundError:
         print(f"Input file not found: {path}")
         return 1
-    out = go_melt(solver_input, verbose=True)
+    from . import output  # the reference's file output (.vtr records, checkpoints, min / max monitor)
+
+    out = go_melt(solver_input, verbose=True, hooks=output.driver_hooks())
     print(f"End of simulation: {out['time_inc']} steps, {out['sim_seconds']:.6f} s simulated in "
           f"{out['wall_seconds']:.2f} s wall ({out['wall_seconds'] / max(out['sim_seconds'], 1e-30):.1f} wall-s per sim-s)")
     return 0

@@ -65,6 +65,18 @@ def level_step(props, grid, T0, S1, T_out, dt, *, rhs=None, src=None, topflux=No
     return T_out
 
 
+def minmax(x, out=None):
+    """gomelt_minmax_f32: device tensor [min, max, n_nonfinite] of a float32 field (one fused reduction)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    _chk_f32(x, x.numel(), "x")
+    if out is None:
+        out = torch.empty(3, device=x.device, dtype=torch.float32)
+    _lib.check(lib.gomelt_minmax_f32(_lib.ptr(x), int(x.numel()), _lib.ptr(out), _lib.stream_ptr()), "gomelt_minmax_f32")
+    _count()
+    return out
+
+
 def state_props(props, T, S1, n_substrate=0, *, S1_out=None, S2_out=None, k_out=None, rhocp_out=None):
     """computeStateProperties cF:2567-2614 (gomelt_state_props_f32)."""
     lib = _lib.load()

@@ -265,6 +265,10 @@ typedef struct gomelt_substeps_args {
 
 int gomelt_l3_substeps_f32(const gomelt_props_t *props, const gomelt_substeps_args_t *args, void *stream);
 
+/* Monitor (printLevelMaxMin cF:3635-3665): out3 = {min, max over the finite values, number of non-finite values}
+ * of x[0..n) in one reduction (device memory, 3 floats; read it back when convenient). */
+int gomelt_minmax_f32(const float *x, int64_t n, float *out3, void *stream);
+
 const char *gomelt_last_error(void);
 int gomelt_abi_version(void);
 /* Kernels launched by this library in this process so far (every <<< >>> site counts itself). */

@@ -64,6 +64,7 @@ static void launch_v3(const StepParams& sp, int nch, cudaStream_t st) {
 // constant faces from face_const_kernel (the step itself never stores a face node).
 static bool try_launch_v3(const StepParams& sp, int nch, cudaStream_t st) {
     static const int off = env_int("GOMELT_K1_V2", 0);  // dev A/B: force the v2 path
+    static const int pf = env_int("GOMELT_K1_PF", 0);
     constexpr int RY = 4;
     const int f = sp.feat;
     if (off || (sp.flags & GOMELT_STEP_GENERAL_KERNEL) || !(f & (K1F_SKIP | K1F_BCCONST)) ||
@@ -81,10 +82,15 @@ static bool try_launch_v3(const StepParams& sp, int nch, cudaStream_t st) {
         case V3_L3_SUB: launch_v3<RY, V3_L3_SUB>(sp, nch, st); break;  // (prefetch: no gain, 53.3 us either way)
         case V3_L3_STEP: launch_v3<RY, V3_L3_STEP>(sp, nch, st); break;
         case V3_RHS: launch_v3<RY, V3_RHS>(sp, nch, st); break;        // (prefetch: 57.3 -> 61.5 us, off)
-        // the dwell shapes (few planes per warp, several waves of warps) are latency-bound: the plane three ahead
-        // is pulled into L2 while the registers prefetch the next one (121.7 -> 111.6 us per 25 M-node sweep)
-        case V3_DWELL: launch_v3<RY, V3_DWELL | K1F_PF>(sp, nch, st); break;
-        case V3_DWELL_PEER: launch_v3<RY, V3_DWELL_PEER | K1F_PF>(sp, nch, st); break;
+        // The dwell shapes (few planes per warp, several waves of warps) are latency-bound; pulling the plane three
+        // ahead into L2 (prefetch.global.L2) takes a 25 M-node sweep from 121.7 to 111.6 us on cudaMalloc memory -
+        // but on peer-mapped symmetric memory (the multi-GPU slabs) the same instruction costs 5.7 ms per sweep
+        // (measured at 4 and 8 GPUs), so it is opt-in (GOMELT_K1_PF=1) and never used with peer pointers.
+        case V3_DWELL:
+            if (pf) launch_v3<RY, V3_DWELL | K1F_PF>(sp, nch, st);
+            else launch_v3<RY, V3_DWELL>(sp, nch, st);
+            break;
+        case V3_DWELL_PEER: launch_v3<RY, V3_DWELL_PEER>(sp, nch, st); break;
         default: return false;
     }
     if (f & K1F_BCCONST) {

@@ -45,7 +45,21 @@ def run_gomelt_multi(args, read_peaks, ClockSampler, host_properties, single_gpu
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1 and not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=device)
+        # keep stdout to the ONE JSON line: the NCCL communicator set-up prints "NCCL version ..." on fd 1, so
+        # fd 1 points at stderr while the process group (and its first collective) is created
+        import sys
+
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     gm.load()
     P = host_properties()
     props = gm._lib.make_props(P)

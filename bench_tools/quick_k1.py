@@ -32,8 +32,8 @@ def run(shape, zc=0):
     kw, bpd = {}, 16
     if shape == "nat":
         kw = dict(src=(tx, ty, tz, 1e-3), flags=ops.STEP_CLAMP | ops.STEP_WRITE_S1 | ops.STEP_FUSED_FLUX, S1_out=S1o)
-    elif shape in ("sub", "subg"):
-        kw = dict(src=(tx, ty, tz, 1e-3), S1_out=S1o, n_substrate=2 * nx * ny,
+    elif shape in ("sub", "subg", "subi"):  # subi: S1 updated in place (what the steppers do)
+        kw = dict(src=(tx, ty, tz, 1e-3), S1_out=(S1 if shape == "subi" else S1o), n_substrate=2 * nx * ny,
                   flags=ops.STEP_CLAMP | ops.STEP_WRITE_S1 | ops.STEP_FUSED_FLUX | ops.STEP_SKIP_FACES |
                   (ops.STEP_GENERAL_KERNEL if shape == "subg" else 0))
     elif shape in ("l2", "l2g"):

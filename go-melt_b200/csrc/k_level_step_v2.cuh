@@ -179,6 +179,7 @@ enum : int {
     K1F_NSUB = 1 << 9,     // substrate override present (n_substrate > 0)
     K1F_FLUX = 1 << 10,    // top-surface flux (computeConvRadBC) evaluated in the step from T0's top plane
     K1F_PEER = 1 << 11,    // boundary planes of T_out are also stored to the z-neighbours' ghost planes (NVLink)
+    K1F_S1INPLACE = 1 << 13,  // v3: S1_out is S1: a node's state is stored only when it changed (it rarely does)
     K1F_PF = 1 << 12,      // v3: L2 prefetch of the plane three ahead (latency-bound many-wave shapes)
     K1F_ALL = (1 << 12) - 1,
     K1F_GENERIC = 1 << 30,

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     constexpr int NR = RY + 2;
     constexpr bool F_RHS = (FEAT & K1F_RHS) != 0, F_SRC = (FEAT & K1F_SRC) != 0, F_FLUX = (FEAT & K1F_FLUX) != 0;
     constexpr bool F_S1 = (FEAT & K1F_S1OUT) != 0, F_CLAMP = (FEAT & K1F_CLAMP) != 0, F_NSUB = (FEAT & K1F_NSUB) != 0;
-    constexpr bool F_PEER = (FEAT & K1F_PEER) != 0, F_PF = (FEAT & K1F_PF) != 0;
+    constexpr bool F_PEER = (FEAT & K1F_PEER) != 0, F_PF = (FEAT & K1F_PF) != 0, F_INPLACE = (FEAT & K1F_S1INPLACE) != 0;
     const int lane = threadIdx.x;
     const int nx = p.nx, ny = p.ny, nz = p.nz, nzl = p.nzl;
     const int c0 = min((int)blockIdx.x * (2 * K1_TX), nx - (2 * K1_TX + 2));  // column of lane 0, half .x
@@ -161,7 +161,10 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
             f2 s1f;
             props3(p.pk, p.n_cmushy, p.n_cfluid, T.v.x, S.v.x, thr, kb.v.x, cs.v.x, kn.v.x, mn.v.x, s1f.v.x);
             props3(p.pk, p.n_cmushy, p.n_cfluid, T.v.y, S.v.y, thr, kb.v.y, cs.v.y, kn.v.y, mn.v.y, s1f.v.y);
-            st2(so + off[r], sa, sb, s1f);
+            if (F_INPLACE)  // in place (the steppers): S1' == S1 for all but the nodes that melt in this substep
+                st2(so + off[r], (s1f.v.x != S.v.x) ? sa : 0, (s1f.v.y != S.v.y) ? sb : 0, s1f);
+            else
+                st2(so + off[r], sa, sb, s1f);
         } else {
             props3_km(p.pk, p.n_cmushy, p.n_cfluid, T.v.x, S.v.x, thr, kb.v.x, cs.v.x, kn.v.x, mn.v.x);
             props3_km(p.pk, p.n_cmushy, p.n_cfluid, T.v.y, S.v.y, thr, kb.v.y, cs.v.y, kn.v.y, mn.v.y);

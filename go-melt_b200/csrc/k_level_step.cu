@@ -68,12 +68,13 @@ static bool try_launch_v3(const StepParams& sp, int nch, cudaStream_t st) {
     constexpr int RY = 4;
     const int f = sp.feat;
     if (off || (sp.flags & GOMELT_STEP_GENERAL_KERNEL) || !(f & (K1F_SKIP | K1F_BCCONST)) ||
-        (f & (K1F_S2OUT | K1F_ACCUM | K1F_TOP)))
+        (f & K1F_TOP))
         return false;
     if (sp.nx < 2 * K1_TX + 2 || sp.ny < RY + 2 || sp.nzl < 2 || sp.nsub_rem != 0) return false;
     // plane 0 is never finalised: its row stores are redirected to plane 1, which the same warp must overwrite
     if (sp.zbeg == 0 && (sp.zchunk < 2 || sp.zend < 2)) return false;
     constexpr int V3_L3_SUB = K1F_SRC | K1F_FLUX | K1F_S1OUT | K1F_CLAMP | K1F_NSUB;  // subcycleL3_Part1
+    constexpr int V3_L3_SUB2 = V3_L3_SUB | K1F_S2OUT | K1F_ACCUM;                       // subcycleL3_Part2 (melt-time bookkeeping)
     constexpr int V3_L3_STEP = K1F_SRC | K1F_FLUX | K1F_CLAMP | K1F_NSUB;             // stepGOMELT Level 3
     constexpr int V3_RHS = K1F_RHS | K1F_FLUX | K1F_CLAMP | K1F_NSUB;                 // Level 2 and Level 1 (step / subcycle)
     constexpr int V3_DWELL = K1F_FLUX | K1F_NSUB;                                     // stepGOMELTDwellTime (no clamp)
@@ -83,6 +84,10 @@ static bool try_launch_v3(const StepParams& sp, int nch, cudaStream_t st) {
             // in place (the steppers): a node's state is stored only when it changed: 52.2 -> 50.1 us
             if (sp.S1out == sp.S1) launch_v3<RY, V3_L3_SUB | K1F_S1INPLACE>(sp, nch, st);
             else launch_v3<RY, V3_L3_SUB>(sp, nch, st);
+            break;
+        case V3_L3_SUB2:
+            if (sp.S1out == sp.S1) launch_v3<RY, V3_L3_SUB2 | K1F_S1INPLACE>(sp, nch, st);
+            else launch_v3<RY, V3_L3_SUB2>(sp, nch, st);
             break;
         case V3_L3_STEP: launch_v3<RY, V3_L3_STEP>(sp, nch, st); break;
         case V3_RHS: launch_v3<RY, V3_RHS>(sp, nch, st); break;        // (prefetch: 57.3 -> 61.5 us, off)
@@ -247,5 +252,6 @@ extern "C" int gomelt_level_step_f32(const gomelt_props_t* props, const gomelt_s
     }
     sp.zchunk = a->z_chunk > 0 ? a->z_chunk : (zend - zbeg);
     if (any_src && sp.zchunk > K1_SRCZ_MAX) sp.zchunk = K1_SRCZ_MAX;  // the chunk's z-factors live in shared memory
+    if ((sp.feat & (K1F_S2OUT | K1F_ACCUM)) && sp.zchunk > 62) sp.zchunk = 62;  // v3 keeps a 64-bit mask of hot planes per chunk
     return launch_step(sp, (cudaStream_t)stream);
 }

@@ -58,10 +58,86 @@ GM_DI void props3_km(const PropK& q, float c_mushy, float c_fluid, float T, floa
           "f"(c_mushy), "f"(cs), "f"(c_fluid));
 }
 
+// Guarded byte-pair store (S2): half .y at q, half .x 30 nodes below it.
+GM_DI void st2_u8(uint8_t* q, int fa, int fb, int a, int b) {
+    asm volatile("{\n\t.reg .pred pa, pb;\n\t"
+                 "setp.ne.s32 pa, %3, 0;\n\t"
+                 "setp.ne.s32 pb, %4, 0;\n\t"
+                 "@pa st.global.u8 [%0+-30], %1;\n\t"
+                 "@pb st.global.u8 [%0], %2;\n\t}"
+                 ::"l"(q), "r"(a), "r"(b), "r"(fa), "r"(fb)
+                 : "memory");
+}
+static_assert(K1_TX == 30, "st2_u8 hard-codes the half distance");
+
 // Unguarded pair load: half .y at q, half .x 30 columns (120 bytes) below it.
 GM_DI f2 ld2u(const char* q) {
     const float* f = reinterpret_cast<const float*>(q);
     return mk2(__ldg(f - K1_TX), __ldg(f));
+}
+
+// Melt-time bookkeeping (cF:3568-3578) of a plane that holds molten nodes.  It runs only for the few warp-planes
+// that intersect the melt pool (the plane loop only tracks the maximum temperature it loaded and votes once per
+// plane), and only AFTER the warp's z march, when the carried state is dead and its registers are free.  S2 = (T0 >= T_liquidus) is recomputed from T0 for the nodes this warp owns (rowmask:
+// bit r = loaded row r is owned here; qa / qb: this lane's halves are); accum / max_accum change only where the
+// node is molten NOW (s2 = 0: reset = 0, max(0, max_accum) = max_accum for the non-negative times it holds,
+// accum + 0 - 0 = accum), so S2_prev, accum and max_accum are touched only there.  o0..o5 = row byte offsets.
+template <bool F_S2, bool F_ACC>
+GM_DI void bookkeep_plane(const StepParams& p, size_t pl, unsigned rowmask, int qa, int qb, unsigned o0,
+                                            unsigned o1, unsigned o2, unsigned o3, unsigned o4, unsigned o5) {
+    // The few warps over the melt pool are the tail of a single-wave kernel, so this path is written for latency:
+    // every load of a stage is issued before the first use (T0 from cache, then S2_prev / accum / max_accum).
+    const unsigned o[6] = {o0, o1, o2, o3, o4, o5};
+    bool da[6], db[6];
+    float ta[6], tb[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        const bool mine = (rowmask >> r) & 1u;
+        const size_t nb = pl + (o[r] >> 2);
+        ta[r] = (mine && qa) ? __ldg(p.T0 + nb - K1_TX) : 0.f;
+        tb[r] = (mine && qb) ? __ldg(p.T0 + nb) : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        da[r] = ta[r] >= p.pk.T_liq;  // T_liquidus > 0, so a node this warp does not own is never "molten"
+        db[r] = tb[r] >= p.pk.T_liq;
+    }
+    if (F_ACC) {
+        uint8_t pa[6], pb[6];
+        float aca[6], acb[6], mxa[6], mxb[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const size_t nb = pl + (o[r] >> 2), na = nb - K1_TX;
+            pa[r] = da[r] ? p.S2prev[na] : (uint8_t)1;   // S2_prev is read before S2 is written (in place)
+            pb[r] = db[r] ? p.S2prev[nb] : (uint8_t)1;
+            aca[r] = da[r] ? p.accum[na] : 0.f;
+            acb[r] = db[r] ? p.accum[nb] : 0.f;
+            mxa[r] = da[r] ? p.maxacc[na] : 0.f;
+            mxb[r] = db[r] ? p.maxacc[nb] : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const size_t nb = pl + (o[r] >> 2), na = nb - K1_TX;
+            const float ra = pa[r] ? 0.f : aca[r], rb = pb[r] ? 0.f : acb[r];  // reset = accum when the node has just melted
+            if (da[r]) {
+                p.maxacc[na] = fmaxf(ra, mxa[r]);
+                p.accum[na] = aca[r] + p.dt - ra;
+            }
+            if (db[r]) {
+                p.maxacc[nb] = fmaxf(rb, mxb[r]);
+                p.accum[nb] = acb[r] + p.dt - rb;
+            }
+        }
+    }
+    if (F_S2) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const bool mine = (rowmask >> r) & 1u;
+            const size_t nb = pl + (o[r] >> 2);
+            if (mine && qa) p.S2out[nb - K1_TX] = da[r] ? 1 : 0;
+            if (mine && qb) p.S2out[nb] = db[r] ? 1 : 0;
+        }
+    }
 }
 
 template <int RY>
@@ -80,6 +156,7 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     constexpr int NR = RY + 2;
     constexpr bool F_RHS = (FEAT & K1F_RHS) != 0, F_SRC = (FEAT & K1F_SRC) != 0, F_FLUX = (FEAT & K1F_FLUX) != 0;
     constexpr bool F_S1 = (FEAT & K1F_S1OUT) != 0, F_CLAMP = (FEAT & K1F_CLAMP) != 0, F_NSUB = (FEAT & K1F_NSUB) != 0;
+    constexpr bool F_S2 = (FEAT & K1F_S2OUT) != 0, F_ACC = (FEAT & K1F_ACCUM) != 0;
     constexpr bool F_PEER = (FEAT & K1F_PEER) != 0, F_PF = (FEAT & K1F_PF) != 0, F_INPLACE = (FEAT & K1F_S1INPLACE) != 0;
     const int lane = threadIdx.x;
     const int nx = p.nx, ny = p.ny, nz = p.nz, nzl = p.nzl;
@@ -97,6 +174,11 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
 #ifdef GOMELT_K1_ABLATE
     if (p.exp & 32) sa = sb = 0;
 #endif
+    // S2 / melt-time bookkeeping (cF:3568-3578) is a read-modify-write of every node, faces included, so it has
+    // exactly ONE owner per node: the owned lanes / rows that are not the overlap of a shifted tile / strip with
+    // its predecessor, plus the face column / row of the outermost tiles
+    const int x_new = (int)blockIdx.x * (2 * K1_TX) + 1, y_new = (int)blockIdx.y * RY + 1;  // first non-duplicate column / row
+    const int qa = ((own && ia >= x_new) || ia == 0) ? 1 : 0, qb = ((own && ib >= x_new) || ib == nx - 1) ? 1 : 0;
     const int P = nx * ny;
     const int za = p.zbeg + blockIdx.z * p.zchunk;
     const int zb = min(p.zend, za + p.zchunk);  // this warp finalises node planes [za, zb)
@@ -150,12 +232,71 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
         }
     };
 
+    // ---- S2 / melt-time bookkeeping of plane l, after its rows (see bookkeep_plane) -------------------------------
+    f2 tmax = splat(0.f);  // running maximum of the temperatures loaded for the current plane
+    unsigned rows_mine = 0;  // loaded rows whose nodes this strip owns for the bookkeeping (plane-invariant)
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int j = j0 - 1 + r;
+        if ((r >= 1 && r <= RY) ? (j >= y_new) : (r == 0 ? j == 0 : j == ny - 1)) rows_mine |= 1u << r;
+    }
+    // After the rows of plane l (branch-free): one vote; a cold plane (nothing molten among the loaded nodes) gets
+    // S2 = 0 on its owned nodes by guarded byte stores, a hot one is remembered in `hotmask` (bit l - lfirst; the
+    // launcher keeps bookkeeping chunks within 64 planes) and handled by flush_bookkeeping() after the march: the
+    // melt-pool warps are the tail of a single-wave kernel, and there the registers of the carried state are free,
+    // so every load of a hot plane can be in flight at once.
+    unsigned long long hotmask = 0;
+    auto bookkeep = [&](int l, int) {
+        if (!(F_S2 || F_ACC)) return;
+        const float hot = fmaxf(tmax.v.x, tmax.v.y);
+        tmax = splat(0.f);
+        const int mine = (l >= za && l < zb) ? 1 : 0;  // a chunk's halo plane belongs to the neighbouring chunk
+        const int cold = __any_sync(0xffffffffu, hot >= p.pk.T_liq) ? 0 : mine;
+        hotmask |= (unsigned long long)(mine & ~cold & 1) << (l - lfirst);
+        if (F_S2) {
+            const size_t pl = (size_t)l * P;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const int g = (int)((rows_mine >> r) & 1u) & cold;
+                st2_u8(p.S2out + pl + (off[r] >> 2), qa & g, qb & g, 0, 0);
+            }
+        }
+    };
+    auto flush_bookkeeping = [&]() {
+        if (!(F_S2 || F_ACC)) return;
+        static_assert(NR == 6, "bookkeep_plane takes the six row offsets of RY = 4");
+        unsigned long long m = hotmask;  // warp-uniform
+        hotmask = 0;
+#pragma unroll 1
+        while (m) {
+            const int b = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            bookkeep_plane<F_S2, F_ACC>(p, (size_t)(lfirst + b) * P, rows_mine, qa, qb, off[0], off[1], off[2], off[3],
+                                        off[4], off[5]);
+        }
+    };
+
     // ---- node state of loaded row r (+ S1 output) and its x stage ------------------------------------
-    auto row_a = [&](char* so, int r, float thr, f2 T, f2 S, f2& xs, f2& xd, f2& kxr, f2& mxr) {
+    auto row_a = [&](char* so, int r, float thr, f2 T, f2 S, f2& xs, f2& xd, f2& kxr, f2& mxr, size_t pl = 0,
+                     bool wr = false) {
         // masses carry the 1 / (cdt * lambda'[2]) normalisation (StepParams)
         const f2 kb = fma2(splat(p.pk.k_a1), T, splat(p.pk.k_a0)), cs = fma2(splat(p.n_ca1), T, splat(p.n_ca0));
         f2 kn, mn;
-        if (F_S1) {
+        if (F_S2 || F_ACC) {  // the corrector substeps (subcycleL3_Part2): state, S2 and the melt-time accumulators
+            f2 s1f = splat(0.f);
+            if (F_S1) {
+                props3(p.pk, p.n_cmushy, p.n_cfluid, T.v.x, S.v.x, thr, kb.v.x, cs.v.x, kn.v.x, mn.v.x, s1f.v.x);
+                props3(p.pk, p.n_cmushy, p.n_cfluid, T.v.y, S.v.y, thr, kb.v.y, cs.v.y, kn.v.y, mn.v.y, s1f.v.y);
+            } else {
+                props3_km(p.pk, p.n_cmushy, p.n_cfluid, T.v.x, S.v.x, thr, kb.v.x, cs.v.x, kn.v.x, mn.v.x);
+                props3_km(p.pk, p.n_cmushy, p.n_cfluid, T.v.y, S.v.y, thr, kb.v.y, cs.v.y, kn.v.y, mn.v.y);
+            }
+            if (F_S1) {
+                if (F_INPLACE) st2(so + off[r], (s1f.v.x != S.v.x) ? sa : 0, (s1f.v.y != S.v.y) ? sb : 0, s1f);
+                else st2(so + off[r], sa, sb, s1f);
+            }
+            tmax = mk2(fmaxf(tmax.v.x, T.v.x), fmaxf(tmax.v.y, T.v.y));  // bookkeep() votes on it after the rows
+        } else if (F_S1) {
             // S1' is node-local, so every loaded node (halo rows, halo planes of a chunk, face lanes) may be
             // written: its owner writes the same value.  This is what covers the face nodes without a guard.
             f2 s1f;
@@ -182,9 +323,11 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
         const float thr = plane_thr(l);
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-            row_a(so, r, thr, raw.Tr[r], raw.Sr[r], st.Xs[r], st.Xd[r], st.kx[r], st.mx[r]);
+            row_a(so, r, thr, raw.Tr[r], raw.Sr[r], st.Xs[r], st.Xd[r], st.kx[r], st.mx[r], (size_t)l * P,
+                  l >= za && l < zb);
             if (r >= 1 && r <= RY) st.T[r - 1] = raw.Tr[r];
         }
+        bookkeep(l, 0);
     };
 
     // ---- write one finalised owned row of plane f (side faces are not owned; see the header) ---------
@@ -220,7 +363,8 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
 
     // ---- plane l: node state, x stage, then the element layer (l-1, l) row by row; finalises plane l-1
     //      when do_final.  pv = state of plane l-1, cu <- state of plane l.
-    auto step_plane = [&](int l, const K3Raw<RY>& raw, const K3State<RY>& pv, K3State<RY>& cu, bool do_final, f2 sz) {
+    auto step_plane = [&](int l, const K3Raw<RY>& raw, const K3State<RY>& pv, K3State<RY>& cu, bool do_final, f2 sz,
+                          int slot) {
         const int f = l - 1;
         const size_t pl = (size_t)l * P;
         char* so = F_S1 ? (char*)(p.S1out + pl) : nullptr;
@@ -235,7 +379,7 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
             f2 xs, xd, kxr, mxr;
-            row_a(so, r, thr, raw.Tr[r], raw.Sr[r], xs, xd, kxr, mxr);
+            row_a(so, r, thr, raw.Tr[r], raw.Sr[r], xs, xd, kxr, mxr, pl, l >= za && l < zb);
             cu.Xs[r] = xs; cu.Xd[r] = xd; cu.kx[r] = kxr; cu.mx[r] = mxr;
             if (r >= 1 && r <= RY) cu.T[r - 1] = raw.Tr[r];
             // z stage of the analysis
@@ -274,6 +418,7 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
             zl00 = zu00; zl01 = zu01; zl10 = zu10; zl11 = zu11; kzl = kzu; mzl = mzu;
             bl01 = bu01; bl10 = bu10; bl11 = bu11;
         }
+        bookkeep(l, slot);
     };
 
     // ---- the chunk's source z-factors live in shared memory (see v2) ---------------------------------
@@ -345,17 +490,18 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
         for (int l = lfirst + 1; l <= llast; l += 2) {
             if (l + 1 <= llast) load_plane(l + 1, rawA);
             if (F_PF && l + 3 <= llast) l2_prefetch(l + 3);
-            step_plane(l, rawB, stA, stB, l - 1 >= max(za, 1), sfx * splat(srcz_at(l - 1)));
+            step_plane(l, rawB, stA, stB, l - 1 >= max(za, 1), sfx * splat(srcz_at(l - 1)), 0);
             if (l + 1 > llast) break;
             if (l + 2 <= llast) load_plane(l + 2, rawB);
             if (F_PF && l + 4 <= llast) l2_prefetch(l + 4);
-            step_plane(l + 1, rawA, stB, stA, l >= max(za, 1), sfx * splat(srcz_at(l)));
+            step_plane(l + 1, rawA, stB, stA, l >= max(za, 1), sfx * splat(srcz_at(l)), 1);
         }
         if (llast >= za && llast < zb) {
             if (((llast - lfirst) & 1) != 0) last_plane(llast, stB.T, rawB);  // parity of the plane held in stB
             else last_plane(llast, stA.T, rawA);
         }
         fdone = max(za, llast + 1);
+        flush_bookkeeping();
     }
     // planes >= nz_active (substitute_Tbar cF:2183); the side faces belong to the face pass
     for (int f = max(fdone, 1); f < zb; ++f) {

@@ -476,3 +476,51 @@ def test_l3_substeps_compact_faces_equal_per_substep_prolongation(gm, example_pr
     assert np.array_equal(res[0][1], res[1][1])
     face = _faces_mask(nx, ny, nz).ravel()
     assert np.isfinite(res[0][0]).all() and (res[0][0][face] >= np.float32(P["T_amb"])).all()
+
+
+@pytest.mark.parametrize("elements,z_chunk", [((129, 37, 9), 0), ((100, 100, 10), 4), ((61, 5, 4), 0), ((150, 13, 6), 2)])
+def test_fast_kernel_melt_time_bookkeeping_has_one_owner_per_node(gm, example_props, elements, z_chunk):
+    """subcycleL3_Part2's call shape (SKIP_FACES + WRITE_S2 + ACCUM, S2 updated in place) on the fast kernel: S2,
+    accum and max_accum (cF:3568-3578) exact on EVERY node - faces, the overlap of the shifted last tile / strip
+    and chunk boundaries included - against the closed form and the general kernel."""
+    import torch
+
+    ops = gm.ops
+    ex, ey, ez = elements
+    bounds = ((0.0, 0.02 * ex), (0.0, 0.02 * ey), (-0.02 * ez, 0.0))
+    P, lv, T0, S1, nsub = _setup(gm, example_props, elements, bounds, 21, nsub_planes=2)
+    T0 = (T0 * 1.1).astype(np.float32)
+    nn, (nx, ny, nz) = lv["nn"], lv["nodes"]
+    rng = np.random.default_rng(23)
+    prev = rng.random(nn) > 0.5
+    acc = (rng.random(nn) * 1e-3).astype(np.float32)
+    mx = (rng.random(nn) * 1e-3).astype(np.float32)
+    S2 = T0 >= np.float32(P["T_liquidus"])
+    reset = acc * ((~prev) & S2)
+    mx_ref = np.maximum(reset, mx)
+    acc_ref = (acc + np.float32(1e-5) * S2 - reset).astype(np.float32)
+    props = gm._lib.make_props(P)
+    grid = gm._lib.make_grid(lv["nodes"], lv["h"])
+    coords = [_dev(c) for c in lv["node_coords"]]
+    tx, ty, tz = (torch.empty(n, device="cuda") for n in (nx, ny, nz))
+    v = np.array([0.01 * ex, 0.01 * ey, 0.0], np.float32)
+    coef = ops.source_tables(props, grid, coords, v, 285.0, tx, ty, tz)
+    outs = []
+    for extra in (0, ops.STEP_GENERAL_KERNEL):
+        dS2, dacc, dmx = _dev(prev.astype(np.uint8)), _dev(acc), _dev(mx)
+        Tout = torch.full((nn,), -7.0, device="cuda")
+        S1o = torch.empty(nn, device="cuda")
+        ops.level_step(props, grid, _dev(T0), _dev(S1), Tout, 1e-5, src=(tx, ty, tz, coef), n_substrate=nsub,
+                       flags=ops.STEP_SKIP_FACES | ops.STEP_CLAMP | ops.STEP_WRITE_S1 | ops.STEP_WRITE_S2 |
+                       ops.STEP_ACCUM | ops.STEP_FUSED_FLUX | extra,
+                       S1_out=S1o, S2_out=dS2, S2_prev=dS2, accum=dacc, max_accum=dmx, z_chunk=z_chunk)
+        torch.cuda.synchronize()
+        outs.append([t.cpu().numpy() for t in (Tout, S1o, dS2, dacc, dmx)])
+    for T, S1o, s2, a, m in outs:
+        assert np.array_equal(s2.astype(bool), S2)
+        assert np.array_equal(m, mx_ref)
+        assert np.array_equal(a, acc_ref)
+    face = _faces_mask(nx, ny, nz).ravel()
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert _rel(outs[0][0][~face], outs[1][0][~face]) <= 2e-6
+    assert (outs[0][0][face] == -7.0).all()

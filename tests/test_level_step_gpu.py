@@ -524,3 +524,63 @@ def test_fast_kernel_melt_time_bookkeeping_has_one_owner_per_node(gm, example_pr
     assert np.array_equal(outs[0][1], outs[1][1])
     assert _rel(outs[0][0][~face], outs[1][0][~face]) <= 2e-6
     assert (outs[0][0][face] == -7.0).all()
+
+
+@pytest.mark.parametrize("elements,nsub_planes,z_chunk", [((129, 37, 12), 3, 0), ((100, 100, 10), 0, 4), ((61, 5, 9), 9, 0)])
+def test_fast_kernel_in_place_state_on_a_mostly_cold_field(gm, example_props, elements, nsub_planes, z_chunk):
+    """The fast kernel's in-place state update (S1_out == S1, what the steppers pass: a node's state is stored only
+    when it changed) on the kind of field a run has - mostly below the solidus, one melt pool - with fractional,
+    negative-zero, at-threshold and powder-in-substrate states.  In place vs separate S1_out: T and S1' identical;
+    against the general kernel: T to rounding, S1' exact; against the oracle: 1e-5, S1' exact."""
+    import torch
+
+    ops = gm.ops
+    ex, ey, ez = elements
+    bounds = ((0.0, 0.02 * ex), (0.0, 0.02 * ey), (-0.02 * ez, 0.0))
+    P = cF.SetupProperties(example_props)
+    lv = make_level(elements, bounds)
+    nx, ny, nz = lv["nodes"]
+    rng = np.random.default_rng(21)
+    x, y, z = lv["node_coords"]
+    r2 = ((x[None, None, :] - 0.3 * x[-1]) / 0.2) ** 2 + ((y[None, :, None] - 0.5 * y[-1]) / 0.15) ** 2 + (z[:, None, None] / 0.08) ** 2
+    T0 = (320.0 + 600.0 * rng.random((nz, ny, nx)) + 2400.0 * np.exp(-r2)).astype(np.float32).ravel()
+    assert (T0 >= P["T_liquidus"]).sum() > 20 and (T0 < P["T_solidus"]).mean() > 0.8
+    S1 = (rng.random(lv["nn"]) > 0.5).astype(np.float32)
+    odd = rng.choice(lv["nn"], 200, replace=False)
+    S1[odd[:80]] = rng.random(80).astype(np.float32)        # fractional states (Level 1 after interpolation)
+    S1[odd[80:120]] = np.float32(-0.0)
+    S1[odd[120:160]] = np.float32(0.499)
+    S1[odd[160:]] = np.float32(0.4990001)
+    nsub = nsub_planes * nx * ny
+    v = np.array([0.3 * x[-1], 0.5 * y[-1], 0.0], np.float32)
+    dt = 1e-5
+    props = gm._lib.make_props(P)
+    grid = gm._lib.make_grid(lv["nodes"], lv["h"])
+    dT0 = _dev(T0)
+    coords = [_dev(c) for c in lv["node_coords"]]
+    tx, ty, tz = (torch.empty(n, device="cuda") for n in (nx, ny, nz))
+    src = (tx, ty, tz, ops.source_tables(props, grid, coords, v, 285.0, tx, ty, tz))
+    base = ops.STEP_SKIP_FACES | ops.STEP_CLAMP | ops.STEP_WRITE_S1 | ops.STEP_FUSED_FLUX
+
+    def run(extra, in_place):
+        dS1 = _dev(S1)
+        Tout = torch.full((lv["nn"],), -7.0, device="cuda")
+        S1o = dS1 if in_place else torch.full((lv["nn"],), -3.0, device="cuda")
+        ops.level_step(props, grid, dT0, dS1, Tout, dt, src=src, n_substrate=nsub, S1_out=S1o, flags=base | extra,
+                       z_chunk=z_chunk)
+        torch.cuda.synchronize()
+        return Tout.cpu().numpy(), S1o.cpu().numpy()
+
+    Tc, Sc = run(0, False)
+    Ti, Si = run(0, True)
+    Tg, Sg = run(ops.STEP_GENERAL_KERNEL, False)
+    assert np.array_equal(Tc, Ti)
+    assert np.array_equal(Si, Sc)  # -0.0 == 0.0: an unchanged node may keep its bits in place
+    assert np.array_equal(Sc, Sg)
+    face = _faces_mask(nx, ny, nz).ravel()
+    assert (Tc[face] == -7.0).all()
+    assert _rel(Tc[~face], Tg[~face]) <= 2e-6
+    Tref, S1ref, _ = _oracle_step(P, lv, T0, S1, nsub, dt, v, 285.0)
+    Tref = np.maximum(np.float32(P["T_amb"]), Tref)
+    assert _rel(Tc[~face], Tref[~face]) <= RTOL
+    assert np.array_equal(Sc, S1ref)

@@ -18,12 +18,13 @@ PEAK = 6542.1e9
 flush = torch.empty(64 * 1024 * 1024, device="cuda")
 
 
-def run(shape, zc=0):
+def run(shape, zc=0, mods=()):
     nx, ny, nz = (1001, 1001, 25) if shape.startswith("dwell") else (513, 513, 39)
     grid = gm._lib.make_grid((nx, ny, nz), (0.02, 0.02, 0.02))
     nn = nx * ny * nz
     g = torch.Generator(device="cuda").manual_seed(0)
-    hot = os.environ.get("GOMELT_QUICK_HOT", "1") == "1"
+    hot = os.environ.get("GOMELT_QUICK_HOT", "1") == "1" and "cold" not in mods
+    extra = ops.STEP_NO_COLD_PLANES if "nocold" in mods else 0
     T0 = (300 + 2000 * torch.rand(nn, device="cuda", generator=g)) if hot else (300 + 900 * torch.rand(nn, device="cuda", generator=g))
     S1 = (torch.rand(nn, device="cuda", generator=g) > 0.5).float()
     Tout = torch.empty_like(T0); S1o = torch.empty_like(T0)
@@ -49,14 +50,15 @@ def run(shape, zc=0):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.level_step(props, grid, T0, S1, Tout, 1e-5, z_chunk=zc, **kw)
+        ops.level_step(props, grid, T0, S1, Tout, 1e-5, z_chunk=zc, **dict(kw, flags=kw["flags"] | extra))
         e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     t = np.median(ts[3:]) * 1e-3
-    print(f"{shape:6s} z_chunk={zc:3d}: {t*1e6:8.1f} us  {nn/t/1e9:7.2f} G DOF/s  {nn*bpd/t/1e9:7.1f} GB/s algorithmic "
+    print(f"{shape:6s} {','.join(mods):12s} z_chunk={zc:3d}: {t*1e6:8.1f} us  {nn/t/1e9:7.2f} G DOF/s  {nn*bpd/t/1e9:7.1f} GB/s algorithmic "
           f"({nn*bpd/t/PEAK*100:.1f}% of measured HBM peak)", flush=True)
 
 
 for a in sys.argv[1:] or ["nat", "sub", "subg"]:
+    a, _, mods = a.partition("@")   # e.g. subi@cold  subi@cold,nocold  (cold: field below the solidus)
     shape, _, zc = a.partition(":")
-    run(shape, int(zc or 0))
+    run(shape, int(zc or 0), tuple(m for m in mods.split(",") if m))

@@ -101,6 +101,7 @@ STEP_CLAMP, STEP_WRITE_S1, STEP_WRITE_S2 = 0x01, 0x02, 0x04
 STEP_BC_CONST, STEP_SKIP_FACES, STEP_ACCUM = 0x08, 0x10, 0x20
 STEP_FUSED_FLUX = 0x40
 STEP_GENERAL_KERNEL = 0x80
+STEP_NO_COLD_PLANES = 0x100
 
 # name -> (restype, argtypes); kept in one table so tests can check every header symbol loads
 SIGNATURES = {

@@ -53,18 +53,62 @@ constexpr int F_L1_DWELL_SUB = F_L1_DWELL | K1F_NSUB;
 constexpr int F_L1_DWELL_PEER = F_L1_DWELL | K1F_PEER;                         // ... with the fused halo stores
 constexpr int F_L1_DWELL_SUB_PEER = F_L1_DWELL_SUB | K1F_PEER;
 
+// 1-D tensor maps of T0 and S1 for the TMA ring of level_step_v3 (K1F_TMA): nn floats, K3_BOX-element boxes.
+// cuTensorMapEncodeTiled is taken from the driver through the runtime (no link-time dependency on libcuda).
+static bool make_field_tmaps(StepParams& sp) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn enc = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return (encode_fn)f;
+    }();
+    if (!enc) return false;
+    const void* base[2] = {sp.T0, sp.S1};
+    const cuuint64_t nn = (cuuint64_t)sp.nx * sp.ny * sp.nz;
+    const cuuint64_t dim1[1] = {nn}, stride0[1] = {0};  // stride unused for rank 1
+    const cuuint32_t box1[1] = {K3_BOX}, estr[2] = {1, 1};
+    const cuuint64_t dim2[2] = {nn, 6}, stride2[1] = {(cuuint64_t)(sp.nx & ~3) * 4u};
+    const cuuint32_t box2[2] = {K3_BOX, 6};
+    sp.tm2_ok = 1;
+    for (int q = 0; q < 2; ++q) {
+        if (((uintptr_t)base[q] & 15u) != 0) return false;
+        void* b = const_cast<void*>(base[q]);
+        if (enc(&sp.tm[q], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 1, b, dim1, stride0, box1, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+        if (enc(&sp.tm2[q], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, b, dim2, stride2, box2, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            sp.tm2_ok = 0;  // the six 1-D boxes per field and plane serve every tile then
+    }
+    static const int no2d = env_int("GOMELT_K1_TMA_1D", 0);
+    if (no2d) sp.tm2_ok = 0;
+    return true;
+}
+
 template <int RY, int FEAT, int MINB = 1>
 static void launch_v3(const StepParams& sp, int nch, cudaStream_t st) {
     dim3 grid((sp.nx - 2 + 2 * K1_TX - 1) / (2 * K1_TX), (sp.ny - 2 + RY - 1) / RY, nch);
+    if constexpr ((FEAT & K1F_TMA) != 0) {  // 8 resident warps x 20 KB: ask for the large shared-memory carve-out once
+        static const cudaError_t carve = cudaFuncSetAttribute(level_step_v3<RY, FEAT, MINB>,
+                                                               cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                               (int)cudaSharedmemCarveoutMaxShared);
+        (void)carve;
+    }
     level_step_v3<RY, FEAT, MINB><<<grid, 32, 0, st>>>(sp), count_launch();
 }
 
 // v3 (k_level_step_v3.cuh) serves the Dirichlet-side-face shapes of the steppers on grids that hold a full tile.
 // Returns false when the call is not one of them (v2 takes it).  GOMELT_STEP_BC_CONST calls get their five
 // constant faces from face_const_kernel (the step itself never stores a face node).
-static bool try_launch_v3(const StepParams& sp, int nch, cudaStream_t st) {
+static bool try_launch_v3(StepParams& sp, int nch, cudaStream_t st) {
     static const int off = env_int("GOMELT_K1_V2", 0);  // dev A/B: force the v2 path
     static const int pf = env_int("GOMELT_K1_PF", 0);
+    static const int tma = env_int("GOMELT_K1_TMA", 0);
     constexpr int RY = 4;
     const int f = sp.feat;
     if (off || (sp.flags & GOMELT_STEP_GENERAL_KERNEL) || !(f & (K1F_SKIP | K1F_BCCONST)) ||
@@ -82,7 +126,8 @@ static bool try_launch_v3(const StepParams& sp, int nch, cudaStream_t st) {
     switch ((f & ~(K1F_SKIP | K1F_BCCONST)) | K1F_NSUB) {
         case V3_L3_SUB:  // (prefetch: no gain, 53.3 us either way)
             // in place (the steppers): a node's state is stored only when it changed: 52.2 -> 50.1 us
-            if (sp.S1out == sp.S1) launch_v3<RY, V3_L3_SUB | K1F_S1INPLACE>(sp, nch, st);
+            if (sp.S1out == sp.S1 && tma && make_field_tmaps(sp)) launch_v3<RY, V3_L3_SUB | K1F_S1INPLACE | K1F_TMA>(sp, nch, st);
+            else if (sp.S1out == sp.S1) launch_v3<RY, V3_L3_SUB | K1F_S1INPLACE>(sp, nch, st);
             else launch_v3<RY, V3_L3_SUB>(sp, nch, st);
             break;
         case V3_L3_SUB2:
@@ -111,7 +156,7 @@ static bool try_launch_v3(const StepParams& sp, int nch, cudaStream_t st) {
     return true;
 }
 
-static int launch_step(const StepParams& sp, cudaStream_t st) {
+static int launch_step(StepParams& sp, cudaStream_t st) {
     const int nch = (sp.zend - sp.zbeg + sp.zchunk - 1) / sp.zchunk;
     if (try_launch_v3(sp, nch, st)) return check_launch("gomelt_level_step_f32");
     static const int generic_only = env_int("GOMELT_K1_GENERIC", 0);

@@ -18,6 +18,8 @@
 //  * analysis, element layer and explicit update are fused row by row, so the only arrays that
 //    live across the row loop are the carried state and the prefetched next plane.
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace gomelt {
@@ -57,6 +59,9 @@ struct StepParams {
     // v3 normalisation: stiffness modes divided by s = lambda'[2], masses by cdt * s, loads by s (so that
     // T_new = T + (rr/s - KT/s) / (mnode/(cdt s)) needs neither the lambda'[2] nor the cdt multiply)
     float n_ca0, n_ca1, n_cmushy, n_cfluid, n_inv_s, n_wq;
+    alignas(64) CUtensorMap tm[2];   // K1F_TMA: T0 and S1 as 1-D tensors of nn floats, one box = one ring row
+    alignas(64) CUtensorMap tm2[2];  // ... and as overlapping 2-D views (x + y (nx & ~3)), one box = six ring rows
+    int tm2_ok;
 };
 
 #define GM_DI __device__ __forceinline__
@@ -180,6 +185,7 @@ enum : int {
     K1F_FLUX = 1 << 10,    // top-surface flux (computeConvRadBC) evaluated in the step from T0's top plane
     K1F_PEER = 1 << 11,    // boundary planes of T_out are also stored to the z-neighbours' ghost planes (NVLink)
     K1F_S1INPLACE = 1 << 13,  // v3: S1_out is S1: a node's state is stored only when it changed (it rarely does)
+    K1F_TMA = 1 << 14,     // v3: raw planes through a TMA ring in shared memory (1-D tensor maps StepParams::tm)
     K1F_PF = 1 << 12,      // v3: L2 prefetch of the plane three ahead (latency-bound many-wave shapes)
     K1F_ALL = (1 << 12) - 1,
     K1F_GENERIC = 1 << 30,

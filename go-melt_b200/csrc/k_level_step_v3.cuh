@@ -58,6 +58,54 @@ GM_DI void props3_km(const PropK& q, float c_mushy, float c_fluid, float T, floa
           "f"(c_mushy), "f"(cs), "f"(c_fluid));
 }
 
+// Three-input maximum (one FMNMX3 on sm_100a); NaN operands are ignored like fmaxf does.
+GM_DI float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+struct ColdTag { static constexpr bool value = true; };
+struct HotTag { static constexpr bool value = false; };
+
+// ---- TMA plane ring (K1F_TMA) ------------------------------------------------------------------------------
+// A field is described to the TMA unit as a ONE-dimensional tensor of nn floats (StepParams::tm): a 1-D box of 64
+// elements needs no row stride; StepParams::tm2 is an overlapping 2-D view of the same array (see the ring in the
+// kernel for why and how the two are used).
+constexpr int K3_BOX = 96;  // elements per box row: 62 columns + up to 3 + 5 * 3 of alignment slack, 384-byte pitch
+constexpr int K3_NS = 4;  // ring depth: planes l .. l+3 are resident / in flight while plane l is processed
+GM_DI void mbar_init(unsigned bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+GM_DI void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+GM_DI void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile("{\n\t.reg .pred P1;\n\t"
+                 "WAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+                 "@!P1 bra WAIT_%=;\n\t}" ::"r"(bar), "r"(parity)
+                 : "memory");
+}
+GM_DI bool elect_one() {  // one lane of the (converged) warp; lets the compiler keep the TMA operands in uniform registers
+    unsigned pred;
+    asm volatile("{\n\t.reg .pred P1;\n\t"
+                 "elect.sync _|P1, 0xffffffff;\n\t"
+                 "selp.u32 %0, 1, 0, P1;\n\t}"
+                 : "=r"(pred));
+    return pred != 0;
+}
+GM_DI void tma_load_row(unsigned dst, const void* tmap, int elem, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.1d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2}], [%3];" ::"r"(dst),
+                 "l"(tmap), "r"(elem), "r"(bar)
+                 : "memory");
+}
+
+GM_DI void tma_load_box2(unsigned dst, const void* tmap, int x, unsigned bar) {  // rows y = 0 .. of the 2-D view at column x
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(tmap), "r"(x), "r"(0), "r"(bar)
+                 : "memory");
+}
+
 // Guarded byte-pair store (S2): half .y at q, half .x 30 nodes below it.
 GM_DI void st2_u8(uint8_t* q, int fa, int fb, int a, int b) {
     asm volatile("{\n\t.reg .pred pa, pb;\n\t"
@@ -158,6 +206,11 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     constexpr bool F_S1 = (FEAT & K1F_S1OUT) != 0, F_CLAMP = (FEAT & K1F_CLAMP) != 0, F_NSUB = (FEAT & K1F_NSUB) != 0;
     constexpr bool F_S2 = (FEAT & K1F_S2OUT) != 0, F_ACC = (FEAT & K1F_ACCUM) != 0;
     constexpr bool F_PEER = (FEAT & K1F_PEER) != 0, F_PF = (FEAT & K1F_PF) != 0, F_INPLACE = (FEAT & K1F_S1INPLACE) != 0;
+    constexpr bool F_TMA = (FEAT & K1F_TMA) != 0;
+    // the cold-plane path needs the whole plane before its first row, i.e. the TMA ring (see plane_is_cold); the
+    // corrector substeps keep the general selects (their bookkeeping votes on the liquidus after the rows)
+    constexpr bool USE_COLD = F_TMA && !(F_S2 || F_ACC);
+    constexpr int NS = K3_NS;
     const int lane = threadIdx.x;
     const int nx = p.nx, ny = p.ny, nz = p.nz, nzl = p.nzl;
     const int c0 = min((int)blockIdx.x * (2 * K1_TX), nx - (2 * K1_TX + 2));  // column of lane 0, half .x
@@ -219,6 +272,54 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
         }
     };
 
+    // K1F_TMA: the raw planes arrive through a ring of NS stages in shared memory, [stage][T|S][row][96 floats],
+    // filled by the TMA unit three planes ahead of their use (one elected lane issues the plane's boxes against the
+    // stage's mbarrier), instead of one plane ahead into 48 registers.  A box must start on a 16-byte boundary of the
+    // field (the TMA unit faults otherwise) and a 2-D map wants a row stride that is a multiple of 16 bytes, which
+    // the rows of an odd nx do not give.  So the field is described as rows of S = nx & ~3 elements that START
+    // anywhere (an overlapping 2-D view of the flat array: element (x, y) is x + y S): box row r begins at
+    // a = (first element of the tile's row 0, rounded down to a multiple of four) + r S, and the tile's row r begins
+    // sh0 + r (nx & 3) elements into it (sh0 = the rounding remainder, warp-uniform per plane).  One 96 x 6 box per
+    // field and plane.  Where that box would reach past the end of the array (the last rows of the last plane) the
+    // same rows are fetched by six 1-D boxes per field, which the 1-D map clips at nn.
+    constexpr int RW = K3_BOX;  // floats per ring row (384-byte pitch: every 1-D box destination is 128-byte aligned)
+    __shared__ alignas(128) float s_ring[F_TMA ? NS : 1][2][F_TMA ? NR : 1][F_TMA ? RW : 1];
+    __shared__ alignas(8) unsigned long long s_bar[F_TMA ? NS : 1];
+    const int row0 = (j0 - 1) * nx + c0;  // in-plane element of the tile's first loaded row, column c0
+    const int Sq = nx & ~3, dq = nx & 3;
+    const int nn_all = P * nz;
+    auto ring_issue = [&](int l) {
+        if (l > llast) return;
+        const int s = (l - lfirst) & (NS - 1);
+        __syncwarp();  // every lane has read what the stage held before
+        if (elect_one()) {
+            const unsigned bar = smem_u32(&s_bar[s]);
+            mbar_expect_tx(bar, 2u * NR * RW * 4u);
+            const int a = (l * P + row0) & ~3;
+            if (p.tm2_ok && a + (NR - 1) * Sq + RW <= nn_all) {
+                tma_load_box2(smem_u32(&s_ring[s][0][0][0]), &p.tm2[0], a, bar);
+                tma_load_box2(smem_u32(&s_ring[s][1][0][0]), &p.tm2[1], a, bar);
+            } else {
+#pragma unroll 1
+                for (int r = 0; r < NR; ++r) {
+                    tma_load_row(smem_u32(&s_ring[s][0][r][0]), &p.tm[0], a + r * Sq, bar);
+                    tma_load_row(smem_u32(&s_ring[s][1][r][0]), &p.tm[1], a + r * Sq, bar);
+                }
+            }
+        }
+    };
+    auto ring_fetch = [&](int l, K3Raw<RY>& raw) {
+        const int k = l - lfirst, s = k & (NS - 1);
+        mbar_wait(smem_u32(&s_bar[s]), (unsigned)(k / NS) & 1u);
+        const float* b = &s_ring[s][0][0][((l * P + row0) & 3) + lane];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const float* bT = b + r * (RW + dq);
+            raw.Tr[r] = mk2(bT[0], bT[K1_TX]);
+            raw.Sr[r] = mk2(bT[NR * RW], bT[NR * RW + K1_TX]);
+        }
+    };
+
     // L2 prefetch of plane l: one instruction per loaded row and field, lane i touching 8 bytes further than lane
     // i-1, so that the 32 lanes cover the 256 bytes both halves of the row segment span
     const unsigned pf_lane = 8u * (unsigned)lane - 4u * (unsigned)K1_TX;
@@ -277,44 +378,81 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     };
 
     // ---- node state of loaded row r (+ S1 output) and its x stage ------------------------------------
-    auto row_a = [&](char* so, int r, float thr, f2 T, f2 S, f2& xs, f2& xd, f2& kxr, f2& mxr, size_t pl = 0,
-                     bool wr = false) {
+    // `cold` (ColdTag): the warp has voted that no node it loaded of this plane is above the solidus / at the liquidus
+    // (plane_is_cold below), so S2 = S3 = 0 there and computeStateProperties cF:2567-2614 collapses to
+    // k = S1' ? k_solid(T) : k_powder, rho cp = rho cp_solid(T), S1' = S1 > thr: two selects per node instead of
+    // seven.  The values are the ones the general selects produce, bit for bit.
+    // In place (F_INPLACE) a node's state is stored only when it changed, which it rarely does: on a cold plane the
+    // rows only OR the bit difference of S1' and S1 into `chg`, and the plane's tail (flush_state) stores the changed
+    // nodes after one vote - no compare / guard / predicated-off store per node in the plane body.
+    unsigned chg = 0;
+    auto row_a = [&](auto cold, char* so, int r, float thr, f2 T, f2 S, f2& xs, f2& xd, f2& kxr, f2& mxr) {
+        constexpr bool COLD = decltype(cold)::value;
         // masses carry the 1 / (cdt * lambda'[2]) normalisation (StepParams)
         const f2 kb = fma2(splat(p.pk.k_a1), T, splat(p.pk.k_a0)), cs = fma2(splat(p.n_ca1), T, splat(p.n_ca0));
-        f2 kn, mn;
-        if (F_S2 || F_ACC) {  // the corrector substeps (subcycleL3_Part2): state, S2 and the melt-time accumulators
-            f2 s1f = splat(0.f);
-            if (F_S1) {
-                props3(p.pk, p.n_cmushy, p.n_cfluid, T.v.x, S.v.x, thr, kb.v.x, cs.v.x, kn.v.x, mn.v.x, s1f.v.x);
-                props3(p.pk, p.n_cmushy, p.n_cfluid, T.v.y, S.v.y, thr, kb.v.y, cs.v.y, kn.v.y, mn.v.y, s1f.v.y);
-            } else {
-                props3_km(p.pk, p.n_cmushy, p.n_cfluid, T.v.x, S.v.x, thr, kb.v.x, cs.v.x, kn.v.x, mn.v.x);
-                props3_km(p.pk, p.n_cmushy, p.n_cfluid, T.v.y, S.v.y, thr, kb.v.y, cs.v.y, kn.v.y, mn.v.y);
-            }
-            if (F_S1) {
-                if (F_INPLACE) st2(so + off[r], (s1f.v.x != S.v.x) ? sa : 0, (s1f.v.y != S.v.y) ? sb : 0, s1f);
-                else st2(so + off[r], sa, sb, s1f);
-            }
-            tmax = mk2(fmaxf(tmax.v.x, T.v.x), fmaxf(tmax.v.y, T.v.y));  // bookkeep() votes on it after the rows
+        f2 kn, mn, s1f = splat(0.f);
+        if (COLD) {
+            const bool pa = S.v.x > thr, pb = S.v.y > thr;
+            kn = mk2(pa ? kb.v.x : p.pk.k_powder, pb ? kb.v.y : p.pk.k_powder);
+            mn = cs;
+            if (F_S1) s1f = mk2(pa ? 1.f : 0.f, pb ? 1.f : 0.f);
         } else if (F_S1) {
             // S1' is node-local, so every loaded node (halo rows, halo planes of a chunk, face lanes) may be
             // written: its owner writes the same value.  This is what covers the face nodes without a guard.
-            f2 s1f;
             props3(p.pk, p.n_cmushy, p.n_cfluid, T.v.x, S.v.x, thr, kb.v.x, cs.v.x, kn.v.x, mn.v.x, s1f.v.x);
             props3(p.pk, p.n_cmushy, p.n_cfluid, T.v.y, S.v.y, thr, kb.v.y, cs.v.y, kn.v.y, mn.v.y, s1f.v.y);
-            if (F_INPLACE)  // in place (the steppers): S1' == S1 for all but the nodes that melt in this substep
-                st2(so + off[r], (s1f.v.x != S.v.x) ? sa : 0, (s1f.v.y != S.v.y) ? sb : 0, s1f);
-            else
-                st2(so + off[r], sa, sb, s1f);
         } else {
             props3_km(p.pk, p.n_cmushy, p.n_cfluid, T.v.x, S.v.x, thr, kb.v.x, cs.v.x, kn.v.x, mn.v.x);
             props3_km(p.pk, p.n_cmushy, p.n_cfluid, T.v.y, S.v.y, thr, kb.v.y, cs.v.y, kn.v.y, mn.v.y);
         }
+        if (F_S1) {
+            if (F_INPLACE && COLD)  // cold planes: deferred (flush_state)
+                chg |= (__float_as_uint(s1f.v.x) ^ __float_as_uint(S.v.x)) | (__float_as_uint(s1f.v.y) ^ __float_as_uint(S.v.y));
+            else if (F_INPLACE)     // in place (the steppers): S1' == S1 for all but the nodes that melt in this substep
+                st2(so + off[r], (s1f.v.x != S.v.x) ? sa : 0, (s1f.v.y != S.v.y) ? sb : 0, s1f);
+            else
+                st2(so + off[r], sa, sb, s1f);
+        }
+        // the corrector substeps (subcycleL3_Part2) track the plane's maximum: bookkeep() votes on it after the rows
+        if (F_S2 || F_ACC) tmax = mk2(fmaxf(tmax.v.x, T.v.x), fmaxf(tmax.v.y, T.v.y));
         const f2 Tr = shdn(T), kr = shdn(kn), mr = shdn(mn);
         xs = Tr + T;
         xd = Tr - T;
         kxr = kr + kn;
         mxr = mr + mn;
+    };
+    // In-place state of a cold plane l: nothing to do unless some loaded node's S1' differs from its S1 (a powder node
+    // of a substrate plane, a fractional Level-1 state).  The rare path re-reads the plane (cache hits; another warp
+    // may already have stored the same S1' for a shared halo node, which S1' maps to itself) and stores the changed
+    // nodes with the guards of the direct form.
+    auto flush_state = [&](int l) {
+        if (!(F_S1 && F_INPLACE && USE_COLD)) return;
+        const bool any = __any_sync(0xffffffffu, chg != 0);
+        chg = 0;
+        if (!any) return;
+        const float thr = (F_NSUB && l < nsub_planes) ? -1.0f : 0.499f;
+        const char* Tl = (const char*)(p.T0 + (size_t)l * P);
+        const char* Sl = (const char*)(p.S1 + (size_t)l * P);
+        char* so = (char*)(p.S1out + (size_t)l * P);
+#pragma unroll 1
+        for (int r = 0; r < NR; ++r) {
+            const unsigned o = 4u * (unsigned)((j0 - 1 + r) * nx + ib);
+            const float* tf = reinterpret_cast<const float*>(Tl + o);
+            const volatile float* sf = reinterpret_cast<const volatile float*>(Sl + o);
+            const f2 T = mk2(__ldg(tf - K1_TX), __ldg(tf)), S = mk2(sf[-K1_TX], sf[0]);
+            f2 s1f;
+            s1f.v.x = (S.v.x > thr || T.v.x >= p.pk.T_liq) ? 1.f : 0.f;
+            s1f.v.y = (S.v.y > thr || T.v.y >= p.pk.T_liq) ? 1.f : 0.f;
+            st2(so + o, (s1f.v.x != S.v.x) ? sa : 0, (s1f.v.y != S.v.y) ? sb : 0, s1f);
+        }
+    };
+    // One vote per plane on the temperatures the warp loaded for it (6 three-input maxima + 1).
+    auto plane_is_cold = [&](const K3Raw<RY>& raw) -> bool {
+        static_assert(NR == 6, "six loaded rows");
+        const float m0 = fmax3(raw.Tr[0].v.x, raw.Tr[0].v.y, raw.Tr[1].v.x), m1 = fmax3(raw.Tr[1].v.y, raw.Tr[2].v.x, raw.Tr[2].v.y);
+        const float m2 = fmax3(raw.Tr[3].v.x, raw.Tr[3].v.y, raw.Tr[4].v.x), m3 = fmax3(raw.Tr[4].v.y, raw.Tr[5].v.x, raw.Tr[5].v.y);
+        const float m = fmaxf(fmax3(m0, m1, m2), m3);
+        return !__any_sync(0xffffffffu, (m > p.pk.T_sol) || (m >= p.pk.T_liq));
     };
     auto plane_thr = [&](int l) -> float { return (F_NSUB && l < nsub_planes) ? -1.0f : 0.499f; };
 
@@ -323,8 +461,7 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
         const float thr = plane_thr(l);
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-            row_a(so, r, thr, raw.Tr[r], raw.Sr[r], st.Xs[r], st.Xd[r], st.kx[r], st.mx[r], (size_t)l * P,
-                  l >= za && l < zb);
+            row_a(HotTag{}, so, r, thr, raw.Tr[r], raw.Sr[r], st.Xs[r], st.Xd[r], st.kx[r], st.mx[r]);
             if (r >= 1 && r <= RY) st.T[r - 1] = raw.Tr[r];
         }
         bookkeep(l, 0);
@@ -363,8 +500,8 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
 
     // ---- plane l: node state, x stage, then the element layer (l-1, l) row by row; finalises plane l-1
     //      when do_final.  pv = state of plane l-1, cu <- state of plane l.
-    auto step_plane = [&](int l, const K3Raw<RY>& raw, const K3State<RY>& pv, K3State<RY>& cu, bool do_final, f2 sz,
-                          int slot) {
+    auto step_plane = [&](auto cold, int l, const K3Raw<RY>& raw, const K3State<RY>& pv, K3State<RY>& cu, bool do_final,
+                          f2 sz, int slot) {
         const int f = l - 1;
         const size_t pl = (size_t)l * P;
         char* so = F_S1 ? (char*)(p.S1out + pl) : nullptr;
@@ -379,7 +516,7 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
             f2 xs, xd, kxr, mxr;
-            row_a(so, r, thr, raw.Tr[r], raw.Sr[r], xs, xd, kxr, mxr, pl, l >= za && l < zb);
+            row_a(cold, so, r, thr, raw.Tr[r], raw.Sr[r], xs, xd, kxr, mxr);
             cu.Xs[r] = xs; cu.Xd[r] = xd; cu.kx[r] = kxr; cu.mx[r] = mxr;
             if (r >= 1 && r <= RY) cu.T[r - 1] = raw.Tr[r];
             // z stage of the analysis
@@ -418,7 +555,19 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
             zl00 = zu00; zl01 = zu01; zl10 = zu10; zl11 = zu11; kzl = kzu; mzl = mzu;
             bl01 = bu01; bl10 = bu10; bl11 = bu11;
         }
+        if (decltype(cold)::value) flush_state(l);
         bookkeep(l, slot);
+    };
+    const bool allow_cold = !(p.flags & GOMELT_STEP_NO_COLD_PLANES);
+    auto run_plane = [&](int l, const K3Raw<RY>& raw, const K3State<RY>& pv, K3State<RY>& cu, bool do_final, f2 sz,
+                         int slot) {
+        if constexpr (USE_COLD) {
+            if (allow_cold && plane_is_cold(raw)) {
+                step_plane(ColdTag{}, l, raw, pv, cu, do_final, sz, slot);
+                return;
+            }
+        }
+        step_plane(HotTag{}, l, raw, pv, cu, do_final, sz, slot);
     };
 
     // ---- the chunk's source z-factors live in shared memory (see v2) ---------------------------------
@@ -480,25 +629,54 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
 
     int fdone = za;  // planes [za, fdone) are finalised
     if (lfirst <= llast) {
-        K3Raw<RY> rawA, rawB;
         K3State<RY> stA, stB;
-        load_plane(lfirst, rawA);
-        if (lfirst + 1 <= llast) load_plane(lfirst + 1, rawB);
-        first_plane(lfirst, rawA, stA);
-        // main loop, unrolled by two so the carried state ping-pongs: (stA, rawB) -> stB, (stB, rawA) -> stA
-        // plane 0 is the Dirichlet bottom face: never finalised (l - 1 >= 1)
-        for (int l = lfirst + 1; l <= llast; l += 2) {
-            if (l + 1 <= llast) load_plane(l + 1, rawA);
-            if (F_PF && l + 3 <= llast) l2_prefetch(l + 3);
-            step_plane(l, rawB, stA, stB, l - 1 >= max(za, 1), sfx * splat(srcz_at(l - 1)), 0);
-            if (l + 1 > llast) break;
-            if (l + 2 <= llast) load_plane(l + 2, rawB);
-            if (F_PF && l + 4 <= llast) l2_prefetch(l + 4);
-            step_plane(l + 1, rawA, stB, stA, l >= max(za, 1), sfx * splat(srcz_at(l)), 1);
-        }
-        if (llast >= za && llast < zb) {
-            if (((llast - lfirst) & 1) != 0) last_plane(llast, stB.T, rawB);  // parity of the plane held in stB
-            else last_plane(llast, stA.T, rawA);
+        if constexpr (F_TMA) {
+            if (lane == 0) {
+#pragma unroll
+                for (int s = 0; s < NS; ++s) mbar_init(smem_u32(&s_bar[s]), 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncwarp();
+            K3Raw<RY> raw;
+            ring_issue(lfirst);
+            ring_issue(lfirst + 1);
+            ring_issue(lfirst + 2);
+            ring_issue(lfirst + 3);
+            ring_fetch(lfirst, raw);
+            first_plane(lfirst, raw, stA);
+            for (int l = lfirst + 1; l <= llast; l += 2) {
+                ring_issue(l + 3);  // into the stage plane l - 1 has just left
+                ring_fetch(l, raw);
+                run_plane(l, raw, stA, stB, l - 1 >= max(za, 1), sfx * splat(srcz_at(l - 1)), 0);
+                if (l + 1 > llast) break;
+                ring_issue(l + 4);
+                ring_fetch(l + 1, raw);
+                run_plane(l + 1, raw, stB, stA, l >= max(za, 1), sfx * splat(srcz_at(l)), 1);
+            }
+            if (llast >= za && llast < zb) {  // raw holds plane llast
+                if (((llast - lfirst) & 1) != 0) last_plane(llast, stB.T, raw);
+                else last_plane(llast, stA.T, raw);
+            }
+        } else {
+            K3Raw<RY> rawA, rawB;
+            load_plane(lfirst, rawA);
+            if (lfirst + 1 <= llast) load_plane(lfirst + 1, rawB);
+            first_plane(lfirst, rawA, stA);
+            // main loop, unrolled by two so the carried state ping-pongs: (stA, rawB) -> stB, (stB, rawA) -> stA
+            // plane 0 is the Dirichlet bottom face: never finalised (l - 1 >= 1)
+            for (int l = lfirst + 1; l <= llast; l += 2) {
+                if (l + 1 <= llast) load_plane(l + 1, rawA);
+                if (F_PF && l + 3 <= llast) l2_prefetch(l + 3);
+                run_plane(l, rawB, stA, stB, l - 1 >= max(za, 1), sfx * splat(srcz_at(l - 1)), 0);
+                if (l + 1 > llast) break;
+                if (l + 2 <= llast) load_plane(l + 2, rawB);
+                if (F_PF && l + 4 <= llast) l2_prefetch(l + 4);
+                run_plane(l + 1, rawA, stB, stA, l >= max(za, 1), sfx * splat(srcz_at(l)), 1);
+            }
+            if (llast >= za && llast < zb) {
+                if (((llast - lfirst) & 1) != 0) last_plane(llast, stB.T, rawB);  // parity of the plane held in stB
+                else last_plane(llast, stA.T, rawA);
+            }
         }
         fdone = max(za, llast + 1);
         flush_bookkeeping();

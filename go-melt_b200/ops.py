@@ -5,6 +5,7 @@ import ctypes as C
 
 from . import _lib
 from ._lib import (STEP_ACCUM, STEP_BC_CONST, STEP_CLAMP, STEP_FUSED_FLUX, STEP_GENERAL_KERNEL,  # noqa: F401
+                   STEP_NO_COLD_PLANES,
                    STEP_SKIP_FACES,
                    STEP_WRITE_S1, STEP_WRITE_S2)
 

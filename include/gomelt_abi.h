@@ -74,6 +74,9 @@ typedef struct gomelt_props {
 #define GOMELT_STEP_GENERAL_KERNEL 0x80 /* run the general (natural-boundary capable) kernel even when the call
                                         qualifies for the Dirichlet-side-face fast kernel; results agree to f32
                                         rounding (tests A/B the two kernels through this bit)               */
+#define GOMELT_STEP_NO_COLD_PLANES 0x100 /* fast kernel: evaluate the general property selects on every plane,
+                                        also where the warp voted "nothing above the solidus" (bit-identical
+                                        results; tests and timings A/B the cold-plane path through this bit) */
 
 typedef struct gomelt_step_args {
     gomelt_grid_t grid;

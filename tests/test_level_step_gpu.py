@@ -573,8 +573,9 @@ def test_fast_kernel_in_place_state_on_a_mostly_cold_field(gm, example_props, el
 
     Tc, Sc = run(0, False)
     Ti, Si = run(0, True)
+    Tih, Sih = run(ops.STEP_NO_COLD_PLANES, True)  # general property selects on every plane
     Tg, Sg = run(ops.STEP_GENERAL_KERNEL, False)
-    assert np.array_equal(Tc, Ti)
+    assert np.array_equal(Tc, Ti) and np.array_equal(Tc, Tih) and np.array_equal(Sih, Sc)
     assert np.array_equal(Si, Sc)  # -0.0 == 0.0: an unchanged node may keep its bits in place
     assert np.array_equal(Sc, Sg)
     face = _faces_mask(nx, ny, nz).ravel()

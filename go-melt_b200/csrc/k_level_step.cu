@@ -108,7 +108,7 @@ static void launch_v3(const StepParams& sp, int nch, cudaStream_t st) {
 static bool try_launch_v3(StepParams& sp, int nch, cudaStream_t st) {
     static const int off = env_int("GOMELT_K1_V2", 0);  // dev A/B: force the v2 path
     static const int pf = env_int("GOMELT_K1_PF", 0);
-    static const int tma = env_int("GOMELT_K1_TMA", 0);
+    static const int tma = env_int("GOMELT_K1_TMA", 1);
     constexpr int RY = 4;
     const int f = sp.feat;
     if (off || (sp.flags & GOMELT_STEP_GENERAL_KERNEL) || !(f & (K1F_SKIP | K1F_BCCONST)) ||
@@ -123,30 +123,38 @@ static bool try_launch_v3(StepParams& sp, int nch, cudaStream_t st) {
     constexpr int V3_RHS = K1F_RHS | K1F_FLUX | K1F_CLAMP | K1F_NSUB;                 // Level 2 and Level 1 (step / subcycle)
     constexpr int V3_DWELL = K1F_FLUX | K1F_NSUB;                                     // stepGOMELTDwellTime (no clamp)
     constexpr int V3_DWELL_PEER = V3_DWELL | K1F_PEER;                                // ... with the fused halo stores
+    // The TMA plane ring (+ cold-plane path) needs 16-byte aligned field pointers and the driver's tensor-map encoder;
+    // GOMELT_K1_TMA=0 keeps every shape on the register-prefetch form (A/B).
+    const bool t = tma && make_field_tmaps(sp);
+#define GM_V3(FEATS)                                              \
+    do {                                                          \
+        if (t) launch_v3<RY, (FEATS) | K1F_TMA>(sp, nch, st);     \
+        else launch_v3<RY, (FEATS)>(sp, nch, st);                 \
+    } while (0)
     switch ((f & ~(K1F_SKIP | K1F_BCCONST)) | K1F_NSUB) {
-        case V3_L3_SUB:  // (prefetch: no gain, 53.3 us either way)
-            // in place (the steppers): a node's state is stored only when it changed: 52.2 -> 50.1 us
-            if (sp.S1out == sp.S1 && tma && make_field_tmaps(sp)) launch_v3<RY, V3_L3_SUB | K1F_S1INPLACE | K1F_TMA>(sp, nch, st);
-            else if (sp.S1out == sp.S1) launch_v3<RY, V3_L3_SUB | K1F_S1INPLACE>(sp, nch, st);
-            else launch_v3<RY, V3_L3_SUB>(sp, nch, st);
+        case V3_L3_SUB:
+            // in place (the steppers): a node's state is stored only when it changed
+            if (sp.S1out == sp.S1) GM_V3(V3_L3_SUB | K1F_S1INPLACE);
+            else GM_V3(V3_L3_SUB);
             break;
         case V3_L3_SUB2:
-            if (sp.S1out == sp.S1) launch_v3<RY, V3_L3_SUB2 | K1F_S1INPLACE>(sp, nch, st);
-            else launch_v3<RY, V3_L3_SUB2>(sp, nch, st);
+            if (sp.S1out == sp.S1) GM_V3(V3_L3_SUB2 | K1F_S1INPLACE);
+            else GM_V3(V3_L3_SUB2);
             break;
-        case V3_L3_STEP: launch_v3<RY, V3_L3_STEP>(sp, nch, st); break;
-        case V3_RHS: launch_v3<RY, V3_RHS>(sp, nch, st); break;        // (prefetch: 57.3 -> 61.5 us, off)
-        // The dwell shapes (few planes per warp, several waves of warps) are latency-bound; pulling the plane three
-        // ahead into L2 (prefetch.global.L2) takes a 25 M-node sweep from 121.7 to 111.6 us on cudaMalloc memory -
-        // but on peer-mapped symmetric memory (the multi-GPU slabs) the same instruction costs 5.7 ms per sweep
-        // (measured at 4 and 8 GPUs), so it is opt-in (GOMELT_K1_PF=1) and never used with peer pointers.
+        case V3_L3_STEP: GM_V3(V3_L3_STEP); break;
+        case V3_RHS: launch_v3<RY, V3_RHS>(sp, nch, st); break;  // (TMA ring: 59.4 -> 63.0 us - the rhs rows would have to ride the ring too)
+        // The dwell shapes (few planes per warp, several waves of warps) are latency-bound.  An L2 prefetch three
+        // planes ahead (prefetch.global.L2, opt-in GOMELT_K1_PF=1) took a 25 M-node sweep from 121.7 to 111.6 us on
+        // one box, but the same instruction has been seen to cost ~4.5 ns EACH, serialised (5.7 ms per sweep on
+        // peer-mapped symmetric memory, 1.2-2.4 ms per 10 M-node sweep on plain cudaMalloc memory of another box).
         case V3_DWELL:
             if (pf) launch_v3<RY, V3_DWELL | K1F_PF>(sp, nch, st);
-            else launch_v3<RY, V3_DWELL>(sp, nch, st);
+            else GM_V3(V3_DWELL);
             break;
-        case V3_DWELL_PEER: launch_v3<RY, V3_DWELL_PEER>(sp, nch, st); break;
+        case V3_DWELL_PEER: GM_V3(V3_DWELL_PEER); break;
         default: return false;
     }
+#undef GM_V3
     if (f & K1F_BCCONST) {
         const long long n = (long long)(2 * sp.nx + 2 * sp.ny) * (sp.zend - sp.zbeg) + (sp.zbeg == 0 ? (long long)sp.nx * sp.ny : 0);
         const int blocks = (int)((n + 255) / 256 < 4 * GOMELT_SM_COUNT ? (n + 255) / 256 : 4 * GOMELT_SM_COUNT);

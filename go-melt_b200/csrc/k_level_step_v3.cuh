@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     const int row0 = (j0 - 1) * nx + c0;  // in-plane element of the tile's first loaded row, column c0
     const int Sq = nx & ~3, dq = nx & 3;
     const int nn_all = P * nz;
+    static_assert((NS & (NS - 1)) == 0, "stage = plane & (NS - 1)");
     auto ring_issue = [&](int l) {
         if (l > llast) return;
         const int s = (l - lfirst) & (NS - 1);
@@ -580,8 +581,15 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
 
     // ---- computeConvRadBC cF:2207-2301 fused (see v2): every element of the tile exists here ----------
     auto fused_top_flux = [&](const K3Raw<RY>& raw, f2* fl) {
-        __shared__ float2 sT[NR][32];
-        __shared__ float2 sA[RY + 1][4][32];
+        // staging: 6.5 KB of its own, or - with the TMA ring - the ring itself: the top plane is the last one, every
+        // stage has been read by then and nothing is in flight
+        __shared__ float2 sT_own[F_TMA ? 1 : NR][F_TMA ? 1 : 32];
+        __shared__ float2 sA_own[F_TMA ? 1 : RY + 1][F_TMA ? 1 : 4][F_TMA ? 1 : 32];
+        static_assert(!F_TMA || sizeof(float2) * 32 * (NR + 4 * (RY + 1)) <= sizeof(float) * 2 * 2 * NR * K3_BOX, "ring too small");
+        float2(*sT)[32] = F_TMA ? reinterpret_cast<float2(*)[32]>(&s_ring[0][0][0][0]) : reinterpret_cast<float2(*)[32]>(&sT_own[0][0]);
+        float2(*sA)[4][32] = F_TMA ? reinterpret_cast<float2(*)[4][32]>(&s_ring[0][0][0][0] + 2 * 32 * NR)
+                                   : reinterpret_cast<float2(*)[4][32]>(&sA_own[0][0][0]);
+        __syncwarp();
 #pragma unroll
         for (int r = 0; r < NR; ++r) sT[r][lane] = raw.Tr[r].v;
         __syncwarp();
@@ -638,18 +646,16 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
             }
             __syncwarp();
             K3Raw<RY> raw;
-            ring_issue(lfirst);
-            ring_issue(lfirst + 1);
-            ring_issue(lfirst + 2);
-            ring_issue(lfirst + 3);
+#pragma unroll
+            for (int q = 0; q < NS; ++q) ring_issue(lfirst + q);
             ring_fetch(lfirst, raw);
             first_plane(lfirst, raw, stA);
             for (int l = lfirst + 1; l <= llast; l += 2) {
-                ring_issue(l + 3);  // into the stage plane l - 1 has just left
+                ring_issue(l + NS - 1);  // into the stage plane l - 1 has just left
                 ring_fetch(l, raw);
                 run_plane(l, raw, stA, stB, l - 1 >= max(za, 1), sfx * splat(srcz_at(l - 1)), 0);
                 if (l + 1 > llast) break;
-                ring_issue(l + 4);
+                ring_issue(l + NS);
                 ring_fetch(l + 1, raw);
                 run_plane(l + 1, raw, stB, stA, l >= max(za, 1), sfx * splat(srcz_at(l)), 1);
             }

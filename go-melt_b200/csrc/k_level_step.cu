@@ -126,12 +126,20 @@ static bool try_launch_v3(StepParams& sp, int nch, cudaStream_t st) {
     // The TMA plane ring (+ cold-plane path) needs 16-byte aligned field pointers and the driver's tensor-map encoder;
     // GOMELT_K1_TMA=0 keeps every shape on the register-prefetch form (A/B).
     const bool t = tma && make_field_tmaps(sp);
+    // z-slab ranks: the boundary planes go to the neighbours by halo_push_kernel after the step (GOMELT_K1_PEER_PUSH=0:
+    // stored from inside the stencil kernel, K1F_PEER)
+    static const int push = env_int("GOMELT_K1_PEER_PUSH", 1);
+    float* const push_lo = sp.peer_lo;
+    float* const push_hi = sp.peer_hi;
+    const bool do_push = push && (f & K1F_PEER) && (sp.zend - sp.zbeg) >= 1;
+    int fsw = (f & ~(K1F_SKIP | K1F_BCCONST)) | K1F_NSUB;
+    if (do_push) fsw &= ~K1F_PEER;
 #define GM_V3(FEATS)                                              \
     do {                                                          \
         if (t) launch_v3<RY, (FEATS) | K1F_TMA>(sp, nch, st);     \
         else launch_v3<RY, (FEATS)>(sp, nch, st);                 \
     } while (0)
-    switch ((f & ~(K1F_SKIP | K1F_BCCONST)) | K1F_NSUB) {
+    switch (fsw) {
         case V3_L3_SUB:
             // in place (the steppers): a node's state is stored only when it changed
             if (sp.S1out == sp.S1) GM_V3(V3_L3_SUB | K1F_S1INPLACE);
@@ -160,6 +168,11 @@ static bool try_launch_v3(StepParams& sp, int nch, cudaStream_t st) {
         const int blocks = (int)((n + 255) / 256 < 4 * GOMELT_SM_COUNT ? (n + 255) / 256 : 4 * GOMELT_SM_COUNT);
         face_const_kernel<<<blocks, 256, 0, st>>>(sp.Tout, sp.nx, sp.ny, sp.nz, sp.zbeg, sp.zend, sp.bc[0], sp.bc[1], sp.bc[2],
                                                   sp.bc[3], sp.bc[4], sp.peer_lo, sp.peer_hi), count_launch();
+    }
+    if (do_push) {
+        const int plane = sp.nx * sp.ny;
+        dim3 grid((plane / 4 + 255) / 256, 2);
+        halo_push_kernel<<<grid, 256, 0, st>>>(sp.Tout, plane, sp.zbeg, sp.zend - 1, push_lo, push_hi), count_launch();
     }
     return true;
 }

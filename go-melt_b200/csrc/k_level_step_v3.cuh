@@ -726,4 +726,28 @@ __global__ void face_const_kernel(float* __restrict__ T, int nx, int ny, int nz,
     }
 }
 
+// Fused-halo push for a z-slab rank: the first / last owned plane of T_out (faces included) copied into the lower /
+// upper neighbour's ghost plane in peer-mapped memory.  Every thread stores one 16-byte quad that is aligned on the
+// DESTINATION side (the source is read with four scalar loads, it is L2-resident and arbitrarily misaligned relative
+// to it), so a warp puts 512 contiguous, aligned bytes on NVLink per store; the ragged head and tail of the plane go
+// as scalars.  The 120-byte row segments stored from inside the stencil kernel (K1F_PEER) cost 13-20 us per sweep
+// once the TMA ring no longer leaves load stalls to hide them in.
+__global__ void halo_push_kernel(const float* __restrict__ T, int plane, int zlo, int zhi, float* __restrict__ peer_lo,
+                                 float* __restrict__ peer_hi) {
+    const float* src = blockIdx.y == 0 ? T + (size_t)zlo * plane : T + (size_t)zhi * plane;
+    float* dst = blockIdx.y == 0 ? peer_lo : peer_hi;
+    if (!dst) return;
+    const int head = (int)((4u - (((uintptr_t)dst >> 2) & 3u)) & 3u);  // scalars before the first aligned quad
+    const int nquad = (plane - head) / 4;
+    const long long t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    for (long long q = t0; q < nquad; q += stride) {
+        const long long i = head + 4 * q;
+        const float4 v = make_float4(__ldcg(src + i), __ldcg(src + i + 1), __ldcg(src + i + 2), __ldcg(src + i + 3));
+        *reinterpret_cast<float4*>(dst + i) = v;
+    }
+    if (t0 < head) dst[t0] = __ldcg(src + t0);
+    const int tail0 = head + 4 * nquad;
+    if (t0 < plane - tail0) dst[tail0 + t0] = __ldcg(src + tail0 + t0);
+}
+
 }  // namespace gomelt

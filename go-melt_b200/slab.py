@@ -89,7 +89,8 @@ class Level1Slab:
             # one symmetric allocation of two halves (T and T_next), sized for the largest slab so that
             # every rank's layout is the same; half h of rank q starts at ptrs[q] + 4 * h * nmax
             parts = partition_planes(nz, world)
-            self._nmax = self.plane * (max(b - a for a, b in parts) + 2)
+            # (rounded up to 128 bytes: K1's TMA plane ring wants 16-byte aligned field pointers for both halves)
+            self._nmax = -(-self.plane * (max(b - a for a, b in parts) + 2) // 32) * 32
             self._buf = symm_mem.empty(2 * self._nmax, dtype=torch.float32, device=device)
             self._hdl = symm_mem.rendezvous(self._buf, dist.group.WORLD.group_name)
             self._ptrs = [int(q) for q in self._hdl.buffer_ptrs]

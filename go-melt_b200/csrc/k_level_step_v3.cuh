@@ -86,6 +86,12 @@ GM_DI void mbar_wait(unsigned bar, unsigned parity) {
                  "@!P1 bra WAIT_%=;\n\t}" ::"r"(bar), "r"(parity)
                  : "memory");
 }
+template <unsigned OFF>
+GM_DI float lds_f32(unsigned addr) {  // ordered with the mbarrier wait before it (both volatile)
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
 GM_DI bool elect_one() {  // one lane of the (converged) warp; lets the compiler keep the TMA operands in uniform registers
     unsigned pred;
     asm volatile("{\n\t.reg .pred P1;\n\t"
@@ -289,35 +295,43 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     const int Sq = nx & ~3, dq = nx & 3;
     const int nn_all = P * nz;
     static_assert((NS & (NS - 1)) == 0, "stage = plane & (NS - 1)");
+    // shared-window addresses and the running plane element are formed once (every cvta costs an S2UR + ULEA pair)
+    // (laundered through an opaque move: the compiler otherwise rematerialises the conversion at every use)
+    unsigned ring0 = F_TMA ? smem_u32(&s_ring[0][0][0][0]) : 0u, bar0 = F_TMA ? smem_u32(&s_bar[0]) : 0u;
+    if (F_TMA) asm volatile("mov.b32 %0, %0;\n\tmov.b32 %1, %1;" : "+r"(ring0), "+r"(bar0));
+    constexpr unsigned STAGE_B = 2u * NR * RW * 4u, FIELD_B = NR * RW * 4u;
+    const int a_max = nn_all - (NR - 1) * Sq - RW;  // last box start whose six rows stay inside the array
+    const bool use2d = p.tm2_ok != 0;
+    const unsigned row_pitch = 4u * (unsigned)(RW + dq);  // bytes from a tile row to the next inside a stage
     auto ring_issue = [&](int l) {
         if (l > llast) return;
-        const int s = (l - lfirst) & (NS - 1);
+        const unsigned s = (unsigned)(l - lfirst) & (NS - 1);
         __syncwarp();  // every lane has read what the stage held before
         if (elect_one()) {
-            const unsigned bar = smem_u32(&s_bar[s]);
-            mbar_expect_tx(bar, 2u * NR * RW * 4u);
+            const unsigned bar = bar0 + 8u * s, dst = ring0 + STAGE_B * s;
+            mbar_expect_tx(bar, STAGE_B);
             const int a = (l * P + row0) & ~3;
-            if (p.tm2_ok && a + (NR - 1) * Sq + RW <= nn_all) {
-                tma_load_box2(smem_u32(&s_ring[s][0][0][0]), &p.tm2[0], a, bar);
-                tma_load_box2(smem_u32(&s_ring[s][1][0][0]), &p.tm2[1], a, bar);
+            if (use2d && a <= a_max) {
+                tma_load_box2(dst, &p.tm2[0], a, bar);
+                tma_load_box2(dst + FIELD_B, &p.tm2[1], a, bar);
             } else {
 #pragma unroll 1
                 for (int r = 0; r < NR; ++r) {
-                    tma_load_row(smem_u32(&s_ring[s][0][r][0]), &p.tm[0], a + r * Sq, bar);
-                    tma_load_row(smem_u32(&s_ring[s][1][r][0]), &p.tm[1], a + r * Sq, bar);
+                    tma_load_row(dst + RW * 4u * r, &p.tm[0], a + r * Sq, bar);
+                    tma_load_row(dst + FIELD_B + RW * 4u * r, &p.tm[1], a + r * Sq, bar);
                 }
             }
         }
     };
     auto ring_fetch = [&](int l, K3Raw<RY>& raw) {
-        const int k = l - lfirst, s = k & (NS - 1);
-        mbar_wait(smem_u32(&s_bar[s]), (unsigned)(k / NS) & 1u);
-        const float* b = &s_ring[s][0][0][((l * P + row0) & 3) + lane];
+        const unsigned k = (unsigned)(l - lfirst), s = k & (NS - 1);
+        mbar_wait(bar0 + 8u * s, (k / NS) & 1u);
+        const unsigned b = ring0 + STAGE_B * s + 4u * (unsigned)(((l * P + row0) & 3) + lane);
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-            const float* bT = b + r * (RW + dq);
-            raw.Tr[r] = mk2(bT[0], bT[K1_TX]);
-            raw.Sr[r] = mk2(bT[NR * RW], bT[NR * RW + K1_TX]);
+            const unsigned q = b + (unsigned)r * row_pitch;
+            raw.Tr[r] = mk2(lds_f32<0>(q), lds_f32<4 * K1_TX>(q));
+            raw.Sr[r] = mk2(lds_f32<FIELD_B>(q), lds_f32<FIELD_B + 4 * K1_TX>(q));
         }
     };
 
@@ -641,7 +655,7 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
         if constexpr (F_TMA) {
             if (lane == 0) {
 #pragma unroll
-                for (int s = 0; s < NS; ++s) mbar_init(smem_u32(&s_bar[s]), 1);
+                for (int s = 0; s < NS; ++s) mbar_init(bar0 + 8u * s, 1);
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             }
             __syncwarp();

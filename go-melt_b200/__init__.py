@@ -10,7 +10,7 @@ from ._lib import GomeltError, load  # noqa: F401
 
 __all__ = ["build", "ops", "schema", "load", "GomeltError"]
 
-_LAZY = ("slab",)  # sub-modules that import torch at module level
+_LAZY = ("slab", "hostpipe")  # sub-modules that import torch at module level
 
 
 def __getattr__(name):

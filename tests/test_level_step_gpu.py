@@ -585,3 +585,42 @@ def test_fast_kernel_in_place_state_on_a_mostly_cold_field(gm, example_props, el
     Tref = np.maximum(np.float32(P["T_amb"]), Tref)
     assert _rel(Tc[~face], Tref[~face]) <= RTOL
     assert np.array_equal(Sc, S1ref)
+
+
+def test_host_block_pipeline_equals_device_blocks(gm, example_props):
+    """hostpipe.HostBlockPipeline (host buffers, two blocks in flight on three streams) returns, for every block,
+    exactly what the same gomelt_l3_substeps_f32 call returns on device-resident fields."""
+    import torch
+
+    ops = gm.ops
+    elements = (75, 23, 7)
+    bounds = ((0.0, 1.5), (0.0, 0.46), (-0.14, 0.0))
+    P, lv, T0, S1, nsub = _setup(gm, example_props, elements, bounds, 41, nsub_planes=2)
+    props = gm._lib.make_props(P)
+    grid = gm._lib.make_grid(lv["nodes"], lv["h"])
+    nx, ny, nz = lv["nodes"]
+    coords = [_dev(c) for c in lv["node_coords"]]
+    n = 5
+    flags = ops.STEP_CLAMP  # natural boundaries: every node of every substep is defined by the block's own input
+    pipe = gm.hostpipe.HostBlockPipeline(ops, props, grid, coords, depth=2, n_rows=n, n_substrate=nsub, flags=flags)
+    rng = np.random.default_rng(3)
+    jobs = []
+    for j in range(5):
+        rows = np.zeros((n, 7), np.float32)
+        for i in range(n):
+            rows[i] = (0.5 + 0.05 * j + 0.01 * i, 0.23, 0.0, 1, 1, 1e-5, 285.0)
+        Tj = (T0 * (0.6 + 0.1 * j)).astype(np.float32)
+        Sj = (rng.random(lv["nn"]) > 0.4).astype(np.float32)
+        hT, hS = torch.as_tensor(Tj).pin_memory(), torch.as_tensor(Sj).pin_memory()
+        oT, oS = torch.empty(lv["nn"]).pin_memory(), torch.empty(lv["nn"]).pin_memory()
+        pipe.submit(hT, hS, rows, oT, oS)
+        jobs.append((rows, Tj, Sj, oT, oS))
+    pipe.drain()
+    tables = torch.empty(n * (nx + ny + nz), device="cuda")
+    for rows, Tj, Sj, oT, oS in jobs:
+        A, S = _dev(Tj), _dev(Sj)
+        B = torch.empty_like(A)
+        last = ops.l3_substeps(props, grid, coords, rows, A, B, A, S, tables, n_substrate=nsub, flags=flags)
+        torch.cuda.synchronize()
+        assert np.array_equal(oT.numpy(), last.cpu().numpy())
+        assert np.array_equal(oS.numpy(), S.cpu().numpy())

@@ -303,17 +303,20 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     const int a_max = nn_all - (NR - 1) * Sq - RW;  // last box start whose six rows stay inside the array
     const bool use2d = p.tm2_ok != 0;
     const unsigned row_pitch = 4u * (unsigned)(RW + dq);  // bytes from a tile row to the next inside a stage
+    // descriptor addresses (generic addresses of the __grid_constant__ parameter), formed once as well
+    unsigned long long d2T = (unsigned long long)&p.tm2[0], d2S = (unsigned long long)&p.tm2[1];
+    if (F_TMA) asm volatile("mov.b64 %0, %0;\n\tmov.b64 %1, %1;" : "+l"(d2T), "+l"(d2S));
     auto ring_issue = [&](int l) {
         if (l > llast) return;
         const unsigned s = (unsigned)(l - lfirst) & (NS - 1);
-        __syncwarp();  // every lane has read what the stage held before
+        // (no __syncwarp: the stage was last read a whole plane ago, and the votes since then are warp-wide)
         if (elect_one()) {
             const unsigned bar = bar0 + 8u * s, dst = ring0 + STAGE_B * s;
             mbar_expect_tx(bar, STAGE_B);
             const int a = (l * P + row0) & ~3;
             if (use2d && a <= a_max) {
-                tma_load_box2(dst, &p.tm2[0], a, bar);
-                tma_load_box2(dst + FIELD_B, &p.tm2[1], a, bar);
+                tma_load_box2(dst, (const void*)d2T, a, bar);
+                tma_load_box2(dst + FIELD_B, (const void*)d2S, a, bar);
             } else {
 #pragma unroll 1
                 for (int r = 0; r < NR; ++r) {

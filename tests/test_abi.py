@@ -59,3 +59,13 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_step_flag_values_match_the_header(gm):
+    """The GOMELT_STEP_* bits of include/gomelt_abi.h and the STEP_* constants of the Python binding are one table."""
+    txt = open(os.path.join(ROOT, "include", "gomelt_abi.h")).read()
+    header = {m.group(1): int(m.group(2), 16) for m in re.finditer(r"#define\s+GOMELT_STEP_([A-Z0-9_]+)\s+(0x[0-9a-fA-F]+)", txt)}
+    assert {"CLAMP", "WRITE_S1", "SKIP_FACES", "GENERAL_KERNEL", "NO_COLD_PLANES"} <= set(header)
+    for name, value in header.items():
+        assert getattr(gm._lib, "STEP_" + name) == value, name
+    assert len(set(header.values())) == len(header)  # no two flags share a bit

@@ -213,9 +213,9 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     constexpr bool F_S2 = (FEAT & K1F_S2OUT) != 0, F_ACC = (FEAT & K1F_ACCUM) != 0;
     constexpr bool F_PEER = (FEAT & K1F_PEER) != 0, F_PF = (FEAT & K1F_PF) != 0, F_INPLACE = (FEAT & K1F_S1INPLACE) != 0;
     constexpr bool F_TMA = (FEAT & K1F_TMA) != 0;
-    // the cold-plane path needs the whole plane before its first row, i.e. the TMA ring (see plane_is_cold); the
-    // corrector substeps keep the general selects (their bookkeeping votes on the liquidus after the rows)
-    constexpr bool USE_COLD = F_TMA && !(F_S2 || F_ACC);
+    // the cold-plane path needs the whole plane before its first row, i.e. the TMA ring (see plane_is_cold); in the
+    // corrector substeps a plane that took it also needs no vote on the liquidus for its melt-time bookkeeping
+    constexpr bool USE_COLD = F_TMA;
     constexpr int NS = K3_NS;
     const int lane = threadIdx.x;
     const int nx = p.nx, ny = p.ny, nz = p.nz, nzl = p.nzl;
@@ -365,12 +365,16 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     // melt-pool warps are the tail of a single-wave kernel, and there the registers of the carried state are free,
     // so every load of a hot plane can be in flight at once.
     unsigned long long hotmask = 0;
-    auto bookkeep = [&](int l, int) {
+    // known_cold: the plane went through the cold body (plane_is_cold: nothing above the solidus, so nothing molten)
+    auto bookkeep = [&](int l, bool known_cold) {
         if (!(F_S2 || F_ACC)) return;
-        const float hot = fmaxf(tmax.v.x, tmax.v.y);
-        tmax = splat(0.f);
         const int mine = (l >= za && l < zb) ? 1 : 0;  // a chunk's halo plane belongs to the neighbouring chunk
-        const int cold = __any_sync(0xffffffffu, hot >= p.pk.T_liq) ? 0 : mine;
+        int cold = mine;
+        if (!known_cold) {
+            const float hot = fmaxf(tmax.v.x, tmax.v.y);
+            tmax = splat(0.f);
+            cold = __any_sync(0xffffffffu, hot >= p.pk.T_liq) ? 0 : mine;
+        }
         hotmask |= (unsigned long long)(mine & ~cold & 1) << (l - lfirst);
         if (F_S2) {
             const size_t pl = (size_t)l * P;
@@ -432,7 +436,7 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
                 st2(so + off[r], sa, sb, s1f);
         }
         // the corrector substeps (subcycleL3_Part2) track the plane's maximum: bookkeep() votes on it after the rows
-        if (F_S2 || F_ACC) tmax = mk2(fmaxf(tmax.v.x, T.v.x), fmaxf(tmax.v.y, T.v.y));
+        if ((F_S2 || F_ACC) && !COLD) tmax = mk2(fmaxf(tmax.v.x, T.v.x), fmaxf(tmax.v.y, T.v.y));
         const f2 Tr = shdn(T), kr = shdn(kn), mr = shdn(mn);
         xs = Tr + T;
         xd = Tr - T;
@@ -574,7 +578,7 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
             bl01 = bu01; bl10 = bu10; bl11 = bu11;
         }
         if (decltype(cold)::value) flush_state(l);
-        bookkeep(l, slot);
+        bookkeep(l, decltype(cold)::value);
     };
     const bool allow_cold = !(p.flags & GOMELT_STEP_NO_COLD_PLANES);
     auto run_plane = [&](int l, const K3Raw<RY>& raw, const K3State<RY>& pv, K3State<RY>& cu, bool do_final, f2 sz,

@@ -150,7 +150,7 @@ static bool try_launch_v3(StepParams& sp, int nch, cudaStream_t st) {
             else GM_V3(V3_L3_SUB2);
             break;
         case V3_L3_STEP: GM_V3(V3_L3_STEP); break;
-        case V3_RHS: launch_v3<RY, V3_RHS>(sp, nch, st); break;  // (TMA ring: 59.4 -> 63.0 us - the rhs rows would have to ride the ring too)
+        case V3_RHS: GM_V3(V3_RHS); break;  // (the rhs rows are fetched a plane ahead into registers there)
         // The dwell shapes (few planes per warp, several waves of warps) are latency-bound.  An L2 prefetch three
         // planes ahead (prefetch.global.L2, opt-in GOMELT_K1_PF=1) took a 25 M-node sweep from 121.7 to 111.6 us on
         // one box, but the same instruction has been seen to cost ~4.5 ns EACH, serialised (5.7 ms per sweep on

@@ -500,15 +500,16 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     };
 
     // use_fl is a literal at every call site (the lambdas are inlined): only the top plane carries a flux
-    auto final_row = [&](int f, char* out, const char* rhs, int r, f2 sz, f2 Tf, f2 z0, f2 z1, f2 mz, bool use_fl,
-                         f2 fl) {
+    // rq: the plane's rhs rows prefetched a plane ahead (TMA variant), or nullptr: loaded here
+    auto final_row = [&](int f, char* out, const char* rhs, const f2* rq, int r, f2 sz, f2 Tf, f2 z0, f2 z1, f2 mz,
+                         bool use_fl, f2 fl) {
         const f2 nKT = (z1 - z0) - shup(z0 + z1);  // minus the stiffness action on this node
         const f2 mnode = mz + shup(mz);
         const f2 rc = mk2(rcp_approx(mnode.v.x), rcp_approx(mnode.v.y));
         // normalised form: T_new = T + (rr / s - KT / s) / (mnode / (cdt s)); rc is the reciprocal of the latter
         if (F_RHS || F_SRC || (F_FLUX && use_fl)) {
             f2 rr = nKT;
-            if (F_RHS) rr = fma2(ld2u(rhs + off[r + 1]), splat(p.n_inv_s), rr);
+            if (F_RHS) rr = fma2(rq ? rq[r] : ld2u(rhs + off[r + 1]), splat(p.n_inv_s), rr);
             if (F_SRC) rr = fma2(sz, splat(sfy[r]), rr);
             if (F_FLUX && use_fl) rr = rr + fl;
             store_row(f, out, r, fma2(rr, rc, Tf));
@@ -523,7 +524,7 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     // ---- plane l: node state, x stage, then the element layer (l-1, l) row by row; finalises plane l-1
     //      when do_final.  pv = state of plane l-1, cu <- state of plane l.
     auto step_plane = [&](auto cold, int l, const K3Raw<RY>& raw, const K3State<RY>& pv, K3State<RY>& cu, bool do_final,
-                          f2 sz, int slot) {
+                          f2 sz, const f2* rq) {
         const int f = l - 1;
         const size_t pl = (size_t)l * P;
         char* so = F_S1 ? (char*)(p.S1out + pl) : nullptr;
@@ -564,7 +565,7 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
                     const f2 my = cm + m8;
                     const f2 mz = myp[e - 1] + my;
                     myp[e - 1] = my;
-                    final_row(f, out, rhs, e - 1, sz, pv.T[e - 1], z0, z1, mz, false, splat(0.f));
+                    final_row(f, out, rhs, rq, e - 1, sz, pv.T[e - 1], z0, z1, mz, false, splat(0.f));
                 }
                 if (e < RY) {
                     c00 = q00;
@@ -582,14 +583,22 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     };
     const bool allow_cold = !(p.flags & GOMELT_STEP_NO_COLD_PLANES);
     auto run_plane = [&](int l, const K3Raw<RY>& raw, const K3State<RY>& pv, K3State<RY>& cu, bool do_final, f2 sz,
-                         int slot) {
+                         const f2* rq) {
         if constexpr (USE_COLD) {
             if (allow_cold && plane_is_cold(raw)) {
-                step_plane(ColdTag{}, l, raw, pv, cu, do_final, sz, slot);
+                step_plane(ColdTag{}, l, raw, pv, cu, do_final, sz, rq);
                 return;
             }
         }
-        step_plane(HotTag{}, l, raw, pv, cu, do_final, sz, slot);
+        step_plane(HotTag{}, l, raw, pv, cu, do_final, sz, rq);
+    };
+    // rhs rows of the owned nodes of plane f, fetched a plane before final_row needs them (TMA variant: T and S1 no
+    // longer come through the LSU, so these are the only long-latency loads left in the plane body)
+    auto load_rhs = [&](int f, f2* rq) {
+        if (!F_RHS) return;
+        const char* q = (const char*)(p.rhs + (size_t)f * P);
+#pragma unroll
+        for (int r = 0; r < RY; ++r) rq[r] = ld2u(q + off[r + 1]);
     };
 
     // ---- the chunk's source z-factors live in shared memory (see v2) ---------------------------------
@@ -643,7 +652,7 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     };
 
     // ---- last data plane of a chunk top: no layer above, its action is (Tt0, Tt1, myp) --------------
-    auto last_plane = [&](int f, const f2* Tf, const K3Raw<RY>& raw) {
+    auto last_plane = [&](int f, const f2* Tf, const K3Raw<RY>& raw, const f2* rq = nullptr) {
         f2 sz = splat(0.f);
         if (F_SRC) sz = sfx * splat(srcz_at(f));
         f2 fl[RY];
@@ -653,7 +662,7 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
         char* out = (char*)(p.Tout + (size_t)f * P);
         const char* rhs = F_RHS ? (const char*)(p.rhs + (size_t)f * P) : nullptr;
 #pragma unroll
-        for (int r = 0; r < RY; ++r) final_row(f, out, rhs, r, sz, Tf[r], Tt0[r], Tt1[r], myp[r], true, fl[r]);
+        for (int r = 0; r < RY; ++r) final_row(f, out, rhs, rq, r, sz, Tf[r], Tt0[r], Tt1[r], myp[r], true, fl[r]);
     };
 
     int fdone = za;  // planes [za, fdone) are finalised
@@ -669,20 +678,26 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
             K3Raw<RY> raw;
 #pragma unroll
             for (int q = 0; q < NS; ++q) ring_issue(lfirst + q);
+            f2 rqA[RY], rqB[RY];  // rhs rows of the plane finalised by the next step (ping-pong like the state)
+#pragma unroll
+            for (int r = 0; r < RY; ++r) rqA[r] = rqB[r] = splat(0.f);
             ring_fetch(lfirst, raw);
+            load_rhs(lfirst, rqA);
             first_plane(lfirst, raw, stA);
             for (int l = lfirst + 1; l <= llast; l += 2) {
                 ring_issue(l + NS - 1);  // into the stage plane l - 1 has just left
                 ring_fetch(l, raw);
-                run_plane(l, raw, stA, stB, l - 1 >= max(za, 1), sfx * splat(srcz_at(l - 1)), 0);
+                load_rhs(l, rqB);
+                run_plane(l, raw, stA, stB, l - 1 >= max(za, 1), sfx * splat(srcz_at(l - 1)), F_RHS ? rqA : nullptr);
                 if (l + 1 > llast) break;
                 ring_issue(l + NS);
                 ring_fetch(l + 1, raw);
-                run_plane(l + 1, raw, stB, stA, l >= max(za, 1), sfx * splat(srcz_at(l)), 1);
+                load_rhs(l + 1, rqA);
+                run_plane(l + 1, raw, stB, stA, l >= max(za, 1), sfx * splat(srcz_at(l)), F_RHS ? rqB : nullptr);
             }
             if (llast >= za && llast < zb) {  // raw holds plane llast
-                if (((llast - lfirst) & 1) != 0) last_plane(llast, stB.T, raw);
-                else last_plane(llast, stA.T, raw);
+                if (((llast - lfirst) & 1) != 0) last_plane(llast, stB.T, raw, F_RHS ? rqB : nullptr);
+                else last_plane(llast, stA.T, raw, F_RHS ? rqA : nullptr);
             }
         } else {
             K3Raw<RY> rawA, rawB;
@@ -694,11 +709,11 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
             for (int l = lfirst + 1; l <= llast; l += 2) {
                 if (l + 1 <= llast) load_plane(l + 1, rawA);
                 if (F_PF && l + 3 <= llast) l2_prefetch(l + 3);
-                run_plane(l, rawB, stA, stB, l - 1 >= max(za, 1), sfx * splat(srcz_at(l - 1)), 0);
+                run_plane(l, rawB, stA, stB, l - 1 >= max(za, 1), sfx * splat(srcz_at(l - 1)), nullptr);
                 if (l + 1 > llast) break;
                 if (l + 2 <= llast) load_plane(l + 2, rawB);
                 if (F_PF && l + 4 <= llast) l2_prefetch(l + 4);
-                run_plane(l + 1, rawA, stB, stA, l >= max(za, 1), sfx * splat(srcz_at(l)), 1);
+                run_plane(l + 1, rawA, stB, stA, l >= max(za, 1), sfx * splat(srcz_at(l)), nullptr);
             }
             if (llast >= za && llast < zb) {
                 if (((llast - lfirst) & 1) != 0) last_plane(llast, stB.T, rawB);  // parity of the plane held in stB

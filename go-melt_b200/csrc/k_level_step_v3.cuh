@@ -18,6 +18,11 @@
 //      l_s (zu + zl) - l_d (zu - zl) = B zu + A zl,     l_s (zu + zl) + l_d (zu - zl) = A zu + B zl,
 //    and B z is formed once per loaded row: 42 instead of 84 packed instructions per warp-plane.
 //
+//  * TMA plane ring + cold-plane path (K1F_TMA, the default): the raw planes of T0 and S1 arrive three planes ahead
+//    through a 4-stage ring in shared memory filled by the TMA unit (an overlapping 2-D tensor-map view of the flat
+//    field, see the ring in the kernel), and one vote per plane picks a plane body with 2 instead of 7 property
+//    selects per node where nothing is above the solidus (bit-identical values).  DESIGN.md section 3.
+//
 // Measured on B200 the packed-FP instruction stream is bound by register-file read bandwidth (FADD2 / FFMA2
 // with register operands occupy the scheduler for 2 / 3 cycles and nothing co-issues in their shadow:
 // bench_tools/ubench_pipes.cu), i.e. by the instruction count itself - hence this variant.

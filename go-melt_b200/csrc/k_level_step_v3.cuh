@@ -141,61 +141,74 @@ GM_DI f2 ld2u(const char* q) {
 // bit r = loaded row r is owned here; qa / qb: this lane's halves are); accum / max_accum change only where the
 // node is molten NOW (s2 = 0: reset = 0, max(0, max_accum) = max_accum for the non-negative times it holds,
 // accum + 0 - 0 = accum), so S2_prev, accum and max_accum are touched only there.  o0..o5 = row byte offsets.
-template <bool F_S2, bool F_ACC>
-GM_DI void bookkeep_plane(const StepParams& p, size_t pl, unsigned rowmask, int qa, int qb, unsigned o0,
-                                            unsigned o1, unsigned o2, unsigned o3, unsigned o4, unsigned o5) {
+template <bool F_S2, bool F_ACC, int NP>
+GM_DI void bookkeep_planes(const StepParams& p, const size_t* pl, const unsigned* rowmask, int qa, int qb, unsigned o0,
+                           unsigned o1, unsigned o2, unsigned o3, unsigned o4, unsigned o5) {
     // The few warps over the melt pool are the tail of a single-wave kernel, so this path is written for latency:
-    // every load of a stage is issued before the first use (T0 from cache, then S2_prev / accum / max_accum).
+    // NP planes at a time, and every load of a stage - of all NP planes - is issued before the first use (T0 from
+    // cache, then S2_prev / accum / max_accum): two dependent memory round trips per NP planes.  rowmask[q] = 0
+    // switches plane q off (an odd plane out).
     const unsigned o[6] = {o0, o1, o2, o3, o4, o5};
-    bool da[6], db[6];
-    float ta[6], tb[6];
+    bool da[NP][6], db[NP][6];
+    float ta[NP][6], tb[NP][6];
 #pragma unroll
-    for (int r = 0; r < 6; ++r) {
-        const bool mine = (rowmask >> r) & 1u;
-        const size_t nb = pl + (o[r] >> 2);
-        ta[r] = (mine && qa) ? __ldg(p.T0 + nb - K1_TX) : 0.f;
-        tb[r] = (mine && qb) ? __ldg(p.T0 + nb) : 0.f;
-    }
+    for (int q = 0; q < NP; ++q)
 #pragma unroll
-    for (int r = 0; r < 6; ++r) {
-        da[r] = ta[r] >= p.pk.T_liq;  // T_liquidus > 0, so a node this warp does not own is never "molten"
-        db[r] = tb[r] >= p.pk.T_liq;
-    }
+        for (int r = 0; r < 6; ++r) {
+            const bool mine = (rowmask[q] >> r) & 1u;
+            const size_t nb = pl[q] + (o[r] >> 2);
+            ta[q][r] = (mine && qa) ? __ldg(p.T0 + nb - K1_TX) : 0.f;
+            tb[q][r] = (mine && qb) ? __ldg(p.T0 + nb) : 0.f;
+        }
+#pragma unroll
+    for (int q = 0; q < NP; ++q)
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            da[q][r] = ta[q][r] >= p.pk.T_liq;  // T_liquidus > 0, so a node this warp does not own is never "molten"
+            db[q][r] = tb[q][r] >= p.pk.T_liq;
+        }
     if (F_ACC) {
-        uint8_t pa[6], pb[6];
-        float aca[6], acb[6], mxa[6], mxb[6];
+        uint8_t pa[NP][6], pb[NP][6];
+        float aca[NP][6], acb[NP][6], mxa[NP][6], mxb[NP][6];
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
-            const size_t nb = pl + (o[r] >> 2), na = nb - K1_TX;
-            pa[r] = da[r] ? p.S2prev[na] : (uint8_t)1;   // S2_prev is read before S2 is written (in place)
-            pb[r] = db[r] ? p.S2prev[nb] : (uint8_t)1;
-            aca[r] = da[r] ? p.accum[na] : 0.f;
-            acb[r] = db[r] ? p.accum[nb] : 0.f;
-            mxa[r] = da[r] ? p.maxacc[na] : 0.f;
-            mxb[r] = db[r] ? p.maxacc[nb] : 0.f;
-        }
+        for (int q = 0; q < NP; ++q)
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
-            const size_t nb = pl + (o[r] >> 2), na = nb - K1_TX;
-            const float ra = pa[r] ? 0.f : aca[r], rb = pb[r] ? 0.f : acb[r];  // reset = accum when the node has just melted
-            if (da[r]) {
-                p.maxacc[na] = fmaxf(ra, mxa[r]);
-                p.accum[na] = aca[r] + p.dt - ra;
+            for (int r = 0; r < 6; ++r) {
+                const size_t nb = pl[q] + (o[r] >> 2), na = nb - K1_TX;
+                pa[q][r] = da[q][r] ? p.S2prev[na] : (uint8_t)1;   // S2_prev is read before S2 is written (in place)
+                pb[q][r] = db[q][r] ? p.S2prev[nb] : (uint8_t)1;
+                aca[q][r] = da[q][r] ? p.accum[na] : 0.f;
+                acb[q][r] = db[q][r] ? p.accum[nb] : 0.f;
+                mxa[q][r] = da[q][r] ? p.maxacc[na] : 0.f;
+                mxb[q][r] = db[q][r] ? p.maxacc[nb] : 0.f;
             }
-            if (db[r]) {
-                p.maxacc[nb] = fmaxf(rb, mxb[r]);
-                p.accum[nb] = acb[r] + p.dt - rb;
+#pragma unroll
+        for (int q = 0; q < NP; ++q)
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                const size_t nb = pl[q] + (o[r] >> 2), na = nb - K1_TX;
+                // reset = accum when the node has just melted
+                const float ra = pa[q][r] ? 0.f : aca[q][r], rb = pb[q][r] ? 0.f : acb[q][r];
+                if (da[q][r]) {
+                    p.maxacc[na] = fmaxf(ra, mxa[q][r]);
+                    p.accum[na] = aca[q][r] + p.dt - ra;
+                }
+                if (db[q][r]) {
+                    p.maxacc[nb] = fmaxf(rb, mxb[q][r]);
+                    p.accum[nb] = acb[q][r] + p.dt - rb;
+                }
             }
-        }
     }
     if (F_S2) {
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
-            const bool mine = (rowmask >> r) & 1u;
-            const size_t nb = pl + (o[r] >> 2);
-            if (mine && qa) p.S2out[nb - K1_TX] = da[r] ? 1 : 0;
-            if (mine && qb) p.S2out[nb] = db[r] ? 1 : 0;
-        }
+        for (int q = 0; q < NP; ++q)
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                const bool mine = (rowmask[q] >> r) & 1u;
+                const size_t nb = pl[q] + (o[r] >> 2);
+                if (mine && qa) p.S2out[nb - K1_TX] = da[q][r] ? 1 : 0;
+                if (mine && qb) p.S2out[nb] = db[q][r] ? 1 : 0;
+            }
     }
 }
 
@@ -392,15 +405,21 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     };
     auto flush_bookkeeping = [&]() {
         if (!(F_S2 || F_ACC)) return;
-        static_assert(NR == 6, "bookkeep_plane takes the six row offsets of RY = 4");
+        static_assert(NR == 6, "bookkeep_planes takes the six row offsets of RY = 4");
         unsigned long long m = hotmask;  // warp-uniform
         hotmask = 0;
 #pragma unroll 1
-        while (m) {
-            const int b = __ffsll((long long)m) - 1;
-            m &= m - 1;
-            bookkeep_plane<F_S2, F_ACC>(p, (size_t)(lfirst + b) * P, rows_mine, qa, qb, off[0], off[1], off[2], off[3],
-                                        off[4], off[5]);
+        while (m) {  // two hot planes per pass
+            size_t pl[2];
+            unsigned rm[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int b = m ? __ffsll((long long)m) - 1 : 0;
+                rm[q] = m ? rows_mine : 0u;
+                m &= m - 1;  // (0 stays 0)
+                pl[q] = (size_t)(lfirst + b) * P;
+            }
+            bookkeep_planes<F_S2, F_ACC, 2>(p, pl, rm, qa, qb, off[0], off[1], off[2], off[3], off[4], off[5]);
         }
     };
 

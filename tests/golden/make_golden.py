@@ -28,6 +28,24 @@ def main():
     np.savez_compressed(os.path.join(HERE, "small_run_reference.npz"), **flat)
     print(f"small_run_reference.npz: {len(flat)} arrays, {time.time() - t0:.1f} s")
     toolpath_golden(cF)
+    toolpath_golden_serpentine(cF)
+
+
+def toolpath_golden_serpentine(cF):
+    """The reference's parser on a two-layer serpentine scan with rapid (G0) moves between the tracks, a layer change
+    and dwell rows (scenario.SERPENTINE_GCODE / SERPENTINE_NONMESH): BASELINE.json configs[2] / [3] in miniature."""
+    import importlib
+    import shutil
+    import tempfile
+
+    cP = importlib.import_module("createPath")
+    tmp = tempfile.mkdtemp() + "/"
+    with open(tmp + "serp.gcode", "w") as fh:
+        fh.write(scenario.SERPENTINE_GCODE)
+    nm = dict(scenario.SERPENTINE_NONMESH, save_path=tmp, toolpath=tmp + "toolpath.txt", gcode=tmp + "serp.gcode")
+    n = cP.parsingGcode(cF.SetupNonmesh(nm), {"laser_power": 285.0}, [0.04, 0.04, 0.04])
+    shutil.copy(tmp + "toolpath.txt", os.path.join(HERE, "toolpath_serpentine.txt"))
+    print(f"toolpath_serpentine.txt: {n} rows")
 
 
 def toolpath_golden(cF):
@@ -48,4 +66,9 @@ def toolpath_golden(cF):
 
 
 if __name__ == "__main__":
-    main()
+    if "--toolpaths-only" in sys.argv:  # the .npz is left as committed
+        _cF = shim.load_reference()
+        toolpath_golden(_cF)
+        toolpath_golden_serpentine(_cF)
+    else:
+        main()

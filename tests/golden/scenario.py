@@ -34,6 +34,17 @@ SMALL_INPUT = {
 }
 
 
+# Two layers of three serpentine tracks joined by rapid moves (tests/golden/toolpath_serpentine.txt is the reference
+# parser's output for it, see make_golden.py)
+SERPENTINE_GCODE = ("G0 X0.40 Y0.36 Z0.04\nG1 X0.88 Y0.36 Z0.04\nG0 X0.88 Y0.40 Z0.04\nG1 X0.40 Y0.40 Z0.04\n"
+                    "G0 X0.40 Y0.44 Z0.04\nG1 X0.88 Y0.44 Z0.04\n"
+                    "G0 X0.88 Y0.44 Z0.08\nG1 X0.40 Y0.44 Z0.08\nG0 X0.40 Y0.40 Z0.08\nG1 X0.88 Y0.40 Z0.08\n"
+                    "G0 X0.88 Y0.36 Z0.08\nG1 X0.40 Y0.36 Z0.08\n")
+SERPENTINE_NONMESH = {"timestep_L3": 1e-05, "dwell_time": 0.002, "wait_time": 20, "output_files": 1, "record_step": 25,
+                      "Level1_record_step": 1, "laser_velocity": 800, "layer_num": 0, "subcycle_num_L2": 3,
+                      "subcycle_num_L3": 4, "info_T": 0, "dwell_time_multiplier": 5, "use_txt": 0}
+
+
 def toolpath_rows():
     """x, y, z, Ljump, Ldwell, dt, P (cP:71-74).  Large x increments so that the windows shift
     within a handful of steps; dt kept at the physical 1e-5 s."""

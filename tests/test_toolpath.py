@@ -35,3 +35,37 @@ def test_oracle_toolpath_is_byte_identical_to_the_reference(tmp_path):
     golden = open(os.path.join(HERE, "golden", "toolpath_example.txt"), "rb").read()
     n, text = _run(cF.parsingGcode, cF.SetupNonmesh, tmp_path, "oracle")
     assert n == 1299 and text == golden
+
+
+def _run_serpentine(parse, setup_nonmesh, tmp_path, tag):
+    import sys
+
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import scenario
+
+    g = tmp_path / "serp.gcode"
+    g.write_text(scenario.SERPENTINE_GCODE)
+    nm = dict(scenario.SERPENTINE_NONMESH, save_path=str(tmp_path) + "/", gcode=str(g),
+              toolpath=str(tmp_path / f"{tag}.txt"))
+    n = parse(setup_nonmesh(nm), {"laser_power": 285.0})
+    return n, (tmp_path / f"{tag}.txt").read_bytes()
+
+
+def test_serpentine_two_layer_toolpath_is_byte_identical_to_the_reference(tmp_path):
+    """Two layers of three serpentine tracks with rapid (G0) moves, a layer change and dwell rows - the reference's
+    own parser wrote tests/golden/toolpath_serpentine.txt (make_golden.py --toolpaths-only): jump rows, the dwell
+    multiplier and the wait rows of both parsers are byte-identical to it."""
+    from oracle import computeFunctions as cF
+
+    tp = importlib.import_module("go-melt_b200.toolpath")
+    sc = importlib.import_module("go-melt_b200.schema")
+    golden = open(os.path.join(HERE, "golden", "toolpath_serpentine.txt"), "rb").read()
+    rows = golden.splitlines()
+    assert len(rows) == 428
+    cols = [r.split(b",") for r in rows]
+    assert any(int(c[3]) == 0 for c in cols) and any(int(c[4]) == 0 for c in cols)  # jump rows and dwell rows exist
+    assert len({c[2] for c in cols}) == 2                                            # two layers
+    n, text = _run_serpentine(tp.parsingGcode, sc.SetupNonmesh, tmp_path, "product")
+    assert n == 428 and text == golden
+    n, text = _run_serpentine(cF.parsingGcode, cF.SetupNonmesh, tmp_path, "oracle")
+    assert n == 428 and text == golden

@@ -31,6 +31,30 @@ def main():
     toolpath_golden_serpentine(cF)
 
 
+def driver_golden():
+    """The reference's own DRIVER (go_melt.go_melt gm:16-530, unmodified) on top of its own computeFunctions, both
+    through the NumPy ``jax`` shim, on the two-layer G-code run of tests/driver_support.small_two_layer_input
+    (57 toolpath rows: layer start, single steps, subcycle blocks, dwell, a layer change; ~25 min here) ->
+    two_layer_reference_driver.npz = its FinalTemperatureFields (+ accum_time)."""
+    import importlib
+    import tempfile
+
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    from driver_support import small_two_layer_input
+
+    shim.load_reference()
+    gm = importlib.import_module("go_melt")
+    tmp = tempfile.mkdtemp()
+    t0 = time.time()
+    gm.go_melt(small_two_layer_input(tmp))
+    out = dict(np.load(os.path.join(tmp, "FinalTemperatureFields.npz")))
+    # melt-time field of Level 0: written at the layer change (layer 0) and at the end of the run (layer 1)
+    out["accum_time_layer0"] = np.load(os.path.join(tmp, "accum_time0000.npz"))["accum_time"]
+    out["accum_time"] = np.load(os.path.join(tmp, "accum_time0001.npz"))["accum_time"]
+    np.savez_compressed(os.path.join(HERE, "two_layer_reference_driver.npz"), **out)
+    print(f"two_layer_reference_driver.npz: {sorted(out)} in {time.time() - t0:.0f} s")
+
+
 def toolpath_golden_serpentine(cF):
     """The reference's parser on a two-layer serpentine scan with rapid (G0) moves between the tracks, a layer change
     and dwell rows (scenario.SERPENTINE_GCODE / SERPENTINE_NONMESH): BASELINE.json configs[2] / [3] in miniature."""
@@ -66,7 +90,9 @@ def toolpath_golden(cF):
 
 
 if __name__ == "__main__":
-    if "--toolpaths-only" in sys.argv:  # the .npz is left as committed
+    if "--driver" in sys.argv:
+        driver_golden()
+    elif "--toolpaths-only" in sys.argv:  # the .npz is left as committed
         _cF = shim.load_reference()
         toolpath_golden(_cF)
         toolpath_golden_serpentine(_cF)

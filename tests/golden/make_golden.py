@@ -90,7 +90,12 @@ def toolpath_golden(cF):
 
 
 if __name__ == "__main__":
-    if "--driver" in sys.argv:
+    if "--edge" in sys.argv:  # per-function edge cases (tests/golden/edge_cases.py), seconds
+        import edge_cases
+
+        np.savez_compressed(os.path.join(HERE, "edge_cases_reference.npz"),
+                            **edge_cases.run(shim.load_reference(), wrap=shim._wrap))
+    elif "--driver" in sys.argv:
         driver_golden()
     elif "--toolpaths-only" in sys.argv:  # the .npz is left as committed
         _cF = shim.load_reference()

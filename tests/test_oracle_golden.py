@@ -67,3 +67,26 @@ def test_windows_moved(runs):
     _, ref = runs
     assert ref["step2/L3_x"][0] > ref["step0/L3_x"][0]  # the Level-3 window followed the laser
     assert ref["subcycle/move_hist"].shape == (3,)
+
+
+def test_oracle_matches_reference_on_edge_cases():
+    """Per-function pin on crafted inputs (tests/golden/edge_cases.py; the reference's own functions, run through the
+    shim by make_golden.py --edge, wrote edge_cases_reference.npz): computeStateProperties exactly at / one ulp around
+    the solidus, the liquidus and the 0.499 state threshold (incl. -0.0 and a substrate prefix) - bit-exact;
+    computeConvRadBC on a surface running from ambient past the T_boiling + 1000 cap; interpolatePoints at targets
+    outside, on and a hair inside / outside the parent's faces (the +-1e-2 validity window)."""
+    import edge_cases
+
+    ref = np.load(os.path.join(HERE, "golden", "edge_cases_reference.npz"))
+    got = edge_cases.run(cF)
+    assert set(got) == set(ref.files) and len(got) == 10
+    for k in ref.files:
+        a, b = np.asarray(got[k]), np.asarray(ref[k])
+        assert a.shape == b.shape, k
+        if k.startswith("state_properties_at_thresholds/"):
+            assert np.array_equal(a, b), k                      # selects of constants / one FMA: no rounding freedom
+        else:
+            scale = float(np.max(np.abs(b)))
+            assert float(np.max(np.abs(a.astype(np.float64) - b))) <= FLOAT_RTOL * scale, k
+            assert np.array_equal(a == 0, b == 0), k            # same support (zeroed weights outside the parent)
+    assert (ref["interpolation_outside_the_parent/u_new"] == 0).sum() > 100   # the case does reach outside

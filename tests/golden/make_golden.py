@@ -31,28 +31,41 @@ def main():
     toolpath_golden_serpentine(cF)
 
 
-def driver_golden():
+def driver_golden(case="two_layers"):
     """The reference's own DRIVER (go_melt.go_melt gm:16-530, unmodified) on top of its own computeFunctions, both
-    through the NumPy ``jax`` shim, on the two-layer G-code run of tests/driver_support.small_two_layer_input
-    (57 toolpath rows: layer start, single steps, subcycle blocks, dwell, a layer change; ~25 min here) ->
-    two_layer_reference_driver.npz = its FinalTemperatureFields (+ accum_time)."""
+    through the NumPy ``jax`` shim, on a G-code run of tests/driver_support.py -> <case>_reference_driver.npz = its
+    FinalTemperatureFields + the Level-0 melt-time field(s).
+      two_layers: small_two_layer_input, 57 toolpath rows - layer start, single steps, subcycle blocks, dwell, a
+                  layer change (28 min here);
+      serpentine: serpentine_input, 70 rows - one layer, three tracks joined by rapid (G0) moves: jump rows and the
+                  faster-than-100x-velocity single-step trigger gm:168-171 (~35 min)."""
     import importlib
     import tempfile
 
     sys.path.insert(0, os.path.join(HERE, ".."))
-    from driver_support import small_two_layer_input
+    import driver_support
 
+    make = {"two_layers": driver_support.small_two_layer_input, "serpentine": driver_support.serpentine_input}[case]
     shim.load_reference()
     gm = importlib.import_module("go_melt")
     tmp = tempfile.mkdtemp()
     t0 = time.time()
-    gm.go_melt(small_two_layer_input(tmp))
+    gm.go_melt(make(tmp))
+    out = collect_driver_outputs(tmp)
+    np.savez_compressed(os.path.join(HERE, {"two_layers": "two_layer", "serpentine": "serpentine"}[case]
+                                     + "_reference_driver.npz"), **out)
+    print(f"{case}: {sorted(out)} in {time.time() - t0:.0f} s")
+
+
+def collect_driver_outputs(tmp):
+    """FinalTemperatureFields + accum_time files the reference driver left in its save_path."""
     out = dict(np.load(os.path.join(tmp, "FinalTemperatureFields.npz")))
-    # melt-time field of Level 0: written at the layer change (layer 0) and at the end of the run (layer 1)
-    out["accum_time_layer0"] = np.load(os.path.join(tmp, "accum_time0000.npz"))["accum_time"]
-    out["accum_time"] = np.load(os.path.join(tmp, "accum_time0001.npz"))["accum_time"]
-    np.savez_compressed(os.path.join(HERE, "two_layer_reference_driver.npz"), **out)
-    print(f"two_layer_reference_driver.npz: {sorted(out)} in {time.time() - t0:.0f} s")
+    # melt-time field of Level 0: written at every layer change and at the end of the run (the last one = final)
+    acc = sorted(f for f in os.listdir(tmp) if f.startswith("accum_time") and f.endswith(".npz"))
+    for f in acc[:-1]:
+        out["accum_time_layer" + str(int(f[len("accum_time"):-4]))] = np.load(os.path.join(tmp, f))["accum_time"]
+    out["accum_time"] = np.load(os.path.join(tmp, acc[-1]))["accum_time"]
+    return out
 
 
 def toolpath_golden_serpentine(cF):
@@ -95,8 +108,9 @@ if __name__ == "__main__":
 
         np.savez_compressed(os.path.join(HERE, "edge_cases_reference.npz"),
                             **edge_cases.run(shim.load_reference(), wrap=shim._wrap))
-    elif "--driver" in sys.argv:
-        driver_golden()
+    elif "--driver" in sys.argv:  # --driver [two_layers|serpentine]
+        i = sys.argv.index("--driver")
+        driver_golden(sys.argv[i + 1] if i + 1 < len(sys.argv) else "two_layers")
     elif "--toolpaths-only" in sys.argv:  # the .npz is left as committed
         _cF = shim.load_reference()
         toolpath_golden(_cF)

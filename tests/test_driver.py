@@ -69,6 +69,15 @@ def test_whole_run_matches_oracle(tmp_path, case):
     assert np.allclose(acc_g, acc_r, rtol=1e-5, atol=1e-9)
     final = np.load(tmp_path / "gpu" / "FinalTemperatureFields.npz")
     assert np.array_equal(final["L3T"], host(got["Levels"][3]["T0"]))
+    # ... and directly against what the REFERENCE'S OWN driver + computeFunctions wrote for the same G-code run
+    # (tests/golden/*_reference_driver.npz, see test_driver_loop_reproduces_the_reference_driver): north-star tolerance
+    gold = np.load(os.path.join(ROOT, "tests", "golden",
+                                ("two_layer" if case == "two_layers" else "serpentine") + "_reference_driver.npz"))
+    for lvl in (1, 2, 3):
+        a, b = host(got["Levels"][lvl]["T0"]), np.asarray(gold[f"L{lvl}T"], np.float32)
+        err = float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0)))
+        assert err <= 1.2e-5, (lvl, err)
+    assert np.allclose(acc_g, np.asarray(gold["accum_time"], np.float32), rtol=1e-5, atol=1e-9)
 
 
 @pytest.mark.parametrize("case", ["two_layers", "serpentine"])

@@ -9,8 +9,9 @@ N = 1  workload "L3-10M": BASELINE.json configs[1] — single laser track, Level
        fused level step (computeStateProperties + solveMatrixFreeFE + clamp) + face prolongation
        from the Level-2 parent (assignBCsFine), laser advancing along +x.  metric = Level-3 DOF-updates/s (1 DOF-update = one node advanced one sweep).
 N > 1  workload "L1-slab": BASELINE.json configs[4] — part-scale Level-1 mesh z-slab-decomposed, one
-       rank per GPU, dwell sweeps (stepGOMELTDwellTime cF:2617-2664) with one-plane halo exchange
-       per sweep over NCCL; weak scaling (fixed slab per GPU).  metric = Level-1 DOF-updates/s.
+       rank per GPU, dwell sweeps (stepGOMELTDwellTime cF:2617-2664) with a one-plane halo exchange
+       per sweep (boundary planes stored into the neighbours' ghost planes over NVLink peer memory;
+       GOMELT_SLAB_NCCL=1: NCCL send/recv); weak scaling (fixed slab per GPU).  metric = Level-1 DOF-updates/s.
 
 `--impl reference` times the reference algorithm on the host cores: the NumPy float32 oracle
 (oracle/, "restated reference, not JAX/XLA": JAX is not installable here or on the GPU box) on a

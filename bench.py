@@ -307,7 +307,7 @@ def run_gomelt_single(args):
 
 
 def run_e2e_hostbuffers(blk, K):
-    """Same block through the host-buffer API (go-melt_b200/hostpipe.py): pinned host T0,S1 -> device -> N3 substeps
+    """Same block through the host-buffer API (gomelt_b200/hostpipe.py): pinned host T0,S1 -> device -> N3 substeps
     through gomelt_l3_substeps_f32 -> pinned host T,S1, every step, copies inside the timed region.  Consecutive
     steps are independent batches, so the pipeline keeps two in flight (upload of step i+1 | substeps of step i |
     download of step i-1 on three streams); `serial` is the same loop with one step in flight."""

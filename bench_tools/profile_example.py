@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "bench_tools"))
 import torch
 import gomelt_b200 as gm
 from run_example import load_input
-drv = importlib.import_module("go-melt_b200.driver")
+drv = importlib.import_module("gomelt_b200.driver")
 drv.go_melt(load_input(tempfile.mkdtemp()), write_final=False)   # warm
 torch.cuda.synchronize()
 pr = cProfile.Profile()

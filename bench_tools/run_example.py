@@ -22,8 +22,8 @@ def load_input(tmp, rows=None):
     inp["nonmesh"].update(save_path=tmp + "/", toolpath=os.path.join(tmp, "toolpath.txt"),
                           gcode=os.path.join(ROOT, "examples", "gcodefiles", "example.gcode"), info_T=0)
     if rows is not None:  # truncated toolpath: generate it, keep the first rows, switch to use_txt
-        tp = importlib.import_module("go-melt_b200.toolpath")
-        sc = importlib.import_module("go-melt_b200.schema")
+        tp = importlib.import_module("gomelt_b200.toolpath")
+        sc = importlib.import_module("gomelt_b200.schema")
         tp.parsingGcode(sc.SetupNonmesh(inp["nonmesh"]), sc.SetupProperties(inp["properties"]))
         lines = open(inp["nonmesh"]["toolpath"]).readlines()[:rows]
         open(inp["nonmesh"]["toolpath"], "w").writelines(lines)
@@ -36,7 +36,7 @@ def main():
     ap.add_argument("--oracle-rows", type=int, default=75)
     ap.add_argument("--skip-gpu", action="store_true")
     args = ap.parse_args()
-    drv = importlib.import_module("go-melt_b200.driver")
+    drv = importlib.import_module("gomelt_b200.driver")
     out = {}
     if not args.skip_gpu:
         import torch

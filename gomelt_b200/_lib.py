@@ -161,7 +161,7 @@ def load(build_if_missing=False):
             _build.build_library()
         else:
             raise GomeltError(
-                f"{path} is missing: run `python go-melt_b200/build.py` (or __graft_entry__.build()); "
+                f"{path} is missing: run `python gomelt_b200/build.py` (or __graft_entry__.build()); "
                 "there is no CPU fallback for the GO-MELT step")
     lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():

@@ -2,7 +2,7 @@
 // of BASELINE.json's north_star.  COMPILE-GUARDED: jaxlib (which ships xla/ffi/api/ffi.h) is not in
 // this image nor on the GPU box, so build.py compiles this file only when the header is found
 // (GOMELT_XLA_INCLUDE=<jaxlib>/include, or `python -c "import jaxlib"` succeeding).  Everything that
-// is testable here goes through the same extern "C" symbols by ctypes (go-melt_b200/_lib.py).
+// is testable here goes through the same extern "C" symbols by ctypes (gomelt_b200/_lib.py).
 //
 // Registration on the JAX side:
 //     jax.ffi.register_ffi_target("gomelt_level_step_f32", jax.ffi.pycapsule(lib.GomeltLevelStepFfi),

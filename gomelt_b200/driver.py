@@ -14,7 +14,7 @@ dependency-free implementations (``.vtr`` files with the reference's names, raw-
 min / max monitor) and the CLI installs them.  The checkpoint *flags* that influence the stepping mode
 (gm:179-193, 390-411) are kept in the loop itself.
 
-CLI (gm:533-580):  python go-melt_b200/driver.py [DEVICE_ID] [input.json]
+CLI (gm:533-580):  python gomelt_b200/driver.py [DEVICE_ID] [input.json]
 """
 import copy
 import json
@@ -320,4 +320,4 @@ if __name__ == "__main__":
 
     _root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, _root)
-    sys.exit(importlib.import_module("go-melt_b200.driver").main(sys.argv))
+    sys.exit(importlib.import_module("gomelt_b200.driver").main(sys.argv))

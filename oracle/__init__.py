@@ -2,7 +2,7 @@
 
 THIS PACKAGE IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``,
 ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of
-``bench.py`` may import it.  The product path (``go-melt_b200/``) never does, and fails
+``bench.py`` may import it.  The product path (``gomelt_b200/``) never does, and fails
 loudly when its CUDA library is missing.
 
 What it is: a float32 NumPy restatement of the reference's algorithm *as written*

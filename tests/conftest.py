@@ -14,7 +14,7 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def gm():
-    """The product package (go-melt_b200/) with its C-ABI library loaded."""
+    """The product package (gomelt_b200/) with its C-ABI library loaded."""
     import gomelt_b200
 
     gomelt_b200.load()

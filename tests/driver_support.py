@@ -1,4 +1,4 @@
-"""Test infrastructure for go-melt_b200/driver.py: a NumPy array adapter (drives the oracle through the
+"""Test infrastructure for gomelt_b200/driver.py: a NumPy array adapter (drives the oracle through the
 same loop) and a recording stub namespace (exercises the control flow without arithmetic)."""
 import copy  # noqa: F401
 import os

@@ -53,7 +53,7 @@ def test_no_cpu_fallback(gm):
 
 
 def test_product_never_imports_oracle():
-    pkg = os.path.join(ROOT, "go-melt_b200")
+    pkg = os.path.join(ROOT, "gomelt_b200")
     for dp, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):

@@ -1,4 +1,4 @@
-"""go-melt_b200/driver.py: (CPU) the loop's control flow on the reference's own example toolpath, and (GPU)
+"""gomelt_b200/driver.py: (CPU) the loop's control flow on the reference's own example toolpath, and (GPU)
 the whole drop-in run against the oracle driven through the same loop."""
 import importlib
 import json
@@ -16,9 +16,9 @@ def test_mode_sequence_on_the_example_toolpath(tmp_path):
     """the default example is 25 single-step rows (layer start), 30 subcycle blocks, 25
     single-step rows (wait counter near wait_time), 499 Level-1 dwell rows; moveEverything runs on every
     single-step / dwell row and once per subcycle block (gm:292, 422)."""
-    drv = importlib.import_module("go-melt_b200.driver")
-    sc = importlib.import_module("go-melt_b200.schema")
-    tp = importlib.import_module("go-melt_b200.toolpath")
+    drv = importlib.import_module("gomelt_b200.driver")
+    sc = importlib.import_module("gomelt_b200.schema")
+    tp = importlib.import_module("gomelt_b200.toolpath")
 
     class Real:
         SetupProperties, SetupNonmesh, getStaticSubcycle = sc.SetupProperties, sc.SetupNonmesh, sc.getStaticSubcycle
@@ -46,7 +46,7 @@ def test_whole_run_matches_oracle(tmp_path, case):
     Temperatures within 1e-5 relative, states / melt flags / melt-time bookkeeping exact or to rounding."""
     from oracle import computeFunctions as cF
 
-    drv = importlib.import_module("go-melt_b200.driver")
+    drv = importlib.import_module("gomelt_b200.driver")
     make = small_two_layer_input if case == "two_layers" else serpentine_input
     (tmp_path / "gpu").mkdir()
     (tmp_path / "cpu").mkdir()
@@ -82,7 +82,7 @@ def test_whole_run_matches_oracle(tmp_path, case):
 
 @pytest.mark.parametrize("case", ["two_layers", "serpentine"])
 def test_driver_loop_reproduces_the_reference_driver(tmp_path, case):
-    """go-melt_b200/driver.py (the loop) + oracle/ (the arithmetic) against the REFERENCE'S OWN driver: the goldens
+    """gomelt_b200/driver.py (the loop) + oracle/ (the arithmetic) against the REFERENCE'S OWN driver: the goldens
     tests/golden/{two_layer,serpentine}_reference_driver.npz hold the FinalTemperatureFields / accum_time that the
     unmodified go_melt.go_melt (gm:16-530) wrote on top of the unmodified computeFunctions.py, both executed through
     the NumPy jax shim (tests/golden/make_golden.py --driver <case>): two layers with single steps, subcycle blocks,
@@ -93,7 +93,7 @@ def test_driver_loop_reproduces_the_reference_driver(tmp_path, case):
     name = {"two_layers": "two_layer", "serpentine": "serpentine"}[case]
     ref = np.load(os.path.join(ROOT, "tests", "golden", name + "_reference_driver.npz"))
     make = small_two_layer_input if case == "two_layers" else serpentine_input
-    drv = importlib.import_module("go-melt_b200.driver")
+    drv = importlib.import_module("gomelt_b200.driver")
     got = drv.go_melt(make(str(tmp_path)), cf=cF, xp=NumpyArrays(), write_final=False)
     c = got["counts"]
     assert c["layers"] == (2 if case == "two_layers" else 1)

@@ -1,4 +1,4 @@
-"""Host-side level geometry of the product (go-melt_b200/levels.py, JAX-free) against the oracle's SetupLevels
+"""Host-side level geometry of the product (gomelt_b200/levels.py, JAX-free) against the oracle's SetupLevels
 (cF:115-264, itself pinned to the reference's own source by tests/test_oracle_golden.py): coordinates, overlap
 index sets, Level-0 scatter indices, travel limits, static sizes - on examples/example.json and on the scaled-down
 scenario of tests/golden/scenario.py.  CPU only: no field is allocated."""
@@ -27,8 +27,8 @@ def _inputs():
 
 @pytest.mark.parametrize("name,inp", list(_inputs()))
 def test_geometry_matches_oracle(name, inp):
-    lev = importlib.import_module("go-melt_b200.levels")
-    sc = importlib.import_module("go-melt_b200.schema")
+    lev = importlib.import_module("gomelt_b200.levels")
+    sc = importlib.import_module("gomelt_b200.schema")
     P_o = osetup.SetupProperties(copy.deepcopy(inp["properties"]))
     P_p = sc.SetupProperties(copy.deepcopy(inp["properties"]))
     assert set(P_o) == set(P_p)

@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-out = importlib.import_module("go-melt_b200.output")
+out = importlib.import_module("gomelt_b200.output")
 
 
 def _level(nodes=(5, 4, 3), seed=0):

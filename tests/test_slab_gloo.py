@@ -35,7 +35,7 @@ def _free_port():
 
 
 class _OracleOps:
-    """Test double for go-melt_b200.ops on CPU tensors: the oracle's dwell step on the local slab."""
+    """Test double for gomelt_b200.ops on CPU tensors: the oracle's dwell step on the local slab."""
     STEP_BC_CONST = 0x08
     STEP_FUSED_FLUX = 0x40
     LAUNCHES = 0
@@ -90,8 +90,8 @@ def _worker(rank, world, port, out):
         from oracle import computeFunctions as cF
         from oracle.util import make_level, smooth_field
 
-        slab = importlib.import_module("go-melt_b200.slab")
-        lib = importlib.import_module("go-melt_b200._lib")
+        slab = importlib.import_module("gomelt_b200.slab")
+        lib = importlib.import_module("gomelt_b200._lib")
         P = cF.SetupProperties(PROPS_IN)
         lv = make_level(ELEMENTS, BOUNDS)
         nx, ny, nz = lv["nodes"]
@@ -144,7 +144,7 @@ def _cpu_sweep(sl, dt):
 def test_partition_planes():
     import importlib
 
-    slab = importlib.import_module("go-melt_b200.slab")
+    slab = importlib.import_module("gomelt_b200.slab")
     assert slab.partition_planes(10, 3) == [(0, 4), (4, 7), (7, 10)]
     assert slab.partition_planes(8, 8) == [(i, i + 1) for i in range(8)]
     with pytest.raises(ValueError):

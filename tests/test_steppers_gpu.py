@@ -22,7 +22,7 @@ RTOL_T = 1e-5
 
 @pytest.fixture(scope="module")
 def product_run(tmp_path_factory):
-    cf = importlib.import_module("go-melt_b200.computeFunctions")
+    cf = importlib.import_module("gomelt_b200.computeFunctions")
     return scenario.run(cf, save_path=str(tmp_path_factory.mktemp("prod")) + "/")
 
 

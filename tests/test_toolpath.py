@@ -20,8 +20,8 @@ def _run(parse, setup_nonmesh, tmp_path, tag):
 
 
 def test_product_toolpath_is_byte_identical_to_the_reference(tmp_path):
-    tp = importlib.import_module("go-melt_b200.toolpath")
-    sc = importlib.import_module("go-melt_b200.schema")
+    tp = importlib.import_module("gomelt_b200.toolpath")
+    sc = importlib.import_module("gomelt_b200.schema")
     golden = open(os.path.join(HERE, "golden", "toolpath_example.txt"), "rb").read()
     n, text = _run(tp.parsingGcode, sc.SetupNonmesh, tmp_path, "product")
     assert n == 1299 and text == golden
@@ -57,8 +57,8 @@ def test_serpentine_two_layer_toolpath_is_byte_identical_to_the_reference(tmp_pa
     multiplier and the wait rows of both parsers are byte-identical to it."""
     from oracle import computeFunctions as cF
 
-    tp = importlib.import_module("go-melt_b200.toolpath")
-    sc = importlib.import_module("go-melt_b200.schema")
+    tp = importlib.import_module("gomelt_b200.toolpath")
+    sc = importlib.import_module("gomelt_b200.schema")
     golden = open(os.path.join(HERE, "golden", "toolpath_serpentine.txt"), "rb").read()
     rows = golden.splitlines()
     assert len(rows) == 428

@@ -172,6 +172,18 @@ def _surface_flux(L, T, nz_active, properties):
     return ops.surface_flux(_props(properties), _grid(L), T, flux, nz_active=nz_active)
 
 
+def computeConvRadBC(Level, LevelT0, ne, nn, properties, F):
+    """cF:2207-2301 with the reference's signature: convection + radiation + evaporation load of the top face of the
+    elements [ne - ne_x*ne_y, ne) added to ``F`` (exact-libm stand-alone kernel; the steppers use K1's fused
+    epilogue).  Returns a new [nn] CUDA tensor."""
+    nx, ny = int(Level["nodes"][0]), int(Level["nodes"][1])
+    nz_active = int(ne) // ((nx - 1) * (ny - 1)) + 1
+    out = _f(F).clone()
+    top = out[(nz_active - 1) * nx * ny: nz_active * nx * ny]
+    ops.surface_flux(_props(properties), _grid(Level), _f(LevelT0), top, nz_active=nz_active, add=True)
+    return out
+
+
 def _nz_active(L, tmp_nn):
     return int(tmp_nn) // (L["nodes"][0] * L["nodes"][1])
 

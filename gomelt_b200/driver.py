@@ -154,13 +154,30 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
     move_hist = [0, 0, 0]
     force_move = move_vert = new_checkpoint = load_chkpt = False
     ongoing = True
+    stopped_at_layer_check = False
     layer_check = Nonmesh["layer_num"] + Nonmesh["restart_layer_num"]
+    if "on_record" in hooks:  # the initial saveResults(Levels, Nonmesh, 1) of gm:83-84
+        hooks["on_record"](Levels, Nonmesh, int(time_inc / Nonmesh["record_step"]) + 1)
     counts = {"stepGOMELT": 0, "subcycleGOMELT": 0, "stepGOMELTDwellTime": 0, "moveEverything": 0, "layers": 0}
     Shapes = tmp_ne_nn = substrate = None
     nblock = subcycle[0] * subcycle[1]
     T_amb = Properties["T_amb"]
 
     fh = open(Nonmesh["toolpath"], "r")
+    if Nonmesh["layer_num"] > 0:  # ---- restart from the checkpoint of this layer gm:108-129 ----
+        if "load_checkpoint" not in hooks:
+            fh.close()
+            raise RuntimeError(f"nonmesh.layer_num = {Nonmesh['layer_num']} asks for a restart from "
+                               f"Checkpoint{str(Nonmesh['layer_num']).zfill(4)}, but no 'load_checkpoint' hook was given "
+                               "(use hooks=output.driver_hooks())")
+        say(f"Checkpoint loading for start of Layer {Nonmesh['layer_num']}")
+        Levels, accum_time, max_accum_time, time_inc_loaded, record_inc = hooks["load_checkpoint"](
+            Nonmesh, "cuda" if isinstance(xp, TorchArrays) else None)
+        accum_time, max_accum_time = xp.f32(accum_time), xp.f32(max_accum_time)
+        load_chkpt = True
+        line_len = len(fh.readline())
+        fh.seek(int(time_inc_loaded) * line_len)
+        time_inc += int(time_inc_loaded)
     try:
         while ongoing:
             t_loop = time.time()
@@ -201,6 +218,8 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
                             if "on_layer_state" in hooks:  # saveState(Level0) gm:245
                                 hooks["on_layer_state"](Levels, Nonmesh)
                             accum_time = xp.maximum(accum_time, max_accum_time)
+                            if "on_layer_accum" in hooks:  # accum_time<layer_num>.npz gm:253-261, before the shift
+                                hooks["on_layer_accum"](accum_time, Nonmesh)
                             L0 = Levels[0]
                             nxy = int(L0["nodes"][0]) * int(L0["nodes"][1])
                             n1 = nxy * int(L0["layer_idx_delta"])
@@ -244,7 +263,8 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
                     Nonmesh["layer_num"] += 1
                     if "on_checkpoint" in hooks:  # dill dump gm:390-402
                         hooks["on_checkpoint"](Levels, accum_time, max_accum_time, time_inc, record_inc, Nonmesh)
-                    if Nonmesh["layer_num"] == layer_check:
+                    if Nonmesh["layer_num"] == layer_check:  # gm:405-406: return right here, no final output
+                        stopped_at_layer_check = True
                         break
                     new_checkpoint = False
                     load_chkpt = True
@@ -284,15 +304,15 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
     if hasattr(xp, "sync"):
         xp.sync()
     wall = time.time() - tstart
-    if "on_final" in hooks:  # saveState(Level 0) + saveResultsFinal gm:501-502
+    if "on_final" in hooks and not stopped_at_layer_check:  # saveState(Level 0) + saveResultsFinal gm:501-502
         hooks["on_final"](Levels, Nonmesh)
-    if write_final:  # gm:504-516
+    if write_final and not stopped_at_layer_check:  # gm:504-516
         np.savez(f"{Nonmesh['save_path']}FinalTemperatureFields", L1T=xp.host(Levels[1]["T0"]),
                  L2T=xp.host(Levels[2]["T0"]), L3T=xp.host(Levels[3]["T0"]))
         np.savez(Nonmesh["save_path"] + "accum_time" + str(Nonmesh["layer_num"]).zfill(4), accum_time=xp.host(accum_time))
     return {"Levels": Levels, "accum_time": accum_time, "time_inc": time_inc, "total_t_inc": total_t_inc,
             "sim_seconds": t_output, "wall_seconds": wall, "counts": counts, "Properties": Properties, "Nonmesh": Nonmesh,
-            "ne_nn": ne_nn, "dwell_seconds": dwell_count}
+            "ne_nn": ne_nn, "dwell_seconds": dwell_count, "stopped_at_layer_check": stopped_at_layer_check}
 
 
 def main(argv):

@@ -218,14 +218,28 @@ def driver_hooks():
         save_checkpoint(d, Levels, accum_time, max_accum_time, time_inc, record_inc)
 
     def on_info(Levels):
+        """printLevelMaxMin cF:3635-3665: the monitor stops the run on invalid physics (sys.exit(1) there)."""
+        stop = False
         for i, (lo, hi, bad) in enumerate(level_minmax(Levels), start=1):
             print(f"Level {i}: min {lo:.3f} K, max {hi:.3f} K" + (f", {bad} non-finite values" if bad else ""))
+            stop = stop or bad or not (0 < lo <= 1e5) or not (0 < hi <= 1e5)
+        if stop:
+            print("Terminating program: temperature out of range")
+            raise SystemExit(1)
+
+    def load_ckpt(Nonmesh, device):
+        d = os.path.join(Nonmesh["save_path"] + "checkpoint", f"Checkpoint{str(Nonmesh['layer_num']).zfill(4)}")
+        return load_checkpoint(d, device=device)
+
+    def on_layer_accum(accum_time, Nonmesh):
+        np.savez(Nonmesh["save_path"] + "accum_time" + str(Nonmesh["layer_num"]).zfill(4), accum_time=_to_host(accum_time))
 
     def on_final(Levels, Nonmesh):
         saveState(Levels[0], "Level0_", Nonmesh["layer_num"], Nonmesh["save_path"], 0)
         saveResultsFinal(Levels, Nonmesh)
 
     return {"on_record": saveResults, "on_checkpoint": on_checkpoint, "on_info": on_info, "on_final": on_final,
+            "load_checkpoint": load_ckpt, "on_layer_accum": on_layer_accum,
             "on_layer_state": lambda Levels, Nonmesh: saveState(Levels[0], "Level0_", Nonmesh["layer_num"],
                                                                 Nonmesh["save_path"], 0)}
 

@@ -31,17 +31,18 @@ def _pause(x, y, z, jump, nm):
     """Laser-off rows at a fixed position: up to ``wait_time`` fine steps, then the remaining dwell in
     coarse steps of dwell_time_multiplier*N2*N3 fine steps, then what is left (cP:66-103, 162-187)."""
     dt = nm["timestep_L3"]
-    big = dt * float(nm["dwell_time_multiplier"] * nm["subcycle_num_L2"] * nm["subcycle_num_L3"])
+    coef = float(nm["dwell_time_multiplier"] * nm["subcycle_num_L2"] * nm["subcycle_num_L3"])
+    big = dt * coef
     for i in range(1, int(nm["wait_time"]) + 1):
         if i * dt > nm["dwell_time"]:
             break
         yield (x, y, z, jump, 0, dt, 0)
     # the reference's max(dwell - wait*dt, dwell) is just dwell (cP:14-17)
     remaining = max(0, max(nm["dwell_time"] - nm["wait_time"] * dt, nm["dwell_time"]) - nm["wait_time"] * dt)
-    n_big = int(remaining / big)
+    n_big = int(remaining / dt / coef)  # the reference's operation order (cP:82-84, 173): it decides the row count
     for _ in range(n_big):
         yield (x, y, z, jump, 0, big, 0)
-    tail = remaining - n_big * big
+    tail = remaining - n_big * dt * coef
     if tail > 0:
         yield (x, y, z, jump, 0, tail, 0)
 

@@ -29,6 +29,7 @@ def main():
     print(f"small_run_reference.npz: {len(flat)} arrays, {time.time() - t0:.1f} s")
     toolpath_golden(cF)
     toolpath_golden_serpentine(cF)
+    toolpath_golden_dwell(cF)
 
 
 def driver_golden(case="two_layers"):
@@ -85,6 +86,49 @@ def toolpath_golden_serpentine(cF):
     print(f"toolpath_serpentine.txt: {n} rows")
 
 
+DWELL_CASES = [  # round-number dwell configurations: int(dwell / dt / coef) vs int(dwell / (dt * coef)) differ in some
+    {"dwell_time": 0.1, "timestep_L3": 2e-5, "wait_time": 1000, "subcycle_num_L2": 5, "subcycle_num_L3": 5,
+     "dwell_time_multiplier": 1},
+    {"dwell_time": 0.3, "timestep_L3": 1e-5, "wait_time": 100, "subcycle_num_L2": 3, "subcycle_num_L3": 4,
+     "dwell_time_multiplier": 5},
+    {"dwell_time": 0.7, "timestep_L3": 1e-5, "wait_time": 500, "subcycle_num_L2": 5, "subcycle_num_L3": 5,
+     "dwell_time_multiplier": 8},
+    {"dwell_time": 0.06, "timestep_L3": 3e-5, "wait_time": 50, "subcycle_num_L2": 2, "subcycle_num_L3": 2,
+     "dwell_time_multiplier": 10},
+    {"dwell_time": 0.002, "timestep_L3": 1e-5, "wait_time": 500, "subcycle_num_L2": 5, "subcycle_num_L3": 5,
+     "dwell_time_multiplier": 8},
+    {"dwell_time": 1.2, "timestep_L3": 2e-5, "wait_time": 200, "subcycle_num_L2": 4, "subcycle_num_L3": 6,
+     "dwell_time_multiplier": 3},
+    {"dwell_time": 0.1, "timestep_L3": 1e-5, "wait_time": 100, "subcycle_num_L2": 3, "subcycle_num_L3": 4,
+     "dwell_time_multiplier": 1},
+    {"dwell_time": 0.1, "timestep_L3": 2e-5, "wait_time": 200, "subcycle_num_L2": 3, "subcycle_num_L3": 4,
+     "dwell_time_multiplier": 8},
+]
+
+
+def toolpath_golden_dwell(cF):
+    """Row count and text digest of the reference parser's output on the two-layer serpentine G-code for DWELL_CASES
+    -> toolpath_dwell_cases.json (the dwell row count depends on the float operation order of cP:82-84 / 173)."""
+    import hashlib
+    import importlib
+    import json
+    import tempfile
+
+    cP = importlib.import_module("createPath")
+    out = []
+    for case in DWELL_CASES:
+        tmp = tempfile.mkdtemp() + "/"
+        with open(tmp + "serp.gcode", "w") as fh:
+            fh.write(scenario.SERPENTINE_GCODE)
+        nm = dict(scenario.SERPENTINE_NONMESH, save_path=tmp, toolpath=tmp + "toolpath.txt", gcode=tmp + "serp.gcode")
+        nm.update(case)
+        n = cP.parsingGcode(cF.SetupNonmesh(nm), {"laser_power": 285.0}, [0.04, 0.04, 0.04])
+        text = open(tmp + "toolpath.txt", "rb").read()
+        out.append({"nonmesh": case, "rows": int(n), "sha256": hashlib.sha256(text).hexdigest()})
+    json.dump(out, open(os.path.join(HERE, "toolpath_dwell_cases.json"), "w"), indent=1)
+    print("toolpath_dwell_cases.json:", [c["rows"] for c in out])
+
+
 def toolpath_golden(cF):
     """The reference's own G-code parser (createPath.parsingGcode cP:6-188, unmodified) on its own example."""
     import importlib
@@ -115,5 +159,6 @@ if __name__ == "__main__":
         _cF = shim.load_reference()
         toolpath_golden(_cF)
         toolpath_golden_serpentine(_cF)
+        toolpath_golden_dwell(_cF)
     else:
         main()

@@ -107,3 +107,88 @@ def test_driver_loop_reproduces_the_reference_driver(tmp_path, case):
     a, b = np.asarray(got["accum_time"], np.float32), np.asarray(ref["accum_time"], np.float32)
     assert a.shape == b.shape and b.max() > 0
     assert np.allclose(a, b, rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_example_json_first_rows_match_oracle(tmp_path):
+    """BASELINE.json configs[0]: examples/example.json verbatim (Level 1 50x20x30, Levels 2/3 100x100x10 elements,
+    N2 = N3 = 5) through go_melt() on the GPU against the oracle through the same loop, on the first 75 toolpath rows
+    = the 25 layer-start single steps (window shifts included) + two 25-row subcycle blocks.  The oracle needs about
+    a minute of one host core for them.  Temperatures within 1e-5 relative on every level, the melt pool (S2, T >=
+    T_liquidus), the states and the Level-0 index sets identical."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "bench_tools"))
+    import run_example
+    from oracle import computeFunctions as cF
+
+    drv = importlib.import_module("gomelt_b200.driver")
+    (tmp_path / "gpu").mkdir()
+    (tmp_path / "cpu").mkdir()
+    got = drv.go_melt(run_example.load_input(str(tmp_path / "gpu"), 75), write_final=False)
+    ref = drv.go_melt(run_example.load_input(str(tmp_path / "cpu"), 75), cf=cF, xp=NumpyArrays(), write_final=False)
+    assert got["counts"] == ref["counts"] and got["time_inc"] == ref["time_inc"] == 75
+    assert (got["counts"]["stepGOMELT"], got["counts"]["subcycleGOMELT"]) == (25, 2)
+    host = lambda a: a.detach().cpu().numpy() if hasattr(a, "detach") else np.asarray(a)
+    for lvl in (1, 2, 3):
+        a, b = host(got["Levels"][lvl]["T0"]), host(ref["Levels"][lvl]["T0"])
+        err = float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0)))
+        assert err <= 1e-5, (lvl, err)
+        assert np.array_equal(host(got["Levels"][lvl]["S1"]), host(ref["Levels"][lvl]["S1"])), lvl
+    s2g, s2r = host(got["Levels"][3]["S2"]).astype(bool), host(ref["Levels"][3]["S2"]).astype(bool)
+    assert s2r.sum() > 100 and np.array_equal(s2g, s2r)          # the melt pool exists and is identical
+    assert np.array_equal(host(got["Levels"][0]["S2"]).astype(bool), host(ref["Levels"][0]["S2"]).astype(bool))
+    assert np.array_equal(host(got["Levels"][0]["idx"]), host(ref["Levels"][0]["idx"]))
+    assert np.allclose(host(got["accum_time"]), host(ref["accum_time"]), rtol=1e-5, atol=1e-9)
+
+
+def _restart_vs_uninterrupted(tmp_path, cf, xp):
+    """gm:108-129 + 390-411: a two-layer run stopped at its first checkpoint (restart_layer_num = 1: the driver
+    returns right after writing Checkpoint0001, no final output) and restarted with layer_num = 1 must end exactly
+    where the uninterrupted run ends; the per-layer melt-time file accum_time0000.npz (gm:253-261) is written at the
+    layer change in both."""
+    drv = importlib.import_module("gomelt_b200.driver")
+    out = importlib.import_module("gomelt_b200.output")
+    hooks = {k: v for k, v in out.driver_hooks().items() if k in ("on_checkpoint", "load_checkpoint", "on_layer_accum")}
+    kw = dict(hooks=hooks, write_final=True)
+    if cf is not None:
+        kw.update(cf=cf, xp=xp)
+    for d in ("whole", "split"):
+        (tmp_path / d).mkdir()
+    whole = drv.go_melt(small_two_layer_input(str(tmp_path / "whole")), **kw)
+    assert whole["counts"]["layers"] == 2 and not whole["stopped_at_layer_check"]
+    assert os.path.exists(tmp_path / "whole" / "checkpoint" / "Checkpoint0001" / "header.json")
+    assert os.path.exists(tmp_path / "whole" / "accum_time0000.npz") and os.path.exists(tmp_path / "whole" / "accum_time0001.npz")
+    inp = small_two_layer_input(str(tmp_path / "split"))
+    inp["nonmesh"]["restart_layer_num"] = 1
+    first = drv.go_melt(inp, **kw)
+    assert first["stopped_at_layer_check"] and first["time_inc"] < whole["time_inc"]
+    assert not os.path.exists(tmp_path / "split" / "FinalTemperatureFields.npz")   # early return: no final files
+    inp = small_two_layer_input(str(tmp_path / "split"))
+    inp["nonmesh"].update(layer_num=1, use_txt=1)
+    second = drv.go_melt(inp, **kw)
+    assert second["time_inc"] == whole["time_inc"]
+    host = lambda a: a.detach().cpu().numpy() if hasattr(a, "detach") else np.asarray(a)
+    for lvl in (1, 2, 3):
+        for f in ("T0", "S1"):
+            assert np.array_equal(host(second["Levels"][lvl][f]), host(whole["Levels"][lvl][f])), (lvl, f)
+    assert np.array_equal(host(second["Levels"][3]["S2"]), host(whole["Levels"][3]["S2"]))
+    assert np.array_equal(host(second["Levels"][0]["S1"]), host(whole["Levels"][0]["S1"]))
+    assert host(whole["accum_time"]).max() > 0 and np.array_equal(host(second["accum_time"]), host(whole["accum_time"]))
+    a = np.load(tmp_path / "whole" / "accum_time0000.npz")["accum_time"]
+    b = np.load(tmp_path / "split" / "accum_time0000.npz")["accum_time"]
+    assert a.max() > 0 and np.array_equal(a, b)
+    # a restart without the checkpoint hook is an error, not a silent run from t = 0
+    with pytest.raises(RuntimeError, match="load_checkpoint"):
+        drv.go_melt(inp, **{**kw, "hooks": {}})
+
+
+def test_restart_from_checkpoint_equals_uninterrupted_run_oracle(tmp_path):
+    from oracle import computeFunctions as cF
+
+    _restart_vs_uninterrupted(tmp_path, cF, NumpyArrays())
+
+
+@pytest.mark.gpu
+def test_restart_from_checkpoint_equals_uninterrupted_run_gpu(tmp_path):
+    _restart_vs_uninterrupted(tmp_path, None, None)

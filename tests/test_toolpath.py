@@ -69,3 +69,33 @@ def test_serpentine_two_layer_toolpath_is_byte_identical_to_the_reference(tmp_pa
     assert n == 428 and text == golden
     n, text = _run_serpentine(cF.parsingGcode, cF.SetupNonmesh, tmp_path, "oracle")
     assert n == 428 and text == golden
+
+
+def test_dwell_row_counts_follow_the_reference_operation_order(tmp_path):
+    """Round-number dwell configurations (tests/golden/toolpath_dwell_cases.json: row count + sha256 of the text the
+    reference's own parser wrote, make_golden.py --toolpaths-only): the number of coarse dwell rows is
+    int(dwell / dt / coef) in that float operation order (cP:82-84, 173) - int(dwell / (dt * coef)) is off by one row
+    in about one configuration in seven.  Both parsers reproduce every case byte for byte."""
+    import hashlib
+    import json
+    import sys
+
+    from oracle import computeFunctions as cF
+
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import scenario
+
+    tp = importlib.import_module("gomelt_b200.toolpath")
+    sc = importlib.import_module("gomelt_b200.schema")
+    cases = json.load(open(os.path.join(HERE, "golden", "toolpath_dwell_cases.json")))
+    assert len(cases) >= 6
+    g = tmp_path / "serp.gcode"
+    g.write_text(scenario.SERPENTINE_GCODE)
+    for i, case in enumerate(cases):
+        for tag, parse, setup in (("product", tp.parsingGcode, sc.SetupNonmesh), ("oracle", cF.parsingGcode, cF.SetupNonmesh)):
+            out = tmp_path / f"{tag}{i}.txt"
+            nm = dict(scenario.SERPENTINE_NONMESH, save_path=str(tmp_path) + "/", gcode=str(g), toolpath=str(out))
+            nm.update(case["nonmesh"])
+            n = parse(setup(nm), {"laser_power": 285.0})
+            assert n == case["rows"], (tag, case["nonmesh"], n, case["rows"])
+            assert hashlib.sha256(out.read_bytes()).hexdigest() == case["sha256"], (tag, case["nonmesh"])

@@ -44,6 +44,8 @@ class StepArgs(C.Structure):
         ("z_chunk", C.c_int32),
         ("z_begin", C.c_int32), ("z_end", C.c_int32),
         ("peer_lo", C.c_void_p), ("peer_hi", C.c_void_p),
+        ("halo_sync", C.c_void_p), ("halo_sync_lo", C.c_void_p), ("halo_sync_hi", C.c_void_p),
+        ("halo_seq", C.c_uint32),
     ]
 
 
@@ -107,6 +109,7 @@ STEP_NO_COLD_PLANES = 0x100
 SIGNATURES = {
     "gomelt_abi_version": (C.c_int, []),
     "gomelt_launch_count": (C.c_longlong, []),
+    "gomelt_halo_sync_words": (C.c_longlong, [C.c_int32]),
     "gomelt_minmax_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "gomelt_last_error": (C.c_char_p, []),
     "gomelt_xla_ffi_available": (C.c_int, []),

@@ -7,12 +7,13 @@
 #include "gomelt_abi.h"
 
 #ifndef GOMELT_SM_COUNT
-#define GOMELT_SM_COUNT 148  // B200: 2 dies x 74 SMs
+#define GOMELT_SM_COUNT 148  // fallback when the device attribute cannot be read (B200: 2 dies x 74 SMs)
 #endif
 
 namespace gomelt {
 
 void set_error(const char* fmt, ...);
+int sm_count();  // multiprocessors of the current device (cudaDevAttrMultiProcessorCount, cached)
 void count_launch(int n = 1);  // process-wide count of kernels launched by the library (gomelt_launch_count)
 
 inline int check_launch(const char* what) {

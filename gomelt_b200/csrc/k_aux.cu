@@ -203,7 +203,7 @@ extern "C" int gomelt_minmax_f32(const float* x, int64_t n, float* out3, void* s
     cudaStream_t st = (cudaStream_t)stream;
     minmax_init_kernel<<<1, 1, 0, st>>>(out3), count_launch();
     long long blocks = (n + 4 * 256 - 1) / (4 * 256);
-    if (blocks > 8 * GOMELT_SM_COUNT) blocks = 8 * GOMELT_SM_COUNT;
+    if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
     minmax_kernel<<<(int)blocks, 256, 0, st>>>(x, n, out3), count_launch();
     return check_launch("gomelt_minmax_f32");
 }
@@ -225,7 +225,7 @@ extern "C" int gomelt_state_props_f32(const gomelt_props_t* props, const float* 
     }
     const int threads = 256;
     const long long want = (nn + threads - 1) / threads;
-    const int blocks = (int)(want < GOMELT_SM_COUNT * 8 ? want : GOMELT_SM_COUNT * 8);
+    const int blocks = (int)(want < sm_count() * 8 ? want : sm_count() * 8);
     state_props_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(fold_props(*props), T, S1, nn, n_substrate,
                                                                      S1_out, S2_out, k_out, rhocp_out), count_launch();
     return check_launch("gomelt_state_props_f32");

@@ -23,12 +23,34 @@
 #include "k_level_step_v2.cuh"
 #include "k_level_step_v3.cuh"
 
+static_assert(GOMELT_HALO_SYNC_HEAD >= 2, "two arrival counters precede the strip counters");
+
 namespace gomelt {
 
 
+// Development switches (A/B of kernel variants) exist only in a -DGOMELT_DEBUG build (GOMELT_NVCC_FLAGS=-DGOMELT_DEBUG
+// python gomelt_b200/build.py --force); the shipped library reads no environment variable on the step path.
+#ifdef GOMELT_DEBUG
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
+}
+#define GM_DEV_SWITCH(name, dflt) ([] { static const int v = env_int(name, dflt); return v; }())
+#else
+#define GM_DEV_SWITCH(name, dflt) (dflt)
+#endif
+
+int sm_count() {  // SMs of the current device (148 on B200), asked once per device
+    static thread_local int cached_dev = -1, cached_n = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = GOMELT_SM_COUNT;
+        cached_dev = dev;
+        cached_n = n;
+    }
+    return cached_n;
 }
 
 template <int RY, int WPB, int FEAT, int MINB = 1, bool STAGE = false>
@@ -39,23 +61,28 @@ static void launch_v2(const StepParams& sp, int nch, cudaStream_t st) {
     level_step_v2<RY, WPB, FEAT, MINB, STAGE><<<grid, block, 0, st>>>(sp), count_launch();
 }
 
-// Exact-feature instances for the call shapes the steppers issue; anything else runs the generic instance.
-// Except for the two benchmark shapes the substrate override is compiled in (its test is two integer
-// compares per row and n_substrate = 0 switches it off), so a shape is looked up with K1F_NSUB set.
-constexpr int F_L3_BENCH = K1F_SRC | K1F_FLUX | K1F_S1OUT | K1F_CLAMP;       // bench.py L3-10M window
-constexpr int F_L3_SUB = F_L3_BENCH | K1F_SKIP | K1F_NSUB;                     // subcycleL3_Part1 cF:3367-3412
+// Exact-feature instances of the general kernel for the call shapes the steppers issue on grids too small for the
+// fast kernel; anything else runs the generic instance.  The substrate override is compiled in (its test is two
+// integer compares per row and n_substrate = 0 switches it off), so a shape is looked up with K1F_NSUB set.
+constexpr int F_L3_SUB = K1F_SRC | K1F_FLUX | K1F_S1OUT | K1F_CLAMP | K1F_SKIP | K1F_NSUB;  // subcycleL3_Part1 cF:3367-3412
 constexpr int F_L3_SUB2 = F_L3_SUB | K1F_S2OUT | K1F_ACCUM;                    // subcycleL3_Part2 cF:3530-3590
 constexpr int F_L3_STEP = K1F_SRC | K1F_FLUX | K1F_CLAMP | K1F_SKIP | K1F_NSUB;  // stepGOMELT Level 3
 constexpr int F_L2 = K1F_RHS | K1F_FLUX | K1F_CLAMP | K1F_SKIP | K1F_NSUB;     // Level 2 (step / subcycle)
 constexpr int F_L1 = K1F_RHS | K1F_FLUX | K1F_CLAMP | K1F_BCCONST | K1F_NSUB;  // Level 1 (step / subcycle)
-constexpr int F_L1_DWELL = K1F_FLUX | K1F_BCCONST;                             // stepGOMELTDwellTime / slab bench
-constexpr int F_L1_DWELL_SUB = F_L1_DWELL | K1F_NSUB;
-constexpr int F_L1_DWELL_PEER = F_L1_DWELL | K1F_PEER;                         // ... with the fused halo stores
-constexpr int F_L1_DWELL_SUB_PEER = F_L1_DWELL_SUB | K1F_PEER;
+constexpr int F_L1_DWELL_SUB = K1F_FLUX | K1F_BCCONST | K1F_NSUB;              // stepGOMELTDwellTime
+constexpr int F_L1_DWELL_SUB_PEER = F_L1_DWELL_SUB | K1F_PEER;                 // ... with in-kernel peer stores (legacy)
 
-// 1-D tensor maps of T0 and S1 for the TMA ring of level_step_v3 (K1F_TMA): nn floats, K3_BOX-element boxes.
-// cuTensorMapEncodeTiled is taken from the driver through the runtime (no link-time dependency on libcuda).
-static bool make_field_tmaps(StepParams& sp) {
+// Tensor maps of a field for the TMA ring of level_step_v3 (K1F_TMA): nn floats as a 1-D tensor with K3_BOX-element
+// boxes, and as the overlapping 2-D view.  cuTensorMapEncodeTiled is taken from the driver through the runtime (no
+// link-time dependency on libcuda).  The steppers ping-pong a handful of buffers, so the encoded maps are kept in a
+// small per-thread cache keyed by (pointer, nn, nx): no driver call on the hot path after the first sweeps.
+struct TmapPair {
+    const void* base;
+    unsigned long long nn;
+    int nx, ok2;
+    CUtensorMap m1, m2;
+};
+static bool field_tmaps(const void* base, unsigned long long nn, int nx, CUtensorMap& m1, CUtensorMap& m2, int& ok2) {
     typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -67,32 +94,47 @@ static bool make_field_tmaps(StepParams& sp) {
             f = nullptr;
         return (encode_fn)f;
     }();
-    if (!enc) return false;
-    const void* base[2] = {sp.T0, sp.S1};
-    const cuuint64_t nn = (cuuint64_t)sp.nx * sp.ny * sp.nz;
+    if (!enc || ((uintptr_t)base & 15u) != 0) return false;
+    constexpr int NC = 16;
+    static thread_local TmapPair cache[NC];
+    static thread_local int next = 0;
+    for (int i = 0; i < NC; ++i)
+        if (cache[i].base == base && cache[i].nn == nn && cache[i].nx == nx) {
+            m1 = cache[i].m1; m2 = cache[i].m2; ok2 = cache[i].ok2;
+            return true;
+        }
+    TmapPair e;
+    e.base = base; e.nn = nn; e.nx = nx; e.ok2 = 1;
     const cuuint64_t dim1[1] = {nn}, stride0[1] = {0};  // stride unused for rank 1
     const cuuint32_t box1[1] = {K3_BOX}, estr[2] = {1, 1};
-    const cuuint64_t dim2[2] = {nn, 6}, stride2[1] = {(cuuint64_t)(sp.nx & ~3) * 4u};
+    const cuuint64_t dim2[2] = {nn, 6}, stride2[1] = {(cuuint64_t)(nx & ~3) * 4u};
     const cuuint32_t box2[2] = {K3_BOX, 6};
-    sp.tm2_ok = 1;
-    for (int q = 0; q < 2; ++q) {
-        if (((uintptr_t)base[q] & 15u) != 0) return false;
-        void* b = const_cast<void*>(base[q]);
-        if (enc(&sp.tm[q], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 1, b, dim1, stride0, box1, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return false;
-        if (enc(&sp.tm2[q], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, b, dim2, stride2, box2, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            sp.tm2_ok = 0;  // the six 1-D boxes per field and plane serve every tile then
-    }
-    static const int no2d = env_int("GOMELT_K1_TMA_1D", 0);
-    if (no2d) sp.tm2_ok = 0;
+    void* b = const_cast<void*>(base);
+    if (enc(&e.m1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 1, b, dim1, stride0, box1, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    if (enc(&e.m2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, b, dim2, stride2, box2, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        e.ok2 = 0;  // the six 1-D boxes per field and plane serve every tile then
+    cache[next] = e;
+    next = (next + 1) % NC;
+    m1 = e.m1; m2 = e.m2; ok2 = e.ok2;
+    return true;
+}
+static bool make_field_tmaps(StepParams& sp) {
+    const unsigned long long nn = (unsigned long long)sp.nx * sp.ny * sp.nz;
+    int okT = 0, okS = 0;
+    if (!field_tmaps(sp.T0, nn, sp.nx, sp.tm[0], sp.tm2[0], okT)) return false;
+    if (!field_tmaps(sp.S1, nn, sp.nx, sp.tm[1], sp.tm2[1], okS)) return false;
+    sp.tm2_ok = (okT && okS && !GM_DEV_SWITCH("GOMELT_K1_TMA_1D", 0)) ? 1 : 0;
     return true;
 }
 
 template <int RY, int FEAT, int MINB = 1>
 static void launch_v3(const StepParams& sp, int nch, cudaStream_t st) {
-    dim3 grid((sp.nx - 2 + 2 * K1_TX - 1) / (2 * K1_TX), (sp.ny - 2 + RY - 1) / RY, nch);
+    // Level-1 shapes: one extra z layer of CTAs writes the Dirichlet constants of the five faces (see the kernel)
+    const int face_layer = (sp.feat & K1F_BCCONST) ? 1 : 0;
+    dim3 grid((sp.nx - 2 + 2 * K1_TX - 1) / (2 * K1_TX), (sp.ny - 2 + RY - 1) / RY, nch + face_layer);
     if constexpr ((FEAT & K1F_TMA) != 0) {  // 8 resident warps x 20 KB: ask for the large shared-memory carve-out once
         static const cudaError_t carve = cudaFuncSetAttribute(level_step_v3<RY, FEAT, MINB>,
                                                                cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -103,15 +145,11 @@ static void launch_v3(const StepParams& sp, int nch, cudaStream_t st) {
 }
 
 // v3 (k_level_step_v3.cuh) serves the Dirichlet-side-face shapes of the steppers on grids that hold a full tile.
-// Returns false when the call is not one of them (v2 takes it).  GOMELT_STEP_BC_CONST calls get their five
-// constant faces from face_const_kernel (the step itself never stores a face node).
+// Returns false when the call is not one of them (v2 takes it).
 static bool try_launch_v3(StepParams& sp, int nch, cudaStream_t st) {
-    static const int off = env_int("GOMELT_K1_V2", 0);  // dev A/B: force the v2 path
-    static const int pf = env_int("GOMELT_K1_PF", 0);
-    static const int tma = env_int("GOMELT_K1_TMA", 1);
     constexpr int RY = 4;
     const int f = sp.feat;
-    if (off || (sp.flags & GOMELT_STEP_GENERAL_KERNEL) || !(f & (K1F_SKIP | K1F_BCCONST)) ||
+    if (GM_DEV_SWITCH("GOMELT_K1_V2", 0) || (sp.flags & GOMELT_STEP_GENERAL_KERNEL) || !(f & (K1F_SKIP | K1F_BCCONST)) ||
         (f & K1F_TOP))
         return false;
     if (sp.nx < 2 * K1_TX + 2 || sp.ny < RY + 2 || sp.nzl < 2 || sp.nsub_rem != 0) return false;
@@ -121,24 +159,19 @@ static bool try_launch_v3(StepParams& sp, int nch, cudaStream_t st) {
     constexpr int V3_L3_SUB2 = V3_L3_SUB | K1F_S2OUT | K1F_ACCUM;                       // subcycleL3_Part2 (melt-time bookkeeping)
     constexpr int V3_L3_STEP = K1F_SRC | K1F_FLUX | K1F_CLAMP | K1F_NSUB;             // stepGOMELT Level 3
     constexpr int V3_RHS = K1F_RHS | K1F_FLUX | K1F_CLAMP | K1F_NSUB;                 // Level 2 and Level 1 (step / subcycle)
+    constexpr int V3_RHS_NC = K1F_RHS | K1F_FLUX | K1F_NSUB;                          // ... without the clamp (stepGOMELT parents)
     constexpr int V3_DWELL = K1F_FLUX | K1F_NSUB;                                     // stepGOMELTDwellTime (no clamp)
-    constexpr int V3_DWELL_PEER = V3_DWELL | K1F_PEER;                                // ... with the fused halo stores
     // The TMA plane ring (+ cold-plane path) needs 16-byte aligned field pointers and the driver's tensor-map encoder;
-    // GOMELT_K1_TMA=0 keeps every shape on the register-prefetch form (A/B).
-    const bool t = tma && make_field_tmaps(sp);
-    // z-slab ranks: the boundary planes go to the neighbours by halo_push_kernel after the step (GOMELT_K1_PEER_PUSH=0:
-    // stored from inside the stencil kernel, K1F_PEER)
-    static const int push = env_int("GOMELT_K1_PEER_PUSH", 1);
-    float* const push_lo = sp.peer_lo;
-    float* const push_hi = sp.peer_hi;
-    const bool do_push = push && (f & K1F_PEER) && (sp.zend - sp.zbeg) >= 1;
-    int fsw = (f & ~(K1F_SKIP | K1F_BCCONST)) | K1F_NSUB;
-    if (do_push) fsw &= ~K1F_PEER;
-#define GM_V3(FEATS)                                              \
-    do {                                                          \
-        if (t) launch_v3<RY, (FEATS) | K1F_TMA>(sp, nch, st);     \
-        else launch_v3<RY, (FEATS)>(sp, nch, st);                 \
-    } while (0)
+    // without them the general kernel takes the call.
+    if (!make_field_tmaps(sp)) return false;
+    // z-slab ranks.  halo_sync given: the fused protocol (K1F_HALO).  Only peer pointers: the boundary planes go out by
+    // halo_push_kernel after the step and the caller orders the sweeps (legacy; kept for A/B and for callers that
+    // bring their own barrier).
+    const bool halo = (f & K1F_PEER) && sp.hsync != nullptr;
+    const bool do_push = (f & K1F_PEER) && !halo && (sp.zend - sp.zbeg) >= 1;
+    if (halo && nch != 1) return false;  // one chunk per slab: the strip counters expect one finaliser per tile
+    const int fsw = ((f & ~(K1F_SKIP | K1F_BCCONST | K1F_PEER)) | K1F_NSUB) | (halo ? K1F_HALO : 0);
+#define GM_V3(FEATS) launch_v3<RY, (FEATS) | K1F_TMA>(sp, nch, st)
     switch (fsw) {
         case V3_L3_SUB:
             // in place (the steppers): a node's state is stored only when it changed
@@ -151,28 +184,25 @@ static bool try_launch_v3(StepParams& sp, int nch, cudaStream_t st) {
             break;
         case V3_L3_STEP: GM_V3(V3_L3_STEP); break;
         case V3_RHS: GM_V3(V3_RHS); break;  // (the rhs rows are fetched a plane ahead into registers there)
-        // The dwell shapes (few planes per warp, several waves of warps) are latency-bound.  An L2 prefetch three
-        // planes ahead (prefetch.global.L2, opt-in GOMELT_K1_PF=1) took a 25 M-node sweep from 121.7 to 111.6 us on
-        // one box, but the same instruction has been seen to cost ~4.5 ns EACH, serialised (5.7 ms per sweep on
-        // peer-mapped symmetric memory, 1.2-2.4 ms per 10 M-node sweep on plain cudaMalloc memory of another box).
-        case V3_DWELL:
-            if (pf) launch_v3<RY, V3_DWELL | K1F_PF>(sp, nch, st);
-            else GM_V3(V3_DWELL);
-            break;
-        case V3_DWELL_PEER: GM_V3(V3_DWELL_PEER); break;
+        case V3_RHS_NC: GM_V3(V3_RHS_NC); break;
+        case V3_DWELL: GM_V3(V3_DWELL); break;
+        case V3_RHS | K1F_HALO: GM_V3(V3_RHS | K1F_HALO); break;
+        case V3_DWELL | K1F_HALO: GM_V3(V3_DWELL | K1F_HALO); break;
         default: return false;
     }
 #undef GM_V3
-    if (f & K1F_BCCONST) {
-        const long long n = (long long)(2 * sp.nx + 2 * sp.ny) * (sp.zend - sp.zbeg) + (sp.zbeg == 0 ? (long long)sp.nx * sp.ny : 0);
-        const int blocks = (int)((n + 255) / 256 < 4 * GOMELT_SM_COUNT ? (n + 255) / 256 : 4 * GOMELT_SM_COUNT);
-        face_const_kernel<<<blocks, 256, 0, st>>>(sp.Tout, sp.nx, sp.ny, sp.nz, sp.zbeg, sp.zend, sp.bc[0], sp.bc[1], sp.bc[2],
-                                                  sp.bc[3], sp.bc[4], sp.peer_lo, sp.peer_hi), count_launch();
-    }
     if (do_push) {
+        // legacy z-slab path: the neighbours' ghost planes also get the face constants of the boundary planes
+        if (f & K1F_BCCONST) {
+            const long long n = (long long)(2 * sp.nx + 2 * sp.ny) * (sp.zend - sp.zbeg) + (sp.zbeg == 0 ? (long long)sp.nx * sp.ny : 0);
+            const int cap = 4 * sm_count();
+            const int blocks = (int)((n + 255) / 256 < cap ? (n + 255) / 256 : cap);
+            face_const_kernel<<<blocks, 256, 0, st>>>(sp.Tout, sp.nx, sp.ny, sp.nz, sp.zbeg, sp.zend, sp.bc[0], sp.bc[1], sp.bc[2],
+                                                      sp.bc[3], sp.bc[4], sp.peer_lo, sp.peer_hi), count_launch();
+        }
         const int plane = sp.nx * sp.ny;
         dim3 grid((plane / 4 + 255) / 256, 2);
-        halo_push_kernel<<<grid, 256, 0, st>>>(sp.Tout, plane, sp.zbeg, sp.zend - 1, push_lo, push_hi), count_launch();
+        halo_push_kernel<<<grid, 256, 0, st>>>(sp.Tout, plane, sp.zbeg, sp.zend - 1, sp.peer_lo, sp.peer_hi), count_launch();
     }
     return true;
 }
@@ -180,20 +210,15 @@ static bool try_launch_v3(StepParams& sp, int nch, cudaStream_t st) {
 static int launch_step(StepParams& sp, cudaStream_t st) {
     const int nch = (sp.zend - sp.zbeg + sp.zchunk - 1) / sp.zchunk;
     if (try_launch_v3(sp, nch, st)) return check_launch("gomelt_level_step_f32");
-    static const int generic_only = env_int("GOMELT_K1_GENERIC", 0);
-    static const int exp = env_int("GOMELT_K1_EXP", 0);  // dev A/B of the benchmark shape
+    if (sp.hsync) {
+        set_error("gomelt_level_step_f32: halo_sync (the fused halo protocol) needs the fast kernel: nx >= %d, ny >= 6, >= 2 "
+                  "active planes, whole-plane substrate, 16-byte aligned T0 / S1, Dirichlet side faces", 2 * K1_TX + 2);
+        return GOMELT_E_FLAGS;
+    }
     constexpr int RY = 4, WPB = 1;  // one warp per CTA: warps are independent, finest SM balance
     const int f = sp.feat;
-    if (generic_only) {
+    if (GM_DEV_SWITCH("GOMELT_K1_GENERIC", 0)) {
         launch_v2<RY, WPB, K1F_ALL | K1F_GENERIC>(sp, nch, st);
-    } else if (f == F_L3_BENCH) {
-        if (exp == 1) launch_v2<4, 1, F_L3_BENCH, 1, true>(sp, nch, st);        // cp.async-staged prefetch
-        else if (exp == 2) launch_v2<3, 1, F_L3_BENCH, 12, true>(sp, nch, st);  // ... RY = 3, 12 warps / SM
-        else launch_v2<RY, WPB, F_L3_BENCH>(sp, nch, st);
-    } else if (f == F_L1_DWELL) {
-        launch_v2<RY, WPB, F_L1_DWELL>(sp, nch, st);
-    } else if (f == F_L1_DWELL_PEER) {
-        launch_v2<RY, WPB, F_L1_DWELL_PEER>(sp, nch, st);
     } else {
         switch (f | K1F_NSUB) {
             case F_L3_SUB: launch_v2<RY, WPB, F_L3_SUB>(sp, nch, st); break;
@@ -212,6 +237,8 @@ static int launch_step(StepParams& sp, cudaStream_t st) {
 }  // namespace gomelt
 
 using namespace gomelt;
+
+extern "C" long long gomelt_halo_sync_words(int32_t ny) { return GOMELT_HALO_SYNC_HEAD + 2LL * ((ny - 2 + 3) / 4 + 1); }
 
 extern "C" int gomelt_level_step_f32(const gomelt_props_t* props, const gomelt_step_args_t* a, void* stream) {
     if (!props || !a || !a->T0 || !a->S1 || !a->T_out) {
@@ -292,9 +319,17 @@ extern "C" int gomelt_level_step_f32(const gomelt_props_t* props, const gomelt_s
     sp.flags = a->flags;
     sp.zbeg = zbeg; sp.zend = zend;
     sp.peer_lo = a->peer_lo; sp.peer_hi = a->peer_hi;
-    {
-        static const int exp_env = env_int("GOMELT_K1_EXP", 0);
-        sp.exp = exp_env;
+    sp.exp = GM_DEV_SWITCH("GOMELT_K1_EXP", 0);
+    sp.hsync = a->halo_sync; sp.hsync_lo = a->halo_sync_lo; sp.hsync_hi = a->halo_sync_hi;
+    if (sp.hsync) {
+        if ((a->peer_lo != nullptr) != (a->halo_sync_lo != nullptr) || (a->peer_hi != nullptr) != (a->halo_sync_hi != nullptr) ||
+            !(a->flags & GOMELT_STEP_BC_CONST)) {
+            set_error("gomelt_level_step_f32: halo_sync needs GOMELT_STEP_BC_CONST and a peer plane + a peer counter block per neighbour");
+            return GOMELT_E_FLAGS;
+        }
+        sp.hneed = (unsigned)((g.ny - 2 + 3) / 4) * a->halo_seq;  // strips per plane (RY = 4) x sweeps so far
+    } else {
+        sp.hneed = 0;
     }
     {
         const long long Pn = (long long)g.nx * g.ny;

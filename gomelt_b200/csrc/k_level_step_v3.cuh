@@ -212,6 +212,54 @@ GM_DI void bookkeep_planes(const StepParams& p, const size_t* pl, const unsigned
     }
 }
 
+
+// ---- fused halo exchange (K1F_HALO) --------------------------------------------------------------------------
+// Counter block of a z-slab rank (uint32 words in peer-visible memory, all monotonic, zeroed once at set-up):
+//   [0] strips of the LOWER neighbour's top plane that have arrived in this rank's lower ghost plane
+//   [1] strips of the UPPER neighbour's bottom plane that have arrived in this rank's upper ghost plane
+//   [GOMELT_HALO_SYNC_HEAD + s]            tiles of strip s that have finalised this rank's first owned plane
+//   [GOMELT_HALO_SYNC_HEAD + nstrips + s]  ... its last owned plane
+// Protocol of sweep q (q = 0, 1, ...): every warp that finalises its rows of a boundary plane bumps the strip's tile
+// counter; the warp that arrives LAST (all tiles of the strip are stored) copies the strip's RY full rows into the
+// neighbour's ghost plane with destination-aligned 16-byte stores - the x- / x+ face columns get their Dirichlet
+// constants, which the step itself never stores - and then adds 1 to the neighbour's arrival counter with a
+// system-scope release.  A warp of sweep q + 1 reads a ghost plane only after an acquire-load sees nstrips (q + 1)
+// arrivals.  The temperature buffers rotate through THREE halves, so the ghost plane written during sweep q + 1
+// was last read in sweep q - 1, which every rank has left before its neighbour can have started sweep q + 1:
+// no second (write-after-read) flag, no barrier launch, no separate push kernel.
+GM_DI unsigned ld_acquire_sys(const unsigned* q) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(q) : "memory");
+    return v;
+}
+GM_DI void red_release_sys_add(unsigned* q, unsigned v) {
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(q), "r"(v) : "memory");
+}
+GM_DI void halo_wait(const unsigned* flag, unsigned need) {
+    // (int) difference: the counters are monotonic modulo 2^32
+    while ((int)(ld_acquire_sys(flag) - need) < 0) __nanosleep(64);
+}
+// rows [j0, j0 + nrows) of plane `src` (nx floats each, contiguous) -> the same rows of the peer ghost plane `dst`
+GM_DI void halo_push_rows(const float* __restrict__ src, float* __restrict__ dst, int nx, int j0, int nrows, float bx0, float bx1,
+                          int lane) {
+    const int e0 = j0 * nx, e1 = (j0 + nrows) * nx;
+    auto value = [&](int e) -> float {
+        const int i = e % nx;
+        const float v = __ldcg(src + e);
+        return i == 0 ? bx0 : (i == nx - 1 ? bx1 : v);
+    };
+    const int head = (int)((4u - ((unsigned)((uintptr_t)(dst + e0) >> 2) & 3u)) & 3u);  // scalars before the first aligned quad
+    const int q0 = e0 + head, nquad = (e1 - q0) >> 2;
+    if (lane < head) dst[e0 + lane] = value(e0 + lane);
+#pragma unroll 4
+    for (int q = lane; q < nquad; q += 32) {
+        const int e = q0 + 4 * q;
+        *reinterpret_cast<float4*>(dst + e) = make_float4(value(e), value(e + 1), value(e + 2), value(e + 3));
+    }
+    const int t0 = q0 + 4 * nquad;
+    if (lane < e1 - t0) dst[t0 + lane] = value(t0 + lane);
+}
+
 template <int RY>
 struct K3State {  // x-staged fields of one plane (loaded rows) + T of the owned rows
     f2 Xs[RY + 2], Xd[RY + 2], kx[RY + 2], mx[RY + 2], T[RY];
@@ -231,6 +279,8 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     constexpr bool F_S2 = (FEAT & K1F_S2OUT) != 0, F_ACC = (FEAT & K1F_ACCUM) != 0;
     constexpr bool F_PEER = (FEAT & K1F_PEER) != 0, F_PF = (FEAT & K1F_PF) != 0, F_INPLACE = (FEAT & K1F_S1INPLACE) != 0;
     constexpr bool F_TMA = (FEAT & K1F_TMA) != 0;
+    constexpr bool F_HALO = (FEAT & K1F_HALO) != 0;
+    static_assert(!F_HALO || F_TMA, "the fused halo protocol lives in the TMA variant");
     // the cold-plane path needs the whole plane before its first row, i.e. the TMA ring (see plane_is_cold); in the
     // corrector substeps a plane that took it also needs no vote on the liquidus for its melt-time bookkeeping
     constexpr bool USE_COLD = F_TMA;
@@ -258,6 +308,31 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     const int qa = ((own && ia >= x_new) || ia == 0) ? 1 : 0, qb = ((own && ib >= x_new) || ib == nx - 1) ? 1 : 0;
     const int P = nx * ny;
     const int za = p.zbeg + blockIdx.z * p.zchunk;
+    if (za >= p.zend) {
+        // extra z layer of the grid (Level-1 shapes, K1F_BCCONST): assignBCs cF:1568-1595 - the Dirichlet constants on
+        // the five faces of T_out, planes [zbeg, zend), order y-, y+, x-, x+, z- (the later face wins on shared edges).
+        // The step never stores a face node, so these CTAs are independent of the stencil CTAs of the same launch.
+        const int per_plane = 2 * nx + 2 * ny;
+        const long long nside = (long long)per_plane * (p.zend - p.zbeg);
+        const long long nbot = (p.zbeg == 0) ? (long long)P : 0;
+        const long long stride = (long long)gridDim.x * gridDim.y * 32;
+        for (long long t = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 32 + lane; t < nside + nbot; t += stride) {
+            if (t < nside) {
+                const int z = p.zbeg + (int)(t / per_plane), q = (int)(t % per_plane);
+                if (z == 0) continue;  // the bottom plane is written whole below
+                int i, j;
+                float v;
+                if (q < nx) { i = q; j = 0; v = (i == 0) ? p.bc[2] : (i == nx - 1) ? p.bc[3] : p.bc[0]; }
+                else if (q < 2 * nx) { i = q - nx; j = ny - 1; v = (i == 0) ? p.bc[2] : (i == nx - 1) ? p.bc[3] : p.bc[1]; }
+                else if (q < 2 * nx + ny) { i = 0; j = q - 2 * nx; v = p.bc[2]; }
+                else { i = nx - 1; j = q - 2 * nx - ny; v = p.bc[3]; }
+                p.Tout[(size_t)z * P + (size_t)j * nx + i] = v;
+            } else {
+                p.Tout[t - nside] = p.bc[4];
+            }
+        }
+        return;
+    }
     const int zb = min(p.zend, za + p.zchunk);  // this warp finalises node planes [za, zb)
     const int lfirst = max(za - 1, 0);
     const int llast = min(min(zb, nz - 1), nzl - 1);  // last plane that carries data
@@ -326,6 +401,7 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     if (F_TMA) asm volatile("mov.b64 %0, %0;\n\tmov.b64 %1, %1;" : "+l"(d2T), "+l"(d2S));
     auto ring_issue = [&](int l) {
         if (l > llast) return;
+        if (F_HALO && l == p.zend && p.hsync_hi) halo_wait(p.hsync + 1, p.hneed);  // the upper neighbour's bottom plane
         const unsigned s = (unsigned)(l - lfirst) & (NS - 1);
         // (no __syncwarp: the stage was last read a whole plane ago, and the votes since then are warp-wide)
         if (elect_one()) {
@@ -689,6 +765,27 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
         for (int r = 0; r < RY; ++r) final_row(f, out, rhs, rq, r, sz, Tf[r], Tt0[r], Tt1[r], myp[r], true, fl[r]);
     };
 
+    // fused halo: this warp has stored its rows of boundary plane f (which = 0: first owned plane -> lower neighbour,
+    // 1: last owned plane -> upper neighbour); see the protocol above
+    auto halo_strip_done = [&](int which, int f) {
+        if (!F_HALO) return;
+        unsigned* peer_sync = which == 0 ? p.hsync_lo : p.hsync_hi;
+        float* peer_plane = which == 0 ? p.peer_lo : p.peer_hi;
+        if (!peer_sync) return;
+        __syncwarp();
+        __threadfence();
+        unsigned old = 0;
+        if (lane == 0) old = atomicAdd(p.hsync + GOMELT_HALO_SYNC_HEAD + which * (int)gridDim.y + (int)blockIdx.y, 1u);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if ((old + 1u) % gridDim.x != 0u) return;
+        __threadfence();
+        halo_push_rows(p.Tout + (size_t)f * P, peer_plane, nx, j0, RY, p.bc[2], p.bc[3], lane);
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) red_release_sys_add(peer_sync + (which == 0 ? 1 : 0), 1u);
+    };
+    if (F_HALO && p.hsync_lo && za == p.zbeg) halo_wait(p.hsync + 0, p.hneed);  // the lower neighbour's top plane
+
     int fdone = za;  // planes [za, fdone) are finalised
     if (lfirst <= llast) {
         K3State<RY> stA, stB;
@@ -713,11 +810,13 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
                 ring_fetch(l, raw);
                 load_rhs(l, rqB);
                 run_plane(l, raw, stA, stB, l - 1 >= max(za, 1), sfx * splat(srcz_at(l - 1)), F_RHS ? rqA : nullptr);
+                if (F_HALO && l - 1 == p.zbeg && l - 1 < p.zend - 1) halo_strip_done(0, l - 1);
                 if (l + 1 > llast) break;
                 ring_issue(l + NS);
                 ring_fetch(l + 1, raw);
                 load_rhs(l + 1, rqA);
                 run_plane(l + 1, raw, stB, stA, l >= max(za, 1), sfx * splat(srcz_at(l)), F_RHS ? rqB : nullptr);
+                if (F_HALO && l == p.zbeg && l < p.zend - 1) halo_strip_done(0, l);
             }
             if (llast >= za && llast < zb) {  // raw holds plane llast
                 if (((llast - lfirst) & 1) != 0) last_plane(llast, stB.T, raw, F_RHS ? rqB : nullptr);
@@ -752,6 +851,12 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
         char* out = (char*)(p.Tout + (size_t)f * P);
 #pragma unroll
         for (int r = 0; r < RY; ++r) st2(out + off[r + 1], owna, ownb, splat(p.pk.T_amb));
+    }
+    if (F_HALO) {
+        // every owned plane of this chunk is stored now: the last owned plane goes up; the first one goes down here only
+        // when the march did not reach it (a one-plane slab, or the plane lies in the inactive region)
+        if (za == p.zbeg && !(p.zbeg >= max(za, 1) && p.zbeg + 1 <= llast && p.zbeg < p.zend - 1)) halo_strip_done(0, p.zbeg);
+        if (zb == p.zend) halo_strip_done(1, p.zend - 1);
     }
 }
 

@@ -439,7 +439,7 @@ __global__ void project_nodes_kernel(const float* __restrict__ cellsum, int c0x,
 
 static inline int grid_for(long long n, int threads) {
     long long b = (n + threads - 1) / threads;
-    const long long cap = (long long)GOMELT_SM_COUNT * 16;
+    const long long cap = (long long)sm_count() * 16;
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 

@@ -29,10 +29,12 @@ def _chk_f32(t, n, name):
 
 def level_step(props, grid, T0, S1, T_out, dt, *, rhs=None, src=None, topflux=None, nz_active=None,
                n_substrate=0, flags=0, bc5=None, S1_out=None, S2_out=None, S2_prev=None, accum=None,
-               max_accum=None, z_chunk=0, z_range=None, peer_lo=None, peer_hi=None):
+               max_accum=None, z_chunk=0, z_range=None, peer_lo=None, peer_hi=None, halo=None):
     """K1 (gomelt_level_step_f32): one explicit sweep of one level.  ``src`` = (tx, ty, tz, coef).
     ``peer_lo`` / ``peer_hi`` = raw device addresses (int) of the z-neighbours' ghost planes in peer-mapped
-    memory: the boundary planes of ``T_out`` are stored there by the same kernel."""
+    memory.  ``halo`` = (sync, sync_lo, sync_hi, seq): the fused halo protocol of gomelt_abi.h (raw addresses of this
+    rank's and the neighbours' counter blocks, sweep sequence number); without it the boundary planes are pushed after
+    the step and the caller orders the sweeps."""
     lib = _lib.load()
     nn = grid.nx * grid.ny * grid.nz
     for t, name in ((T0, "T0"), (S1, "S1"), (T_out, "T_out"), (rhs, "rhs"), (S1_out, "S1_out"),
@@ -61,6 +63,10 @@ def level_step(props, grid, T0, S1, T_out, dt, *, rhs=None, src=None, topflux=No
     if z_range is not None:
         a.z_begin, a.z_end = int(z_range[0]), int(z_range[1])
     a.peer_lo, a.peer_hi = (int(peer_lo) if peer_lo else None), (int(peer_hi) if peer_hi else None)
+    if halo is not None:
+        sync, slo, shi, seq = halo
+        a.halo_sync, a.halo_sync_lo, a.halo_sync_hi = int(sync), (int(slo) if slo else None), (int(shi) if shi else None)
+        a.halo_seq = int(seq)
     _lib.check(lib.gomelt_level_step_f32(C.byref(props), C.byref(a), _lib.stream_ptr()), "gomelt_level_step_f32")
     _count()
     return T_out

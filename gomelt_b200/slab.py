@@ -6,13 +6,14 @@ contiguous floats and a halo is a zero-copy slice.  Each rank stores its owned p
 plus one ghost plane per neighbour; an explicit sweep (stepGOMELTDwellTime cF:2617-2664) needs the
 neighbour's boundary plane of T (27-point stencil, radius 1) and - once - of S1.
 
-Per sweep, fused path (``symmetric=True``, the default on GPUs): the temperature buffers live in
-peer-mapped symmetric memory (torch.distributed._symmetric_memory: CUDA VMM handles exchanged once), and
-ONE launch of K1 over the owned planes also stores its two boundary planes straight into the
-neighbours' ghost planes with plain st.global over NVLink (gomelt_step_args_t.peer_lo / peer_hi) - the
-halo exchange is fused into the step.  A device-side barrier on the stream then orders sweep s+1 after
-every rank's sweep s (it protects both the ghost planes just written and the buffers about to be
-overwritten).  No NCCL call, no pack / copy kernel, no boundary / interior split.
+Per sweep, fused path (``symmetric=True``, the default on GPUs): the temperature lives in peer-mapped symmetric
+memory (torch.distributed._symmetric_memory: CUDA VMM handles exchanged once) as THREE rotating buffers plus a block
+of uint32 counters, and a sweep is ONE kernel launch (gomelt_level_step_f32 with ``halo_sync``, see gomelt_abi.h):
+a warp reads a ghost plane only after an acquire on this rank's arrival counter, the last warp to finish a 4-row
+strip of a boundary plane copies it into the neighbour's ghost plane with 16-byte stores over NVLink and bumps the
+neighbour's counter with a system-scope release, and one extra layer of CTAs writes the Dirichlet face constants.
+No NCCL call, no barrier launch, no pack / push kernel, no boundary / interior split.  (``fused=False`` keeps the
+round-1 form for A/B: two buffers, ``halo_push_kernel`` after the step, a symmetric-memory barrier per sweep.)
 
 Fallback path (``symmetric=False``; CPU tensors in the gloo tests, or GOMELT_SLAB_NCCL=1 for A/B):
   1. K1 on the two boundary planes of the owned range,
@@ -62,10 +63,11 @@ def exchange_planes(field, plane, z_begin, z_end, rank, world, group=None):
 
 
 class Level1Slab:
-    """One rank's slab of Level 1 in dwell mode (stepGOMELTDwellTime cF:2617-2664)."""
+    """One rank's slab of Level 1: explicit sweeps in dwell mode (stepGOMELTDwellTime cF:2617-2664) or with a load
+    vector and the clamp (the Level-1 sweeps of stepGOMELT / subcycleGOMELT, cF:2172-2185, 2813-2854)."""
 
     def __init__(self, gm, props, nodes, h, rank, world, bc5, nz_active=None, n_substrate=0, device=None,
-                 symmetric=False):
+                 symmetric=False, fused=True):
         self.gm, self.ops, self.props = gm, gm.ops, props
         self.rank, self.world = rank, world
         nx, ny, nz = (int(v) for v in nodes)
@@ -74,29 +76,32 @@ class Level1Slab:
         self.k0, self.k1 = partition_planes(nz, world)[rank]
         self.g0, self.nzl, self.zb, self.ze = local_extent(rank, world, self.k0, self.k1)
         self.grid = gm._lib.make_grid((nx, ny, self.nzl), h)
-        nza = nz if nz_active is None else int(nz_active)
-        self.nz_active_global = nza
-        self.nz_active = min(max(nza - self.g0, 0), self.nzl)
-        self.n_substrate = max(int(n_substrate) - self.g0 * self.plane, 0)
-        self.owns_top = self.k0 <= nza - 1 < self.k1
         self.bc5 = list(bc5)
         self.device = device
+        self.set_active(nz if nz_active is None else int(nz_active), n_substrate)
         n = self.plane * self.nzl
         self.symmetric = bool(symmetric) and world > 1 and device is not None
+        # the one-launch protocol needs the fast kernel (gomelt_abi.h: nx >= 62, ny >= 6) and two owned planes
+        self.fused = self.symmetric and bool(fused) and nx >= 62 and ny >= 6 and (self.k1 - self.k0) >= 2
         if self.symmetric:
             import torch.distributed._symmetric_memory as symm_mem
 
-            # one symmetric allocation of two halves (T and T_next), sized for the largest slab so that
-            # every rank's layout is the same; half h of rank q starts at ptrs[q] + 4 * h * nmax
+            # one symmetric allocation of three buffers, sized for the largest slab so that every rank's layout is
+            # the same (buffer b of rank q starts at ptrs[q] + 4 * b * nmax), followed by the counter block
             parts = partition_planes(nz, world)
-            # (rounded up to 128 bytes: K1's TMA plane ring wants 16-byte aligned field pointers for both halves)
+            # (rounded up to 128 bytes: K1's TMA plane ring wants 16-byte aligned field pointers for every buffer)
             self._nmax = -(-self.plane * (max(b - a for a, b in parts) + 2) // 32) * 32
-            self._buf = symm_mem.empty(2 * self._nmax, dtype=torch.float32, device=device)
+            self._nbuf = 3 if self.fused else 2
+            self._nsync = int(gm._lib.load().gomelt_halo_sync_words(ny))
+            self._buf = symm_mem.empty(self._nbuf * self._nmax + self._nsync, dtype=torch.float32, device=device)
             self._hdl = symm_mem.rendezvous(self._buf, dist.group.WORLD.group_name)
             self._ptrs = [int(q) for q in self._hdl.buffer_ptrs]
-            self._halves = [self._buf[:n], self._buf[self._nmax:self._nmax + n]]
+            self._halves = [self._buf[b * self._nmax:b * self._nmax + n] for b in range(self._nbuf)]
+            self._sync = self._buf[self._nbuf * self._nmax:].view(torch.int32)
+            self._sync.zero_()
+            self._seq = 0
             self._cur = 0
-            self.T, self.Tn = self._halves
+            self.T, self.Tn = self._halves[0], self._halves[1]
             # local index of the plane of each neighbour that mirrors my boundary plane
             self._ghost_lo = None if rank == 0 else local_extent(rank - 1, world, *parts[rank - 1])[3]  # its z_end
             self._ghost_hi = None if rank == world - 1 else 0                                            # its plane 0
@@ -104,9 +109,15 @@ class Level1Slab:
             self.T = torch.empty(n, dtype=torch.float32, device=device)
             self.Tn = torch.empty(n, dtype=torch.float32, device=device)
         self.S1 = torch.empty(n, dtype=torch.float32, device=device)
-        self.top = torch.zeros(self.plane, dtype=torch.float32, device=device)
         self.comm = torch.cuda.Stream(device=device) if (device is not None and world > 1 and not self.symmetric) else None
         self.sweeps = 0
+
+    def set_active(self, nz_active_global, n_substrate_global):
+        """tmp_ne_nn / substrate of the whole grid (cF:495-517, 562-579) -> this slab's local planes / node ids."""
+        self.nz_active_global = int(nz_active_global)
+        self.nz_active = min(max(self.nz_active_global - self.g0, 0), self.nzl)
+        self.n_substrate = min(max(int(n_substrate_global) - self.g0 * self.plane, 0), self.nzl * self.plane)
+        self.owns_top = self.k0 <= self.nz_active_global - 1 < self.k1
 
     # ---- state ---------------------------------------------------------------------------
     def owned(self, field):
@@ -118,7 +129,8 @@ class Level1Slab:
         self.fill_ghosts()
 
     def fill_ghosts(self):
-        """Initial ghost planes of T and S1 (S1 never changes in dwell mode)."""
+        """Ghost planes of T and S1 from the neighbours (collective); restarts the fused protocol: every buffer gets the
+        current field (so the Dirichlet face nodes of all ghost planes hold their constants), counters zeroed."""
         if self.world == 1:
             return
         for f in (self.T, self.S1):
@@ -126,55 +138,81 @@ class Level1Slab:
                 w.wait()
         if self.device is not None:
             torch.cuda.synchronize(self.device)
+        if self.symmetric:
+            for b in self._halves:
+                if b is not self.T:
+                    b.copy_(self.T)
+            self._sync.zero_()
+            self._seq = 0
+            torch.cuda.synchronize(self.device)
+            self._hdl.barrier(channel=0)
+            torch.cuda.synchronize(self.device)
 
     # ---- one sweep -----------------------------------------------------------------------
-    def _k1(self, dt, z0, z1, topflux):
+    def _flags(self, rhs, clamp, topflux=None):
+        return (self.ops.STEP_BC_CONST | (self.ops.STEP_FUSED_FLUX if topflux is None else 0)
+                | (self.ops.STEP_CLAMP if clamp else 0))
+
+    def _k1(self, dt, z0, z1, topflux, rhs=None, clamp=False):
         if z1 <= z0:
             return
         # the surface load of the top active plane (computeConvRadBC) is evaluated inside K1 by the launch
         # that finalises that plane; `topflux` is kept for callers that pre-computed it
-        flags = self.ops.STEP_BC_CONST | (self.ops.STEP_FUSED_FLUX if topflux is None else 0)
-        self.ops.level_step(self.props, self.grid, self.T, self.S1, self.Tn, dt, topflux=topflux,
+        self.ops.level_step(self.props, self.grid, self.T, self.S1, self.Tn, dt, topflux=topflux, rhs=rhs,
                             nz_active=self.nz_active, n_substrate=self.n_substrate,
-                            flags=flags, bc5=self.bc5, z_range=(z0, z1))
+                            flags=self._flags(rhs, clamp, topflux), bc5=self.bc5, z_range=(z0, z1))
 
     def _peer(self, q, half, ghost_plane):
         return self._ptrs[q] + 4 * (half * self._nmax + ghost_plane * self.plane)
 
-    def dwell_sweep_fused(self, dt):
-        """One launch: K1 over the owned planes, boundary planes also stored into the neighbours' ghost planes
-        of their next-temperature buffer; then a device-side barrier on the stream."""
-        nxt = 1 - self._cur
-        lo = self._peer(self.rank - 1, nxt, self._ghost_lo) if self.rank > 0 else None
-        hi = self._peer(self.rank + 1, nxt, self._ghost_hi) if self.rank < self.world - 1 else None
-        self.ops.level_step(self.props, self.grid, self._halves[self._cur], self.S1, self._halves[nxt], dt,
+    def _peer_sync(self, q):
+        return self._ptrs[q] + 4 * self._nbuf * self._nmax
+
+    def sweep_fused(self, dt, rhs=None, clamp=False):
+        """ONE launch: the fused level step over the owned planes with the halo protocol (see the module docstring)."""
+        cur = self._cur
+        nxt = (cur + 1) % self._nbuf
+        lo_rank, hi_rank = self.rank - 1, self.rank + 1
+        lo = self._peer(lo_rank, nxt, self._ghost_lo) if self.rank > 0 else None
+        hi = self._peer(hi_rank, nxt, self._ghost_hi) if self.rank < self.world - 1 else None
+        halo = None
+        if self.fused:
+            halo = (self._peer_sync(self.rank), self._peer_sync(lo_rank) if lo else None,
+                    self._peer_sync(hi_rank) if hi else None, self._seq)
+        self.ops.level_step(self.props, self.grid, self._halves[cur], self.S1, self._halves[nxt], dt, rhs=rhs,
                             nz_active=self.nz_active, n_substrate=self.n_substrate,
-                            flags=self.ops.STEP_BC_CONST | self.ops.STEP_FUSED_FLUX, bc5=self.bc5,
-                            z_range=(self.zb, self.ze), peer_lo=lo, peer_hi=hi)
-        self._hdl.barrier(channel=0)
+                            flags=self._flags(rhs, clamp), bc5=self.bc5,
+                            z_range=(self.zb, self.ze), peer_lo=lo, peer_hi=hi, halo=halo)
+        if self.fused:
+            self._seq += 1
+        else:
+            self._hdl.barrier(channel=0)  # round-1 form: pushed after the step, sweeps ordered by a barrier launch
         self._cur = nxt
-        self.T, self.Tn = self._halves[nxt], self._halves[1 - nxt]
+        self.T, self.Tn = self._halves[nxt], self._halves[(nxt + 1) % self._nbuf]
         self.sweeps += 1
         return self.T
 
     def dwell_sweep(self, dt):
+        return self.sweep(dt)
+
+    def sweep(self, dt, rhs=None, clamp=False):
         if self.symmetric:
-            return self.dwell_sweep_fused(dt)
+            return self.sweep_fused(dt, rhs, clamp)
         top = None
         zb, ze = self.zb, self.ze
         if self.world == 1:
-            self._k1(dt, zb, ze, top)
+            self._k1(dt, zb, ze, top, rhs, clamp)
         else:
             lo = zb + 1 if self.rank > 0 else zb
             hi = ze - 1 if self.rank < self.world - 1 else ze
             hi = max(hi, lo)
-            self._k1(dt, zb, lo, top)            # first owned plane (needed by the rank below)
-            self._k1(dt, hi, ze, top)            # last owned plane (needed by the rank above)
+            self._k1(dt, zb, lo, top, rhs, clamp)            # first owned plane (needed by the rank below)
+            self._k1(dt, hi, ze, top, rhs, clamp)            # last owned plane (needed by the rank above)
             main = torch.cuda.current_stream(self.device)
             self.comm.wait_stream(main)
             with torch.cuda.stream(self.comm):
                 works = exchange_planes(self.Tn, self.plane, zb, ze, self.rank, self.world)
-            self._k1(dt, lo, hi, top)            # interior overlaps the halo transfer
+            self._k1(dt, lo, hi, top, rhs, clamp)            # interior overlaps the halo transfer
             with torch.cuda.stream(self.comm):
                 for w in works:
                     w.wait()

@@ -21,7 +21,7 @@ def test_library_exports_every_header_symbol(gm):
         assert hasattr(lib, s), f"{s} declared in gomelt_abi.h but not exported"
     # and the python binding table covers the header
     assert set(syms) == set(gm._lib.SIGNATURES), set(syms) ^ set(gm._lib.SIGNATURES)
-    assert lib.gomelt_abi_version() == 1
+    assert lib.gomelt_abi_version() == 2
 
 
 def test_bad_arguments_are_rejected_without_a_gpu(gm):

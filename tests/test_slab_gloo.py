@@ -38,6 +38,7 @@ class _OracleOps:
     """Test double for gomelt_b200.ops on CPU tensors: the oracle's dwell step on the local slab."""
     STEP_BC_CONST = 0x08
     STEP_FUSED_FLUX = 0x40
+    STEP_CLAMP = 0x01
     LAUNCHES = 0
 
     def __init__(self, cF, P, make_level, h):
@@ -70,7 +71,10 @@ class _OracleOps:
         ne = (nx - 1) * (ny - 1) * max(nz_active - 1, 0)
         if (flags & self.STEP_FUSED_FLUX) and nz_active >= 2:  # computeConvRadBC inside the step
             F = cF.computeConvRadBC(lv, T, ne, nn, self.P, F)
-        Tn = cF.solveMatrixFreeFE(lv, nn, ne, k, rc, dt, T, F, 0)
+        rhs = kw.get("rhs")
+        Tn = cF.solveMatrixFreeFE(lv, nn, ne, k, rc, dt, T, F, 0 if rhs is None else rhs.numpy())
+        if flags & self.STEP_CLAMP:
+            Tn = np.maximum(Tn, np.float32(self.P["T_amb"]))
         Tn[nz_active * P_:] = np.float32(self.P["T_amb"])
         T3 = Tn.reshape(nz, ny, nx)
         T3[:, 0, :] = bc5[0]; T3[:, -1, :] = bc5[1]; T3[:, :, 0] = bc5[2]; T3[:, :, -1] = bc5[3]

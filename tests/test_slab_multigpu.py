@@ -1,6 +1,8 @@
-"""Level-1 z-slabs on real GPUs (needs >= 2 devices; skipped on a 1-GPU box): the fused halo path (K1 stores
-its boundary planes into the neighbours' ghost planes in peer-mapped symmetric memory) and the NCCL
-send/recv path both reproduce the single-GPU sweeps bit for bit."""
+"""Level-1 z-slabs on real GPUs (needs >= 2 devices; skipped on a 1-GPU box; uses EVERY device of the box): the
+one-launch fused halo protocol (strip-wise peer stores + release / acquire counters inside the step kernel, three
+rotating buffers), the round-1 form (push kernel + barrier launch) and the NCCL send/recv path all reproduce the
+single-GPU sweeps bit for bit - in dwell mode and in the load-vector + clamp shape of the stepGOMELT / subcycleGOMELT
+Level-1 sweeps.  The driver-visible copy of this check is the ``parity_check`` of the multi-GPU bench line."""
 import os
 import socket
 import sys
@@ -14,7 +16,7 @@ pytestmark = pytest.mark.gpu
 NODES = (131, 67, 23)
 H = (0.2, 0.2, 0.2)
 NZ_ACTIVE = 20
-NSWEEPS = 4
+NSWEEPS = 8   # > 2 turns of the three rotating buffers
 DT = 2e-3
 PROPS_IN = {"laser_radius": 0.1, "laser_depth": 0.1, "laser_absorptivity": 0.45, "T_amb": 298.15,
             "T_solidus": 1533, "T_liquidus": 1609, "h_conv": 1.5e-05, "emissivity": 0.3,
@@ -31,7 +33,17 @@ def _state():
     return T.astype(np.float32).reshape(-1), S1.reshape(-1)
 
 
-def _worker(rank, world, port, out, symmetric):
+def _rhs():
+    rng = np.random.default_rng(6)
+    nx, ny, nz = NODES
+    return (2e-4 * rng.standard_normal(nx * ny * nz)).astype(np.float32)
+
+
+MODES = {"fused": dict(symmetric=True, fused=True), "push_barrier": dict(symmetric=True, fused=False),
+         "nccl": dict(symmetric=False)}
+
+
+def _worker(rank, world, port, out, mode, shape):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -49,14 +61,18 @@ def _worker(rank, world, port, out, symmetric):
         T0, S1 = _state()
         nx, ny, nz = NODES
         sl = gm.slab.Level1Slab(gm, props, NODES, H, rank, world, BC5, nz_active=NZ_ACTIVE, n_substrate=3 * nx * ny,
-                                device=dev, symmetric=symmetric)
-        assert sl.symmetric == symmetric
+                                device=dev, **MODES[mode])
+        assert sl.symmetric == MODES[mode]["symmetric"] and sl.fused == (mode == "fused")
         pl = nx * ny
         sl.set_owned(torch.as_tensor(T0[sl.k0 * pl:sl.k1 * pl]).to(dev), torch.as_tensor(S1[sl.k0 * pl:sl.k1 * pl]).to(dev))
-        if symmetric:
-            sl._hdl.barrier(channel=0)
+        rhs = None
+        if shape == "rhs":
+            rhs = torch.as_tensor(_rhs()[sl.g0 * pl:(sl.g0 + sl.nzl) * pl]).to(dev)
+        l0 = gm.ops.LAUNCHES
         for _ in range(NSWEEPS):
-            sl.dwell_sweep(DT)
+            sl.sweep(DT, rhs=rhs, clamp=(shape == "rhs"))
+        if mode == "fused":
+            assert gm.ops.LAUNCHES - l0 == NSWEEPS, "the fused protocol is one launch per sweep"
         torch.cuda.synchronize()
         np.save(os.path.join(out, f"rank{rank}.npy"), sl.owned(sl.T).cpu().numpy())
         dist.barrier()
@@ -72,12 +88,13 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("symmetric", [True, False])
-def test_slabs_match_single_gpu_bitwise(tmp_path, gm, symmetric):
+@pytest.mark.parametrize("shape", ["dwell", "rhs"])
+@pytest.mark.parametrize("mode", list(MODES))
+def test_slabs_match_single_gpu_bitwise(tmp_path, gm, mode, shape):
     import torch
     import torch.multiprocessing as mp
 
-    world = min(torch.cuda.device_count(), 4)
+    world = torch.cuda.device_count()
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
     # single-GPU reference: the same sweeps on the whole grid
@@ -88,10 +105,11 @@ def test_slabs_match_single_gpu_bitwise(tmp_path, gm, symmetric):
     ref = gm.slab.Level1Slab(gm, props, NODES, H, 0, 1, BC5, nz_active=NZ_ACTIVE, n_substrate=3 * nx * ny,
                              device=torch.device("cuda", 0))
     ref.set_owned(torch.as_tensor(T0).cuda(), torch.as_tensor(S1).cuda())
+    rhs = torch.as_tensor(_rhs()).cuda() if shape == "rhs" else None
     for _ in range(NSWEEPS):
-        ref.dwell_sweep(DT)
+        ref.sweep(DT, rhs=rhs, clamp=(shape == "rhs"))
     want = ref.T.cpu().numpy()
-    mp.start_processes(_worker, args=(world, _free_port(), str(tmp_path), symmetric), nprocs=world, join=True,
+    mp.start_processes(_worker, args=(world, _free_port(), str(tmp_path), mode, shape), nprocs=world, join=True,
                        start_method="spawn")
     got = np.concatenate([np.load(tmp_path / f"rank{r}.npy") for r in range(world)])
     assert got.shape == want.shape

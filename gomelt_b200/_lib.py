@@ -75,6 +75,59 @@ class ProjectArgs(C.Structure):
         ("first_x", C.c_void_p), ("first_y", C.c_void_p), ("first_z", C.c_void_p),
         ("elems_per_cell_hint", C.c_int32),
         ("cellsum", C.c_void_p), ("V", C.c_void_p), ("accumulate", C.c_int32),
+        ("coef_T", C.c_void_p), ("coef_S1", C.c_void_p), ("coef_n_substrate", C.c_int64),
+        ("coef_props", C.POINTER(Props)),
+    ]
+
+
+class ShiftArgs(C.Structure):
+    _fields_ = [
+        ("L1", Axis * 3), ("T1", C.c_void_p),
+        ("mid", Axis * 3), ("Tp_mid", C.c_void_p),
+        ("old", Axis * 3), ("Tp_old", C.c_void_p),
+        ("tx", C.c_void_p), ("ty", C.c_void_p), ("tz", C.c_void_p),
+        ("ntx", C.c_int32), ("nty", C.c_int32), ("ntz", C.c_int32),
+        ("Tp_new", C.c_void_p), ("T_new", C.c_void_p),
+    ]
+
+
+class Level(C.Structure):
+    _fields_ = [
+        ("grid", Grid),
+        ("x", C.c_void_p), ("y", C.c_void_p), ("z", C.c_void_p),
+        ("T0", C.c_void_p), ("S1", C.c_void_p), ("Tprime0", C.c_void_p), ("S2", C.c_void_p),
+        ("n_substrate", C.c_int64),
+    ]
+
+
+class Pair(C.Structure):
+    _fields_ = [
+        ("cell0", C.c_int32 * 3), ("ncell", C.c_int32 * 3),
+        ("first_x", C.c_void_p), ("first_y", C.c_void_p), ("first_z", C.c_void_p),
+        ("elems_per_cell_hint", C.c_int32),
+    ]
+
+
+class Overlap(C.Structure):
+    _fields_ = [
+        ("ix", C.c_void_p), ("iy", C.c_void_p), ("iz", C.c_void_p),
+        ("cx", C.c_void_p), ("cy", C.c_void_p), ("cz", C.c_void_p),
+        ("n", C.c_int32 * 3),
+    ]
+
+
+class Hier(C.Structure):
+    _fields_ = [
+        ("L1", Level), ("L2", Level), ("L3", Level),
+        ("L2L1", Pair), ("L3L1", Pair), ("L3L2", Pair),
+        ("ov2", Overlap), ("ov3", Overlap),
+        ("L0_S1", C.c_void_p), ("L0_S2", C.c_void_p),
+        ("L0_nx", C.c_int32), ("L0_ny", C.c_int32), ("L0_nz", C.c_int32),
+        ("l0_ix", C.c_void_p), ("l0_iy", C.c_void_p), ("l0_iz", C.c_void_p),
+        ("bc5", C.c_float * 5),
+        ("nz_active_L1", C.c_int32),
+        ("L1_spare", C.c_void_p),
+        ("work", C.c_void_p), ("work_floats", C.c_int64),
     ]
 
 
@@ -138,6 +191,19 @@ SIGNATURES = {
                                                   C.POINTER(C.c_float * 3), C.c_float, C.c_void_p, C.c_void_p,
                                                   C.c_void_p, c_float_p, C.c_void_p]),
     "gomelt_project_f32": (C.c_int, [C.POINTER(ProjectArgs), C.c_void_p]),
+    "gomelt_projected_source_f32": (C.c_int, [C.POINTER(Props), C.POINTER(Axis * 3), C.POINTER(Axis * 3), C.c_float,
+                                              C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "gomelt_shift_window_f32": (C.c_int, [C.POINTER(ShiftArgs), C.c_void_p]),
+    "gomelt_clamp_min_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
+    "gomelt_hier_work_floats": (C.c_longlong, [C.POINTER(Hier), C.c_int32, C.c_int32]),
+    "gomelt_subcycle_f32": (C.c_int, [C.POINTER(Props), C.POINTER(Hier), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                      C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
+    "gomelt_step_f32": (C.c_int, [C.POINTER(Props), C.POINTER(Hier), C.c_void_p, C.c_void_p, C.POINTER(C.c_int32),
+                                  C.c_void_p]),
+    "gomelt_dwell_step_f32": (C.c_int, [C.POINTER(Props), C.POINTER(Hier), C.c_float, C.POINTER(C.c_int32), C.c_void_p]),
+    "gomelt_accum_single_step_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                               C.c_int32, C.c_int32, C.c_void_p]),
     "gomelt_diag_fp32_rate": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                         C.POINTER(C.c_double), C.c_void_p]),
 }

@@ -13,6 +13,9 @@ What differs from the reference *by construction* (results agree to float32 roun
     passes around as ``Lk`` / ``Lrhocp`` are only materialised where a correction term integrates them;
   * the corrector sweep of Level 3 in ``stepGOMELT`` re-uses the predictor interior (identical inputs,
     cF:2199-2201 vs 2355/2375) and only re-applies the Dirichlet faces;
+  * ``stepGOMELT`` / ``subcycleGOMELT`` / ``stepGOMELTDwellTime`` are ONE native call each (csrc/k_steppers.cu) and
+    update the state tensors of ``Levels`` IN PLACE (the reference returns new arrays): keep a ``.clone()`` if you need
+    the field of an earlier step;
   * the subcycle histories ``L2all, L3all, L3pall`` (returned and dropped by the driver, gm:437) are
     returned as ``None``.
 There is no CPU path: every entry point raises ``GomeltError`` without the library or a GPU.
@@ -165,13 +168,6 @@ def computeStateProperties(T, S1, properties, n_substrate):
     return S1o, S2o, k, rc
 
 
-def _surface_flux(L, T, nz_active, properties):
-    """computeConvRadBC cF:2207-2301 -> [nx*ny] load of the top active plane."""
-    torch = _torch()
-    flux = torch.empty(L["nodes"][0] * L["nodes"][1], device="cuda", dtype=torch.float32)
-    return ops.surface_flux(_props(properties), _grid(L), T, flux, nz_active=nz_active)
-
-
 def computeConvRadBC(Level, LevelT0, ne, nn, properties, F):
     """cF:2207-2301 with the reference's signature: convection + radiation + evaporation load of the top face of the
     elements [ne - ne_x*ne_y, ne) added to ``F`` (exact-libm stand-alone kernel; the steppers use K1's fused
@@ -188,32 +184,24 @@ def _nz_active(L, tmp_nn):
     return int(tmp_nn) // (L["nodes"][0] * L["nodes"][1])
 
 
-def _l3_source(L3, v, properties, laserP):
-    """computeSourcesL3 cF:2960-3012 as rank-1 tables (tx, ty, tz, coef)."""
-    torch = _torch()
-    nx, ny, nz = L3["nodes"]
-    tx, ty, tz = (torch.empty(n, device="cuda", dtype=torch.float32) for n in (nx, ny, nz))
-    coef = ops.source_tables(_props(properties), _grid(L3), _coords(L3["node_coords"]), _host(v)[:3], float(laserP),
-                             tx, ty, tz)
-    return (tx, ty, tz, coef)
-
-
 def _projected_source(L3, parent, rows, powers, properties, F=None):
     """computeSources cF:928-988 (one row) / computeLevelSource cF:2667-2730 (mean over rows): the laser
-    source integrated at Level-3 Gauss points, projected on ``parent`` -> [nn_parent] load vector."""
+    source integrated at Level-3 Gauss points, projected on ``parent`` -> [nn_parent] load vector (two launches for any
+    number of rows: gomelt_projected_source_f32)."""
     torch = _torch()
-    nx, ny, nz = parent["nodes"]
+    nx, ny, nz = (int(v) for v in parent["nodes"])
+    accumulate = F is not None
     if F is None:
-        F = torch.zeros(nx * ny * nz, device="cuda", dtype=torch.float32)
-    tx, ty, tz = (torch.empty(n, device="cuda", dtype=torch.float32) for n in (nx, ny, nz))
+        F = torch.empty(nx * ny * nz, device="cuda", dtype=torch.float32)
+    n = len(powers)
+    r = np.zeros((n, 7), F32)
+    r[:, :3] = np.asarray([np.asarray(_host(q), F32)[:3] for q in rows], F32)
+    r[:, 6] = np.asarray(_host(powers), F32)
     h3 = L3["h"]
     wq = F32(F32(F32(h3[0]) * F32(h3[1])) * F32(h3[2])) * F32(0.125)
-    n = len(powers)
-    fine, par = _coords(L3["node_coords"]), _coords(parent["node_coords"])
-    for r in range(n):
-        pc = ops.coarse_source_tables(_props(properties), fine, par, rows[r][:3], float(powers[r]), tx, ty, tz)
-        ops.rank1(F, tx, ty, tz, float(F32(pc) * wq) / n, accumulate=True)
-    return F
+    tables = torch.empty(n * (nx + ny + nz), device="cuda", dtype=torch.float32)
+    return ops.projected_source(_props(properties), _coords(L3["node_coords"]), _coords(parent["node_coords"]), float(wq), r,
+                                tables, F, accumulate=accumulate)
 
 
 _PAIR_CACHE = {}
@@ -259,43 +247,9 @@ def _project(cells, A, coef, V, mode, scale=1.0, A2=None):
                        accumulate=True)
 
 
-def _zeros_like_level(L):
-    return _torch().zeros(L["nn"], device="cuda", dtype=_torch().float32)
-
-
-def _faces_from_parent(parent, Tparent, child, Tchild, T_amb=None, blend=None):
-    """assignBCsFine cF:1598-1620 (+ the following max(T_amb, .)): the 5 Dirichlet faces of ``Tchild`` <-
-    parent field interpolated at the child's nodes.  ``blend`` = (alpha, beta, Tparent_old)."""
-    kw = {}
-    if blend is not None:
-        kw = dict(alpha=blend[0], beta=blend[1], u2=blend[2])
-    return ops.interp(_coords(parent["node_coords"]), Tparent, _coords(child["node_coords"]), Tchild,
-                      faces_only=True, clamp_min=T_amb, **kw)
-
-
 def _bc5(L1):
     c = L1["conditions"]
     return [c["y"][0], c["y"][1], c["x"][0], c["x"][1], c["z"][0]]
-
-
-def _solve_L1(Levels, T0, S1, rhs, tmp_ne_nn, dt, properties, n_sub, clamp=True):
-    """computeConvRadBC + solveMatrixFreeFE + substitute_Tbar + assignBCs (+ clamp) on Level 1
-    (cF:2207-2301, 2172-2185, 2813-2854); the surface load of the top active plane is evaluated inside K1."""
-    L1 = Levels[1]
-    out = _torch().empty_like(T0)
-    flags = ops.STEP_BC_CONST | ops.STEP_FUSED_FLUX | (ops.STEP_CLAMP if clamp else 0)
-    return ops.level_step(_props(properties), _grid(L1), T0, S1, out, float(dt), rhs=rhs,
-                          nz_active=_nz_active(L1, tmp_ne_nn[1]), n_substrate=int(n_sub), flags=flags,
-                          bc5=_bc5(L1))
-
-
-def _solve_child(L, T0, S1, rhs, src, dt, properties, n_sub, **kw):
-    """computeConvRadBC + solveMatrixFreeFE on a window level (surface load fused into K1); the 5 Dirichlet
-    faces are left for _faces_from_parent."""
-    out = _torch().empty_like(T0)
-    flags = ops.STEP_SKIP_FACES | ops.STEP_CLAMP | ops.STEP_FUSED_FLUX | kw.pop("flags", 0)
-    return ops.level_step(_props(properties), _grid(L), T0, S1, out, float(dt), rhs=rhs, src=src,
-                          n_substrate=int(n_sub), flags=flags, **kw)
 
 
 def getNewTprime(Fine, FineT0, CoarseT, Coarse, C2F=None):
@@ -318,23 +272,47 @@ def getBothNewTprimes(Levels, FineT, MesoT, M2F, CoarseT, C2M):
     return lTp, mTp, mT0, uT0
 
 
-def _push_S1_to_L1(Levels, substrate):
-    """cF:2546-2556 / 3272-3278: Level-2 S1 -> Level-1 overlap nodes, substrate planes -> 1."""
-    L1, L2 = Levels[1], Levels[2]
-    L1["S1"] = _f(L1["S1"])
-    ops.interp(_coords(L2["node_coords"]), _f(L2["S1"]), _coords(L2["overlapCoords"]), L1["S1"],
-               index_map=(*_index3(L2["overlapNodes"]), L1["nodes"][0], L1["nodes"][1]))
-    L1["S1"][: int(substrate[1])] = 1.0
+class BoxIndex:
+    """``Levels[0]["idx"]`` / ``["idx_L2"]``: the flat Level-0 ids of a window's nodes (getOverlapRegion cF:1642-1669)
+    as the three index vectors they are the tensor product of.  The ids themselves (one int64 per window node, rebuilt
+    on every moveEverything in the reference) are materialised only when somebody asks for an array (``np.asarray``);
+    the device side gathers / scatters through the vectors (gomelt_box_copy)."""
+
+    def __init__(self, vectors, nx, ny):
+        self.vectors = [np.ascontiguousarray(np.asarray(v), dtype=np.int32) for v in vectors]
+        self.nx, self.ny = int(nx), int(ny)
+        self._ids = None
+
+    @property
+    def shape(self):
+        return (self.vectors[0].size * self.vectors[1].size * self.vectors[2].size,)
+
+    @property
+    def size(self):
+        return self.shape[0]
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __array__(self, dtype=None, copy=None):
+        if self._ids is None:
+            self._ids = levels.overlap_ids(self.vectors, self.nx, self.ny)
+        return self._ids if dtype is None else self._ids.astype(dtype)
+
+    def device(self):
+        return _index3(self.vectors)
 
 
-def _scatter_L0(Levels):
-    """cF:2390-2392 / 3628-3630."""
-    L0, L3 = Levels[0], Levels[3]
-    L0["S1"], L0["S2"] = _f(L0["S1"]), _dev(L0["S2"], _torch().bool)
-    idx3 = _index3(L0["overlapNodes"])
-    ops.box_copy(_f(L3["S1"]), L0["S1"], idx3, L0["nodes"][0], L0["nodes"][1], scatter=True)
-    L0["S2"].zero_()
-    ops.box_copy(_dev(L3["S2"], _torch().bool), L0["S2"], idx3, L0["nodes"][0], L0["nodes"][1], scatter=True)
+def take_box(a, idx):
+    """a[idx] for a BoxIndex (float32 / bool / uint8 CUDA tensor) -> new tensor."""
+    torch = _torch()
+    out = torch.empty(idx.size, device="cuda", dtype=a.dtype)
+    return ops.box_copy(a, out, idx.device(), idx.nx, idx.ny, scatter=False)
+
+
+def put_box(a, idx, v):
+    """a[idx] = v in place."""
+    return ops.box_copy(v.to(a.dtype).contiguous(), a, idx.device(), idx.nx, idx.ny, scatter=True)
 
 
 def _ensure_fields(Levels):
@@ -344,160 +322,147 @@ def _ensure_fields(Levels):
     for i in (2, 3):
         Levels[i]["Tprime0"] = _f(Levels[i]["Tprime0"])
     Levels[3]["S2"] = _dev(Levels[3]["S2"], torch.bool)
+    Levels[0]["S1"], Levels[0]["S2"] = _f(Levels[0]["S1"]), _dev(Levels[0]["S2"], torch.bool)
+
+
+class _Workspace:
+    """Device scratch that belongs to one ``Levels`` list: the work block of the native steppers, the second Level-1
+    temperature buffer (the new part-scale field is left there and the handles are swapped: no copy), and the second
+    T0 / T'0 buffers of the windows that moveEverything writes into."""
+
+    def __init__(self):
+        self.work = None
+        self.l1_spare = None
+        self.alt = {}
+
+    def buffer(self, key, like):
+        t = self.alt.get(key)
+        if t is None or t.numel() != like.numel() or t.dtype != like.dtype or t.data_ptr() == like.data_ptr():
+            t = self.alt[key] = _torch().empty_like(like)
+        return t
+
+    def spare_for(self, T1):
+        t = self.l1_spare
+        if t is None or t.numel() != T1.numel() or t.data_ptr() == T1.data_ptr():
+            t = self.l1_spare = _torch().empty_like(T1)
+        return t
+
+    def work_for(self, nfloats):
+        if self.work is None or self.work.numel() < nfloats:
+            self.work = _torch().empty(int(nfloats), device="cuda", dtype=_torch().float32)
+        return self.work
+
+
+def _workspace(Levels):
+    ws = Levels[0].get("_gomelt_ws")
+    if ws is None:
+        ws = Levels[0]["_gomelt_ws"] = _Workspace()
+    return ws
+
+
+def _fill_level(dst, L, n_substrate, with_state=True):
+    nx, ny, nz = (int(v) for v in L["nodes"])
+    dst.grid = _lib.make_grid((nx, ny, nz), L["h"])
+    c = _coords(L["node_coords"])
+    dst.x, dst.y, dst.z = (t.data_ptr() for t in c)
+    dst.T0, dst.S1 = L["T0"].data_ptr(), L["S1"].data_ptr()
+    if with_state:
+        dst.Tprime0 = L["Tprime0"].data_ptr()
+    dst.n_substrate = int(n_substrate)
+    return c
+
+
+def _fill_pair(dst, cells):
+    for d in range(3):
+        dst.cell0[d], dst.ncell[d] = int(cells["cell0"][d]), int(cells["ncell"][d])
+    dst.first_x, dst.first_y, dst.first_z = (t.data_ptr() for t in cells["first"])
+    dst.elems_per_cell_hint = int(cells["hint"])
+
+
+def _fill_overlap(dst, L):
+    ix = _index3(L["overlapNodes"])
+    cx = _coords(L["overlapCoords"])
+    dst.ix, dst.iy, dst.iz = (t.data_ptr() for t in ix)
+    dst.cx, dst.cy, dst.cz = (t.data_ptr() for t in cx)
+    for d in range(3):
+        dst.n[d] = int(ix[d].numel())
+    return ix, cx
+
+
+def _hier(Levels, Shapes, tmp_ne_nn, substrate, properties, N2=1, N3=1, windows=True):
+    """gomelt_hier_t of the current ``Levels`` (+ the tensors that must stay alive through the call)."""
+    ws = _workspace(Levels)
+    L0, L1, L2, L3 = Levels
+    h = _lib.Hier()
+    keep = [_fill_level(h.L1, L1, substrate[1], with_state=False)]
+    h.bc5 = (_lib.C.c_float * 5)(*[float(v) for v in _bc5(L1)])
+    h.nz_active_L1 = _nz_active(L1, tmp_ne_nn[1])
+    spare = ws.spare_for(L1["T0"])
+    h.L1_spare = spare.data_ptr()
+    if windows:
+        keep.append(_fill_level(h.L2, L2, substrate[2]))
+        keep.append(_fill_level(h.L3, L3, substrate[3]))
+        h.L3.S2 = L3["S2"].data_ptr()
+        _fill_pair(h.L2L1, Shapes["L2L1"])
+        _fill_pair(h.L3L1, Shapes["L3L1"])
+        _fill_pair(h.L3L2, Shapes["L3L2"])
+        keep.append(_fill_overlap(h.ov2, L2))
+        keep.append(_fill_overlap(h.ov3, L3))
+        h.L0_S1, h.L0_S2 = L0["S1"].data_ptr(), L0["S2"].data_ptr()
+        h.L0_nx, h.L0_ny, h.L0_nz = (int(v) for v in L0["nodes"])
+        i3 = _index3(L0["overlapNodes"])
+        h.l0_ix, h.l0_iy, h.l0_iz = (t.data_ptr() for t in i3)
+        keep.append(i3)
+        need = ops.hier_work_floats(h, N2, N3)
+    else:
+        need = 0 if spare is not None else int(L1["nn"])
+    work = ws.work_for(max(need, 64))
+    h.work, h.work_floats = work.data_ptr(), int(work.numel())
+    return h, keep, ws
+
+
+def _swap_l1(Levels, ws, in_spare):
+    if in_spare:
+        Levels[1]["T0"], ws.l1_spare = ws.l1_spare, Levels[1]["T0"]
 
 
 # ----------------------------------------------------------------------------------------------
-# step orchestrators
+# step orchestrators: one native call each (csrc/k_steppers.cu); state is updated IN PLACE in the Levels' tensors
 # ----------------------------------------------------------------------------------------------
 def stepGOMELT(Levels, ne_nn, tmp_ne_nn, Shapes, LInterp, v, properties, dt, laserP, substrate):
-    """cF:2304-2397: one single-step predictor / corrector update of Levels 1-3."""
+    """cF:2304-2397: one single-step predictor / corrector update of Levels 1-3 (gomelt_step_f32)."""
     torch = _torch()
     _ensure_fields(Levels)
-    L1, L2, L3 = Levels[1], Levels[2], Levels[3]
-    T_amb = float(F32(properties["T_amb"]))
-    v = _host(v)
-    dt, laserP = float(_host(dt)), float(_host(laserP))
-    preS2 = L3["S2"]
-    # updateStateProperties cF:2513-2564
-    L3["S1"], L3["S2"], k3, rc3 = computeStateProperties(L3["T0"], L3["S1"], properties, substrate[3])
-    L2["S1"], _, k2, rc2 = computeStateProperties(L2["T0"], L2["S1"], properties, substrate[2])
-    _push_S1_to_L1(Levels, substrate)
-    # loads: laser source on Level 3 (rank-1 tables) and its projections on Levels 1-2; the surface fluxes
-    # (computeConvRadBC cF:2348-2350) are evaluated inside each level step from that level's T0
-    src3 = _l3_source(L3, v, properties, laserP)
-    F1 = _projected_source(L3, L1, [v], [laserP], properties)
-    F2 = _projected_source(L3, L2, [v], [laserP], properties)
-    # computeCoarseTprimeTerm_jax cF:1477-1565
-    Vcu, Vmu = _zeros_like_level(L1), _zeros_like_level(L2)
-    _project(Shapes["L3L1"], L3["Tprime0"], k3, Vcu, mode=0)
-    _project(Shapes["L2L1"], L2["Tprime0"], k2, Vcu, mode=0)
-    _project(Shapes["L3L2"], L3["Tprime0"], k3, Vmu, mode=0)
-
-    def solutions(Vc, Vm, L3_interior=None):
-        T1 = _solve_L1(Levels, L1["T0"], L1["S1"], F1 + Vc, tmp_ne_nn, dt, properties, substrate[1])
-        T2 = _solve_child(L2, L2["T0"], L2["S1"], F2 + Vm, None, dt, properties, substrate[2])
-        _faces_from_parent(L1, T1, L2, T2, T_amb)
-        if L3_interior is None:
-            T3 = _solve_child(L3, L3["T0"], L3["S1"], None, src3, dt, properties, substrate[3])
-        else:
-            T3 = L3_interior  # same T0, F, k, rho*cp, Corr = 0: only the faces change (cF:2199-2201)
-        _faces_from_parent(L2, T2, L3, T3, T_amb)
-        return T1, T2, T3
-
-    T1, T2, T3 = solutions(Vcu, Vmu)
-    L3Tp, L2Tp, T2, T1 = getBothNewTprimes(Levels, T3, T2, None, T1, None)
-    # computeCoarseTprimeMassTerm_jax cF:1396-1474
-    _project(Shapes["L3L1"], L3Tp, rc3, Vcu, mode=1, scale=1.0 / F32(dt), A2=L3["Tprime0"])
-    _project(Shapes["L2L1"], L2Tp, rc2, Vcu, mode=1, scale=1.0 / F32(dt), A2=L2["Tprime0"])
-    _project(Shapes["L3L2"], L3Tp, rc3, Vmu, mode=1, scale=1.0 / F32(dt), A2=L3["Tprime0"])
-    T1, T2, T3 = solutions(Vcu, Vmu, L3_interior=T3)
-    L3["T0"] = T3
-    L3["Tprime0"], L2["Tprime0"], L2["T0"], L1["T0"] = getBothNewTprimes(Levels, L3["T0"], T2, None, T1, None)
-    _scatter_L0(Levels)
-    resetmask = torch.logical_and(torch.logical_not(_dev(preS2, torch.bool)), L3["S2"])
+    row = np.zeros(7, F32)
+    row[:3] = np.asarray(_host(v), F32)[:3]
+    row[5], row[6] = F32(_host(dt)), F32(_host(laserP))
+    h, keep, ws = _hier(Levels, Shapes, tmp_ne_nn, substrate, properties)
+    resetmask = torch.empty(int(Levels[3]["nn"]), device="cuda", dtype=torch.bool)
+    _swap_l1(Levels, ws, ops.step(_props(properties), h, row, resetmask))
     return Levels, resetmask
 
 
 def stepGOMELTDwellTime(Levels, tmp_ne_nn, ne_nn, properties, dt, substrate):
-    """cF:2617-2664: Level 1 only, no clamp."""
+    """cF:2617-2664: Level 1 only, no clamp (gomelt_dwell_step_f32)."""
     L1 = Levels[1]
     L1["T0"], L1["S1"] = _f(L1["T0"]), _f(L1["S1"])
-    L1["T0"] = _solve_L1(Levels, L1["T0"], L1["S1"], None, tmp_ne_nn, float(_host(dt)), properties,
-                         substrate[1], clamp=False)
+    h, keep, ws = _hier(Levels, None, tmp_ne_nn, substrate, properties, windows=False)
+    _swap_l1(Levels, ws, ops.dwell_step(_props(properties), h, float(_host(dt))))
     return Levels
 
 
 def subcycleGOMELT(Levels, ne_nn, Shapes, substrate, LInterp, tmp_ne_nn, laser_position, properties, laserP,
                    subcycle, max_accum_L3, accum_L3):
-    """cF:3224-3632: Level 1 once, Level 2 x N2, Level 3 x N2*N3, predictor pass then corrector pass."""
-    torch = _torch()
+    """cF:3224-3632: Level 1 once, Level 2 x N2, Level 3 x N2*N3, predictor pass then corrector pass
+    (gomelt_subcycle_f32).  ``max_accum_L3`` / ``accum_L3`` (the melt-time windows, gm:448-449) are updated in place when
+    they are CUDA tensors and returned."""
     _ensure_fields(Levels)
-    L1, L2, L3 = Levels[1], Levels[2], Levels[3]
-    T_amb = float(F32(properties["T_amb"]))
-    rows = np.asarray(_host(laser_position), F32)
-    P = np.asarray(_host(laserP), F32)
+    rows = np.array(_host(laser_position), F32, copy=True).reshape(-1, 7)
+    rows[:, 6] = np.asarray(_host(laserP), F32)
     N2, N3 = int(subcycle[0]), int(subcycle[1])
-    fN2, fN3 = F32(subcycle[3]), F32(subcycle[4])
-
-    _, _, k3_L1, rc3_L1 = computeStateProperties(L3["T0"], L3["S1"], properties, substrate[3])
-    _, _, k2_L1, rc2_L1 = computeStateProperties(L2["T0"], L2["S1"], properties, substrate[2])
-    _push_S1_to_L1(Levels, substrate)
-    dt_all = float(rows[:, 5].sum(dtype=F32))
-    F1 = _projected_source(L3, L1, rows, P, properties)
-    V1 = _zeros_like_level(L1)
-    _project(Shapes["L3L1"], L3["Tprime0"], k3_L1, V1, mode=0)
-    _project(Shapes["L2L1"], L2["Tprime0"], k2_L1, V1, mode=0)
-    L1T = _solve_L1(Levels, L1["T0"], L1["S1"], F1 + V1, tmp_ne_nn, dt_all, properties, substrate[1])
-
-    def L2_common(T2, S12, T3, Tp3, S13, isub):
-        a2 = F32(isub + 1) / fN2
-        b2 = F32(1) - a2
-        sl = slice(isub * N3, (isub + 1) * N3)
-        _, _, k3, rc3 = computeStateProperties(T3, S13, properties, substrate[3])
-        S12n, _, k2, rc2 = computeStateProperties(T2, S12, properties, substrate[2])
-        F2 = _projected_source(L3, L2, rows[sl], P[sl], properties)
-        V2 = _zeros_like_level(L2)
-        _project(Shapes["L3L2"], Tp3, k3, V2, mode=0)
-        dt2 = float(rows[sl, 5].sum(dtype=F32))
-        return float(a2), float(b2), rc3, S12n, F2, V2, dt2
-
-    def solve_L2(T2, S12, F2, V2, dt2, a2, b2, L1new):
-        T2n = _solve_child(L2, T2, S12, F2 + V2, None, dt2, properties, substrate[2])
-        _faces_from_parent(L1, L1new, L2, T2n, T_amb, blend=(a2, b2, L1["T0"]))
-        return T2n
-
-    # the inner scan (subcycleL3_Part1 / _Part2, cF:3367-3412 / 3530-3590) is one C-ABI call per Level-2 substep:
-    # all N3 source tables in one launch, then N3 x (fused level step + face prolongation from Level 2)
-    rowsP = rows.copy()
-    rowsP[:, 6] = P
-    nx3, ny3, nz3 = L3["nodes"]
-    scratch = {"T": [torch.empty_like(L3["T0"]) for _ in range(2)], "S1": torch.empty_like(L3["S1"]),
-               "tables": torch.empty(N3 * (nx3 + ny3 + nz3), device="cuda", dtype=torch.float32)}
-    c3, c2 = _coords(L3["node_coords"]), _coords(L2["node_coords"])
-
-    def L3_block(T3, S13, i2, L2new, L2prev, accum=None):
-        A, B = scratch["T"]
-        Ta, Tb = (B, A) if T3 is A else (A, B)  # T_a != T_in; T_in may be T_b
-        kw, flags = {}, ops.STEP_SKIP_FACES | ops.STEP_CLAMP
-        if accum is not None:
-            S2w, mx_, ac_ = accum
-            kw = dict(S2=S2w, accum=ac_, max_accum=mx_)
-            flags |= ops.STEP_WRITE_S2 | ops.STEP_ACCUM
-        T3n = ops.l3_substeps(_props(properties), _grid(L3), c3, rowsP[i2 * N3:(i2 + 1) * N3], T3, Ta, Tb,
-                              scratch["S1"], scratch["tables"], S1_in=S13, n_substrate=int(substrate[3]),
-                              flags=flags, faces=(c2, L2new, L2prev, fN3, T_amb), **kw)
-        return T3n, scratch["S1"]
-
-    # ---- predictor pass cF:3308-3430 ----
-    T2, S12, T3, Tp3, S13 = L2["T0"], L2["S1"], L3["T0"], L3["Tprime0"], L3["S1"]
-    Tp3_hist = []
-    for i2 in range(N2):
-        a2, b2, _, S12n, F2, V2, dt2 = L2_common(T2, S12, T3, Tp3, S13, i2)
-        T2n = solve_L2(T2, S12, F2, V2, dt2, a2, b2, L1T)
-        T3, S13 = L3_block(T3, S13, i2, T2n, T2)
-        Tp3, T2n = getNewTprime(L3, T3, T2n, L2)
-        T2, S12 = T2n, S12n
-        Tp3_hist.append(Tp3)
-    # ---- Level-1 corrector cF:3432-3456 ----
-    Tp2, L1T = getNewTprime(L2, T2, L1T, L1)
-    _project(Shapes["L3L1"], Tp3, rc3_L1, V1, mode=1, scale=1.0 / F32(dt_all), A2=L3["Tprime0"])
-    _project(Shapes["L2L1"], Tp2, rc2_L1, V1, mode=1, scale=1.0 / F32(dt_all), A2=L2["Tprime0"])
-    L1T = _solve_L1(Levels, L1["T0"], L1["S1"], F1 + V1, tmp_ne_nn, dt_all, properties, substrate[1])
-    # ---- corrector pass cF:3458-3622 ----
-    T2, S12, T3, Tp3, S13 = L2["T0"], L2["S1"], L3["T0"], L3["Tprime0"], L3["S1"]
-    S23 = L3["S2"].clone()  # updated in place by the corrector substeps
-    mx = _f(max_accum_L3).clone()
-    ac = _f(accum_L3).clone()
-    for i2 in range(N2):
-        a2, b2, rc3, S12n, F2, V2, dt2 = L2_common(T2, S12, T3, Tp3, S13, i2)
-        _project(Shapes["L3L2"], Tp3_hist[i2], rc3, V2, mode=1, scale=1.0 / F32(dt2), A2=Tp3)
-        T2n = solve_L2(T2, S12, F2, V2, dt2, a2, b2, L1T)
-        T3, S13 = L3_block(T3, S13, i2, T2n, T2, accum=(S23, mx, ac))
-        Tp3, T2n = getNewTprime(L3, T3, T2n, L2)
-        T2, S12 = T2n, S12n
-    L2["T0"], L2["S1"], L3["T0"], L3["Tprime0"], L3["S1"], L3["S2"] = T2, S12, T3, Tp3, S13, S23
-    L2["Tprime0"], L1["T0"] = getNewTprime(L2, L2["T0"], L1T, L1)
-    _scatter_L0(Levels)
+    mx, ac = _f(max_accum_L3), _f(accum_L3)
+    h, keep, ws = _hier(Levels, Shapes, tmp_ne_nn, substrate, properties, N2, N3)
+    _swap_l1(Levels, ws, ops.subcycle(_props(properties), h, rows, N2, N3, mx, ac))
     return Levels, None, None, None, mx, ac
 
 
@@ -516,12 +481,14 @@ def _constrain(vtot, L):
 
 def moveEverything(v, vstart, Levels, move_v, LInterp, L1L2Eratio, L2L3Eratio, height):
     """cF:2400-2510: integer-cell shift of the Level-3 / Level-2 windows; T0 / T'0 re-interpolated at the new
-    window nodes; overlap index sets updated; S1 / S2 regathered from Level 0.  ``Shapes`` = per-pair
-    fine-element -> parent-cell grouping (three small int arrays each)."""
+    window nodes (one launch per window: gomelt_shift_window_f32); overlap index sets updated; S1 / S2 regathered from
+    Level 0.  ``Shapes`` = per-pair fine-element -> parent-cell grouping (three small int arrays each)."""
     torch = _torch()
     _ensure_fields(Levels)
+    ws = _workspace(Levels)
     L0, L1, L2, L3 = Levels
     vtot = np.asarray(_host(v), F32) - np.asarray(_host(vstart), F32)
+    c1, c2_old, c3_old = _coords(L1["node_coords"]), _coords(L2["node_coords"]), _coords(L3["node_coords"])
     # ---- Level 3 (shifts in Level-2 cells) ----
     v3 = _constrain(vtot, L3)
     h2 = L2["h"]
@@ -530,14 +497,9 @@ def moveEverything(v, vstart, Levels, move_v, LInterp, L1L2Eratio, L2L3Eratio, h
     L3["overlapNodes"] = [np.asarray(L3["orig_overlap_nodes"][i]) + s3[i] for i in range(3)]
     L3["overlapCoords"] = [(np.asarray(L3["orig_overlap_coors"][i], F32) + F32(h2[i]) * s3[i]).astype(F32)
                            for i in range(3)]
-    tgt = _coords(new3)
-    n3 = L3["nn"]
-    Tp3 = ops.interp(_coords(L3["node_coords"]), L3["Tprime0"], tgt, torch.empty(n3, device="cuda"))
-    Tp2on3 = ops.interp(_coords(L2["node_coords"]), L2["Tprime0"], tgt, torch.empty(n3, device="cuda"))
-    T1on3 = ops.interp(_coords(L1["node_coords"]), L1["T0"], tgt, torch.empty(n3, device="cuda"))
-    L3["T0"] = T1on3 + (Tp2on3 + Tp3)
-    L3["Tprime0"] = Tp3
-    L3["node_coords"] = new3
+    # T'3 <- I_3(T'3), T3 <- I_1(T1) + (I_2(T'2) + T'3) at the new nodes (cF:2439-2443), with the OLD Level-2 window
+    Tp3n, T3n = ops.shift_window(c1, L1["T0"], c3_old, L3["Tprime0"], _coords(new3), ws.buffer("Tp3", L3["Tprime0"]),
+                                 ws.buffer("T3", L3["T0"]), mid_coords=c2_old, Tp_mid=L2["Tprime0"])
     # ---- Level 2 (shifts in Level-1 cells in x, y; whole layers in z) ----
     v2 = _constrain(vtot, L2)
     h1 = [L1["h"][0], L1["h"][1], F32(height)]
@@ -550,13 +512,14 @@ def moveEverything(v, vstart, Levels, move_v, LInterp, L1L2Eratio, L2L3Eratio, h
     L2["overlapCoords"] = [(np.asarray(c[0], F32) + F32(L1["h"][0]) * s2[0]).astype(F32),
                            (np.asarray(c[1], F32) + F32(L1["h"][1]) * s2[1]).astype(F32),
                            (np.asarray(c[2], F32) + F32(height) * _trunc_shift(v2[2], height)).astype(F32)]
-    tgt = _coords(new2)
-    n2 = L2["nn"]
-    Tp2 = ops.interp(_coords(L2["node_coords"]), L2["Tprime0"], tgt, torch.empty(n2, device="cuda"))
-    T1on2 = ops.interp(_coords(L1["node_coords"]), L1["T0"], tgt, torch.empty(n2, device="cuda"))
-    L2["Tprime0"] = Tp2
-    L2["T0"] = T1on2 + Tp2
-    L2["node_coords"] = new2
+    Tp2n, T2n = ops.shift_window(c1, L1["T0"], c2_old, L2["Tprime0"], _coords(new2), ws.buffer("Tp2", L2["Tprime0"]),
+                                 ws.buffer("T2", L2["T0"]))
+    # the new fields become the Levels' fields, the old tensors become the spare buffers of the next move
+    ws.alt["Tp3"], L3["Tprime0"] = L3["Tprime0"], Tp3n
+    ws.alt["T3"], L3["T0"] = L3["T0"], T3n
+    ws.alt["Tp2"], L2["Tprime0"] = L2["Tprime0"], Tp2n
+    ws.alt["T2"], L2["T0"] = L2["T0"], T2n
+    L3["node_coords"], L2["node_coords"] = new3, new2
     LInterp = [interpolatePointsMatrix(L1, new2), None]
     # Level-3 overlap indices are relative to Level 2, which has itself moved
     L3["overlapNodes"] = [L3["overlapNodes"][i] - move_v[i] for i in range(3)]
@@ -573,15 +536,13 @@ def moveEverything(v, vstart, Levels, move_v, LInterp, L1L2Eratio, L2L3Eratio, h
                               for i in range(3)]
     L0["overlapNodes"][2] = L0["overlapNodes"][2] - move_v[2] * r3[2]
     L0["overlapNodes_L2"][2] = L0["overlapNodes_L2"][2] - move_v[2] * r3[2]
-    L0["idx"] = levels.overlap_ids(L0["overlapNodes"], L0["nodes"][0], L0["nodes"][1])
-    L0["idx_L2"] = levels.overlap_ids(L0["overlapNodes_L2"], L0["nodes"][0], L0["nodes"][1])
-    # ---- state regather from Level 0 (cF:2500-2502) ----
-    L0["S1"], L0["S2"] = _f(L0["S1"]), _dev(L0["S2"], torch.bool)
-    i3, i2 = _index3(L0["overlapNodes"]), _index3(L0["overlapNodes_L2"])
-    L2["S1"] = ops.box_copy(L0["S1"], torch.empty(n2, device="cuda"), i2, L0["nodes"][0], L0["nodes"][1], scatter=False)
-    L3["S1"] = ops.box_copy(L0["S1"], torch.empty(n3, device="cuda"), i3, L0["nodes"][0], L0["nodes"][1], scatter=False)
-    L3["S2"] = ops.box_copy(L0["S2"], torch.empty(n3, device="cuda", dtype=torch.bool), i3, L0["nodes"][0],
-                            L0["nodes"][1], scatter=False)
+    L0["idx"] = BoxIndex(L0["overlapNodes"], L0["nodes"][0], L0["nodes"][1])
+    L0["idx_L2"] = BoxIndex(L0["overlapNodes_L2"], L0["nodes"][0], L0["nodes"][1])
+    # ---- state regather from Level 0 (cF:2500-2502), in place: every node of the windows is overwritten ----
+    i3, i2 = L0["idx"].device(), L0["idx_L2"].device()
+    ops.box_copy(L0["S1"], L2["S1"], i2, L0["nodes"][0], L0["nodes"][1], scatter=False)
+    ops.box_copy(L0["S1"], L3["S1"], i3, L0["nodes"][0], L0["nodes"][1], scatter=False)
+    ops.box_copy(L0["S2"], L3["S2"], i3, L0["nodes"][0], L0["nodes"][1], scatter=False)
     LInterp[1] = interpolatePointsMatrix(L2, new3)
     Shapes = {"L2L1": _pair_cells(L2, L1), "L3L1": _pair_cells(L3, L1), "L3L2": _pair_cells(L3, L2)}
     return Levels, Shapes, LInterp, move_v
@@ -590,11 +551,22 @@ def moveEverything(v, vstart, Levels, move_v, LInterp, L1L2Eratio, L2L3Eratio, h
 # ----------------------------------------------------------------------------------------------
 # melt-time bookkeeping and monitors
 # ----------------------------------------------------------------------------------------------
+def accumSingleStepFused(Levels, all_reset, accum_time, max_accum_time, dt, T_liquidus):
+    """gm:339-357 + melting_temp cF:3696-3712 on the Level-0 melt-time arrays, in place, one launch."""
+    torch = _torch()
+    L0 = Levels[0]
+    idx = L0["idx"] if isinstance(L0["idx"], BoxIndex) else BoxIndex(L0["overlapNodes"], L0["nodes"][0], L0["nodes"][1])
+    ops.accum_single_step(_f(Levels[3]["T0"]), _dev(all_reset, torch.bool), float(F32(_host(dt))), float(F32(T_liquidus)),
+                          accum_time, max_accum_time, idx.device(), idx.nx, idx.ny)
+    return accum_time, max_accum_time
+
+
 def melting_temp(temps, delt_T, T_melt, accum_time, idx):
     """cF:3696-3712: accum_time[idx] += (temps > T_melt) * dt."""
     torch = _torch()
     acc = _f(accum_time).clone()
-    idx_t = _dev(np.asarray(_host(idx)).astype(np.int64)) if not isinstance(idx, torch.Tensor) else idx.long()
+    idx_t = _dev(np.asarray(idx if isinstance(idx, BoxIndex) else _host(idx)).astype(np.int64)) \
+        if not isinstance(idx, torch.Tensor) else idx.long()
     above = (_f(temps) > float(F32(T_melt))).to(torch.float32) * float(F32(_host(delt_T)))
     acc.index_add_(0, idx_t, above)
     return acc

@@ -38,6 +38,11 @@ __global__ void state_props_kernel(PropK pk, const float* __restrict__ T, const 
     }
 }
 
+__global__ void clamp_min_kernel(float* __restrict__ x, long long n, float lo) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        x[i] = fmaxf(x[i], lo);
+}
+
 // ---- computeConvRadBC cF:2207-2301 -------------------------------------------------------
 // One thread per top-plane node; gathers its <= 4 adjacent top elements in increasing element
 // id (the order the reference's scatter-add applies them), recomputing each element's 4 Gauss
@@ -206,6 +211,17 @@ extern "C" int gomelt_minmax_f32(const float* x, int64_t n, float* out3, void* s
     if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
     minmax_kernel<<<(int)blocks, 256, 0, st>>>(x, n, out3), count_launch();
     return check_launch("gomelt_minmax_f32");
+}
+
+extern "C" int gomelt_clamp_min_f32(float* x, int64_t n, float lo, void* stream) {
+    if (!x || n < 1) {
+        set_error("gomelt_clamp_min_f32: NULL argument / empty field");
+        return GOMELT_E_NULL;
+    }
+    long long blocks = (n + 255) / 256;
+    if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+    clamp_min_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, lo), count_launch();
+    return check_launch("gomelt_clamp_min_f32");
 }
 
 extern "C" int gomelt_abi_version(void) { return GOMELT_ABI_VERSION; }

@@ -185,6 +185,10 @@ static bool try_launch_v3(StepParams& sp, int nch, cudaStream_t st) {
         case V3_L3_STEP: GM_V3(V3_L3_STEP); break;
         case V3_RHS: GM_V3(V3_RHS); break;  // (the rhs rows are fetched a plane ahead into registers there)
         case V3_RHS_NC: GM_V3(V3_RHS_NC); break;
+        case V3_RHS | K1F_S1OUT:  // Level 2 inside subcycleGOMELT: the state advances in place with the solve
+            if (sp.S1out != sp.S1) return false;
+            GM_V3(V3_RHS | K1F_S1OUT | K1F_S1INPLACE);
+            break;
         case V3_DWELL: GM_V3(V3_DWELL); break;
         case V3_RHS | K1F_HALO: GM_V3(V3_RHS | K1F_HALO); break;
         case V3_DWELL | K1F_HALO: GM_V3(V3_DWELL | K1F_HALO); break;

@@ -239,25 +239,53 @@ GM_DI void halo_wait(const unsigned* flag, unsigned need) {
     // (int) difference: the counters are monotonic modulo 2^32
     while ((int)(ld_acquire_sys(flag) - need) < 0) __nanosleep(64);
 }
-// rows [j0, j0 + nrows) of plane `src` (nx floats each, contiguous) -> the same rows of the peer ghost plane `dst`
-GM_DI void halo_push_rows(const float* __restrict__ src, float* __restrict__ dst, int nx, int j0, int nrows, float bx0, float bx1,
-                          int lane) {
-    const int e0 = j0 * nx, e1 = (j0 + nrows) * nx;
-    auto value = [&](int e) -> float {
-        const int i = e % nx;
-        const float v = __ldcg(src + e);
+// rows [j0, j1) of plane `src` (nx floats each, contiguous) -> the same rows of the peer ghost plane `dst`.  The step
+// never stores a face node, so the Dirichlet constants go out with the copy: rows 0 / ny-1 (pushed by the first / last
+// strip) carry by0 / by1, columns 0 / nx-1 carry bx0 / bx1 (assignBCs order y-, y+, x-, x+: x wins on the edges).
+GM_DI void halo_push_rows(const float* __restrict__ src, float* __restrict__ dst, int nx, int ny, int j0, int j1, float by0,
+                          float by1, float bx0, float bx1, int lane) {
+    const int e0 = j0 * nx, e1 = j1 * nx;
+    const int elast = (ny - 1) * nx;
+    // element e of the plane: loaded value, or the Dirichlet constant on a face row / column
+    auto fix = [&](float v, int e, int i) -> float {
+        v = e < nx ? by0 : (e >= elast ? by1 : v);
         return i == 0 ? bx0 : (i == nx - 1 ? bx1 : v);
     };
     const int head = (int)((4u - ((unsigned)((uintptr_t)(dst + e0) >> 2) & 3u)) & 3u);  // scalars before the first aligned quad
     const int q0 = e0 + head, nquad = (e1 - q0) >> 2;
-    if (lane < head) dst[e0 + lane] = value(e0 + lane);
-#pragma unroll 4
-    for (int q = lane; q < nquad; q += 32) {
-        const int e = q0 + 4 * q;
-        *reinterpret_cast<float4*>(dst + e) = make_float4(value(e), value(e + 1), value(e + 2), value(e + 3));
+    if (lane < head) dst[e0 + lane] = fix(__ldcg(src + e0 + lane), e0 + lane, (e0 + lane) % nx);
+    // NB quads per lane and pass: all their loads are issued before the first store (L2 round trips overlap)
+    constexpr int NB = 8;
+    for (int base = 0; base < nquad; base += 32 * NB) {
+        float4 v[NB];
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int q = base + u * 32 + lane;
+            if (q < nquad) {
+                const float* s4 = src + q0 + 4 * q;
+                v[u] = make_float4(__ldcg(s4), __ldcg(s4 + 1), __ldcg(s4 + 2), __ldcg(s4 + 3));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int q = base + u * 32 + lane;
+            if (q < nquad) {
+                const int e = q0 + 4 * q;
+                int i = e % nx;  // column of the quad's first element; the quad may wrap into the next row
+                float4 w;
+                w.x = fix(v[u].x, e, i);
+                i = (i + 1 == nx) ? 0 : i + 1;
+                w.y = fix(v[u].y, e + 1, i);
+                i = (i + 1 == nx) ? 0 : i + 1;
+                w.z = fix(v[u].z, e + 2, i);
+                i = (i + 1 == nx) ? 0 : i + 1;
+                w.w = fix(v[u].w, e + 3, i);
+                *reinterpret_cast<float4*>(dst + e) = w;
+            }
+        }
     }
     const int t0 = q0 + 4 * nquad;
-    if (lane < e1 - t0) dst[t0 + lane] = value(t0 + lane);
+    if (lane < e1 - t0) dst[t0 + lane] = fix(__ldcg(src + t0 + lane), t0 + lane, (t0 + lane) % nx);
 }
 
 template <int RY>
@@ -401,7 +429,6 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     if (F_TMA) asm volatile("mov.b64 %0, %0;\n\tmov.b64 %1, %1;" : "+l"(d2T), "+l"(d2S));
     auto ring_issue = [&](int l) {
         if (l > llast) return;
-        if (F_HALO && l == p.zend && p.hsync_hi) halo_wait(p.hsync + 1, p.hneed);  // the upper neighbour's bottom plane
         const unsigned s = (unsigned)(l - lfirst) & (NS - 1);
         // (no __syncwarp: the stage was last read a whole plane ago, and the votes since then are warp-wide)
         if (elect_one()) {
@@ -779,12 +806,18 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
         old = __shfl_sync(0xffffffffu, old, 0);
         if ((old + 1u) % gridDim.x != 0u) return;
         __threadfence();
-        halo_push_rows(p.Tout + (size_t)f * P, peer_plane, nx, j0, RY, p.bc[2], p.bc[3], lane);
+        // (the first / last strip also carries the y- / y+ face row)
+        const int ja = blockIdx.y == 0 ? 0 : j0, jb = blockIdx.y == gridDim.y - 1 ? ny : j0 + RY;
+        halo_push_rows(p.Tout + (size_t)f * P, peer_plane, nx, ny, ja, jb, p.bc[0], p.bc[1], p.bc[2], p.bc[3], lane);
         __threadfence_system();
         __syncwarp();
         if (lane == 0) red_release_sys_add(peer_sync + (which == 0 ? 1 : 0), 1u);
     };
-    if (F_HALO && p.hsync_lo && za == p.zbeg) halo_wait(p.hsync + 0, p.hneed);  // the lower neighbour's top plane
+    if (F_HALO) {
+        // both ghost planes before the march: the neighbours push at the end of their marches, so the two arrive together
+        if (p.hsync_lo && za == p.zbeg) halo_wait(p.hsync + 0, p.hneed);  // the lower neighbour's top plane
+        if (p.hsync_hi && zb == p.zend) halo_wait(p.hsync + 1, p.hneed);  // the upper neighbour's bottom plane
+    }
 
     int fdone = za;  // planes [za, fdone) are finalised
     if (lfirst <= llast) {
@@ -810,13 +843,11 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
                 ring_fetch(l, raw);
                 load_rhs(l, rqB);
                 run_plane(l, raw, stA, stB, l - 1 >= max(za, 1), sfx * splat(srcz_at(l - 1)), F_RHS ? rqA : nullptr);
-                if (F_HALO && l - 1 == p.zbeg && l - 1 < p.zend - 1) halo_strip_done(0, l - 1);
                 if (l + 1 > llast) break;
                 ring_issue(l + NS);
                 ring_fetch(l + 1, raw);
                 load_rhs(l + 1, rqA);
                 run_plane(l + 1, raw, stB, stA, l >= max(za, 1), sfx * splat(srcz_at(l)), F_RHS ? rqB : nullptr);
-                if (F_HALO && l == p.zbeg && l < p.zend - 1) halo_strip_done(0, l);
             }
             if (llast >= za && llast < zb) {  // raw holds plane llast
                 if (((llast - lfirst) & 1) != 0) last_plane(llast, stB.T, raw, F_RHS ? rqB : nullptr);
@@ -853,9 +884,10 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
         for (int r = 0; r < RY; ++r) st2(out + off[r + 1], owna, ownb, splat(p.pk.T_amb));
     }
     if (F_HALO) {
-        // every owned plane of this chunk is stored now: the last owned plane goes up; the first one goes down here only
-        // when the march did not reach it (a one-plane slab, or the plane lies in the inactive region)
-        if (za == p.zbeg && !(p.zbeg >= max(za, 1) && p.zbeg + 1 <= llast && p.zbeg < p.zend - 1)) halo_strip_done(0, p.zbeg);
+        // every owned plane of this chunk is stored now (the carried state is dead, its registers are free for the copy):
+        // the first owned plane goes down, the last one goes up.  Pushing at the end of the march keeps the plane loop
+        // identical to the one of the plain kernel; what a sweep exposes is the copy of the last strips to finish.
+        if (za == p.zbeg) halo_strip_done(0, p.zbeg);
         if (zb == p.zend) halo_strip_done(1, p.zend - 1);
     }
 }

@@ -264,10 +264,12 @@ __global__ void coarse_source_table_kernel(const float* __restrict__ xf, int nf,
         // parent cell of the element = cell of its first Gauss point (cF:1351)
         const int ec = cell_of(xq0, xc[0], hc, nc - 1);
         if (ec != ic && ec + 1 != ic) continue;
-        const float xc0 = xc[ec], xc1 = xc[ec + 1];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             const float xq = q == 0 ? xq0 : xq1;
+            // shape values of the cell that holds this Gauss point, scattered to the element's cell (see project_cells_kernel)
+            const int eq = q == 0 ? ec : cell_of(xq1, xc[0], hc, nc - 1);
+            const float xc0 = xc[eq], xc1 = xc[eq + 1];
             const float w = (ec == ic) ? (xc1 - xq) * inv_hc : (xq - xc0) * inv_hc;
             const float d = xq - v;
             acc += w * (c * expf(-3.f * d * d * inv_s2));
@@ -287,7 +289,11 @@ struct ProjParams {
     AxisView cx, cy, cz;   // parent level
     const float* A;        // fine field
     const float* A2;       // optional: field = A - A2
-    const float* coef;     // fine nodal k (GRAD) or rho*cp (MASS)
+    const float* coef;     // fine nodal k (GRAD) or rho*cp (MASS), or nullptr: evaluated from (cT, cS1)
+    const float* cT;       // fine temperature / state the coefficient is evaluated from (computeStateProperties)
+    const float* cS1;
+    long long cnsub;
+    PropK pk;
     int mode;              // 0 = GRAD, 1 = MASS
     float scale;           // MASS: 1/dt
     // parent-cell box that contains fine elements, and the fine-element range of each parent cell
@@ -317,7 +323,6 @@ __global__ void project_cells_kernel(const ProjParams p) {
         const int ez0 = p.fsz[ck], ez1 = p.fsz[ck + 1];
         const int nex = ex1 - ex0, ney = ey1 - ey0, nez = ez1 - ez0;
         const int nel = nex * ney * nez;
-        const int ecx = p.c0x + ci, ecy = p.c0y + cj, ecz = p.c0z + ck;
         const float hfx = __fsub_rn(p.fx.c[1], p.fx.c[0]), hfy = __fsub_rn(p.fy.c[1], p.fy.c[0]),
                     hfz = __fsub_rn(p.fz.c[1], p.fz.c[0]);
         const float hcx = __fsub_rn(p.cx.c[1], p.cx.c[0]), hcy = __fsub_rn(p.cy.c[1], p.cy.c[0]),
@@ -338,7 +343,14 @@ __global__ void project_cells_kernel(const ProjParams p) {
             for (int n = 0; n < 8; ++n) {
                 a[n] = p.A[nd[n]];
                 if (p.A2) a[n] -= p.A2[nd[n]];
-                cbar += p.coef[nd[n]];
+                if (p.coef) {
+                    cbar += p.coef[nd[n]];
+                } else {
+                    float kk, rr;
+                    bool b1, b2;
+                    node_props(p.pk, p.cT[nd[n]], p.cS1[nd[n]], nd[n] < p.cnsub, kk, rr, b1, b2);
+                    cbar += p.mode == 1 ? rr : kk;
+                }
             }
             cbar *= 0.125f;
             // corner values in (x,y,z)-bit order for separable evaluation: v[bx][by][bz]
@@ -351,20 +363,23 @@ __global__ void project_cells_kernel(const ProjParams p) {
             for (int qz = 0; qz < 2; ++qz) {
                 const float zq = qz == 0 ? Nlo * zf0 + Nhi * zf1 : Nhi * zf0 + Nlo * zf1;
                 const float sz0 = qz == 0 ? Nlo : Nhi, sz1 = qz == 0 ? Nhi : Nlo;  // fine 1-D shape values
+                // the parent's shape functions are those of the cell that holds THIS Gauss point (cF:1283-1335); their
+                // values are scattered to the nodes of the element's cell (Gauss point 0, cF:1351).  The two cells are the
+                // same whenever the fine grid nests in the parent (every GO-MELT configuration: integer element ratios).
                 float cz0, cz1;
-                hat_factors(zq, p.cz.c, ecz, cz0, cz1);
+                hat_factors(zq, p.cz.c, cell_of(zq, p.cz.c[0], hcz, p.cz.n - 1), cz0, cz1);
 #pragma unroll
                 for (int qy = 0; qy < 2; ++qy) {
                     const float yq = qy == 0 ? Nlo * yf0 + Nhi * yf1 : Nhi * yf0 + Nlo * yf1;
                     const float sy0 = qy == 0 ? Nlo : Nhi, sy1 = qy == 0 ? Nhi : Nlo;
                     float cy0, cy1;
-                    hat_factors(yq, p.cy.c, ecy, cy0, cy1);
+                    hat_factors(yq, p.cy.c, cell_of(yq, p.cy.c[0], hcy, p.cy.n - 1), cy0, cy1);
 #pragma unroll
                     for (int qx = 0; qx < 2; ++qx) {
                         const float xq = qx == 0 ? Nlo * xf0 + Nhi * xf1 : Nhi * xf0 + Nlo * xf1;
                         const float sx0 = qx == 0 ? Nlo : Nhi, sx1 = qx == 0 ? Nhi : Nlo;
                         float cx0, cx1;
-                        hat_factors(xq, p.cx.c, ecx, cx0, cx1);
+                        hat_factors(xq, p.cx.c, cell_of(xq, p.cx.c[0], hcx, p.cx.n - 1), cx0, cx1);
                         // fine-side interpolants at this Gauss point
                         const float e00 = sx0 * v000 + sx1 * v100, e10 = sx0 * v010 + sx1 * v110;
                         const float e01 = sx0 * v001 + sx1 * v101, e11 = sx0 * v011 + sx1 * v111;
@@ -434,6 +449,118 @@ __global__ void project_nodes_kernel(const float* __restrict__ cellsum, int c0x,
                 }
         const long long n = (c0x + i) + (long long)(c0y + j) * pnx + (long long)(c0z + k) * pnx * pny;
         V[n] = accumulate ? V[n] + s : s;
+    }
+}
+
+
+// ---- batched projected source: tables of all rows in one launch, then one pass over the parent ------------------
+struct SrcBatch {
+    float v[GOMELT_MAX_SUBSTEPS][3];
+    float c[GOMELT_MAX_SUBSTEPS];
+    int n;
+};
+__global__ void coarse_source_table_batch_kernel(const float* __restrict__ fx, const float* __restrict__ fy,
+                                                 const float* __restrict__ fz, int nfx, int nfy, int nfz,
+                                                 const float* __restrict__ cx, const float* __restrict__ cy,
+                                                 const float* __restrict__ cz, int ncx, int ncy, int ncz,
+                                                 const __grid_constant__ SrcBatch sb, float inv_r2, float inv_d2, float rc, float dc,
+                                                 float* __restrict__ tables) {
+    const int axis = blockIdx.y, r = blockIdx.z;
+    const float* xf = axis == 0 ? fx : (axis == 1 ? fy : fz);
+    const float* xc = axis == 0 ? cx : (axis == 1 ? cy : cz);
+    const int nf = axis == 0 ? nfx : (axis == 1 ? nfy : nfz), nc = axis == 0 ? ncx : (axis == 1 ? ncy : ncz);
+    const int ic = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ic >= nc) return;
+    const float v = sb.v[r][axis], inv_s2 = axis == 2 ? inv_d2 : inv_r2, c = axis == 2 ? dc : rc;
+    const float g = 0.57735026918962576f;
+    const float Nlo = 0.5f * (1.f + g), Nhi = 0.5f * (1.f - g);
+    const float hc = xc[1] - xc[0];
+    const float inv_hc = 1.0f / hc;
+    float acc = 0.f;
+    for (int e = 0; e < nf - 1; ++e) {  // same loop as coarse_source_table_kernel
+        const float x0 = xf[e], x1 = xf[e + 1];
+        const float xq0 = Nlo * x0 + Nhi * x1, xq1 = Nhi * x0 + Nlo * x1;
+        const int ec = cell_of(xq0, xc[0], hc, nc - 1);
+        if (ec != ic && ec + 1 != ic) continue;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const float xq = q == 0 ? xq0 : xq1;
+            const int eq = q == 0 ? ec : cell_of(xq1, xc[0], hc, nc - 1);
+            const float xc0 = xc[eq], xc1 = xc[eq + 1];
+            const float w = (ec == ic) ? (xc1 - xq) * inv_hc : (xq - xc0) * inv_hc;
+            const float d = xq - v;
+            acc += w * (c * expf(-3.f * d * d * inv_s2));
+        }
+    }
+    tables[(size_t)r * (ncx + ncy + ncz) + (axis == 0 ? 0 : (axis == 1 ? ncx : ncx + ncy)) + ic] = acc;
+}
+__global__ void rank_n_kernel(float* __restrict__ F, const float* __restrict__ tables, int nx, int ny, int nz,
+                              const __grid_constant__ SrcBatch sb, int accumulate) {
+    const long long total = (long long)nx * ny * nz;
+    const int stride = nx + ny + nz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t % nx);
+        const int j = (int)((t / nx) % ny);
+        const int k = (int)(t / ((long long)nx * ny));
+        float f = accumulate ? F[t] : 0.f;
+        for (int r = 0; r < sb.n; ++r) {  // rows in order, like the row-by-row accumulation of gomelt_rank1_f32
+            const float* tb = tables + (size_t)r * stride;
+            f = f + sb.c[r] * ((tb[i] * tb[nx + j]) * tb[nx + ny + k]);
+        }
+        F[t] = f;
+    }
+}
+
+// ---- K5: fused window shift -----------------------------------------------------------------------------------------
+struct ShiftParams {
+    AxisView ax, ay, az;  const float* T1;      // Level 1
+    AxisView mx, my, mz;  const float* Tpm;     // Level-2 window at its old position (or nullptr)
+    AxisView ox, oy, oz;  const float* Tpo;     // this window at its old position
+    const float *tx, *ty, *tz;
+    int ntx, nty, ntz;
+    float *Tp_new, *T_new;
+};
+// the interpolant of interp_kernel (same operations in the same order) at one point
+__device__ __forceinline__ float trilinear_at(const AxisView& sx, const AxisView& sy, const AxisView& sz, const float* __restrict__ u,
+                                              float x, float y, float z) {
+    const float hx = __fsub_rn(sx.c[1], sx.c[0]), hy = __fsub_rn(sy.c[1], sy.c[0]), hz = __fsub_rn(sz.c[1], sz.c[0]);
+    const float inv_vol = __fdiv_rn(1.0f, __fmul_rn(__fmul_rn(hx, hy), hz));
+    const int nnx = sx.n, nnxy = sx.n * sy.n;
+    const int ex = cell_of(x, sx.c[0], hx, sx.n - 1), ey = cell_of(y, sy.c[0], hy, sy.n - 1), ez = cell_of(z, sz.c[0], hz, sz.n - 1);
+    const float ax0 = __fsub_rn(sx.c[ex + 1], x), ax1 = __fsub_rn(x, sx.c[ex]);
+    const float ay0 = __fsub_rn(sy.c[ey + 1], y), ay1 = __fsub_rn(y, sy.c[ey]);
+    const float az0 = __fsub_rn(sz.c[ez + 1], z), az1 = __fsub_rn(z, sz.c[ez]);
+    float N[8];
+    N[0] = __fmul_rn(__fmul_rn(__fmul_rn(ax0, ay0), az0), inv_vol);
+    N[1] = __fmul_rn(__fmul_rn(__fmul_rn(ax1, ay0), az0), inv_vol);
+    N[2] = __fmul_rn(__fmul_rn(__fmul_rn(ax1, ay1), az0), inv_vol);
+    N[3] = __fmul_rn(__fmul_rn(__fmul_rn(ax0, ay1), az0), inv_vol);
+    N[4] = __fmul_rn(__fmul_rn(__fmul_rn(ax0, ay0), az1), inv_vol);
+    N[5] = __fmul_rn(__fmul_rn(__fmul_rn(ax1, ay0), az1), inv_vol);
+    N[6] = __fmul_rn(__fmul_rn(__fmul_rn(ax1, ay1), az1), inv_vol);
+    N[7] = __fmul_rn(__fmul_rn(__fmul_rn(ax0, ay1), az1), inv_vol);
+    bool valid = true;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) valid = valid && (N[a] >= -1e-2f) && (N[a] <= 1.0f + 1e-2f);
+    if (!valid) return 0.f;
+    const long long b = ex + (long long)ey * nnx + (long long)ez * nnxy;
+    const long long nd[8] = {b, b + 1, b + 1 + nnx, b + nnx, b + nnxy, b + 1 + nnxy, b + 1 + nnx + nnxy, b + nnx + nnxy};
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) acc = __fadd_rn(acc, __fmul_rn(fminf(fmaxf(N[a], 0.f), 1.f), u[nd[a]]));
+    return acc;
+}
+__global__ void shift_window_kernel(const ShiftParams p) {
+    const long long total = (long long)p.ntx * p.nty * p.ntz;
+    for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < total; w += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(w % p.ntx), j = (int)((w / p.ntx) % p.nty), k = (int)(w / ((long long)p.ntx * p.nty));
+        const float x = p.tx[i], y = p.ty[j], z = p.tz[k];
+        const float tp = trilinear_at(p.ox, p.oy, p.oz, p.Tpo, x, y, z);
+        const float t1 = trilinear_at(p.ax, p.ay, p.az, p.T1, x, y, z);
+        float rest = tp;
+        if (p.Tpm) rest = __fadd_rn(trilinear_at(p.mx, p.my, p.mz, p.Tpm, x, y, z), tp);  // T1on3 + (Tp2on3 + Tp3)
+        p.Tp_new[w] = tp;
+        p.T_new[w] = __fadd_rn(t1, rest);
     }
 }
 
@@ -586,8 +713,9 @@ extern "C" int gomelt_coarse_source_tables_f32(const gomelt_props_t* p, const go
 }
 
 extern "C" int gomelt_project_f32(const gomelt_project_args_t* a, void* stream) {
-    if (!a || !a->A || !a->coef || !a->V || !a->cellsum || !a->first_x || !a->first_y || !a->first_z) {
-        set_error("gomelt_project_f32: NULL argument");
+    if (!a || !a->A || !a->V || !a->cellsum || !a->first_x || !a->first_y || !a->first_z ||
+        (!a->coef && !(a->coef_T && a->coef_S1 && a->coef_props))) {
+        set_error("gomelt_project_f32: NULL argument (coef, or coef_T + coef_S1 + coef_props)");
         return GOMELT_E_NULL;
     }
     for (int d = 0; d < 3; ++d)
@@ -605,6 +733,8 @@ extern "C" int gomelt_project_f32(const gomelt_project_args_t* a, void* stream) 
     p.cx = {a->parent[0].coords, a->parent[0].n}; p.cy = {a->parent[1].coords, a->parent[1].n};
     p.cz = {a->parent[2].coords, a->parent[2].n};
     p.A = a->A; p.A2 = a->A2; p.coef = a->coef; p.mode = a->mode; p.scale = a->scale;
+    p.cT = a->coef_T; p.cS1 = a->coef_S1; p.cnsub = a->coef_n_substrate;
+    if (!a->coef) p.pk = fold_props(*a->coef_props);
     p.c0x = a->cell0[0]; p.c0y = a->cell0[1]; p.c0z = a->cell0[2];
     p.ncx = a->ncell[0]; p.ncy = a->ncell[1]; p.ncz = a->ncell[2];
     p.fsx = a->first_x; p.fsy = a->first_y; p.fsz = a->first_z;
@@ -624,4 +754,74 @@ extern "C" int gomelt_project_f32(const gomelt_project_args_t* a, void* stream) 
     project_nodes_kernel<<<grid_for(nnode, 256), 256, 0, st>>>(a->cellsum, p.c0x, p.c0y, p.c0z, p.ncx, p.ncy, p.ncz,
                                                                a->parent[0].n, a->parent[1].n, a->V, a->accumulate), count_launch();
     return check_launch("gomelt_project_f32 (nodes)");
+}
+
+extern "C" int gomelt_projected_source_f32(const gomelt_props_t* p, const gomelt_axis_t fine[3], const gomelt_axis_t parent[3],
+                                           float wq_fine, const float* rows, int32_t n, float* tables, float* F,
+                                           int32_t accumulate, void* stream) {
+    if (!p || !fine || !parent || !rows || !tables || !F) {
+        set_error("gomelt_projected_source_f32: NULL argument");
+        return GOMELT_E_NULL;
+    }
+    if (n < 1 || n > GOMELT_MAX_SUBSTEPS) {
+        set_error("gomelt_projected_source_f32: n = %d outside 1..%d", n, GOMELT_MAX_SUBSTEPS);
+        return GOMELT_E_SIZE;
+    }
+    for (int d = 0; d < 3; ++d)
+        if (!axis_ok(fine[d]) || !axis_ok(parent[d])) {
+            set_error("gomelt_projected_source_f32: axis %d needs >= 2 nodes", d);
+            return GOMELT_E_SIZE;
+        }
+    const float rcoeff = 1.f / (p->laser_radius * sqrtf((float)M_PI));
+    const float dcoeff = 1.f / (p->laser_depth * sqrtf((float)M_PI));
+    const float rsq = p->laser_radius * p->laser_radius, dsq = p->laser_depth * p->laser_depth;
+    SrcBatch sb;
+    sb.n = n;
+    for (int r = 0; r < n; ++r) {
+        const float* row = rows + 7 * (size_t)r;
+        sb.v[r][0] = row[0]; sb.v[r][1] = row[1]; sb.v[r][2] = row[2];
+        const float pcoeff = 6.f * sqrtf(3.f) * row[6] * p->laser_eta;   // computeSourceFunction_jax cF:1014
+        sb.c[r] = (float)((double)(pcoeff * wq_fine) / (double)n);        // mean over the rows (cF:2726)
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ncx = parent[0].n, ncy = parent[1].n, ncz = parent[2].n;
+    const int nmax = ncx > ncy ? (ncx > ncz ? ncx : ncz) : (ncy > ncz ? ncy : ncz);
+    coarse_source_table_batch_kernel<<<dim3((nmax + 63) / 64, 3, n), 64, 0, st>>>(
+        fine[0].coords, fine[1].coords, fine[2].coords, fine[0].n, fine[1].n, fine[2].n, parent[0].coords, parent[1].coords,
+        parent[2].coords, ncx, ncy, ncz, sb, 1.f / rsq, 1.f / dsq, rcoeff, dcoeff, tables), count_launch();
+    const long long total = (long long)ncx * ncy * ncz;
+    rank_n_kernel<<<grid_for(total, 256), 256, 0, st>>>(F, tables, ncx, ncy, ncz, sb, accumulate), count_launch();
+    return check_launch("gomelt_projected_source_f32");
+}
+
+extern "C" int gomelt_shift_window_f32(const gomelt_shift_args_t* a, void* stream) {
+    if (!a || !a->T1 || !a->Tp_old || !a->tx || !a->ty || !a->tz || !a->Tp_new || !a->T_new) {
+        set_error("gomelt_shift_window_f32: NULL argument");
+        return GOMELT_E_NULL;
+    }
+    for (int d = 0; d < 3; ++d)
+        if (!axis_ok(a->L1[d]) || !axis_ok(a->old[d]) || (a->Tp_mid && !axis_ok(a->mid[d]))) {
+            set_error("gomelt_shift_window_f32: axis %d needs >= 2 nodes", d);
+            return GOMELT_E_SIZE;
+        }
+    if (a->ntx < 1 || a->nty < 1 || a->ntz < 1) {
+        set_error("gomelt_shift_window_f32: empty target grid");
+        return GOMELT_E_SIZE;
+    }
+    if (a->Tp_new == a->Tp_old || a->T_new == a->T1 || a->Tp_new == a->Tp_mid || a->T_new == a->Tp_old || a->T_new == a->Tp_mid) {
+        set_error("gomelt_shift_window_f32: outputs must not alias the inputs");
+        return GOMELT_E_FLAGS;
+    }
+    ShiftParams p;
+    p.ax = {a->L1[0].coords, a->L1[0].n}; p.ay = {a->L1[1].coords, a->L1[1].n}; p.az = {a->L1[2].coords, a->L1[2].n};
+    p.T1 = a->T1;
+    p.mx = {a->mid[0].coords, a->mid[0].n}; p.my = {a->mid[1].coords, a->mid[1].n}; p.mz = {a->mid[2].coords, a->mid[2].n};
+    p.Tpm = a->Tp_mid;
+    p.ox = {a->old[0].coords, a->old[0].n}; p.oy = {a->old[1].coords, a->old[1].n}; p.oz = {a->old[2].coords, a->old[2].n};
+    p.Tpo = a->Tp_old;
+    p.tx = a->tx; p.ty = a->ty; p.tz = a->tz; p.ntx = a->ntx; p.nty = a->nty; p.ntz = a->ntz;
+    p.Tp_new = a->Tp_new; p.T_new = a->T_new;
+    const long long total = (long long)a->ntx * a->nty * a->ntz;
+    shift_window_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p), count_launch();
+    return check_launch("gomelt_shift_window_f32");
 }

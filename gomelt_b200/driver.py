@@ -51,9 +51,17 @@ class TorchArrays:
         return t.maximum(a, b) if isinstance(b, t.Tensor) else t.clamp_min(a, float(b))
 
     def take(self, a, idx):
+        if hasattr(idx, "vectors"):  # computeFunctions.BoxIndex: gather through the three index vectors
+            from .computeFunctions import take_box
+
+            return take_box(a, idx)
         return a[self._idx(idx)]
 
     def put(self, a, idx, v):
+        if hasattr(idx, "vectors"):
+            from .computeFunctions import put_box
+
+            return put_box(a, idx, v)
         a[self._idx(idx)] = v
         return a
 
@@ -155,6 +163,7 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
     force_move = move_vert = new_checkpoint = load_chkpt = False
     ongoing = True
     stopped_at_layer_check = False
+    tprime_test_done = False
     layer_check = Nonmesh["layer_num"] + Nonmesh["restart_layer_num"]
     if "on_record" in hooks:  # the initial saveResults(Levels, Nonmesh, 1) of gm:83-84
         hooks["on_record"](Levels, Nonmesh, int(time_inc / Nonmesh["record_step"]) + 1)
@@ -244,16 +253,26 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
                         Levels, all_reset = cf.stepGOMELT(Levels, ne_nn, tmp_ne_nn, Shapes, LInterp, laser_pos, Properties,
                                                           laser_pos[5], laser_pos[6], substrate)
                         counts["stepGOMELT"] += 1
-                        idx = Levels[0]["idx"]  # gm:339-357
-                        reset = xp.take(accum_time, idx) * xp.positive(all_reset)
-                        max_accum_time = xp.put(max_accum_time, idx, xp.maximum(reset, xp.take(max_accum_time, idx)))
-                        accum_time = xp.add_at(accum_time, idx, -reset)
-                        accum_time = cf.melting_temp(Levels[3]["T0"], laser_pos[5], Properties["T_liquidus"], accum_time, idx)
+                        tprime_test_done = False
+                        if hasattr(cf, "accumSingleStepFused"):  # gm:339-357 + melting_temp as one kernel, in place
+                            accum_time, max_accum_time = cf.accumSingleStepFused(
+                                Levels, all_reset, accum_time, max_accum_time, laser_pos[5], Properties["T_liquidus"])
+                        else:
+                            idx = Levels[0]["idx"]  # gm:339-357
+                            reset = xp.take(accum_time, idx) * xp.positive(all_reset)
+                            max_accum_time = xp.put(max_accum_time, idx, xp.maximum(reset, xp.take(max_accum_time, idx)))
+                            accum_time = xp.add_at(accum_time, idx, -reset)
+                            accum_time = cf.melting_temp(Levels[3]["T0"], laser_pos[5], Properties["T_liquidus"],
+                                                         accum_time, idx)
                     else:
-                        if not xp.all_zero(xp.f32(Levels[2]["Tprime0"])) and not xp.all_zero(xp.f32(Levels[3]["Tprime0"])):
-                            dwell_count = Nonmesh["wait_time"] * Nonmesh["timestep_L3"]
-                            Levels[2]["Tprime0"] = xp.zeros_like(xp.f32(Levels[2]["Tprime0"]))
-                            Levels[3]["Tprime0"] = xp.zeros_like(xp.f32(Levels[3]["Tprime0"]))
+                        # gm:360-368.  The outcome of this test (a device -> host round trip) can only change when a
+                        # stepper has written T'0 again, so it is evaluated once per run of dwell rows.
+                        if not tprime_test_done:
+                            tprime_test_done = True
+                            if not xp.all_zero(xp.f32(Levels[2]["Tprime0"])) and not xp.all_zero(xp.f32(Levels[3]["Tprime0"])):
+                                dwell_count = Nonmesh["wait_time"] * Nonmesh["timestep_L3"]
+                                Levels[2]["Tprime0"] = xp.zeros_like(xp.f32(Levels[2]["Tprime0"]))
+                                Levels[3]["Tprime0"] = xp.zeros_like(xp.f32(Levels[3]["Tprime0"]))
                         Levels = cf.stepGOMELTDwellTime(Levels, tmp_ne_nn, ne_nn, Properties, laser_pos[5], substrate)
                         counts["stepGOMELTDwellTime"] += 1
                         dwell_count += float(laser_pos[5])
@@ -282,6 +301,7 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
                                         laser_all[:, 6], subcycle, xp.take(max_accum_time, idx), xp.take(accum_time, idx))
                 Levels, _max_accum, _accum = res[0], res[4], res[5]
                 counts["subcycleGOMELT"] += 1
+                tprime_test_done = False
                 max_accum_time = xp.put(max_accum_time, idx, xp.f32(_max_accum))
                 accum_time = xp.put(accum_time, idx, xp.f32(_accum))
                 time_inc += t_add

@@ -283,6 +283,97 @@ def project(fine_coords, parent_coords, A, coef, V, cells, *, mode, scale=1.0, A
     return V
 
 
+def projected_source(props, fine_coords, parent_coords, wq_fine, rows, tables, F, accumulate=False):
+    """gomelt_projected_source_f32: computeLevelSource cF:2667-2730 / computeSources cF:928-988 for all laser rows at
+    once (two launches).  ``rows`` = host float32 [n, 7] with the laser power in column 6."""
+    import numpy as np
+
+    lib = _lib.load()
+    rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, 7)
+    fa, pa = _axes(fine_coords), _axes(parent_coords)
+    _lib.check(lib.gomelt_projected_source_f32(C.byref(props), C.byref(fa), C.byref(pa), float(wq_fine), rows.ctypes.data,
+                                               int(rows.shape[0]), _lib.ptr(tables), _lib.ptr(F), int(bool(accumulate)),
+                                               _lib.stream_ptr()), "gomelt_projected_source_f32")
+    _count()
+    return F
+
+
+def shift_window(L1_coords, T1, old_coords, Tp_old, tgt_coords, Tp_new, T_new, mid_coords=None, Tp_mid=None):
+    """gomelt_shift_window_f32: the window shift of moveEverything cF:2400-2510 for one level in one launch."""
+    lib = _lib.load()
+    a = _lib.ShiftArgs()
+    a.L1, a.T1 = _axes(L1_coords), T1.data_ptr()
+    if Tp_mid is not None:
+        a.mid, a.Tp_mid = _axes(mid_coords), Tp_mid.data_ptr()
+    a.old, a.Tp_old = _axes(old_coords), Tp_old.data_ptr()
+    a.tx, a.ty, a.tz = (t.data_ptr() for t in tgt_coords)
+    a.ntx, a.nty, a.ntz = (int(t.numel()) for t in tgt_coords)
+    a.Tp_new, a.T_new = Tp_new.data_ptr(), T_new.data_ptr()
+    _lib.check(lib.gomelt_shift_window_f32(C.byref(a), _lib.stream_ptr()), "gomelt_shift_window_f32")
+    _count()
+    return Tp_new, T_new
+
+
+def clamp_min(x, lo):
+    lib = _lib.load()
+    _lib.check(lib.gomelt_clamp_min_f32(_lib.ptr(x), int(x.numel()), float(lo), _lib.stream_ptr()), "gomelt_clamp_min_f32")
+    _count()
+    return x
+
+
+def hier_work_floats(hier, N2, N3):
+    return int(_lib.load().gomelt_hier_work_floats(C.byref(hier), int(N2), int(N3)))
+
+
+def subcycle(props, hier, rows, N2, N3, max_accum, accum):
+    """gomelt_subcycle_f32 (subcycleGOMELT cF:3224-3632 as one native call).  Returns True when the new Level-1 field
+    was left in ``hier.L1_spare``."""
+    import numpy as np
+
+    lib = _lib.load()
+    rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, 7)
+    flag = C.c_int32(0)
+    _lib.check(lib.gomelt_subcycle_f32(C.byref(props), C.byref(hier), rows.ctypes.data, int(N2), int(N3),
+                                       _lib.ptr(max_accum), _lib.ptr(accum), C.byref(flag), _lib.stream_ptr()),
+               "gomelt_subcycle_f32")
+    _count()
+    return bool(flag.value)
+
+
+def step(props, hier, row, resetmask):
+    """gomelt_step_f32 (stepGOMELT cF:2304-2397 as one native call)."""
+    import numpy as np
+
+    lib = _lib.load()
+    row = np.ascontiguousarray(row, dtype=np.float32).reshape(7)
+    flag = C.c_int32(0)
+    _lib.check(lib.gomelt_step_f32(C.byref(props), C.byref(hier), row.ctypes.data, _lib.ptr(resetmask), C.byref(flag),
+                                   _lib.stream_ptr()), "gomelt_step_f32")
+    _count()
+    return bool(flag.value)
+
+
+def dwell_step(props, hier, dt):
+    """gomelt_dwell_step_f32 (stepGOMELTDwellTime cF:2617-2664)."""
+    lib = _lib.load()
+    flag = C.c_int32(0)
+    _lib.check(lib.gomelt_dwell_step_f32(C.byref(props), C.byref(hier), float(dt), C.byref(flag), _lib.stream_ptr()),
+               "gomelt_dwell_step_f32")
+    _count()
+    return bool(flag.value)
+
+
+def accum_single_step(T3, resetmask, dt, T_liquidus, accum0, max_accum0, idx3, big_nx, big_ny):
+    """gomelt_accum_single_step_f32: gm:339-357 + melting_temp cF:3696-3712 on the Level-0 arrays, one launch."""
+    lib = _lib.load()
+    nx, ny, nz = (int(t.numel()) for t in idx3)
+    _lib.check(lib.gomelt_accum_single_step_f32(_lib.ptr(T3), _lib.ptr(resetmask), float(dt), float(T_liquidus),
+                                                _lib.ptr(accum0), _lib.ptr(max_accum0), _lib.ptr(idx3[0]), _lib.ptr(idx3[1]),
+                                                _lib.ptr(idx3[2]), nx, ny, nz, int(big_nx), int(big_ny), _lib.stream_ptr()),
+               "gomelt_accum_single_step_f32")
+    _count()
+
+
 def diag_fp32_rate(kind, iters=4096, blocks=148 * 8, threads=256):
     """FP32 issue-rate micro-benchmark; returns lane-ops per second (timed with CUDA events)."""
     torch = _lib.require_cuda()

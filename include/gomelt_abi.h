@@ -225,6 +225,32 @@ int gomelt_coarse_source_tables_f32(const gomelt_props_t *props, const gomelt_ax
                                     const gomelt_axis_t parent[3], const float laser_xyz[3], float laserP,
                                     float *tx, float *ty, float *tz, float *coef, void *stream);
 
+/* computeLevelSource cF:2667-2730 / computeSources cF:928-988 in two launches for ANY number of laser rows: the tables
+ * of all rows (one launch), then F[node] (+)= sum_r c_r tx_r[ix] ty_r[iy] tz_r[iz] with c_r = 6 sqrt3 P_r eta wq_fine / n
+ * (wq_fine = hx hy hz / 8 of the FINE level), rows summed in order.  rows = HOST [n][7] toolpath rows (P in column 6); tables = device scratch
+ * [n * (parent nx + ny + nz)]; n <= GOMELT_MAX_SUBSTEPS. */
+int gomelt_projected_source_f32(const gomelt_props_t *props, const gomelt_axis_t fine[3], const gomelt_axis_t parent[3],
+                                float wq_fine, const float *rows, int32_t n, float *tables, float *F, int32_t accumulate,
+                                void *stream);
+
+/* K5 - window shift of moveEverything cF:2400-2510 for one window level in ONE launch: at the nodes of the window's new
+ * position (tx, ty, tz)   Tp_new = I_old(Tp_old),   T_new = I_L1(T1) + (I_mid(Tp_mid) + Tp_new)   (Level 3: mid = the
+ * Level-2 window at its old position; Level 2: Tp_mid = NULL and T_new = I_L1(T1) + Tp_new, cF:2439-2443, 2460-2464).
+ * Interpolants as in gomelt_interp_f32. */
+typedef struct gomelt_shift_args {
+    gomelt_axis_t L1[3];  const float *T1;
+    gomelt_axis_t mid[3]; const float *Tp_mid;
+    gomelt_axis_t old[3]; const float *Tp_old;
+    const float  *tx, *ty, *tz;
+    int32_t       ntx, nty, ntz;
+    float        *Tp_new, *T_new;   /* must not alias the inputs */
+} gomelt_shift_args_t;
+int gomelt_shift_window_f32(const gomelt_shift_args_t *args, void *stream);
+
+/* x[i] = max(x[i], lo) in place (the jnp.maximum(T_amb, .) of stepGOMELT cF:2360-2362 where it has to follow the face
+ * prolongation from the unclamped parent). */
+int gomelt_clamp_min_f32(float *x, int64_t n, float lo, void *stream);
+
 /* K3 - fine -> parent correction vectors, integrated at the fine Gauss points:
  *   mode 0: V[c] (+)= - sum wq * grad Nc . (kbar grad A)          computeCoarseTprimeTerm_jax cF:1477-1565,
  *                                                                  computeL1/L2TprimeTerms_Part1 cF:2733-2914
@@ -244,6 +270,11 @@ typedef struct gomelt_project_args {
     float        *cellsum;
     float        *V;
     int32_t       accumulate;
+    /* coef == NULL: the nodal coefficient is evaluated inside the kernel from the fine level's state with
+     * computeStateProperties cF:2567-2614 (mode 0: k, mode 1: rho*cp) - no k / rho*cp array is materialised */
+    const float  *coef_T, *coef_S1;
+    int64_t       coef_n_substrate;
+    const gomelt_props_t *coef_props;
 } gomelt_project_args_t;
 
 int gomelt_project_f32(const gomelt_project_args_t *args, void *stream);
@@ -286,6 +317,68 @@ typedef struct gomelt_substeps_args {
 } gomelt_substeps_args_t;
 
 int gomelt_l3_substeps_f32(const gomelt_props_t *props, const gomelt_substeps_args_t *args, void *stream);
+
+/* ---- the reference's jitted steppers as single native calls --------------------------------------------------------
+ * stepGOMELT cF:2304-2397, subcycleGOMELT cF:3224-3632, stepGOMELTDwellTime cF:2617-2664 and the device part of
+ * moveEverything cF:2400-2510: the whole kernel sequence of one call is issued from C++ on the caller's stream with no
+ * host synchronisation and no allocation (the reference runs each as one jax.jit; these are the XLA-FFI targets of
+ * INTEGRATION.md).  State is updated IN PLACE in the caller's buffers; intermediates live in `work`. */
+typedef struct gomelt_level {
+    gomelt_grid_t grid;
+    const float  *x, *y, *z;     /* device node-coordinate arrays                                   */
+    float        *T0;            /* [nn] in / out                                                   */
+    float        *S1;            /* [nn] in / out                                                   */
+    float        *Tprime0;       /* [nn] in / out (Levels 2 and 3; NULL on Level 1)                 */
+    uint8_t      *S2;            /* [nn] in / out (Level 3; NULL otherwise)                         */
+    int64_t       n_substrate;   /* getSubstrateNodes cF:562-579                                    */
+} gomelt_level_t;
+
+typedef struct gomelt_pair {     /* fine -> parent element grouping of one level pair (the role of Shapes[.])  */
+    int32_t       cell0[3], ncell[3];
+    const int32_t *first_x, *first_y, *first_z;
+    int32_t       elems_per_cell_hint;
+} gomelt_pair_t;
+
+typedef struct gomelt_overlap {  /* parent nodes under a window: index vectors and their coordinates            */
+    const int32_t *ix, *iy, *iz;
+    const float  *cx, *cy, *cz;
+    int32_t       n[3];
+} gomelt_overlap_t;
+
+typedef struct gomelt_hier {
+    gomelt_level_t   L1, L2, L3;
+    gomelt_pair_t    L2L1, L3L1, L3L2;
+    gomelt_overlap_t ov2, ov3;             /* Level 2 in Level 1, Level 3 in Level 2 (overlapNodes / overlapCoords)   */
+    float           *L0_S1;                /* Level-0 state grid (cF:206-246)                                          */
+    uint8_t         *L0_S2;
+    int32_t          L0_nx, L0_ny, L0_nz;
+    const int32_t   *l0_ix, *l0_iy, *l0_iz; /* the Level-3 window's nodes in Level 0 (lengths = Level-3 nx, ny, nz)    */
+    float            bc5[5];               /* Level-1 Dirichlet values y-, y+, x-, x+, z-                              */
+    int32_t          nz_active_L1;         /* active Level-1 planes (tmp_ne_nn, cF:495-517)                            */
+    float           *L1_spare;             /* [nn1] second Level-1 temperature buffer: the new Level-1 field is left
+                                              THERE and *l1_in_spare is set to 1 (the caller swaps its handles: no
+                                              copy of the part-scale field); NULL = copy back into L1.T0             */
+    float           *work;                 /* device scratch                                                           */
+    int64_t          work_floats;          /* >= gomelt_hier_work_floats(...)                                          */
+} gomelt_hier_t;
+
+long long gomelt_hier_work_floats(const gomelt_hier_t *h, int32_t N2, int32_t N3);
+
+/* rows = HOST [N2*N3][7] toolpath rows with the laser power in column 6; accum / max_accum = device [nn3] melt-time
+ * windows, in / out (cF:3568-3578). */
+int gomelt_subcycle_f32(const gomelt_props_t *props, const gomelt_hier_t *h, const float *rows, int32_t N2, int32_t N3,
+                        float *max_accum, float *accum, int32_t *l1_in_spare, void *stream);
+/* row = HOST [7]; resetmask = device [nn3] out: nodes that have just melted ((1 - 2 preS2) * S2 == 1, cF:2394). */
+int gomelt_step_f32(const gomelt_props_t *props, const gomelt_hier_t *h, const float *row, uint8_t *resetmask,
+                    int32_t *l1_in_spare, void *stream);
+int gomelt_dwell_step_f32(const gomelt_props_t *props, const gomelt_hier_t *h, float dt, int32_t *l1_in_spare, void *stream);
+
+/* Melt-time bookkeeping of a single-step row (gm:339-357 + melting_temp cF:3696-3712) in one launch, on the Level-0
+ * arrays through the Level-3 window's index vectors: reset = accum * resetmask; max_accum = max(reset, max_accum);
+ * accum += -reset; accum += (T3 > T_liquidus) * dt. */
+int gomelt_accum_single_step_f32(const float *T3, const uint8_t *resetmask, float dt, float T_liquidus, float *accum0,
+                                 float *max_accum0, const int32_t *ix, const int32_t *iy, const int32_t *iz, int32_t nx,
+                                 int32_t ny, int32_t nz, int32_t big_nx, int32_t big_ny, void *stream);
 
 /* Monitor (printLevelMaxMin cF:3635-3665): out3 = {min, max over the finite values, number of non-finite values}
  * of x[0..n) in one reduction (device memory, 3 floats; read it back when convenient). */

@@ -27,9 +27,9 @@ def main():
     grid = gm._lib.make_grid((NX, NY, nzl), (0.2, 0.2, 0.2))
     plane = NX * NY
     n = plane * nzl
-    bufs = [torch.full((n,), 400.0, device="cuda") + 5 * torch.rand(n, device="cuda") for _ in range(3)]
+    bufs = [torch.full((n,), 400.0, device="cuda") + 5 * torch.rand(n, device="cuda") for _ in range(2)]
     S1 = torch.ones(n, device="cuda")
-    nsync = int(gm._lib.load().gomelt_halo_sync_words(NY))
+    nsync = int(gm._lib.load().gomelt_halo_sync_words())
     sync = torch.zeros(nsync, dtype=torch.int32, device="cuda")
     bc5 = [P["T_amb"]] * 5
     flags = ops.STEP_BC_CONST | ops.STEP_FUSED_FLUX
@@ -42,7 +42,7 @@ def main():
             if it == W:
                 torch.cuda.synchronize()
                 ev[0].record()
-            nxt = (cur + 1) % 3
+            nxt = (cur + 1) % 2
             kw = {}
             if halo:
                 base = bufs[nxt].data_ptr()
@@ -57,7 +57,8 @@ def main():
         torch.cuda.synchronize()
         return ev[0].elapsed_time(ev[1]) * 1e3 / K
 
-    out = {"planes": PLANES, "plain_us": run(False), "halo_loopback_us": run(True), "plain_again_us": run(False)}
+    out = {"planes": PLANES, "exp": os.environ.get("GOMELT_K1_EXP", "0"), "plain_us": run(False),
+           "halo_loopback_us": run(True), "plain_again_us": run(False)}
     print(json.dumps(out))
 
 

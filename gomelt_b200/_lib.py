@@ -162,7 +162,7 @@ STEP_NO_COLD_PLANES = 0x100
 SIGNATURES = {
     "gomelt_abi_version": (C.c_int, []),
     "gomelt_launch_count": (C.c_longlong, []),
-    "gomelt_halo_sync_words": (C.c_longlong, [C.c_int32]),
+    "gomelt_halo_sync_words": (C.c_longlong, []),
     "gomelt_minmax_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "gomelt_last_error": (C.c_char_p, []),
     "gomelt_xla_ffi_available": (C.c_int, []),

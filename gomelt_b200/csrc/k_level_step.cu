@@ -164,13 +164,11 @@ static bool try_launch_v3(StepParams& sp, int nch, cudaStream_t st) {
     // The TMA plane ring (+ cold-plane path) needs 16-byte aligned field pointers and the driver's tensor-map encoder;
     // without them the general kernel takes the call.
     if (!make_field_tmaps(sp)) return false;
-    // z-slab ranks.  halo_sync given: the fused protocol (K1F_HALO).  Only peer pointers: the boundary planes go out by
-    // halo_push_kernel after the step and the caller orders the sweeps (legacy; kept for A/B and for callers that
-    // bring their own barrier).
-    const bool halo = (f & K1F_PEER) && sp.hsync != nullptr;
-    const bool do_push = (f & K1F_PEER) && !halo && (sp.zend - sp.zbeg) >= 1;
-    if (halo && nch != 1) return false;  // one chunk per slab: the strip counters expect one finaliser per tile
-    const int fsw = ((f & ~(K1F_SKIP | K1F_BCCONST | K1F_PEER)) | K1F_NSUB) | (halo ? K1F_HALO : 0);
+    // z-slab ranks: the boundary planes go to the neighbours after the step - halo_exchange_kernel (launch_step) when
+    // halo_sync is given, else halo_push_kernel here and the caller orders the sweeps (round-1 form, kept for A/B and for
+    // callers that bring their own barrier).
+    const bool do_push = (f & K1F_PEER) && !sp.hsync && (sp.zend - sp.zbeg) >= 1;
+    const int fsw = (f & ~(K1F_SKIP | K1F_BCCONST | K1F_PEER)) | K1F_NSUB;
 #define GM_V3(FEATS) launch_v3<RY, (FEATS) | K1F_TMA>(sp, nch, st)
     switch (fsw) {
         case V3_L3_SUB:
@@ -190,8 +188,6 @@ static bool try_launch_v3(StepParams& sp, int nch, cudaStream_t st) {
             GM_V3(V3_RHS | K1F_S1OUT | K1F_S1INPLACE);
             break;
         case V3_DWELL: GM_V3(V3_DWELL); break;
-        case V3_RHS | K1F_HALO: GM_V3(V3_RHS | K1F_HALO); break;
-        case V3_DWELL | K1F_HALO: GM_V3(V3_DWELL | K1F_HALO); break;
         default: return false;
     }
 #undef GM_V3
@@ -211,14 +207,27 @@ static bool try_launch_v3(StepParams& sp, int nch, cudaStream_t st) {
     return true;
 }
 
+static int launch_kernels(StepParams& sp, cudaStream_t st);
+
 static int launch_step(StepParams& sp, cudaStream_t st) {
+    if (!sp.hsync) return launch_kernels(sp, st);
+    // z-slab rank under the halo protocol: the step, then the exchange of the two boundary planes of T_out
+    float* const plo = sp.peer_lo;
+    float* const phi = sp.peer_hi;
+    sp.peer_lo = sp.peer_hi = nullptr;  // the step itself stores nothing remotely
+    sp.feat &= ~K1F_PEER;
+    const int rc = launch_kernels(sp, st);
+    if (rc) return rc;
+    const int blocks = sm_count() / 2 > 1 ? sm_count() / 2 : 1;  // per plane: every SM hosts one block of the exchange
+    halo_exchange_kernel<<<dim3(blocks, 2), HALO_THREADS, 0, st>>>(sp.Tout, sp.nx, sp.ny, sp.zbeg, sp.zend - 1, plo, phi, sp.bc[0],
+                                                                  sp.bc[1], sp.bc[2], sp.bc[3], sp.hsync, sp.hsync_lo, sp.hsync_hi,
+                                                                  (unsigned)blocks * (sp.hseq + 1u)), count_launch();
+    return check_launch("gomelt_level_step_f32 (halo exchange)");
+}
+
+static int launch_kernels(StepParams& sp, cudaStream_t st) {
     const int nch = (sp.zend - sp.zbeg + sp.zchunk - 1) / sp.zchunk;
     if (try_launch_v3(sp, nch, st)) return check_launch("gomelt_level_step_f32");
-    if (sp.hsync) {
-        set_error("gomelt_level_step_f32: halo_sync (the fused halo protocol) needs the fast kernel: nx >= %d, ny >= 6, >= 2 "
-                  "active planes, whole-plane substrate, 16-byte aligned T0 / S1, Dirichlet side faces", 2 * K1_TX + 2);
-        return GOMELT_E_FLAGS;
-    }
     constexpr int RY = 4, WPB = 1;  // one warp per CTA: warps are independent, finest SM balance
     const int f = sp.feat;
     if (GM_DEV_SWITCH("GOMELT_K1_GENERIC", 0)) {
@@ -242,7 +251,7 @@ static int launch_step(StepParams& sp, cudaStream_t st) {
 
 using namespace gomelt;
 
-extern "C" long long gomelt_halo_sync_words(int32_t ny) { return GOMELT_HALO_SYNC_HEAD + 2LL * ((ny - 2 + 3) / 4 + 1); }
+extern "C" long long gomelt_halo_sync_words(void) { return GOMELT_HALO_SYNC_HEAD; }
 
 extern "C" int gomelt_level_step_f32(const gomelt_props_t* props, const gomelt_step_args_t* a, void* stream) {
     if (!props || !a || !a->T0 || !a->S1 || !a->T_out) {
@@ -331,9 +340,9 @@ extern "C" int gomelt_level_step_f32(const gomelt_props_t* props, const gomelt_s
             set_error("gomelt_level_step_f32: halo_sync needs GOMELT_STEP_BC_CONST and a peer plane + a peer counter block per neighbour");
             return GOMELT_E_FLAGS;
         }
-        sp.hneed = (unsigned)((g.ny - 2 + 3) / 4) * a->halo_seq;  // strips per plane (RY = 4) x sweeps so far
+        sp.hseq = a->halo_seq;
     } else {
-        sp.hneed = 0;
+        sp.hseq = 0;
     }
     {
         const long long Pn = (long long)g.nx * g.ny;

@@ -56,13 +56,12 @@ struct StepParams {
     float* peer_lo;        // neighbour ghost planes in peer memory (K1F_PEER), or nullptr
     float* peer_hi;
     int exp;               // dev experiments (GOMELT_K1_EXP), 0 in production
-    // fused halo protocol (K1F_HALO, z-slab ranks; see halo_strip_done in k_level_step_v3.cuh): this rank's counter
-    // block and the neighbours' (peer-mapped); hneed = arrivals that must have been counted before a ghost plane
-    // is read (strips per plane x sweeps so far)
+    // halo exchange with release / acquire counters (halo_exchange_kernel in k_level_step_v3.cuh): this rank's counter
+    // block, the neighbours' (peer-mapped), sweep sequence number
     unsigned* hsync;
     unsigned* hsync_lo;
     unsigned* hsync_hi;
-    unsigned hneed;
+    unsigned hseq;
     // v3 normalisation: stiffness modes divided by s = lambda'[2], masses by cdt * s, loads by s (so that
     // T_new = T + (rr/s - KT/s) / (mnode/(cdt s)) needs neither the lambda'[2] nor the cdt multiply)
     float n_ca0, n_ca1, n_cmushy, n_cfluid, n_inv_s, n_wq;
@@ -194,9 +193,6 @@ enum : int {
     K1F_S1INPLACE = 1 << 13,  // v3: S1_out is S1: a node's state is stored only when it changed (it rarely does)
     K1F_TMA = 1 << 14,     // v3: raw planes through a TMA ring in shared memory (1-D tensor maps StepParams::tm)
     K1F_PF = 1 << 12,      // v3: L2 prefetch of the plane three ahead (latency-bound many-wave shapes)
-    K1F_HALO = 1 << 15,    // v3: fused halo exchange - the last warp to finish a strip of a boundary plane pushes it to the
-                           //     neighbour's ghost plane (16-byte stores over NVLink) and signals the neighbour's counter;
-                           //     ghost planes are read after an acquire on this rank's counters (no barrier launch)
     K1F_ALL = (1 << 12) - 1,
     K1F_GENERIC = 1 << 30,
 };

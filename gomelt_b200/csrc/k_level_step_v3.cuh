@@ -213,81 +213,6 @@ GM_DI void bookkeep_planes(const StepParams& p, const size_t* pl, const unsigned
 }
 
 
-// ---- fused halo exchange (K1F_HALO) --------------------------------------------------------------------------
-// Counter block of a z-slab rank (uint32 words in peer-visible memory, all monotonic, zeroed once at set-up):
-//   [0] strips of the LOWER neighbour's top plane that have arrived in this rank's lower ghost plane
-//   [1] strips of the UPPER neighbour's bottom plane that have arrived in this rank's upper ghost plane
-//   [GOMELT_HALO_SYNC_HEAD + s]            tiles of strip s that have finalised this rank's first owned plane
-//   [GOMELT_HALO_SYNC_HEAD + nstrips + s]  ... its last owned plane
-// Protocol of sweep q (q = 0, 1, ...): every warp that finalises its rows of a boundary plane bumps the strip's tile
-// counter; the warp that arrives LAST (all tiles of the strip are stored) copies the strip's RY full rows into the
-// neighbour's ghost plane with destination-aligned 16-byte stores - the x- / x+ face columns get their Dirichlet
-// constants, which the step itself never stores - and then adds 1 to the neighbour's arrival counter with a
-// system-scope release.  A warp of sweep q + 1 reads a ghost plane only after an acquire-load sees nstrips (q + 1)
-// arrivals.  The temperature buffers rotate through THREE halves, so the ghost plane written during sweep q + 1
-// was last read in sweep q - 1, which every rank has left before its neighbour can have started sweep q + 1:
-// no second (write-after-read) flag, no barrier launch, no separate push kernel.
-GM_DI unsigned ld_acquire_sys(const unsigned* q) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(q) : "memory");
-    return v;
-}
-GM_DI void red_release_sys_add(unsigned* q, unsigned v) {
-    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(q), "r"(v) : "memory");
-}
-GM_DI void halo_wait(const unsigned* flag, unsigned need) {
-    // (int) difference: the counters are monotonic modulo 2^32
-    while ((int)(ld_acquire_sys(flag) - need) < 0) __nanosleep(64);
-}
-// rows [j0, j1) of plane `src` (nx floats each, contiguous) -> the same rows of the peer ghost plane `dst`.  The step
-// never stores a face node, so the Dirichlet constants go out with the copy: rows 0 / ny-1 (pushed by the first / last
-// strip) carry by0 / by1, columns 0 / nx-1 carry bx0 / bx1 (assignBCs order y-, y+, x-, x+: x wins on the edges).
-GM_DI void halo_push_rows(const float* __restrict__ src, float* __restrict__ dst, int nx, int ny, int j0, int j1, float by0,
-                          float by1, float bx0, float bx1, int lane) {
-    const int e0 = j0 * nx, e1 = j1 * nx;
-    const int elast = (ny - 1) * nx;
-    // element e of the plane: loaded value, or the Dirichlet constant on a face row / column
-    auto fix = [&](float v, int e, int i) -> float {
-        v = e < nx ? by0 : (e >= elast ? by1 : v);
-        return i == 0 ? bx0 : (i == nx - 1 ? bx1 : v);
-    };
-    const int head = (int)((4u - ((unsigned)((uintptr_t)(dst + e0) >> 2) & 3u)) & 3u);  // scalars before the first aligned quad
-    const int q0 = e0 + head, nquad = (e1 - q0) >> 2;
-    if (lane < head) dst[e0 + lane] = fix(__ldcg(src + e0 + lane), e0 + lane, (e0 + lane) % nx);
-    // NB quads per lane and pass: all their loads are issued before the first store (L2 round trips overlap)
-    constexpr int NB = 8;
-    for (int base = 0; base < nquad; base += 32 * NB) {
-        float4 v[NB];
-#pragma unroll
-        for (int u = 0; u < NB; ++u) {
-            const int q = base + u * 32 + lane;
-            if (q < nquad) {
-                const float* s4 = src + q0 + 4 * q;
-                v[u] = make_float4(__ldcg(s4), __ldcg(s4 + 1), __ldcg(s4 + 2), __ldcg(s4 + 3));
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < NB; ++u) {
-            const int q = base + u * 32 + lane;
-            if (q < nquad) {
-                const int e = q0 + 4 * q;
-                int i = e % nx;  // column of the quad's first element; the quad may wrap into the next row
-                float4 w;
-                w.x = fix(v[u].x, e, i);
-                i = (i + 1 == nx) ? 0 : i + 1;
-                w.y = fix(v[u].y, e + 1, i);
-                i = (i + 1 == nx) ? 0 : i + 1;
-                w.z = fix(v[u].z, e + 2, i);
-                i = (i + 1 == nx) ? 0 : i + 1;
-                w.w = fix(v[u].w, e + 3, i);
-                *reinterpret_cast<float4*>(dst + e) = w;
-            }
-        }
-    }
-    const int t0 = q0 + 4 * nquad;
-    if (lane < e1 - t0) dst[t0 + lane] = fix(__ldcg(src + t0 + lane), t0 + lane, (t0 + lane) % nx);
-}
-
 template <int RY>
 struct K3State {  // x-staged fields of one plane (loaded rows) + T of the owned rows
     f2 Xs[RY + 2], Xd[RY + 2], kx[RY + 2], mx[RY + 2], T[RY];
@@ -307,8 +232,6 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     constexpr bool F_S2 = (FEAT & K1F_S2OUT) != 0, F_ACC = (FEAT & K1F_ACCUM) != 0;
     constexpr bool F_PEER = (FEAT & K1F_PEER) != 0, F_PF = (FEAT & K1F_PF) != 0, F_INPLACE = (FEAT & K1F_S1INPLACE) != 0;
     constexpr bool F_TMA = (FEAT & K1F_TMA) != 0;
-    constexpr bool F_HALO = (FEAT & K1F_HALO) != 0;
-    static_assert(!F_HALO || F_TMA, "the fused halo protocol lives in the TMA variant");
     // the cold-plane path needs the whole plane before its first row, i.e. the TMA ring (see plane_is_cold); in the
     // corrector substeps a plane that took it also needs no vote on the liquidus for its melt-time bookkeeping
     constexpr bool USE_COLD = F_TMA;
@@ -792,33 +715,6 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
         for (int r = 0; r < RY; ++r) final_row(f, out, rhs, rq, r, sz, Tf[r], Tt0[r], Tt1[r], myp[r], true, fl[r]);
     };
 
-    // fused halo: this warp has stored its rows of boundary plane f (which = 0: first owned plane -> lower neighbour,
-    // 1: last owned plane -> upper neighbour); see the protocol above
-    auto halo_strip_done = [&](int which, int f) {
-        if (!F_HALO) return;
-        unsigned* peer_sync = which == 0 ? p.hsync_lo : p.hsync_hi;
-        float* peer_plane = which == 0 ? p.peer_lo : p.peer_hi;
-        if (!peer_sync) return;
-        __syncwarp();
-        __threadfence();
-        unsigned old = 0;
-        if (lane == 0) old = atomicAdd(p.hsync + GOMELT_HALO_SYNC_HEAD + which * (int)gridDim.y + (int)blockIdx.y, 1u);
-        old = __shfl_sync(0xffffffffu, old, 0);
-        if ((old + 1u) % gridDim.x != 0u) return;
-        __threadfence();
-        // (the first / last strip also carries the y- / y+ face row)
-        const int ja = blockIdx.y == 0 ? 0 : j0, jb = blockIdx.y == gridDim.y - 1 ? ny : j0 + RY;
-        halo_push_rows(p.Tout + (size_t)f * P, peer_plane, nx, ny, ja, jb, p.bc[0], p.bc[1], p.bc[2], p.bc[3], lane);
-        __threadfence_system();
-        __syncwarp();
-        if (lane == 0) red_release_sys_add(peer_sync + (which == 0 ? 1 : 0), 1u);
-    };
-    if (F_HALO) {
-        // both ghost planes before the march: the neighbours push at the end of their marches, so the two arrive together
-        if (p.hsync_lo && za == p.zbeg) halo_wait(p.hsync + 0, p.hneed);  // the lower neighbour's top plane
-        if (p.hsync_hi && zb == p.zend) halo_wait(p.hsync + 1, p.hneed);  // the upper neighbour's bottom plane
-    }
-
     int fdone = za;  // planes [za, fdone) are finalised
     if (lfirst <= llast) {
         K3State<RY> stA, stB;
@@ -883,13 +779,6 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
 #pragma unroll
         for (int r = 0; r < RY; ++r) st2(out + off[r + 1], owna, ownb, splat(p.pk.T_amb));
     }
-    if (F_HALO) {
-        // every owned plane of this chunk is stored now (the carried state is dead, its registers are free for the copy):
-        // the first owned plane goes down, the last one goes up.  Pushing at the end of the march keeps the plane loop
-        // identical to the one of the plain kernel; what a sweep exposes is the copy of the last strips to finish.
-        if (za == p.zbeg) halo_strip_done(0, p.zbeg);
-        if (zb == p.zend) halo_strip_done(1, p.zend - 1);
-    }
 }
 
 // Level-1 Dirichlet constants on the five faces of T_out (assignBCs cF:1568-1595, order y-, y+, x-, x+, z-:
@@ -945,6 +834,92 @@ __global__ void halo_push_kernel(const float* __restrict__ T, int plane, int zlo
     if (t0 < head) dst[t0] = __ldcg(src + t0);
     const int tail0 = head + 4 * nquad;
     if (t0 < plane - tail0) dst[tail0 + t0] = __ldcg(src + tail0 + t0);
+}
+
+// ---- halo exchange of a z-slab rank with release / acquire counters (gomelt_step_args_t.halo_sync) -------------------
+// One launch right after the step: blockIdx.y = 0 copies the first owned plane of T_out into the lower neighbour's upper
+// ghost plane, blockIdx.y = 1 the last owned plane into the upper neighbour's lower ghost plane - destination-aligned
+// 16-byte stores over NVLink, NB quads per thread in flight, the Dirichlet constants of the face rows / columns
+// substituted on the way (the step never stores a face node).  Every block then publishes its part with a system-scope
+// release add on the neighbour's arrival counter, and waits - acquire - until this rank's own counters show that both
+// neighbours' planes of the same sweep have arrived, so that the NEXT step on this stream may read its ghost planes:
+// no barrier launch, no NCCL call, no host involvement, and two temperature buffers suffice (a neighbour can only push
+// sweep q + 1 after it has seen this rank's signal of sweep q, i.e. after this rank has finished reading sweep q's input).
+// Counter block: [0] blocks of the LOWER neighbour that have delivered into this rank's lower ghost plane, [1] UPPER.
+//
+// An in-kernel variant (the stencil warp that finishes a strip of a boundary plane last pushes it and signals; ghost planes
+// acquired by the warps that read them) was measured and dropped: every latency-bound operation at the end of a warp's march
+// (fence, counter update, copy) holds the CTA slot while it waits, and a sweep is ~3.6 waves of CTAs: +49 us per 150 us
+// sweep in loop-back on one GPU (fence 7, copy 16, counters + last-arriver fences 25), against ~12 us for this kernel.
+GM_DI unsigned ld_acquire_sys(const unsigned* q) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(q) : "memory");
+    return v;
+}
+GM_DI void red_release_sys_add(unsigned* q, unsigned v) {
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(q), "r"(v) : "memory");
+}
+constexpr int HALO_THREADS = 256;
+constexpr int HALO_NB = 4;  // quads per thread and pass
+__global__ void __launch_bounds__(HALO_THREADS) halo_exchange_kernel(const float* __restrict__ T, int nx, int ny, int zlo, int zhi,
+                                                                      float* __restrict__ peer_lo, float* __restrict__ peer_hi,
+                                                                      float by0, float by1, float bx0, float bx1,
+                                                                      unsigned* sync_mine, unsigned* sync_lo, unsigned* sync_hi,
+                                                                      unsigned need) {
+    const int which = blockIdx.y;
+    float* __restrict__ dst = which == 0 ? peer_lo : peer_hi;
+    unsigned* peer_sync = which == 0 ? sync_lo : sync_hi;
+    const int plane = nx * ny;
+    if (dst) {
+        const float* __restrict__ src = T + (size_t)(which == 0 ? zlo : zhi) * plane;
+        const int elast = (ny - 1) * nx;
+        auto fix = [&](float v, int e, int i) -> float {
+            v = e < nx ? by0 : (e >= elast ? by1 : v);
+            return i == 0 ? bx0 : (i == nx - 1 ? bx1 : v);
+        };
+        const int head = (int)((4u - ((unsigned)((uintptr_t)dst >> 2) & 3u)) & 3u);  // scalars before the first aligned quad
+        const int nquad = (plane - head) >> 2;
+        const int t = blockIdx.x * HALO_THREADS + threadIdx.x, nthreads = gridDim.x * HALO_THREADS;
+        if (t < head) dst[t] = fix(__ldcg(src + t), t, t % nx);
+        for (int base = 0; base < nquad; base += nthreads * HALO_NB) {
+            float4 v[HALO_NB];
+#pragma unroll
+            for (int u = 0; u < HALO_NB; ++u) {
+                const int q = base + u * nthreads + t;
+                if (q < nquad) {
+                    const float* s4 = src + head + 4 * q;
+                    v[u] = make_float4(__ldcg(s4), __ldcg(s4 + 1), __ldcg(s4 + 2), __ldcg(s4 + 3));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < HALO_NB; ++u) {
+                const int q = base + u * nthreads + t;
+                if (q < nquad) {
+                    const int e = head + 4 * q;
+                    int i = e % nx;  // column of the quad's first element; the quad may wrap into the next row
+                    float4 w;
+                    w.x = fix(v[u].x, e, i);
+                    i = (i + 1 == nx) ? 0 : i + 1;
+                    w.y = fix(v[u].y, e + 1, i);
+                    i = (i + 1 == nx) ? 0 : i + 1;
+                    w.z = fix(v[u].z, e + 2, i);
+                    i = (i + 1 == nx) ? 0 : i + 1;
+                    w.w = fix(v[u].w, e + 3, i);
+                    *reinterpret_cast<float4*>(dst + e) = w;
+                }
+            }
+        }
+        const int t0 = head + 4 * nquad;
+        if (t < plane - t0) dst[t0 + t] = fix(__ldcg(src + t0 + t), t0 + t, (t0 + t) % nx);
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) red_release_sys_add(peer_sync + (which == 0 ? 1 : 0), 1u);
+    }
+    // arrivals: the lower neighbour's top plane ([0]) and the upper neighbour's bottom plane ([1]) of this sweep
+    if (threadIdx.x == 0) {
+        if (peer_lo) while ((int)(ld_acquire_sys(sync_mine + 0) - need) < 0) __nanosleep(100);
+        if (peer_hi) while ((int)(ld_acquire_sys(sync_mine + 1) - need) < 0) __nanosleep(100);
+    }
 }
 
 }  // namespace gomelt

@@ -256,6 +256,8 @@ def _to_host(a):
 def _dump_tree(obj, root, prefix, index):
     """Arrays -> files, everything else -> JSON-able structure with {"__array__": file} placeholders."""
     obj = _to_host(obj)
+    if hasattr(obj, "vectors") and hasattr(obj, "__array__"):  # computeFunctions.BoxIndex -> the flat ids it stands for
+        obj = np.asarray(obj)
     if isinstance(obj, np.ndarray):
         if obj.ndim == 0:
             return {"__scalar__": obj.item(), "dtype": obj.dtype.str}

@@ -6,14 +6,14 @@ contiguous floats and a halo is a zero-copy slice.  Each rank stores its owned p
 plus one ghost plane per neighbour; an explicit sweep (stepGOMELTDwellTime cF:2617-2664) needs the
 neighbour's boundary plane of T (27-point stencil, radius 1) and - once - of S1.
 
-Per sweep, fused path (``symmetric=True``, the default on GPUs): the temperature lives in peer-mapped symmetric
-memory (torch.distributed._symmetric_memory: CUDA VMM handles exchanged once) as THREE rotating buffers plus a block
-of uint32 counters, and a sweep is ONE kernel launch (gomelt_level_step_f32 with ``halo_sync``, see gomelt_abi.h):
-a warp reads a ghost plane only after an acquire on this rank's arrival counter, the last warp to finish a 4-row
-strip of a boundary plane copies it into the neighbour's ghost plane with 16-byte stores over NVLink and bumps the
-neighbour's counter with a system-scope release, and one extra layer of CTAs writes the Dirichlet face constants.
-No NCCL call, no barrier launch, no pack / push kernel, no boundary / interior split.  (``fused=False`` keeps the
-round-1 form for A/B: two buffers, ``halo_push_kernel`` after the step, a symmetric-memory barrier per sweep.)
+Per sweep, device-side path (``symmetric=True``, the default on GPUs): the two temperature buffers and a block of
+uint32 counters live in peer-mapped symmetric memory (torch.distributed._symmetric_memory: CUDA VMM handles exchanged
+once), and a sweep is ONE C-ABI call (gomelt_level_step_f32 with ``halo_sync``, see gomelt_abi.h) = two launches: the
+fused level step (Dirichlet faces included), then ``halo_exchange_kernel``, which copies the two boundary planes into
+the neighbours' ghost planes with 16-byte stores over NVLink, signals the neighbours' arrival counters (system-scope
+release) and waits (acquire) for theirs.  No NCCL call, no barrier launch, no host involvement between sweeps.
+(``fused=False`` keeps the round-1 form for A/B: ``halo_push_kernel`` after the step, a symmetric-memory barrier
+launch per sweep.)
 
 Fallback path (``symmetric=False``; CPU tensors in the gloo tests, or GOMELT_SLAB_NCCL=1 for A/B):
   1. K1 on the two boundary planes of the owned range,
@@ -81,18 +81,17 @@ class Level1Slab:
         self.set_active(nz if nz_active is None else int(nz_active), n_substrate)
         n = self.plane * self.nzl
         self.symmetric = bool(symmetric) and world > 1 and device is not None
-        # the one-launch protocol needs the fast kernel (gomelt_abi.h: nx >= 62, ny >= 6) and two owned planes
-        self.fused = self.symmetric and bool(fused) and nx >= 62 and ny >= 6 and (self.k1 - self.k0) >= 2
+        self.fused = self.symmetric and bool(fused)
         if self.symmetric:
             import torch.distributed._symmetric_memory as symm_mem
 
-            # one symmetric allocation of three buffers, sized for the largest slab so that every rank's layout is
+            # one symmetric allocation of two buffers, sized for the largest slab so that every rank's layout is
             # the same (buffer b of rank q starts at ptrs[q] + 4 * b * nmax), followed by the counter block
             parts = partition_planes(nz, world)
             # (rounded up to 128 bytes: K1's TMA plane ring wants 16-byte aligned field pointers for every buffer)
             self._nmax = -(-self.plane * (max(b - a for a, b in parts) + 2) // 32) * 32
-            self._nbuf = 3 if self.fused else 2
-            self._nsync = int(gm._lib.load().gomelt_halo_sync_words(ny))
+            self._nbuf = 2
+            self._nsync = int(gm._lib.load().gomelt_halo_sync_words())
             self._buf = symm_mem.empty(self._nbuf * self._nmax + self._nsync, dtype=torch.float32, device=device)
             self._hdl = symm_mem.rendezvous(self._buf, dist.group.WORLD.group_name)
             self._ptrs = [int(q) for q in self._hdl.buffer_ptrs]
@@ -129,8 +128,8 @@ class Level1Slab:
         self.fill_ghosts()
 
     def fill_ghosts(self):
-        """Ghost planes of T and S1 from the neighbours (collective); restarts the fused protocol: every buffer gets the
-        current field (so the Dirichlet face nodes of all ghost planes hold their constants), counters zeroed."""
+        """Ghost planes of T and S1 from the neighbours (collective); restarts the counter protocol (counters zeroed,
+        sequence number 0)."""
         if self.world == 1:
             return
         for f in (self.T, self.S1):
@@ -139,9 +138,6 @@ class Level1Slab:
         if self.device is not None:
             torch.cuda.synchronize(self.device)
         if self.symmetric:
-            for b in self._halves:
-                if b is not self.T:
-                    b.copy_(self.T)
             self._sync.zero_()
             self._seq = 0
             torch.cuda.synchronize(self.device)
@@ -169,7 +165,7 @@ class Level1Slab:
         return self._ptrs[q] + 4 * self._nbuf * self._nmax
 
     def sweep_fused(self, dt, rhs=None, clamp=False):
-        """ONE launch: the fused level step over the owned planes with the halo protocol (see the module docstring)."""
+        """ONE C-ABI call: the fused level step over the owned planes + the device-side halo exchange (module docstring)."""
         cur = self._cur
         nxt = (cur + 1) % self._nbuf
         lo_rank, hi_rank = self.rank - 1, self.rank + 1

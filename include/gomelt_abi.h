@@ -107,28 +107,28 @@ typedef struct gomelt_step_args {
                                 * neighbour's upper ghost plane - by the same kernel (halo exchange fused
                                 * into the step; no separate copy / collective).                         */
     float        *peer_hi;     /* likewise plane z_end-1 -> the upper neighbour's lower ghost plane      */
-    /* Fused halo protocol (ABI 2; Level-1 z-slab ranks, GOMELT_STEP_BC_CONST shapes of the fast kernel).  With halo_sync
-     * set, ONE launch per sweep does everything a slab needs: a warp reads a ghost plane only after this rank's arrival
-     * counter shows that the neighbour's boundary plane of the previous sweep is complete, and the last warp to finish a
-     * strip of a boundary plane of T_out copies that strip into the neighbour's ghost plane (peer_lo / peer_hi) over
-     * NVLink and bumps the neighbour's arrival counter with a system-scope release: no barrier launch, no separate push
-     * kernel, no NCCL call.  Contract: the caller rotates T through THREE buffers (T_out of sweep q is neither T0 of
-     * sweep q nor T0 of sweep q-1), zeroes every rank's counter block once (then a real barrier), fills the ghost
-     * planes of the first T0 - and the Dirichlet face nodes of the ghost planes of all three buffers - itself, and
-     * passes halo_seq = 0, 1, 2, ... in step on all ranks.  S1 ghosts are the caller's business (they do not change in
-     * a sweep).  NULL = off. */
-    uint32_t     *halo_sync;    /* [gomelt_halo_sync_words(ny)] this rank's counter block, peer-visible memory          */
+    /* Halo exchange with release / acquire counters (ABI 2; Level-1 z-slab ranks, GOMELT_STEP_BC_CONST).  With
+     * halo_sync set the call is the step AND the exchange of its two boundary planes, entirely on the device: after the
+     * step one more kernel copies the first / last owned plane of T_out (Dirichlet face constants included) into the
+     * neighbours' ghost planes (peer_lo / peer_hi, NVLink peer stores), bumps the neighbours' arrival counters with a
+     * system-scope release and waits - acquire - until this rank's counters show that both neighbours' planes of the
+     * same sweep have arrived.  When the call has completed on the stream, the ghost planes of T_out are current: the
+     * next sweep can be issued at once; no barrier launch, no NCCL call, no host involvement.  It is a neighbour
+     * collective: every rank of the slab decomposition must issue the same sequence of calls.  Contract: two
+     * temperature buffers that alternate as T0 / T_out, every rank's counter block zeroed once (then a real barrier),
+     * the ghost planes of the first T0 filled by the caller, halo_seq = 0, 1, 2, ... in step on all ranks.  S1 ghosts
+     * are the caller's business (they do not change in a sweep).  NULL = off. */
+    uint32_t     *halo_sync;    /* [gomelt_halo_sync_words()] this rank's counter block, peer-visible memory            */
     uint32_t     *halo_sync_lo; /* the lower neighbour's counter block (peer-mapped), NULL on the lowest rank           */
     uint32_t     *halo_sync_hi; /* the upper neighbour's, NULL on the highest rank                                       */
     uint32_t      halo_seq;     /* number of sweeps this slab has done under the protocol before this one               */
 } gomelt_step_args_t;
 
-/* words of a halo counter block for a grid with ny node rows: 2 arrival counters (padded to GOMELT_HALO_SYNC_HEAD)
- * + one tile counter per 4-row strip and boundary plane */
-#define GOMELT_HALO_SYNC_HEAD 32
-long long gomelt_halo_sync_words(int32_t ny);
-
 int gomelt_level_step_f32(const gomelt_props_t *props, const gomelt_step_args_t *args, void *stream);
+
+/* words of a halo counter block (two arrival counters, padded) */
+#define GOMELT_HALO_SYNC_HEAD 32
+long long gomelt_halo_sync_words(void);
 
 /* computeStateProperties cF:2567-2614 as a stand-alone op (outputs may be NULL). */
 int gomelt_state_props_f32(const gomelt_props_t *props, const float *T, const float *S1, int64_t nn,

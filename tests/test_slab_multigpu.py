@@ -1,6 +1,6 @@
 """Level-1 z-slabs on real GPUs (needs >= 2 devices; skipped on a 1-GPU box; uses EVERY device of the box): the
-one-launch fused halo protocol (strip-wise peer stores + release / acquire counters inside the step kernel, three
-rotating buffers), the round-1 form (push kernel + barrier launch) and the NCCL send/recv path all reproduce the
+device-side halo protocol (the step, then one exchange kernel: peer stores + release / acquire counters; no barrier
+launch, no NCCL), the round-1 form (push kernel + barrier launch) and the NCCL send/recv path all reproduce the
 single-GPU sweeps bit for bit - in dwell mode and in the load-vector + clamp shape of the stepGOMELT / subcycleGOMELT
 Level-1 sweeps.  The driver-visible copy of this check is the ``parity_check`` of the multi-GPU bench line."""
 import os
@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 NODES = (131, 67, 23)
 H = (0.2, 0.2, 0.2)
 NZ_ACTIVE = 20
-NSWEEPS = 8   # > 2 turns of the three rotating buffers
+NSWEEPS = 8
 DT = 2e-3
 PROPS_IN = {"laser_radius": 0.1, "laser_depth": 0.1, "laser_absorptivity": 0.45, "T_amb": 298.15,
             "T_solidus": 1533, "T_liquidus": 1609, "h_conv": 1.5e-05, "emissivity": 0.3,
@@ -72,7 +72,7 @@ def _worker(rank, world, port, out, mode, shape):
         for _ in range(NSWEEPS):
             sl.sweep(DT, rhs=rhs, clamp=(shape == "rhs"))
         if mode == "fused":
-            assert gm.ops.LAUNCHES - l0 == NSWEEPS, "the fused protocol is one launch per sweep"
+            assert gm.ops.LAUNCHES - l0 == 2 * NSWEEPS, "step + halo exchange: two launches per sweep, nothing else"
         torch.cuda.synchronize()
         np.save(os.path.join(out, f"rank{rank}.npy"), sl.owned(sl.T).cpu().numpy())
         dist.barrier()

@@ -1,8 +1,9 @@
 """Multi-GPU arm of bench.py: Level-1 z-slab dwell sweeps with the fused halo exchange (BASELINE.json configs[4];
-SURVEY.md 8e).  Weak scaling: every rank owns SLAB_PLANES planes of a 1001 x 1001 grid (50.1 M nodes per GPU;
-4 GPUs = 200.4 M, 8 GPUs = 400.8 M nodes).  One *step* = one explicit sweep of the whole Level-1 grid
+SURVEY.md 8e).  Weak scaling: every rank owns SLAB_PLANES = 100 planes of a 1001 x 1001 grid (100.2 M nodes and
+1.6 GB of fields per GPU - shards sized for the 180 GB of a B200, so that the two ghost planes and the exchange are
+2-3 % of a sweep; 2 GPUs = 200.4 M, 8 GPUs = 801.6 M nodes).  The line also carries the 50- and 25-plane figures.  One *step* = one explicit sweep of the whole Level-1 grid
 (stepGOMELTDwellTime cF:2617-2664): surface flux on the top plane, fused level step, Dirichlet faces, one-plane halo
-exchange of T with both z-neighbours - ONE kernel launch per rank and sweep (gomelt_abi.h, halo_sync).
+exchange of T with both z-neighbours - ONE C-ABI call = two launches per rank and sweep (gomelt_abi.h, halo_sync).
 
 After the timed region the line gets a ``parity_check``: the same K sweeps are repeated from the deterministic
 initial state, and rank 0 recomputes, alone and without any halo exchange, a cut of planes around every slab
@@ -16,7 +17,7 @@ import sys
 import time
 
 L1_NX, L1_NY = 1001, 1001
-SLAB_PLANES = int(os.environ.get("GOMELT_SLAB_PLANES", "50"))
+SLAB_PLANES = int(os.environ.get("GOMELT_SLAB_PLANES", "100"))
 L1_H = (0.2, 0.2, 0.2)
 DT_DWELL = 2e-3
 B_ALG_L1 = 12
@@ -229,7 +230,8 @@ def run_gomelt_multi(args, read_peaks, ClockSampler, host_properties, single_gpu
         par = parity_check(torch, dist, gm, props, P, sl, rank, world, device)
         del sl
         torch.cuda.empty_cache()
-        for name, planes, fused in (("slab_25_planes", 25, True), ("slab_25_planes_round1_push_barrier", 25, False)):
+        for name, planes, fused in (("slab_50_planes", 50, True), ("slab_25_planes", 25, True),
+                                    ("slab_25_planes_round1_push_barrier", 25, False)):
             if planes == SLAB_PLANES and fused:
                 continue
             s2 = make_slab(gm, props, rank, world, device, P, planes=planes, fused=fused)
@@ -246,10 +248,9 @@ def run_gomelt_multi(args, read_peaks, ClockSampler, host_properties, single_gpu
         peaks = read_peaks()
         value = K * nn_total / total_s
         achieved = B_ALG_L1 * (nn_total / world) * K / total_s / 1e9  # per GPU
-        how = ("fused level step incl. surface flux and Dirichlet faces; a warp reads a ghost plane after an acquire on "
-               "this rank's arrival counter, the last warp of every 4-row strip of a boundary plane copies it into the "
-               "neighbour's ghost plane over NVLink peer memory and signals it: one launch per sweep, no barrier launch, "
-               "no NCCL call" if symmetric else
+        how = ("fused level step incl. surface flux and Dirichlet faces, then one exchange kernel: the two boundary planes "
+               "go into the neighbours' ghost planes over NVLink peer memory, release / acquire counters order the "
+               "sweeps: two launches per sweep, no barrier launch, no NCCL call" if symmetric else
                "fused level step incl. surface flux + one-plane T halo exchange by NCCL send/recv per sweep"
                if world > 1 else "fused level step incl. surface flux and Dirichlet faces, one launch per sweep")
         line = {
@@ -276,7 +277,7 @@ def run_gomelt_multi(args, read_peaks, ClockSampler, host_properties, single_gpu
                         "driver's own `efficiency` divides by the N=1 line, which is a different metric (Level-3 window)"},
             "parity_check": par, "other_configurations": alt,
             "halo_bytes_per_step_per_gpu": 4 * L1_NX * L1_NY * (2 if world > 2 else (1 if world == 2 else 0)),
-            "halo": ("fused into the step kernel: strip-wise peer stores + release / acquire counters (symmetric memory)"
+            "halo": ("exchange kernel after the step: peer stores + release / acquire counters (symmetric memory)"
                      if symmetric else "NCCL send/recv") if world > 1 else "none",
         }
         if single_gpu:

@@ -218,7 +218,7 @@ static int launch_step(StepParams& sp, cudaStream_t st) {
     sp.feat &= ~K1F_PEER;
     const int rc = launch_kernels(sp, st);
     if (rc) return rc;
-    const int blocks = sm_count() / 2 > 1 ? sm_count() / 2 : 1;  // per plane: every SM hosts one block of the exchange
+    const int blocks = sm_count();  // per plane: two co-resident blocks of the exchange per SM
     halo_exchange_kernel<<<dim3(blocks, 2), HALO_THREADS, 0, st>>>(sp.Tout, sp.nx, sp.ny, sp.zbeg, sp.zend - 1, plo, phi, sp.bc[0],
                                                                   sp.bc[1], sp.bc[2], sp.bc[3], sp.hsync, sp.hsync_lo, sp.hsync_hi,
                                                                   (unsigned)blocks * (sp.hseq + 1u)), count_launch();

@@ -109,8 +109,14 @@ def test_slabs_match_single_gpu_bitwise(tmp_path, gm, mode, shape):
     for _ in range(NSWEEPS):
         ref.sweep(DT, rhs=rhs, clamp=(shape == "rhs"))
     want = ref.T.cpu().numpy()
-    mp.start_processes(_worker, args=(world, _free_port(), str(tmp_path), mode, shape), nprocs=world, join=True,
-                       start_method="spawn")
+    for attempt in range(3):  # (a free port can be taken between the probe and the rendezvous)
+        try:
+            mp.start_processes(_worker, args=(world, _free_port(), str(tmp_path), mode, shape), nprocs=world, join=True,
+                               start_method="spawn")
+            break
+        except Exception as exc:
+            if "EADDRINUSE" not in str(exc) or attempt == 2:
+                raise
     got = np.concatenate([np.load(tmp_path / f"rank{r}.npy") for r in range(world)])
     assert got.shape == want.shape
     assert np.isfinite(got).all() and np.abs(got - T0).max() > 1.0  # the sweeps did something

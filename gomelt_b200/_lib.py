@@ -77,6 +77,8 @@ class ProjectArgs(C.Structure):
         ("cellsum", C.c_void_p), ("V", C.c_void_p), ("accumulate", C.c_int32),
         ("coef_T", C.c_void_p), ("coef_S1", C.c_void_p), ("coef_n_substrate", C.c_int64),
         ("coef_props", C.POINTER(Props)),
+        ("wtab_x", C.c_void_p), ("wtab_y", C.c_void_p), ("wtab_z", C.c_void_p),
+        ("rmax", C.c_int32 * 3), ("hf", C.c_float * 3), ("hc", C.c_float * 3),
     ]
 
 
@@ -105,6 +107,8 @@ class Pair(C.Structure):
         ("cell0", C.c_int32 * 3), ("ncell", C.c_int32 * 3),
         ("first_x", C.c_void_p), ("first_y", C.c_void_p), ("first_z", C.c_void_p),
         ("elems_per_cell_hint", C.c_int32),
+        ("wtab_x", C.c_void_p), ("wtab_y", C.c_void_p), ("wtab_z", C.c_void_p),
+        ("rmax", C.c_int32 * 3),
     ]
 
 

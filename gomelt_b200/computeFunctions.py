@@ -224,11 +224,12 @@ def _pair_cells_build(fine, parent):
     torch = _torch()
     g = F32(0.57735026918962576)
     lo, hi = F32(0.5) * (F32(1) + g), F32(0.5) * (F32(1) - g)
-    cell0, ncell, first, hint = [], [], [], 1
+    cell0, ncell, first, hint, wtab, rmax = [], [], [], 1, [], []
     for d in range(3):
         xf = np.asarray(fine["node_coords"][d], F32)
         xc = np.asarray(parent["node_coords"][d], F32)
         xq0 = lo * xf[:-1] + hi * xf[1:]
+        xq1 = hi * xf[:-1] + lo * xf[1:]
         hc = xc[1] - xc[0]
         ec = np.clip(np.floor((xq0 - xc[0]) / hc).astype(np.int64), 0, xc.size - 2)
         c0, c1 = int(ec[0]), int(ec[-1])
@@ -237,14 +238,21 @@ def _pair_cells_build(fine, parent):
         fs = np.searchsorted(ec, np.arange(c0, c1 + 2), side="left").astype(np.int32)
         first.append(_CACHE.get(fs, np.int32))
         hint *= int(np.diff(fs).max())
+        rmax.append(int(np.diff(fs).max()))
+        # parent shape-function factors at both Gauss points of every fine element, each in the parent cell that holds
+        # that Gauss point (cF:1283-1335): (x1 - xq0, xq0 - x0, x1 - xq1, xq1 - x0) - see gomelt_project_args_t.wtab_*
+        e1 = np.clip(np.floor((xq1 - xc[0]) / hc).astype(np.int64), 0, xc.size - 2)
+        tab = np.stack([xc[ec + 1] - xq0, xq0 - xc[ec], xc[e1 + 1] - xq1, xq1 - xc[e1]], axis=1).astype(F32)
+        wtab.append(_CACHE.get(tab.reshape(-1), np.float32))
     cellsum = torch.empty(ncell[0] * ncell[1] * ncell[2] * 8, device="cuda", dtype=torch.float32)
-    return {"cell0": cell0, "ncell": ncell, "first": first, "hint": hint, "cellsum": cellsum,
+    return {"cell0": cell0, "ncell": ncell, "first": first, "hint": hint, "cellsum": cellsum, "wtab": wtab, "rmax": rmax,
+            "hf": [float(F32(v)) for v in fine["h"]], "hc": [float(F32(v)) for v in parent["h"]],
             "fine": _coords(fine["node_coords"]), "parent": _coords(parent["node_coords"])}
 
 
-def _project(cells, A, coef, V, mode, scale=1.0, A2=None):
+def _project(cells, A, coef, V, mode, scale=1.0, A2=None, **kw):
     return ops.project(cells["fine"], cells["parent"], A, coef, V, cells, mode=mode, scale=scale, A2=A2,
-                       accumulate=True)
+                       accumulate=True, **kw)
 
 
 def _bc5(L1):
@@ -377,6 +385,9 @@ def _fill_pair(dst, cells):
         dst.cell0[d], dst.ncell[d] = int(cells["cell0"][d]), int(cells["ncell"][d])
     dst.first_x, dst.first_y, dst.first_z = (t.data_ptr() for t in cells["first"])
     dst.elems_per_cell_hint = int(cells["hint"])
+    dst.wtab_x, dst.wtab_y, dst.wtab_z = (t.data_ptr() for t in cells["wtab"])
+    for d in range(3):
+        dst.rmax[d] = int(cells["rmax"][d])
 
 
 def _fill_overlap(dst, L):

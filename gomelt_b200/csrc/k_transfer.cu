@@ -58,10 +58,19 @@ __global__ void interp_kernel(const InterpParams p) {
     const long long fA = (long long)p.ntx * p.nty, fB = 2LL * p.ntx * (p.ntz - 1),
                     fC = 2LL * (p.nty - 2) * (p.ntz - 1);
     const long long count = p.faces_only ? fA + fB + fC : total;
-    for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < count;
-         w += (long long)gridDim.x * blockDim.x) {
+    // full-grid passes are launched with blockIdx.y / .z = target row / plane (grid3 = 1): no index divisions
+    const bool grid3 = gridDim.y > 1 || gridDim.z > 1;
+    const long long w0 = grid3 ? (long long)blockIdx.x * blockDim.x + threadIdx.x
+                               : blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long wend = grid3 ? p.ntx : count;
+    const long long wstep = grid3 ? (long long)gridDim.x * blockDim.x : (long long)gridDim.x * blockDim.x;
+    for (long long w = w0; w < wend; w += wstep) {
         int i, j, k;
-        if (!p.faces_only) {
+        if (grid3) {
+            i = (int)w;
+            j = blockIdx.y;
+            k = blockIdx.z;
+        } else if (!p.faces_only) {
             i = (int)(w % p.ntx);
             j = (int)((w / p.ntx) % p.nty);
             k = (int)(w / ((long long)p.ntx * p.nty));
@@ -218,6 +227,17 @@ template <typename T>
 __global__ void box_copy_kernel(const T* __restrict__ src, T* __restrict__ dst, const int* __restrict__ ix,
                                 const int* __restrict__ iy, const int* __restrict__ iz, int nx, int ny, int nz,
                                 int big_nx, int big_ny, int scatter) {
+    // blockIdx.y / .z = window row / plane (launched that way when ny, nz <= 65535), else a flat grid-stride loop
+    if (gridDim.y > 1 || gridDim.z > 1) {
+        const int j = blockIdx.y, k = blockIdx.z;
+        const long long gb = (long long)iy[j] * big_nx + (long long)iz[k] * big_nx * big_ny;
+        const long long tb = ((long long)k * ny + j) * nx;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x) {
+            if (scatter) dst[gb + ix[i]] = src[tb + i];
+            else dst[tb + i] = src[gb + ix[i]];
+        }
+        return;
+    }
     const long long total = (long long)nx * ny * nz;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
@@ -430,6 +450,247 @@ __global__ void project_cells_kernel(const ProjParams p) {
     }
 }
 
+
+// ---- K3, tiled form (project_tile_kernel): the fast path of gomelt_project_f32 -------------------------------------------
+// Same sums as project_cells_kernel, organised for the 10 M-node windows: a CTA owns a box of parent cells, stages the
+// fine nodes under it ONCE in shared memory - field value (A - A2) and nodal coefficient, the latter evaluated there from
+// (T, S1) with computeStateProperties when no coefficient array is given - and then walks the fine elements out of
+// shared memory.  The parent's shape-function factors at the two Gauss points of every fine element come from three
+// 1-D tables built once per window position (wtab_[xyz][e] = (x1 - xq0, xq0 - x0, x1 - xq1, xq1 - x0) of the parent cell
+// that holds each Gauss point), and both terms are evaluated by sum factorisation (the hex8 shape functions and their
+// parent counterparts are tensor products; only the element-mean coefficient couples the axes):
+//   MASS  val[q] = N[q,:] . A_e by three 2 x 2 stages, times cbar, then back through the parent factors by three stages;
+//   GRAD  dA/dx at a Gauss point does not depend on its x index (trilinear), so each direction is a 2-D transform of the
+//         four edge differences and the sum over the third Gauss index is a factor 2.
+// ~100 FP operations per fine element instead of ~450, every fine node read once per CTA instead of eight times per
+// element.  Partial sums of the threads that share a parent cell are added in a fixed order: deterministic.
+struct TileParams {
+    int fnx, fny, fnz;           // fine nodes
+    const float* A;
+    const float* A2;
+    const float* coef;
+    const float* cT;
+    const float* cS1;
+    long long cnsub;
+    PropK pk;
+    int mode;
+    float sw;                    // MASS: scale * wq ; GRAD: wq
+    float inv_hfx, inv_hfy, inv_hfz, inv_cvol;
+    const float4* wx;            // [fine elements per axis]
+    const float4* wy;
+    const float4* wz;
+    const int* fsx;              // first fine element of parent cell c0 + i
+    const int* fsy;
+    const int* fsz;
+    int ncx, ncy, ncz;           // parent cells with fine elements
+    int pcx, pcy, pcz;           // parent cells per CTA
+    int G;                       // threads per parent cell (power of two)
+    float* cellsum;
+};
+constexpr int TILE_NODECAP = 2304;
+constexpr int TILE_THREADS = 256;
+
+__global__ void __launch_bounds__(TILE_THREADS) project_tile_kernel(const TileParams p) {
+    __shared__ float2 s_node[TILE_NODECAP];          // (A - A2, coefficient)
+    __shared__ float s_part[TILE_THREADS][9];        // per-thread partial sums (padded)
+    const int tid = threadIdx.x;
+    const int ci0 = blockIdx.x * p.pcx, cj0 = blockIdx.y * p.pcy, ck0 = blockIdx.z * p.pcz;
+    const int ci1 = min(ci0 + p.pcx, p.ncx), cj1 = min(cj0 + p.pcy, p.ncy), ck1 = min(ck0 + p.pcz, p.ncz);
+    const int ex0 = p.fsx[ci0], ey0 = p.fsy[cj0], ez0 = p.fsz[ck0];
+    const int bnx = p.fsx[ci1] - ex0 + 1, bny = p.fsy[cj1] - ey0 + 1, bnz = p.fsz[ck1] - ez0 + 1;  // node box
+    const int bn = bnx * bny * bnz;
+    const long long fnxy = (long long)p.fnx * p.fny;
+    for (int n = tid; n < bn; n += TILE_THREADS) {
+        const int k = n / (bnx * bny), r = n - k * (bnx * bny), j = r / bnx, i = r - j * bnx;
+        const long long g = (ex0 + i) + (long long)(ey0 + j) * p.fnx + (long long)(ez0 + k) * fnxy;
+        float a = __ldg(p.A + g);
+        if (p.A2) a -= __ldg(p.A2 + g);
+        float c;
+        if (p.coef) {
+            c = __ldg(p.coef + g);
+        } else {
+            float kk, rr;
+            bool b1, b2;
+            node_props(p.pk, __ldg(p.cT + g), __ldg(p.cS1 + g), g < p.cnsub, kk, rr, b1, b2);
+            c = p.mode == 1 ? rr : kk;
+        }
+        s_node[n] = make_float2(a, c);
+    }
+    __syncthreads();
+    const int tcx = ci1 - ci0, tcy = cj1 - cj0, tcz = ck1 - ck0;
+    const int ncell_t = tcx * tcy * tcz;
+    const int cl = tid / p.G, gl = tid - cl * p.G;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (cl < ncell_t) {
+        const int lk = cl / (tcx * tcy), lr = cl - lk * (tcx * tcy), lj = lr / tcx, li = lr - lj * tcx;
+        const int fx0 = p.fsx[ci0 + li], fx1 = p.fsx[ci0 + li + 1];
+        const int fy0 = p.fsy[cj0 + lj], fy1 = p.fsy[cj0 + lj + 1];
+        const int fz0 = p.fsz[ck0 + lk], fz1 = p.fsz[ck0 + lk + 1];
+        const int nex = fx1 - fx0, ney = fy1 - fy0, nel = nex * ney * (fz1 - fz0);
+        const float g3 = 0.57735026918962576f;
+        const float Nlo = 0.5f * (1.f + g3), Nhi = 0.5f * (1.f - g3);
+        for (int t = gl; t < nel; t += p.G) {
+            const int ez = t / (nex * ney), tr = t - ez * (nex * ney), ey = tr / nex, ex = tr - ey * nex;
+            const int gx_ = fx0 + ex, gy_ = fy0 + ey, gz_ = fz0 + ez;  // global fine element
+            const int b = (gx_ - ex0) + (gy_ - ey0) * bnx + (gz_ - ez0) * bnx * bny;
+            // corner (bx, by, bz) at b + bx + by * bnx + bz * bnx * bny
+            float a[2][2][2];
+            float csum = 0.f;
+#pragma unroll
+            for (int bz = 0; bz < 2; ++bz)
+#pragma unroll
+                for (int by = 0; by < 2; ++by)
+#pragma unroll
+                    for (int bx = 0; bx < 2; ++bx) {
+                        const float2 v = s_node[b + bx + by * bnx + bz * bnx * bny];
+                        a[bx][by][bz] = v.x;
+                        csum += v.y;
+                    }
+            const float cbar = csum * 0.125f;
+            const float4 tx = __ldg(p.wx + gx_), ty = __ldg(p.wy + gy_), tz = __ldg(p.wz + gz_);
+            const float wX[2][2] = {{tx.x, tx.y}, {tx.z, tx.w}};  // [Gauss point][parent corner]
+            const float wY[2][2] = {{ty.x, ty.y}, {ty.z, ty.w}};
+            const float wZ[2][2] = {{tz.x, tz.y}, {tz.z, tz.w}};
+            const float Nq[2][2] = {{Nlo, Nhi}, {Nhi, Nlo}};       // fine 1-D shape values [Gauss point][corner]
+            float out[2][2][2] = {{{0.f, 0.f}, {0.f, 0.f}}, {{0.f, 0.f}, {0.f, 0.f}}};  // [cx][cy][cz]
+            if (p.mode == 1) {
+                float fx[2][2][2], fy[2][2][2], s[2][2][2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                    for (int by = 0; by < 2; ++by)
+#pragma unroll
+                        for (int bz = 0; bz < 2; ++bz) fx[q][by][bz] = Nq[q][0] * a[0][by][bz] + Nq[q][1] * a[1][by][bz];
+#pragma unroll
+                for (int qx = 0; qx < 2; ++qx)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+#pragma unroll
+                        for (int bz = 0; bz < 2; ++bz) fy[qx][q][bz] = Nq[q][0] * fx[qx][0][bz] + Nq[q][1] * fx[qx][1][bz];
+                const float f = -(p.sw * cbar);
+#pragma unroll
+                for (int qx = 0; qx < 2; ++qx)
+#pragma unroll
+                    for (int qy = 0; qy < 2; ++qy)
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) s[qx][qy][q] = f * (Nq[q][0] * fy[qx][qy][0] + Nq[q][1] * fy[qx][qy][1]);
+                float u[2][2][2], v[2][2][2];
+#pragma unroll
+                for (int cx = 0; cx < 2; ++cx)
+#pragma unroll
+                    for (int qy = 0; qy < 2; ++qy)
+#pragma unroll
+                        for (int qz = 0; qz < 2; ++qz) u[cx][qy][qz] = wX[0][cx] * s[0][qy][qz] + wX[1][cx] * s[1][qy][qz];
+#pragma unroll
+                for (int cx = 0; cx < 2; ++cx)
+#pragma unroll
+                    for (int cy = 0; cy < 2; ++cy)
+#pragma unroll
+                        for (int qz = 0; qz < 2; ++qz) v[cx][cy][qz] = wY[0][cy] * u[cx][0][qz] + wY[1][cy] * u[cx][1][qz];
+#pragma unroll
+                for (int cx = 0; cx < 2; ++cx)
+#pragma unroll
+                    for (int cy = 0; cy < 2; ++cy)
+#pragma unroll
+                        for (int cz = 0; cz < 2; ++cz) out[cx][cy][cz] = (wZ[0][cz] * v[cx][cy][0] + wZ[1][cz] * v[cx][cy][1]) * p.inv_cvol;
+            } else {
+                const float f = -(p.sw * cbar) * p.inv_cvol * 2.0f;  // the Gauss index along the derivative sums to a factor 2
+                // x: edge differences d[by][bz], interpolated to (qy, qz), back through wY, wZ, sign by cx
+                {
+                    float d[2][2], gq[2][2], t1[2][2];
+#pragma unroll
+                    for (int by = 0; by < 2; ++by)
+#pragma unroll
+                        for (int bz = 0; bz < 2; ++bz) d[by][bz] = a[1][by][bz] - a[0][by][bz];
+#pragma unroll
+                    for (int qy = 0; qy < 2; ++qy)
+#pragma unroll
+                        for (int qz = 0; qz < 2; ++qz)
+                            gq[qy][qz] = (f * p.inv_hfx) * (Nq[qz][0] * (Nq[qy][0] * d[0][0] + Nq[qy][1] * d[1][0]) +
+                                                            Nq[qz][1] * (Nq[qy][0] * d[0][1] + Nq[qy][1] * d[1][1]));
+#pragma unroll
+                    for (int cy = 0; cy < 2; ++cy)
+#pragma unroll
+                        for (int qz = 0; qz < 2; ++qz) t1[cy][qz] = wY[0][cy] * gq[0][qz] + wY[1][cy] * gq[1][qz];
+#pragma unroll
+                    for (int cy = 0; cy < 2; ++cy)
+#pragma unroll
+                        for (int cz = 0; cz < 2; ++cz) {
+                            const float o = wZ[0][cz] * t1[cy][0] + wZ[1][cz] * t1[cy][1];
+                            out[0][cy][cz] -= o;
+                            out[1][cy][cz] += o;
+                        }
+                }
+                {  // y: d[bx][bz], interpolated to (qx, qz), back through wX, wZ
+                    float d[2][2], gq[2][2], t1[2][2];
+#pragma unroll
+                    for (int bx = 0; bx < 2; ++bx)
+#pragma unroll
+                        for (int bz = 0; bz < 2; ++bz) d[bx][bz] = a[bx][1][bz] - a[bx][0][bz];
+#pragma unroll
+                    for (int qx = 0; qx < 2; ++qx)
+#pragma unroll
+                        for (int qz = 0; qz < 2; ++qz)
+                            gq[qx][qz] = (f * p.inv_hfy) * (Nq[qz][0] * (Nq[qx][0] * d[0][0] + Nq[qx][1] * d[1][0]) +
+                                                            Nq[qz][1] * (Nq[qx][0] * d[0][1] + Nq[qx][1] * d[1][1]));
+#pragma unroll
+                    for (int cx = 0; cx < 2; ++cx)
+#pragma unroll
+                        for (int qz = 0; qz < 2; ++qz) t1[cx][qz] = wX[0][cx] * gq[0][qz] + wX[1][cx] * gq[1][qz];
+#pragma unroll
+                    for (int cx = 0; cx < 2; ++cx)
+#pragma unroll
+                        for (int cz = 0; cz < 2; ++cz) {
+                            const float o = wZ[0][cz] * t1[cx][0] + wZ[1][cz] * t1[cx][1];
+                            out[cx][0][cz] -= o;
+                            out[cx][1][cz] += o;
+                        }
+                }
+                {  // z: d[bx][by], interpolated to (qx, qy), back through wX, wY
+                    float d[2][2], gq[2][2], t1[2][2];
+#pragma unroll
+                    for (int bx = 0; bx < 2; ++bx)
+#pragma unroll
+                        for (int by = 0; by < 2; ++by) d[bx][by] = a[bx][by][1] - a[bx][by][0];
+#pragma unroll
+                    for (int qx = 0; qx < 2; ++qx)
+#pragma unroll
+                        for (int qy = 0; qy < 2; ++qy)
+                            gq[qx][qy] = (f * p.inv_hfz) * (Nq[qy][0] * (Nq[qx][0] * d[0][0] + Nq[qx][1] * d[1][0]) +
+                                                            Nq[qy][1] * (Nq[qx][0] * d[0][1] + Nq[qx][1] * d[1][1]));
+#pragma unroll
+                    for (int cx = 0; cx < 2; ++cx)
+#pragma unroll
+                        for (int qy = 0; qy < 2; ++qy) t1[cx][qy] = wX[0][cx] * gq[0][qy] + wX[1][cx] * gq[1][qy];
+#pragma unroll
+                    for (int cx = 0; cx < 2; ++cx)
+#pragma unroll
+                        for (int cy = 0; cy < 2; ++cy) {
+                            const float o = wY[0][cy] * t1[cx][0] + wY[1][cy] * t1[cx][1];
+                            out[cx][cy][0] -= o;
+                            out[cx][cy][1] += o;
+                        }
+                }
+            }
+            // hex8 local order: 0 (000) 1 (100) 2 (110) 3 (010) 4 (001) 5 (101) 6 (111) 7 (011), bits = (x, y, z)
+            acc[0] += out[0][0][0]; acc[1] += out[1][0][0]; acc[2] += out[1][1][0]; acc[3] += out[0][1][0];
+            acc[4] += out[0][0][1]; acc[5] += out[1][0][1]; acc[6] += out[1][1][1]; acc[7] += out[0][1][1];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) s_part[tid][c] = acc[c];
+    __syncthreads();
+    // one thread per (parent cell of the tile, corner): the G partial sums in thread order
+    if (tid < ncell_t * 8) {
+        const int cell = tid >> 3, c = tid & 7;
+        float s = 0.f;
+        for (int g = 0; g < p.G; ++g) s += s_part[cell * p.G + g][c];
+        const int lk = cell / (tcx * tcy), lr = cell - lk * (tcx * tcy), lj = lr / tcx, li = lr - lj * tcx;
+        const long long gc = (ci0 + li) + (long long)(cj0 + lj) * p.ncx + (long long)(ck0 + lk) * p.ncx * p.ncy;
+        p.cellsum[gc * 8 + c] = s;
+    }
+}
+
 // parent node (gi,gj,gk) of the box [c0, c0 + nc] (nodes) <- its <= 8 adjacent cells, increasing cell id
 __global__ void project_nodes_kernel(const float* __restrict__ cellsum, int c0x, int c0y, int c0z, int ncx, int ncy,
                                      int ncz, int pnx, int pny, float* __restrict__ V, int accumulate) {
@@ -477,7 +738,15 @@ __global__ void coarse_source_table_batch_kernel(const float* __restrict__ fx, c
     const float hc = xc[1] - xc[0];
     const float inv_hc = 1.0f / hc;
     float acc = 0.f;
-    for (int e = 0; e < nf - 1; ++e) {  // same loop as coarse_source_table_kernel
+    // only fine elements whose first Gauss point lies in parent cell ic - 1 or ic contribute: bracket them (two elements
+    // of slack on either side; the exact cell test below decides)
+    const float hf = xf[1] - xf[0];
+    int elo = (int)floorf((xc[max(ic - 1, 0)] - xf[0]) / hf) - 2, ehi = (int)floorf((xc[min(ic + 1, nc - 1)] - xf[0]) / hf) + 2;
+    if (ic <= 1) elo = 0;            // (clipped cells: everything below / above the parent grid belongs to the end cells)
+    if (ic >= nc - 2) ehi = nf - 2;
+    elo = max(elo, 0);
+    ehi = min(ehi, nf - 2);
+    for (int e = elo; e <= ehi; ++e) {  // same body as coarse_source_table_kernel
         const float x0 = xf[e], x1 = xf[e + 1];
         const float xq0 = Nlo * x0 + Nhi * x1, xq1 = Nhi * x0 + Nlo * x1;
         const int ec = cell_of(xq0, xc[0], hc, nc - 1);
@@ -496,18 +765,23 @@ __global__ void coarse_source_table_batch_kernel(const float* __restrict__ fx, c
 }
 __global__ void rank_n_kernel(float* __restrict__ F, const float* __restrict__ tables, int nx, int ny, int nz,
                               const __grid_constant__ SrcBatch sb, int accumulate) {
-    const long long total = (long long)nx * ny * nz;
+    // blockIdx.y = row j, blockIdx.z = plane k; the (y, z) factors of every laser row are formed once per block
     const int stride = nx + ny + nz;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(t % nx);
-        const int j = (int)((t / nx) % ny);
-        const int k = (int)(t / ((long long)nx * ny));
-        float f = accumulate ? F[t] : 0.f;
+    const int j = blockIdx.y, k = blockIdx.z;
+    __shared__ float s_yz[GOMELT_MAX_SUBSTEPS];
+    for (int r = threadIdx.x; r < sb.n; r += blockDim.x) {
+        const float* tb = tables + (size_t)r * stride;
+        s_yz[r] = tb[nx + j];  // (kept separate from the z factor: the product order below is (tx * ty) * tz)
+    }
+    __syncthreads();
+    const size_t base = ((size_t)k * ny + j) * nx;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x) {
+        float f = accumulate ? F[base + i] : 0.f;
         for (int r = 0; r < sb.n; ++r) {  // rows in order, like the row-by-row accumulation of gomelt_rank1_f32
             const float* tb = tables + (size_t)r * stride;
-            f = f + sb.c[r] * ((tb[i] * tb[nx + j]) * tb[nx + ny + k]);
+            f = f + sb.c[r] * ((tb[i] * s_yz[r]) * tb[nx + ny + k]);
         }
-        F[t] = f;
+        F[base + i] = f;
     }
 }
 
@@ -551,9 +825,9 @@ __device__ __forceinline__ float trilinear_at(const AxisView& sx, const AxisView
     return acc;
 }
 __global__ void shift_window_kernel(const ShiftParams p) {
-    const long long total = (long long)p.ntx * p.nty * p.ntz;
-    for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < total; w += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(w % p.ntx), j = (int)((w / p.ntx) % p.nty), k = (int)(w / ((long long)p.ntx * p.nty));
+    const int j = blockIdx.y, k = blockIdx.z;  // blockIdx.y / .z = target row / plane
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.ntx; i += gridDim.x * blockDim.x) {
+        const size_t w = ((size_t)k * p.nty + j) * p.ntx + i;
         const float x = p.tx[i], y = p.ty[j], z = p.tz[k];
         const float tp = trilinear_at(p.ox, p.oy, p.oz, p.Tpo, x, y, z);
         const float t1 = trilinear_at(p.ax, p.ay, p.az, p.T1, x, y, z);
@@ -603,7 +877,12 @@ extern "C" int gomelt_interp_f32(const gomelt_interp_args_t* a, void* stream) {
     long long total = (long long)a->ntx * a->nty * a->ntz;
     if (a->faces_only)
         total = (long long)a->ntx * a->nty + 2LL * a->ntx * (a->ntz - 1) + 2LL * (a->nty - 2) * (a->ntz - 1);
-    interp_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p), count_launch();
+    if (!a->faces_only && a->nty <= 65535 && a->ntz <= 65535 && (a->nty > 1 || a->ntz > 1)) {
+        const int threads = a->ntx >= 256 ? 256 : (a->ntx >= 128 ? 128 : 64);
+        interp_kernel<<<dim3((a->ntx + threads - 1) / threads, a->nty, a->ntz), threads, 0, (cudaStream_t)stream>>>(p), count_launch();
+    } else {
+        interp_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p), count_launch();
+    }
     return check_launch("gomelt_interp_f32");
 }
 
@@ -662,12 +941,14 @@ extern "C" int gomelt_box_copy(const void* src, void* dst, int32_t elem_size, co
     }
     const long long total = (long long)nx * ny * nz;
     cudaStream_t st = (cudaStream_t)stream;
+    const bool g3 = ny <= 65535 && nz <= 65535 && (ny > 1 || nz > 1);
+    const dim3 grid = g3 ? dim3((nx + 255) / 256, ny, nz) : dim3(grid_for(total, 256));
     if (elem_size == 4)
-        box_copy_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)src, (float*)dst, ix, iy, iz, nx, ny,
-                                                                     nz, big_nx, big_ny, scatter), count_launch();
+        box_copy_kernel<float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, ix, iy, iz, nx, ny,
+                                                     nz, big_nx, big_ny, scatter), count_launch();
     else
-        box_copy_kernel<uint8_t><<<grid_for(total, 256), 256, 0, st>>>((const uint8_t*)src, (uint8_t*)dst, ix, iy, iz,
-                                                                       nx, ny, nz, big_nx, big_ny, scatter), count_launch();
+        box_copy_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)src, (uint8_t*)dst, ix, iy, iz,
+                                                       nx, ny, nz, big_nx, big_ny, scatter), count_launch();
     return check_launch("gomelt_box_copy");
 }
 
@@ -741,7 +1022,46 @@ extern "C" int gomelt_project_f32(const gomelt_project_args_t* a, void* stream) 
     p.cellsum = a->cellsum;
     const long long ncell = (long long)p.ncx * p.ncy * p.ncz;
     cudaStream_t st = (cudaStream_t)stream;
-    if (a->elems_per_cell_hint <= 16) {
+    bool tiled = a->wtab_x && a->wtab_y && a->wtab_z && a->rmax[0] >= 1 && a->rmax[1] >= 1 && a->rmax[2] >= 1;
+    TileParams tp;
+    if (tiled) {
+        // parent cells per CTA: about 32 x 8 x 4 fine elements, the node box within the shared-memory capacity
+        int pc[3] = {32 / a->rmax[0], 8 / a->rmax[1], 4 / a->rmax[2]};
+        for (int d = 0; d < 3; ++d) pc[d] = pc[d] < 1 ? 1 : pc[d];
+        auto nodes = [&] { return (long long)(pc[0] * a->rmax[0] + 1) * (pc[1] * a->rmax[1] + 1) * (pc[2] * a->rmax[2] + 1); };
+        while ((nodes() > TILE_NODECAP || pc[0] * pc[1] * pc[2] > TILE_THREADS) && (pc[0] > 1 || pc[1] > 1 || pc[2] > 1)) {
+            int d = pc[0] >= pc[1] && pc[0] >= pc[2] ? 0 : (pc[1] >= pc[2] ? 1 : 2);
+            if (pc[d] == 1) d = pc[0] > 1 ? 0 : (pc[1] > 1 ? 1 : 2);
+            pc[d] = (pc[d] + 1) / 2;
+        }
+        tiled = nodes() <= TILE_NODECAP && pc[0] * pc[1] * pc[2] <= TILE_THREADS;
+        if (tiled) {
+            tp.fnx = a->fine[0].n; tp.fny = a->fine[1].n; tp.fnz = a->fine[2].n;
+            tp.A = a->A; tp.A2 = a->A2; tp.coef = a->coef; tp.cT = a->coef_T; tp.cS1 = a->coef_S1; tp.cnsub = a->coef_n_substrate;
+            if (!a->coef) tp.pk = fold_props(*a->coef_props);
+            tp.mode = a->mode;
+            tp.wx = reinterpret_cast<const float4*>(a->wtab_x); tp.wy = reinterpret_cast<const float4*>(a->wtab_y);
+            tp.wz = reinterpret_cast<const float4*>(a->wtab_z);
+            tp.fsx = a->first_x; tp.fsy = a->first_y; tp.fsz = a->first_z;
+            tp.ncx = p.ncx; tp.ncy = p.ncy; tp.ncz = p.ncz;
+            tp.pcx = pc[0]; tp.pcy = pc[1]; tp.pcz = pc[2];
+            int G = 1;
+            while (G * 2 * pc[0] * pc[1] * pc[2] <= TILE_THREADS) G *= 2;
+            tp.G = G;
+            tp.cellsum = a->cellsum;
+            // element sizes as the kernels derive them from the coordinate arrays are passed by the caller (hf, hc)
+            const float hfx = a->hf[0], hfy = a->hf[1], hfz = a->hf[2];
+            const float wq = (hfx * hfy * hfz) * 0.125f;
+            tp.sw = a->mode == 1 ? a->scale * wq : wq;
+            tp.inv_hfx = 1.0f / hfx; tp.inv_hfy = 1.0f / hfy; tp.inv_hfz = 1.0f / hfz;
+            tp.inv_cvol = 1.0f / ((a->hc[0] * a->hc[1]) * a->hc[2]);
+            dim3 grid((p.ncx + pc[0] - 1) / pc[0], (p.ncy + pc[1] - 1) / pc[1], (p.ncz + pc[2] - 1) / pc[2]);
+            project_tile_kernel<<<grid, TILE_THREADS, 0, st>>>(tp), count_launch();
+        }
+    }
+    if (tiled) {
+        // (cellsum is complete: fall through to the node pass)
+    } else if (a->elems_per_cell_hint <= 16) {
         const long long threads = ncell * 8;
         project_cells_kernel<8><<<(int)((threads + 127) / 128), 128, 0, st>>>(p), count_launch();
     } else {
@@ -789,8 +1109,11 @@ extern "C" int gomelt_projected_source_f32(const gomelt_props_t* p, const gomelt
     coarse_source_table_batch_kernel<<<dim3((nmax + 63) / 64, 3, n), 64, 0, st>>>(
         fine[0].coords, fine[1].coords, fine[2].coords, fine[0].n, fine[1].n, fine[2].n, parent[0].coords, parent[1].coords,
         parent[2].coords, ncx, ncy, ncz, sb, 1.f / rsq, 1.f / dsq, rcoeff, dcoeff, tables), count_launch();
-    const long long total = (long long)ncx * ncy * ncz;
-    rank_n_kernel<<<grid_for(total, 256), 256, 0, st>>>(F, tables, ncx, ncy, ncz, sb, accumulate), count_launch();
+    if (ncy > 65535 || ncz > 65535) {
+        set_error("gomelt_projected_source_f32: parent grid too large (ny, nz <= 65535)");
+        return GOMELT_E_SIZE;
+    }
+    rank_n_kernel<<<dim3((ncx + 255) / 256, ncy, ncz), 256, 0, st>>>(F, tables, ncx, ncy, ncz, sb, accumulate), count_launch();
     return check_launch("gomelt_projected_source_f32");
 }
 
@@ -821,7 +1144,10 @@ extern "C" int gomelt_shift_window_f32(const gomelt_shift_args_t* a, void* strea
     p.Tpo = a->Tp_old;
     p.tx = a->tx; p.ty = a->ty; p.tz = a->tz; p.ntx = a->ntx; p.nty = a->nty; p.ntz = a->ntz;
     p.Tp_new = a->Tp_new; p.T_new = a->T_new;
-    const long long total = (long long)a->ntx * a->nty * a->ntz;
-    shift_window_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p), count_launch();
+    if (a->nty > 65535 || a->ntz > 65535) {
+        set_error("gomelt_shift_window_f32: target grid too large (nty, ntz <= 65535)");
+        return GOMELT_E_SIZE;
+    }
+    shift_window_kernel<<<dim3((a->ntx + 255) / 256, a->nty, a->ntz), 256, 0, (cudaStream_t)stream>>>(p), count_launch();
     return check_launch("gomelt_shift_window_f32");
 }

@@ -266,17 +266,30 @@ def coarse_source_tables(props, fine_coords, parent_coords, laser_xyz, laserP, t
     return coef.value
 
 
-def project(fine_coords, parent_coords, A, coef, V, cells, *, mode, scale=1.0, A2=None, accumulate=True):
-    """gomelt_project_f32.  ``cells`` = dict(cell0, ncell, first (3 int32 device arrays), cellsum, hint)."""
+def project(fine_coords, parent_coords, A, coef, V, cells, *, mode, scale=1.0, A2=None, accumulate=True, tiled=True,
+            coef_from=None):
+    """gomelt_project_f32.  ``cells`` = dict(cell0, ncell, first (3 int32 device arrays), cellsum, hint, wtab, rmax, hf,
+    hc).  ``tiled=False`` forces the general kernel (A/B).  ``coef_from`` = (props, T, S1, n_substrate) evaluates the
+    coefficient in the kernel (then ``coef`` is None)."""
     lib = _lib.load()
     a = _lib.ProjectArgs()
     a.fine, a.parent = _axes(fine_coords), _axes(parent_coords)
-    a.A, a.A2, a.coef = A.data_ptr(), (A2.data_ptr() if A2 is not None else None), coef.data_ptr()
+    a.A, a.A2 = A.data_ptr(), (A2.data_ptr() if A2 is not None else None)
+    if coef is not None:
+        a.coef = coef.data_ptr()
+    else:
+        cprops, cT, cS1, cnsub = coef_from
+        a.coef_T, a.coef_S1, a.coef_n_substrate, a.coef_props = cT.data_ptr(), cS1.data_ptr(), int(cnsub), C.pointer(cprops)
     a.mode, a.scale = int(mode), float(scale)
     a.cell0 = (C.c_int32 * 3)(*[int(v) for v in cells["cell0"]])
     a.ncell = (C.c_int32 * 3)(*[int(v) for v in cells["ncell"]])
     a.first_x, a.first_y, a.first_z = (t.data_ptr() for t in cells["first"])
     a.elems_per_cell_hint = int(cells["hint"])
+    if tiled and cells.get("wtab") is not None:
+        a.wtab_x, a.wtab_y, a.wtab_z = (t.data_ptr() for t in cells["wtab"])
+        a.rmax = (C.c_int32 * 3)(*[int(v) for v in cells["rmax"]])
+        a.hf = (C.c_float * 3)(*cells["hf"])
+        a.hc = (C.c_float * 3)(*cells["hc"])
     a.cellsum, a.V, a.accumulate = cells["cellsum"].data_ptr(), V.data_ptr(), int(bool(accumulate))
     _lib.check(lib.gomelt_project_f32(C.byref(a), _lib.stream_ptr()), "gomelt_project_f32")
     _count(2)

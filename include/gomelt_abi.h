@@ -275,6 +275,14 @@ typedef struct gomelt_project_args {
     const float  *coef_T, *coef_S1;
     int64_t       coef_n_substrate;
     const gomelt_props_t *coef_props;
+    /* Fast (tiled) form, optional: per fine element e and axis, the parent's shape-function factors at its two Gauss
+     * points, wtab_d[4 e .. 4 e + 3] = (x1 - xq0, xq0 - x0, x1 - xq1, xq1 - x0) with [x0, x1] the parent cell that holds
+     * each Gauss point (device arrays, 16-byte aligned, built once per window position); rmax = the largest number of
+     * fine elements per parent cell along each axis; hf / hc = element sizes of the fine / parent level.  All NULL / 0:
+     * the general kernel derives everything from the coordinate arrays. */
+    const float  *wtab_x, *wtab_y, *wtab_z;
+    int32_t       rmax[3];
+    float         hf[3], hc[3];
 } gomelt_project_args_t;
 
 int gomelt_project_f32(const gomelt_project_args_t *args, void *stream);
@@ -337,6 +345,8 @@ typedef struct gomelt_pair {     /* fine -> parent element grouping of one level
     int32_t       cell0[3], ncell[3];
     const int32_t *first_x, *first_y, *first_z;
     int32_t       elems_per_cell_hint;
+    const float  *wtab_x, *wtab_y, *wtab_z;   /* see gomelt_project_args_t (may be NULL) */
+    int32_t       rmax[3];
 } gomelt_pair_t;
 
 typedef struct gomelt_overlap {  /* parent nodes under a window: index vectors and their coordinates            */

@@ -292,6 +292,18 @@ def test_project_grad_and_mass_terms(gm, T, pair, example_props):
     cf._project(cells, T.f(Tp0), T.f(k), V2, mode=0)
     cf._project(cells, T.f(Tp1), T.f(rc), V2, mode=1, scale=1.0 / dt, A2=T.f(Tp0))
     assert np.array_equal(T.h(V2), got01)
+    # the general kernel (no tables, everything derived from the coordinate arrays) gives the same vectors
+    V3 = T.torch_.zeros(parent["nn"], device="cuda")
+    cf._project(cells, T.f(Tp0), T.f(k), V3, mode=0, tiled=False)
+    cf._project(cells, T.f(Tp1), T.f(rc), V3, mode=1, scale=1.0 / dt, A2=T.f(Tp0), tiled=False)
+    assert _relmax(T.h(V3), want0 + want1) <= TOL_P, pair
+    # ... and so does the form the steppers use: k / rho*cp evaluated inside the kernel from (T, S1) - no coefficient array
+    props = gm._lib.make_props(P)
+    V4 = T.torch_.zeros(parent["nn"], device="cuda")
+    dT, dS = T.f(Tf), T.f(S1)
+    cf._project(cells, T.f(Tp0), None, V4, mode=0, coef_from=(props, dT, dS, 0))
+    cf._project(cells, T.f(Tp1), None, V4, mode=1, scale=1.0 / dt, A2=T.f(Tp0), coef_from=(props, dT, dS, 0))
+    assert _relmax(T.h(V4), want0 + want1) <= TOL_P, pair
 
 
 # ------------------------------------------------------------------------------------------------------------

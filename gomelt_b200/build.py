@@ -23,8 +23,16 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cc")))
 
 
+XLA_FFI_MIN = os.path.join(ROOT, "third_party", "xla_ffi_min")
+
+
 def xla_include_dirs():
-    """jaxlib's header tree (xla/ffi/api/ffi.h) when a jaxlib exists; [] in this image."""
+    """Where xla/ffi/api/c_api.h comes from: GOMELT_XLA_INCLUDE, else an installed jaxlib's header tree, else the minimal
+    subset of the C API in third_party/xla_ffi_min (this image has no jaxlib)."""
+    return _jaxlib_include_dirs() or [XLA_FFI_MIN]
+
+
+def _jaxlib_include_dirs():
     inc = os.environ.get("GOMELT_XLA_INCLUDE")
     if inc:
         return [inc]
@@ -34,7 +42,7 @@ def xla_include_dirs():
         spec = importlib.util.find_spec("jaxlib")
         if spec and spec.submodule_search_locations:
             d = os.path.join(list(spec.submodule_search_locations)[0], "include")
-            if os.path.exists(os.path.join(d, "xla", "ffi", "api", "ffi.h")):
+            if os.path.exists(os.path.join(d, "xla", "ffi", "api", "c_api.h")):
                 return [d]
     except Exception:
         pass

@@ -46,6 +46,90 @@ __device__ __forceinline__ int cell_of(float x, float x0, float h, int ne) {
     return e > ne - 1 ? ne - 1 : e;
 }
 
+constexpr int ROWS3 = 8;  // target rows per block of the 3-D launch forms (a block per row is too little work per block)
+
+// ---- lean form of the interpolant for full tensor-product target grids ---------------------------------------------------
+// The per-axis part of a target's weights (cell by the floor rule, the two distances to the cell's nodes) depends on one
+// target coordinate only: a thread keeps the x part of its column for all the rows it handles, the y part is formed
+// once per row and the z part once per block.  The 8 weights are then the reference's own products
+// ((ax * ay) * az) * inv_vol with its +-1e-2 validity window and [0, 1] clip (cF:1375-1391, 1101-1104): same values as
+// interp_kernel, a quarter of the instructions (no divisions, no coordinate loads, 32-bit indices in the inner part).
+struct Ax1 {
+    int e;
+    float a0, a1;  // x1 - x, x - x0 of cell e
+};
+__device__ __forceinline__ Ax1 ax1_of(const AxisView& ax, float h, float x) {
+    Ax1 r;
+    r.e = cell_of(x, ax.c[0], h, ax.n - 1);
+    r.a0 = __fsub_rn(ax.c[r.e + 1], x);
+    r.a1 = __fsub_rn(x, ax.c[r.e]);
+    return r;
+}
+struct SrcGeom {  // per source level, formed once per thread
+    float hx, hy, hz, inv_vol;
+    int nnx, nnxy;
+};
+__device__ __forceinline__ SrcGeom geom_of(const AxisView& sx, const AxisView& sy, const AxisView& sz) {
+    SrcGeom g;
+    g.hx = __fsub_rn(sx.c[1], sx.c[0]);
+    g.hy = __fsub_rn(sy.c[1], sy.c[0]);
+    g.hz = __fsub_rn(sz.c[1], sz.c[0]);
+    g.inv_vol = __fdiv_rn(1.0f, __fmul_rn(__fmul_rn(g.hx, g.hy), g.hz));
+    g.nnx = sx.n;
+    g.nnxy = sx.n * sy.n;
+    return g;
+}
+template <bool BLEND>
+__device__ __forceinline__ float tri_eval(const float* __restrict__ u, const float* __restrict__ u2, float alpha, float beta,
+                                          const SrcGeom& g, const Ax1& X, const Ax1& Y, const Ax1& Z) {
+    const float xy00 = __fmul_rn(X.a0, Y.a0), xy10 = __fmul_rn(X.a1, Y.a0), xy11 = __fmul_rn(X.a1, Y.a1), xy01 = __fmul_rn(X.a0, Y.a1);
+    float N[8];  // hex8 local order
+    N[0] = __fmul_rn(__fmul_rn(xy00, Z.a0), g.inv_vol);
+    N[1] = __fmul_rn(__fmul_rn(xy10, Z.a0), g.inv_vol);
+    N[2] = __fmul_rn(__fmul_rn(xy11, Z.a0), g.inv_vol);
+    N[3] = __fmul_rn(__fmul_rn(xy01, Z.a0), g.inv_vol);
+    N[4] = __fmul_rn(__fmul_rn(xy00, Z.a1), g.inv_vol);
+    N[5] = __fmul_rn(__fmul_rn(xy10, Z.a1), g.inv_vol);
+    N[6] = __fmul_rn(__fmul_rn(xy11, Z.a1), g.inv_vol);
+    N[7] = __fmul_rn(__fmul_rn(xy01, Z.a1), g.inv_vol);
+    const float lo = fminf(fminf(fminf(N[0], N[1]), fminf(N[2], N[3])), fminf(fminf(N[4], N[5]), fminf(N[6], N[7])));
+    const float hi = fmaxf(fmaxf(fmaxf(N[0], N[1]), fmaxf(N[2], N[3])), fmaxf(fmaxf(N[4], N[5]), fmaxf(N[6], N[7])));
+    if (!(lo >= -1e-2f && hi <= 1.0f + 1e-2f)) return 0.f;
+    const int b = X.e + Y.e * g.nnx + Z.e * g.nnxy;
+    const int nd[8] = {b, b + 1, b + 1 + g.nnx, b + g.nnx, b + g.nnxy, b + 1 + g.nnxy, b + 1 + g.nnx + g.nnxy, b + g.nnx + g.nnxy};
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        float v = __ldg(u + nd[a]);
+        if (BLEND) v = __fadd_rn(__fmul_rn(alpha, v), __fmul_rn(beta, __ldg(u2 + nd[a])));
+        acc = __fadd_rn(acc, __fmul_rn(fminf(fmaxf(N[a], 0.f), 1.f), v));
+    }
+    return acc;
+}
+
+// full target grid, no index map: blockIdx.y = group of ROWS3 target rows, blockIdx.z = target plane
+template <bool BLEND>
+__global__ void interp3_kernel(const InterpParams p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.ntx) return;
+    const SrcGeom g = geom_of(p.sx, p.sy, p.sz);
+    const Ax1 X = ax1_of(p.sx, g.hx, p.tx[i]);
+    const int k = blockIdx.z;
+    const Ax1 Z = ax1_of(p.sz, g.hz, p.tz[k]);
+    const int j1 = min(p.nty, (int)(blockIdx.y + 1) * ROWS3);
+    for (int j = blockIdx.y * ROWS3; j < j1; ++j) {
+        const Ax1 Y = ax1_of(p.sy, g.hy, p.ty[j]);
+        const float acc = tri_eval<BLEND>(p.u, p.u2, p.alpha, p.beta, g, X, Y, Z);
+        const size_t o = ((size_t)k * p.nty + j) * p.ntx + i;
+        float r;
+        if (p.mode == GOMELT_INTERP_SET) r = acc;
+        else if (p.mode == GOMELT_INTERP_ADD) r = __fadd_rn(p.out[o], acc);
+        else r = __fsub_rn(p.base[o], acc);
+        if (p.has_clamp) r = fmaxf(r, p.clamp_min);
+        p.out[o] = r;
+    }
+}
+
 // One thread per target node (x fastest => coalesced output; source reads hit L1/L2).
 __global__ void interp_kernel(const InterpParams p) {
     const long long total = (long long)p.ntx * p.nty * p.ntz;
@@ -229,12 +313,14 @@ __global__ void box_copy_kernel(const T* __restrict__ src, T* __restrict__ dst, 
                                 int big_nx, int big_ny, int scatter) {
     // blockIdx.y / .z = window row / plane (launched that way when ny, nz <= 65535), else a flat grid-stride loop
     if (gridDim.y > 1 || gridDim.z > 1) {
-        const int j = blockIdx.y, k = blockIdx.z;
-        const long long gb = (long long)iy[j] * big_nx + (long long)iz[k] * big_nx * big_ny;
-        const long long tb = ((long long)k * ny + j) * nx;
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x) {
-            if (scatter) dst[gb + ix[i]] = src[tb + i];
-            else dst[tb + i] = src[gb + ix[i]];
+        const int k = blockIdx.z;
+        for (int j = blockIdx.y * ROWS3; j < min(ny, (int)(blockIdx.y + 1) * ROWS3); ++j) {
+            const long long gb = (long long)iy[j] * big_nx + (long long)iz[k] * big_nx * big_ny;
+            const long long tb = ((long long)k * ny + j) * nx;
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x) {
+                if (scatter) dst[gb + ix[i]] = src[tb + i];
+                else dst[tb + i] = src[gb + ix[i]];
+            }
         }
         return;
     }
@@ -681,8 +767,8 @@ __global__ void __launch_bounds__(TILE_THREADS) project_tile_kernel(const TilePa
     for (int c = 0; c < 8; ++c) s_part[tid][c] = acc[c];
     __syncthreads();
     // one thread per (parent cell of the tile, corner): the G partial sums in thread order
-    if (tid < ncell_t * 8) {
-        const int cell = tid >> 3, c = tid & 7;
+    for (int o = tid; o < ncell_t * 8; o += TILE_THREADS) {
+        const int cell = o >> 3, c = o & 7;
         float s = 0.f;
         for (int g = 0; g < p.G; ++g) s += s_part[cell * p.G + g][c];
         const int lk = cell / (tcx * tcy), lr = cell - lk * (tcx * tcy), lj = lr / tcx, li = lr - lj * tcx;
@@ -765,24 +851,26 @@ __global__ void coarse_source_table_batch_kernel(const float* __restrict__ fx, c
 }
 __global__ void rank_n_kernel(float* __restrict__ F, const float* __restrict__ tables, int nx, int ny, int nz,
                               const __grid_constant__ SrcBatch sb, int accumulate) {
-    // blockIdx.y = row j, blockIdx.z = plane k; the (y, z) factors of every laser row are formed once per block
+    // blockIdx.y = group of ROWS3 rows, blockIdx.z = plane k; per laser row the x factor is read once per thread and
+    // the z factor once per block
     const int stride = nx + ny + nz;
-    const int j = blockIdx.y, k = blockIdx.z;
-    __shared__ float s_yz[GOMELT_MAX_SUBSTEPS];
-    for (int r = threadIdx.x; r < sb.n; r += blockDim.x) {
+    const int k = blockIdx.z;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nx) return;
+    const int j0 = blockIdx.y * ROWS3, j1 = min(ny, j0 + ROWS3);
+    float f[ROWS3];
+#pragma unroll
+    for (int q = 0; q < ROWS3; ++q) f[q] = (accumulate && j0 + q < j1) ? F[((size_t)k * ny + j0 + q) * nx + i] : 0.f;
+    for (int r = 0; r < sb.n; ++r) {  // laser rows in order, like the row-by-row accumulation of gomelt_rank1_f32
         const float* tb = tables + (size_t)r * stride;
-        s_yz[r] = tb[nx + j];  // (kept separate from the z factor: the product order below is (tx * ty) * tz)
+        const float txv = tb[i], tzv = tb[nx + ny + k], c = sb.c[r];
+#pragma unroll
+        for (int q = 0; q < ROWS3; ++q)
+            if (j0 + q < j1) f[q] = f[q] + c * ((txv * tb[nx + j0 + q]) * tzv);
     }
-    __syncthreads();
-    const size_t base = ((size_t)k * ny + j) * nx;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x) {
-        float f = accumulate ? F[base + i] : 0.f;
-        for (int r = 0; r < sb.n; ++r) {  // rows in order, like the row-by-row accumulation of gomelt_rank1_f32
-            const float* tb = tables + (size_t)r * stride;
-            f = f + sb.c[r] * ((tb[i] * s_yz[r]) * tb[nx + ny + k]);
-        }
-        F[base + i] = f;
-    }
+#pragma unroll
+    for (int q = 0; q < ROWS3; ++q)
+        if (j0 + q < j1) F[((size_t)k * ny + j0 + q) * nx + i] = f[q];
 }
 
 // ---- K5: fused window shift -----------------------------------------------------------------------------------------
@@ -794,45 +882,29 @@ struct ShiftParams {
     int ntx, nty, ntz;
     float *Tp_new, *T_new;
 };
-// the interpolant of interp_kernel (same operations in the same order) at one point
-__device__ __forceinline__ float trilinear_at(const AxisView& sx, const AxisView& sy, const AxisView& sz, const float* __restrict__ u,
-                                              float x, float y, float z) {
-    const float hx = __fsub_rn(sx.c[1], sx.c[0]), hy = __fsub_rn(sy.c[1], sy.c[0]), hz = __fsub_rn(sz.c[1], sz.c[0]);
-    const float inv_vol = __fdiv_rn(1.0f, __fmul_rn(__fmul_rn(hx, hy), hz));
-    const int nnx = sx.n, nnxy = sx.n * sy.n;
-    const int ex = cell_of(x, sx.c[0], hx, sx.n - 1), ey = cell_of(y, sy.c[0], hy, sy.n - 1), ez = cell_of(z, sz.c[0], hz, sz.n - 1);
-    const float ax0 = __fsub_rn(sx.c[ex + 1], x), ax1 = __fsub_rn(x, sx.c[ex]);
-    const float ay0 = __fsub_rn(sy.c[ey + 1], y), ay1 = __fsub_rn(y, sy.c[ey]);
-    const float az0 = __fsub_rn(sz.c[ez + 1], z), az1 = __fsub_rn(z, sz.c[ez]);
-    float N[8];
-    N[0] = __fmul_rn(__fmul_rn(__fmul_rn(ax0, ay0), az0), inv_vol);
-    N[1] = __fmul_rn(__fmul_rn(__fmul_rn(ax1, ay0), az0), inv_vol);
-    N[2] = __fmul_rn(__fmul_rn(__fmul_rn(ax1, ay1), az0), inv_vol);
-    N[3] = __fmul_rn(__fmul_rn(__fmul_rn(ax0, ay1), az0), inv_vol);
-    N[4] = __fmul_rn(__fmul_rn(__fmul_rn(ax0, ay0), az1), inv_vol);
-    N[5] = __fmul_rn(__fmul_rn(__fmul_rn(ax1, ay0), az1), inv_vol);
-    N[6] = __fmul_rn(__fmul_rn(__fmul_rn(ax1, ay1), az1), inv_vol);
-    N[7] = __fmul_rn(__fmul_rn(__fmul_rn(ax0, ay1), az1), inv_vol);
-    bool valid = true;
-#pragma unroll
-    for (int a = 0; a < 8; ++a) valid = valid && (N[a] >= -1e-2f) && (N[a] <= 1.0f + 1e-2f);
-    if (!valid) return 0.f;
-    const long long b = ex + (long long)ey * nnx + (long long)ez * nnxy;
-    const long long nd[8] = {b, b + 1, b + 1 + nnx, b + nnx, b + nnxy, b + 1 + nnxy, b + 1 + nnx + nnxy, b + nnx + nnxy};
-    float acc = 0.f;
-#pragma unroll
-    for (int a = 0; a < 8; ++a) acc = __fadd_rn(acc, __fmul_rn(fminf(fmaxf(N[a], 0.f), 1.f), u[nd[a]]));
-    return acc;
-}
 __global__ void shift_window_kernel(const ShiftParams p) {
-    const int j = blockIdx.y, k = blockIdx.z;  // blockIdx.y / .z = target row / plane
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.ntx; i += gridDim.x * blockDim.x) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // blockIdx.y = group of ROWS3 target rows, blockIdx.z = target plane
+    if (i >= p.ntx) return;
+    const int k = blockIdx.z;
+    const float x = p.tx[i], z = p.tz[k];
+    const SrcGeom g1 = geom_of(p.ax, p.ay, p.az), go = geom_of(p.ox, p.oy, p.oz);
+    const Ax1 X1 = ax1_of(p.ax, g1.hx, x), Z1 = ax1_of(p.az, g1.hz, z);
+    const Ax1 Xo = ax1_of(p.ox, go.hx, x), Zo = ax1_of(p.oz, go.hz, z);
+    SrcGeom gm = go;
+    Ax1 Xm = Xo, Zm = Zo;
+    if (p.Tpm) {
+        gm = geom_of(p.mx, p.my, p.mz);
+        Xm = ax1_of(p.mx, gm.hx, x);
+        Zm = ax1_of(p.mz, gm.hz, z);
+    }
+    const int j1 = min(p.nty, (int)(blockIdx.y + 1) * ROWS3);
+    for (int j = blockIdx.y * ROWS3; j < j1; ++j) {
+        const float y = p.ty[j];
         const size_t w = ((size_t)k * p.nty + j) * p.ntx + i;
-        const float x = p.tx[i], y = p.ty[j], z = p.tz[k];
-        const float tp = trilinear_at(p.ox, p.oy, p.oz, p.Tpo, x, y, z);
-        const float t1 = trilinear_at(p.ax, p.ay, p.az, p.T1, x, y, z);
+        const float tp = tri_eval<false>(p.Tpo, nullptr, 1.f, 0.f, go, Xo, ax1_of(p.oy, go.hy, y), Zo);
+        const float t1 = tri_eval<false>(p.T1, nullptr, 1.f, 0.f, g1, X1, ax1_of(p.ay, g1.hy, y), Z1);
         float rest = tp;
-        if (p.Tpm) rest = __fadd_rn(trilinear_at(p.mx, p.my, p.mz, p.Tpm, x, y, z), tp);  // T1on3 + (Tp2on3 + Tp3)
+        if (p.Tpm) rest = __fadd_rn(tri_eval<false>(p.Tpm, nullptr, 1.f, 0.f, gm, Xm, ax1_of(p.my, gm.hy, y), Zm), tp);  // T1on3 + (Tp2on3 + Tp3)
         p.Tp_new[w] = tp;
         p.T_new[w] = __fadd_rn(t1, rest);
     }
@@ -877,9 +949,12 @@ extern "C" int gomelt_interp_f32(const gomelt_interp_args_t* a, void* stream) {
     long long total = (long long)a->ntx * a->nty * a->ntz;
     if (a->faces_only)
         total = (long long)a->ntx * a->nty + 2LL * a->ntx * (a->ntz - 1) + 2LL * (a->nty - 2) * (a->ntz - 1);
-    if (!a->faces_only && a->nty <= 65535 && a->ntz <= 65535 && (a->nty > 1 || a->ntz > 1)) {
+    const long long src_nn = (long long)a->src[0].n * a->src[1].n * a->src[2].n;
+    if (!a->faces_only && !a->map_x && a->ntz <= 65535 && src_nn < 2000000000LL) {
         const int threads = a->ntx >= 256 ? 256 : (a->ntx >= 128 ? 128 : 64);
-        interp_kernel<<<dim3((a->ntx + threads - 1) / threads, a->nty, a->ntz), threads, 0, (cudaStream_t)stream>>>(p), count_launch();
+        const dim3 grid((a->ntx + threads - 1) / threads, (a->nty + ROWS3 - 1) / ROWS3, a->ntz);
+        if (a->u2) interp3_kernel<true><<<grid, threads, 0, (cudaStream_t)stream>>>(p), count_launch();
+        else interp3_kernel<false><<<grid, threads, 0, (cudaStream_t)stream>>>(p), count_launch();
     } else {
         interp_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p), count_launch();
     }
@@ -941,8 +1016,8 @@ extern "C" int gomelt_box_copy(const void* src, void* dst, int32_t elem_size, co
     }
     const long long total = (long long)nx * ny * nz;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool g3 = ny <= 65535 && nz <= 65535 && (ny > 1 || nz > 1);
-    const dim3 grid = g3 ? dim3((nx + 255) / 256, ny, nz) : dim3(grid_for(total, 256));
+    const bool g3 = nz <= 65535 && (ny > ROWS3 || nz > 1);
+    const dim3 grid = g3 ? dim3((nx + 255) / 256, (ny + ROWS3 - 1) / ROWS3, nz) : dim3(grid_for(total, 256));
     if (elem_size == 4)
         box_copy_kernel<float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, ix, iy, iz, nx, ny,
                                                      nz, big_nx, big_ny, scatter), count_launch();
@@ -1109,11 +1184,12 @@ extern "C" int gomelt_projected_source_f32(const gomelt_props_t* p, const gomelt
     coarse_source_table_batch_kernel<<<dim3((nmax + 63) / 64, 3, n), 64, 0, st>>>(
         fine[0].coords, fine[1].coords, fine[2].coords, fine[0].n, fine[1].n, fine[2].n, parent[0].coords, parent[1].coords,
         parent[2].coords, ncx, ncy, ncz, sb, 1.f / rsq, 1.f / dsq, rcoeff, dcoeff, tables), count_launch();
-    if (ncy > 65535 || ncz > 65535) {
-        set_error("gomelt_projected_source_f32: parent grid too large (ny, nz <= 65535)");
+    if (ncz > 65535) {
+        set_error("gomelt_projected_source_f32: parent grid too large (nz <= 65535)");
         return GOMELT_E_SIZE;
     }
-    rank_n_kernel<<<dim3((ncx + 255) / 256, ncy, ncz), 256, 0, st>>>(F, tables, ncx, ncy, ncz, sb, accumulate), count_launch();
+    rank_n_kernel<<<dim3((ncx + 255) / 256, (ncy + ROWS3 - 1) / ROWS3, ncz), 256, 0, st>>>(F, tables, ncx, ncy, ncz, sb,
+                                                                                       accumulate), count_launch();
     return check_launch("gomelt_projected_source_f32");
 }
 
@@ -1144,10 +1220,11 @@ extern "C" int gomelt_shift_window_f32(const gomelt_shift_args_t* a, void* strea
     p.Tpo = a->Tp_old;
     p.tx = a->tx; p.ty = a->ty; p.tz = a->tz; p.ntx = a->ntx; p.nty = a->nty; p.ntz = a->ntz;
     p.Tp_new = a->Tp_new; p.T_new = a->T_new;
-    if (a->nty > 65535 || a->ntz > 65535) {
-        set_error("gomelt_shift_window_f32: target grid too large (nty, ntz <= 65535)");
+    if (a->ntz > 65535) {
+        set_error("gomelt_shift_window_f32: target grid too large (ntz <= 65535)");
         return GOMELT_E_SIZE;
     }
-    shift_window_kernel<<<dim3((a->ntx + 255) / 256, a->nty, a->ntz), 256, 0, (cudaStream_t)stream>>>(p), count_launch();
+    shift_window_kernel<<<dim3((a->ntx + 255) / 256, (a->nty + ROWS3 - 1) / ROWS3, a->ntz), 256, 0, (cudaStream_t)stream>>>(p),
+        count_launch();
     return check_launch("gomelt_shift_window_f32");
 }

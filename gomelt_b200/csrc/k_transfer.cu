@@ -573,6 +573,9 @@ struct TileParams {
     int G;                       // threads per parent cell (power of two)
     float* cellsum;
 };
+// floor(n / d) for the small non-negative integers of a tile (n < 4096, d <= 256) without an integer division:
+// n * (1/d) carries a relative error of 1e-7, the half-step offset keeps the truncation on the right side
+__device__ __forceinline__ int fastdiv(int n, float inv_d, float half_step) { return (int)(__int2float_rn(n) * inv_d + half_step); }
 constexpr int TILE_NODECAP = 2304;
 constexpr int TILE_THREADS = 256;
 
@@ -586,8 +589,10 @@ __global__ void __launch_bounds__(TILE_THREADS) project_tile_kernel(const TilePa
     const int bnx = p.fsx[ci1] - ex0 + 1, bny = p.fsy[cj1] - ey0 + 1, bnz = p.fsz[ck1] - ez0 + 1;  // node box
     const int bn = bnx * bny * bnz;
     const long long fnxy = (long long)p.fnx * p.fny;
+    const int bxy = bnx * bny;
+    const float inv_bxy = 1.0f / (float)bxy, hs_bxy = 0.5f * inv_bxy, inv_bnx = 1.0f / (float)bnx, hs_bnx = 0.5f * inv_bnx;
     for (int n = tid; n < bn; n += TILE_THREADS) {
-        const int k = n / (bnx * bny), r = n - k * (bnx * bny), j = r / bnx, i = r - j * bnx;
+        const int k = fastdiv(n, inv_bxy, hs_bxy), r = n - k * bxy, j = fastdiv(r, inv_bnx, hs_bnx), i = r - j * bnx;
         const long long g = (ex0 + i) + (long long)(ey0 + j) * p.fnx + (long long)(ez0 + k) * fnxy;
         float a = __ldg(p.A + g);
         if (p.A2) a -= __ldg(p.A2 + g);
@@ -613,10 +618,12 @@ __global__ void __launch_bounds__(TILE_THREADS) project_tile_kernel(const TilePa
         const int fy0 = p.fsy[cj0 + lj], fy1 = p.fsy[cj0 + lj + 1];
         const int fz0 = p.fsz[ck0 + lk], fz1 = p.fsz[ck0 + lk + 1];
         const int nex = fx1 - fx0, ney = fy1 - fy0, nel = nex * ney * (fz1 - fz0);
+        const int nexy = nex * ney;
+        const float inv_nexy = 1.0f / (float)nexy, hs_nexy = 0.5f * inv_nexy, inv_nex = 1.0f / (float)nex, hs_nex = 0.5f * inv_nex;
         const float g3 = 0.57735026918962576f;
         const float Nlo = 0.5f * (1.f + g3), Nhi = 0.5f * (1.f - g3);
         for (int t = gl; t < nel; t += p.G) {
-            const int ez = t / (nex * ney), tr = t - ez * (nex * ney), ey = tr / nex, ex = tr - ey * nex;
+            const int ez = fastdiv(t, inv_nexy, hs_nexy), tr = t - ez * nexy, ey = fastdiv(tr, inv_nex, hs_nex), ex = tr - ey * nex;
             const int gx_ = fx0 + ex, gy_ = fy0 + ey, gz_ = fz0 + ez;  // global fine element
             const int b = (gx_ - ex0) + (gy_ - ey0) * bnx + (gz_ - ez0) * bnx * bny;
             // corner (bx, by, bz) at b + bx + by * bnx + bz * bnx * bny
@@ -771,7 +778,8 @@ __global__ void __launch_bounds__(TILE_THREADS) project_tile_kernel(const TilePa
         const int cell = o >> 3, c = o & 7;
         float s = 0.f;
         for (int g = 0; g < p.G; ++g) s += s_part[cell * p.G + g][c];
-        const int lk = cell / (tcx * tcy), lr = cell - lk * (tcx * tcy), lj = lr / tcx, li = lr - lj * tcx;
+        const int lk = fastdiv(cell, 1.0f / (float)(tcx * tcy), 0.5f / (float)(tcx * tcy)), lr = cell - lk * (tcx * tcy);
+        const int lj = fastdiv(lr, 1.0f / (float)tcx, 0.5f / (float)tcx), li = lr - lj * tcx;
         const long long gc = (ci0 + li) + (long long)(cj0 + lj) * p.ncx + (long long)(ck0 + lk) * p.ncx * p.ncy;
         p.cellsum[gc * 8 + c] = s;
     }

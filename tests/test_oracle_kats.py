@@ -135,3 +135,32 @@ def test_K7_projected_source_conserves_the_total_load():
     tot = [float(np.sum(np.asarray(a, np.float64))) for a in (Fc, Fm, Ff)]
     assert tot[2] > 0
     assert abs(tot[0] - tot[2]) <= 1e-5 * tot[2] and abs(tot[1] - tot[2]) <= 1e-5 * tot[2], tot
+
+
+def test_torch_cpu_port_matches_the_numpy_oracle():
+    """oracle/torch_cpu.py (the multi-threaded CPU baseline of bench.py: the reference's algorithm as dense tensor
+    operations) against the NumPy oracle on a Level-3 substep with a melt pool: temperatures within 1e-5 relative (the
+    scatter sums run in a different order), state bit-exact."""
+    import torch
+
+    from oracle import computeFunctions as cF
+    from oracle.torch_cpu import L3SubstepCPU
+    from oracle.util import make_level, smooth_field
+
+    props_in = {"laser_radius": 0.1, "laser_depth": 0.1, "laser_absorptivity": 0.45, "T_amb": 298.15, "T_solidus": 1533,
+                "T_liquidus": 1609, "h_conv": 1.5e-05, "emissivity": 0.3, "latent_heat_evap": 6457000.0}
+    P = cF.SetupProperties(props_in)
+    lv = make_level((24, 18, 7), ((1.0, 1.48), (1.0, 1.36), (-0.14, 0.0)))
+    rng = np.random.default_rng(3)
+    T0 = smooth_field(lv, rng)
+    S1 = (rng.random(lv["nn"]) > 0.5).astype(np.float32)
+    v, dt, power = np.array([1.2, 1.15, 0.0], np.float32), 1e-5, 285.0
+    S1r, _, k, rc = cF.computeStateProperties(T0, S1, P, 0)
+    F = cF.computeSourcesL3(lv, v, (0, lv["ne"], 0, 0, lv["nn"]), P, power)
+    F = cF.computeConvRadBC(lv, T0, lv["ne"], lv["nn"], P, F)
+    want = np.maximum(np.float32(P["T_amb"]), cF.solveMatrixFreeFE(lv, lv["nn"], lv["ne"], k, rc, dt, T0, F, 0))
+    port = L3SubstepCPU(lv, P, threads=2)
+    got, S1g = port.substep(torch.from_numpy(T0), torch.from_numpy(S1), v, power, dt)
+    assert (T0 >= P["T_liquidus"]).sum() > 10
+    assert np.array_equal(S1g.numpy(), S1r)
+    assert float(np.max(np.abs(got.numpy() - want) / np.abs(want))) <= 1e-5

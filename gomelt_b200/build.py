@@ -68,7 +68,8 @@ def _digest(files=None):
 
 
 def lib_path():
-    return os.path.join(LIBDIR, LIBNAME)
+    # GOMELT_LIB_PATH: load another build of the library (development A/B of kernel variants on one GPU box)
+    return os.environ.get("GOMELT_LIB_PATH") or os.path.join(LIBDIR, LIBNAME)
 
 
 def _read(path):

@@ -132,9 +132,7 @@ static bool make_field_tmaps(StepParams& sp) {
 
 template <int RY, int FEAT, int MINB = 1>
 static void launch_v3(const StepParams& sp, int nch, cudaStream_t st) {
-    // Level-1 shapes: one extra z layer of CTAs writes the Dirichlet constants of the five faces (see the kernel)
-    const int face_layer = (sp.feat & K1F_BCCONST) ? 1 : 0;
-    dim3 grid((sp.nx - 2 + 2 * K1_TX - 1) / (2 * K1_TX), (sp.ny - 2 + RY - 1) / RY, nch + face_layer);
+    dim3 grid((sp.nx - 2 + 2 * K1_TX - 1) / (2 * K1_TX), (sp.ny - 2 + RY - 1) / RY, nch);
     if constexpr ((FEAT & K1F_TMA) != 0) {  // 8 resident warps x 20 KB: ask for the large shared-memory carve-out once
         static const cudaError_t carve = cudaFuncSetAttribute(level_step_v3<RY, FEAT, MINB>,
                                                                cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -191,15 +189,19 @@ static bool try_launch_v3(StepParams& sp, int nch, cudaStream_t st) {
         default: return false;
     }
 #undef GM_V3
-    if (do_push) {
-        // legacy z-slab path: the neighbours' ghost planes also get the face constants of the boundary planes
-        if (f & K1F_BCCONST) {
+    // Level-1 Dirichlet constants (the step never stores a face node): with halo_sync the exchange kernel writes them
+    // (launch_step), else face_const_kernel - which, on the round-1 z-slab path, also fills the neighbours' ghost planes
+    if ((f & K1F_BCCONST) && !sp.hsync) {
+        {
             const long long n = (long long)(2 * sp.nx + 2 * sp.ny) * (sp.zend - sp.zbeg) + (sp.zbeg == 0 ? (long long)sp.nx * sp.ny : 0);
             const int cap = 4 * sm_count();
             const int blocks = (int)((n + 255) / 256 < cap ? (n + 255) / 256 : cap);
             face_const_kernel<<<blocks, 256, 0, st>>>(sp.Tout, sp.nx, sp.ny, sp.nz, sp.zbeg, sp.zend, sp.bc[0], sp.bc[1], sp.bc[2],
-                                                      sp.bc[3], sp.bc[4], sp.peer_lo, sp.peer_hi), count_launch();
+                                                      sp.bc[3], sp.bc[4], do_push ? sp.peer_lo : nullptr,
+                                                      do_push ? sp.peer_hi : nullptr), count_launch();
         }
+    }
+    if (do_push) {
         const int plane = sp.nx * sp.ny;
         dim3 grid((plane / 4 + 255) / 256, 2);
         halo_push_kernel<<<grid, 256, 0, st>>>(sp.Tout, plane, sp.zbeg, sp.zend - 1, sp.peer_lo, sp.peer_hi), count_launch();
@@ -218,16 +220,23 @@ static int launch_step(StepParams& sp, cudaStream_t st) {
     sp.feat &= ~K1F_PEER;
     const int rc = launch_kernels(sp, st);
     if (rc) return rc;
+    // faces: by the exchange kernel when the fast kernel ran (the general kernel writes its own Dirichlet faces)
+    const bool faces_here = (sp.feat & K1F_BCCONST) && sp.ran_v3;
     const int blocks = sm_count();  // per plane: two co-resident blocks of the exchange per SM
     halo_exchange_kernel<<<dim3(blocks, 2), HALO_THREADS, 0, st>>>(sp.Tout, sp.nx, sp.ny, sp.zbeg, sp.zend - 1, plo, phi, sp.bc[0],
                                                                   sp.bc[1], sp.bc[2], sp.bc[3], sp.hsync, sp.hsync_lo, sp.hsync_hi,
-                                                                  (unsigned)blocks * (sp.hseq + 1u)), count_launch();
+                                                                  (unsigned)blocks * (sp.hseq + 1u), faces_here ? sp.Tout : nullptr, sp.nz,
+                                                                  sp.zbeg, sp.zend, sp.bc[4]), count_launch();
     return check_launch("gomelt_level_step_f32 (halo exchange)");
 }
 
 static int launch_kernels(StepParams& sp, cudaStream_t st) {
     const int nch = (sp.zend - sp.zbeg + sp.zchunk - 1) / sp.zchunk;
-    if (try_launch_v3(sp, nch, st)) return check_launch("gomelt_level_step_f32");
+    sp.ran_v3 = 0;
+    if (try_launch_v3(sp, nch, st)) {
+        sp.ran_v3 = 1;
+        return check_launch("gomelt_level_step_f32");
+    }
     constexpr int RY = 4, WPB = 1;  // one warp per CTA: warps are independent, finest SM balance
     const int f = sp.feat;
     if (GM_DEV_SWITCH("GOMELT_K1_GENERIC", 0)) {

@@ -259,31 +259,6 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
     const int qa = ((own && ia >= x_new) || ia == 0) ? 1 : 0, qb = ((own && ib >= x_new) || ib == nx - 1) ? 1 : 0;
     const int P = nx * ny;
     const int za = p.zbeg + blockIdx.z * p.zchunk;
-    if (za >= p.zend) {
-        // extra z layer of the grid (Level-1 shapes, K1F_BCCONST): assignBCs cF:1568-1595 - the Dirichlet constants on
-        // the five faces of T_out, planes [zbeg, zend), order y-, y+, x-, x+, z- (the later face wins on shared edges).
-        // The step never stores a face node, so these CTAs are independent of the stencil CTAs of the same launch.
-        const int per_plane = 2 * nx + 2 * ny;
-        const long long nside = (long long)per_plane * (p.zend - p.zbeg);
-        const long long nbot = (p.zbeg == 0) ? (long long)P : 0;
-        const long long stride = (long long)gridDim.x * gridDim.y * 32;
-        for (long long t = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 32 + lane; t < nside + nbot; t += stride) {
-            if (t < nside) {
-                const int z = p.zbeg + (int)(t / per_plane), q = (int)(t % per_plane);
-                if (z == 0) continue;  // the bottom plane is written whole below
-                int i, j;
-                float v;
-                if (q < nx) { i = q; j = 0; v = (i == 0) ? p.bc[2] : (i == nx - 1) ? p.bc[3] : p.bc[0]; }
-                else if (q < 2 * nx) { i = q - nx; j = ny - 1; v = (i == 0) ? p.bc[2] : (i == nx - 1) ? p.bc[3] : p.bc[1]; }
-                else if (q < 2 * nx + ny) { i = 0; j = q - 2 * nx; v = p.bc[2]; }
-                else { i = nx - 1; j = q - 2 * nx - ny; v = p.bc[3]; }
-                p.Tout[(size_t)z * P + (size_t)j * nx + i] = v;
-            } else {
-                p.Tout[t - nside] = p.bc[4];
-            }
-        }
-        return;
-    }
     const int zb = min(p.zend, za + p.zchunk);  // this warp finalises node planes [za, zb)
     const int lfirst = max(za - 1, 0);
     const int llast = min(min(zb, nz - 1), nzl - 1);  // last plane that carries data
@@ -865,7 +840,32 @@ __global__ void __launch_bounds__(HALO_THREADS) halo_exchange_kernel(const float
                                                                       float* __restrict__ peer_lo, float* __restrict__ peer_hi,
                                                                       float by0, float by1, float bx0, float bx1,
                                                                       unsigned* sync_mine, unsigned* sync_lo, unsigned* sync_hi,
-                                                                      unsigned need) {
+                                                                      unsigned need, float* __restrict__ Tw, int nz, int zbeg,
+                                                                      int zend, float bz0) {
+    // assignBCs cF:1568-1595 on the owned planes of T_out (the step never stores a face node): y-, y+, x-, x+, z-, the
+    // later face wins on shared edges.  Folded into this launch - a never-taken "am I a face CTA" branch inside the
+    // stencil kernel costs it 5 % (measured), a separate launch costs a launch.
+    if (Tw) {
+        const int per_plane = 2 * nx + 2 * ny;
+        const long long nside = (long long)per_plane * (zend - zbeg);
+        const long long nbot = (zbeg == 0) ? (long long)nx * ny : 0;
+        const long long stride = (long long)gridDim.x * gridDim.y * HALO_THREADS;
+        for (long long t = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * HALO_THREADS + threadIdx.x; t < nside + nbot; t += stride) {
+            if (t < nside) {
+                const int z = zbeg + (int)(t / per_plane), q = (int)(t % per_plane);
+                if (z == 0) continue;
+                int i, j;
+                float v;
+                if (q < nx) { i = q; j = 0; v = (i == 0) ? bx0 : (i == nx - 1) ? bx1 : by0; }
+                else if (q < 2 * nx) { i = q - nx; j = ny - 1; v = (i == 0) ? bx0 : (i == nx - 1) ? bx1 : by1; }
+                else if (q < 2 * nx + ny) { i = 0; j = q - 2 * nx; v = bx0; }
+                else { i = nx - 1; j = q - 2 * nx - ny; v = bx1; }
+                Tw[(size_t)z * nx * ny + (size_t)j * nx + i] = v;
+            } else {
+                Tw[t - nside] = bz0;
+            }
+        }
+    }
     const int which = blockIdx.y;
     float* __restrict__ dst = which == 0 ? peer_lo : peer_hi;
     unsigned* peer_sync = which == 0 ? sync_lo : sync_hi;

@@ -79,6 +79,7 @@ class ProjectArgs(C.Structure):
         ("coef_props", C.POINTER(Props)),
         ("wtab_x", C.c_void_p), ("wtab_y", C.c_void_p), ("wtab_z", C.c_void_p),
         ("rmax", C.c_int32 * 3), ("hf", C.c_float * 3), ("hc", C.c_float * 3),
+        ("uniform_off", C.c_int32 * 3),
     ]
 
 
@@ -109,6 +110,7 @@ class Pair(C.Structure):
         ("elems_per_cell_hint", C.c_int32),
         ("wtab_x", C.c_void_p), ("wtab_y", C.c_void_p), ("wtab_z", C.c_void_p),
         ("rmax", C.c_int32 * 3),
+        ("uniform_off", C.c_int32 * 3),
     ]
 
 

@@ -224,7 +224,7 @@ def _pair_cells_build(fine, parent):
     torch = _torch()
     g = F32(0.57735026918962576)
     lo, hi = F32(0.5) * (F32(1) + g), F32(0.5) * (F32(1) - g)
-    cell0, ncell, first, hint, wtab, rmax = [], [], [], 1, [], []
+    cell0, ncell, first, hint, wtab, rmax, off = [], [], [], 1, [], [], []
     for d in range(3):
         xf = np.asarray(fine["node_coords"][d], F32)
         xc = np.asarray(parent["node_coords"][d], F32)
@@ -239,6 +239,11 @@ def _pair_cells_build(fine, parent):
         first.append(_CACHE.get(fs, np.int32))
         hint *= int(np.diff(fs).max())
         rmax.append(int(np.diff(fs).max()))
+        # nested grouping (gomelt_project_args_t.uniform_off): cell i holds the elements [i r - off, (i + 1) r - off)
+        r_d, n_el = rmax[-1], xf.size - 1
+        o_d = r_d - int(fs[1]) if fs.size > 2 else 0
+        want = np.clip(np.arange(fs.size, dtype=np.int64) * r_d - o_d, 0, n_el)
+        off.append(o_d if (0 <= o_d < r_d and np.array_equal(want, fs)) else -1)
         # parent shape-function factors at both Gauss points of every fine element, each in the parent cell that holds
         # that Gauss point (cF:1283-1335): (x1 - xq0, xq0 - x0, x1 - xq1, xq1 - x0) - see gomelt_project_args_t.wtab_*
         e1 = np.clip(np.floor((xq1 - xc[0]) / hc).astype(np.int64), 0, xc.size - 2)
@@ -246,6 +251,7 @@ def _pair_cells_build(fine, parent):
         wtab.append(_CACHE.get(tab.reshape(-1), np.float32))
     cellsum = torch.empty(ncell[0] * ncell[1] * ncell[2] * 8, device="cuda", dtype=torch.float32)
     return {"cell0": cell0, "ncell": ncell, "first": first, "hint": hint, "cellsum": cellsum, "wtab": wtab, "rmax": rmax,
+            "off": off,
             "hf": [float(F32(v)) for v in fine["h"]], "hc": [float(F32(v)) for v in parent["h"]],
             "fine": _coords(fine["node_coords"]), "parent": _coords(parent["node_coords"])}
 
@@ -388,6 +394,7 @@ def _fill_pair(dst, cells):
     dst.wtab_x, dst.wtab_y, dst.wtab_z = (t.data_ptr() for t in cells["wtab"])
     for d in range(3):
         dst.rmax[d] = int(cells["rmax"][d])
+        dst.uniform_off[d] = int(cells["off"][d])
 
 
 def _fill_overlap(dst, L):

@@ -192,7 +192,7 @@ int project(const Ctx& c, const gomelt_pair_t& pr, float* cellsum, const gomelt_
     a.first_x = pr.first_x; a.first_y = pr.first_y; a.first_z = pr.first_z;
     a.elems_per_cell_hint = pr.elems_per_cell_hint;
     a.wtab_x = pr.wtab_x; a.wtab_y = pr.wtab_y; a.wtab_z = pr.wtab_z;
-    for (int d = 0; d < 3; ++d) a.rmax[d] = pr.rmax[d];
+    for (int d = 0; d < 3; ++d) { a.rmax[d] = pr.rmax[d]; a.uniform_off[d] = pr.uniform_off[d]; }
     const gomelt_grid_t& gf = (fa == c.a3) ? c.h->L3.grid : c.h->L2.grid;
     const gomelt_grid_t& gp = (pa == c.a1) ? c.h->L1.grid : c.h->L2.grid;
     a.hf[0] = gf.hx; a.hf[1] = gf.hy; a.hf[2] = gf.hz;

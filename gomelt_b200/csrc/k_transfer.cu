@@ -785,6 +785,326 @@ __global__ void __launch_bounds__(TILE_THREADS) project_tile_kernel(const TilePa
     }
 }
 
+// ---- K3, marching form (project_march_kernel): the fast path for nested windows ------------------------------------------
+// Every window pair of a GO-MELT run nests with an integer element ratio in x and y (r_x, r_y fine elements per parent
+// cell; in z the counts may differ from cell to cell: whole powder layers shift the windows, so z keeps the fsz table).
+// There the tile kernel's ~400 instructions per fine node (staging, index arithmetic, 8 shared-memory reads and ~150
+// FP operations per element, a serial in-CTA reduction) are the whole cost of a projection - it runs at 8 % of the HBM
+// roofline.  This form has no staging and no synchronisation:
+//   * a warp owns epw = floor(31 / r_x) r_x element columns x RY element rows (RY a multiple of r_y) and marches in z
+//     through a chunk of parent cells; lane l loads node column x0 + l of the RY + 1 node rows of the next plane
+//     (coalesced), evaluates the nodal coefficient there once, and gets column l + 1 by one shuffle per row and field;
+//   * with M_d[c][b] = sum_q W_d[q][c] N[q][b] (the parent's hat factor times the fine shape value, summed over the two
+//     Gauss points of the axis: a 2 x 2 matrix per fine element and axis, formed from the wtab entries) both terms are
+//     tensor products of 1-D operators on the element's 2 x 2 x 2 corner values,
+//         MASS  out[c] = f cbar (Mx (x) My (x) Mz) a,       GRAD  out[c] = f kbar (Dx (x) My (x) Mz + Mx (x) Dy (x) Mz + Mx (x) My (x) Dz) a
+//     (D = corner difference with the sign of the parent corner; the Gauss sum along a derivative axis is the factor 2),
+//     so everything that involves one node plane only (the x / y stages) is computed once per plane and shared by the
+//     element below and the element above, and the per-element work is the z stage, the element-mean coefficient and
+//     12 (GRAD: per term, before the signs) or 8 (MASS) accumulations - ~50 FP operations per element instead of ~150;
+//   * the sums of a parent cell stay in registers until the march leaves the cell (fsz), then the r_x lanes of the cell
+//     are added by a fixed shuffle tree and one lane stores the 8 corner sums: deterministic, no atomics.
+struct MarchParams {
+    int fnx, fny, fnz;
+    const float* A;
+    const float* A2;
+    const float* coef;
+    const float* cT;
+    const float* cS1;
+    long long cnsub;
+    PropK pk;
+    float sw;                    // MASS: scale * wq ; GRAD: wq
+    float inv_hfx, inv_hfy, inv_hfz, inv_cvol;
+    const float4* wx;
+    const float4* wy;
+    const float4* wz;
+    const int* fsz;              // first fine element (z) of parent cell c0z + i
+    int ncx, ncy, ncz;
+    int rx, ry;                  // fine elements per parent cell in x, y (uniform)
+    int offx, offy;              // fine elements missing from the first parent cell (a window that starts inside a cell)
+    int epw;                     // element columns per warp: (31 / rx) * rx
+    int czn;                     // parent z-cells per chunk (blockIdx.z)
+    float* cellsum;
+};
+constexpr int MARCH_WARPS = 4;
+
+struct M22 { float m00, m01, m10, m11; };  // M[c][b]
+__device__ __forceinline__ M22 m_of(const float4 w) {  // w = (W[q0][c0], W[q0][c1], W[q1][c0], W[q1][c1]); N[q0] = (lo, hi), N[q1] = (hi, lo)
+    const float g3 = 0.57735026918962576f;
+    const float lo = 0.5f * (1.f + g3), hi = 0.5f * (1.f - g3);
+    M22 m;
+    m.m00 = w.x * lo + w.z * hi; m.m01 = w.x * hi + w.z * lo;
+    m.m10 = w.y * lo + w.w * hi; m.m11 = w.y * hi + w.w * lo;
+    return m;
+}
+
+// FAST: the steppers' call shape (coefficient evaluated from (T, S1); A2 given exactly in MASS mode) without the run-time
+// selects of the general shape.
+template <int MODE, int RY, int MC, bool FAST>   // RY element rows per thread = MC parent y-cells of r_y = RY / MC rows each
+__global__ void __launch_bounds__(32 * MARCH_WARPS) project_march_kernel(const MarchParams p) {
+    constexpr int NR = RY + 1;
+    constexpr int ry = RY / MC;
+    constexpr int NACC = MODE == 1 ? 8 : 12;
+    static_assert(RY % MC == 0, "a band holds whole parent cells");
+    const int lane = threadIdx.x & 31;
+    const int wchunk = blockIdx.x * MARCH_WARPS + (threadIdx.x >> 5);
+    const int cpw = p.epw / p.rx;                 // parent x-cells per warp
+    if (wchunk * cpw >= p.ncx) return;            // (whole warp)
+    const int cj0 = blockIdx.y * MC;
+    const int ck0 = blockIdx.z * p.czn, ck1 = min(ck0 + p.czn, p.ncz);
+    const int ex = wchunk * p.epw + lane - p.offx;    // element column = node column of this lane
+    const bool colv = lane < p.epw && ex >= 0 && ex < p.fnx - 1;
+    const int ic = min(max(ex, 0), p.fnx - 1);
+    const int seg = lane % p.rx;                  // lane within its parent cell
+    const int ci = wchunk * cpw + lane / p.rx;
+    const M22 Mx = m_of(__ldg(p.wx + min(max(ex, 0), p.fnx - 2)));
+    M22 My[RY];
+    float rowv[RY];                               // 1 where the element row exists (first / last parent cell may be partial)
+    int idx[NR];                                  // flat node index of this lane's node in each row of the current plane
+    const int Pi = p.fnx * p.fny;
+    const int kz0 = __ldg(p.fsz + ck0), kz1 = __ldg(p.fsz + ck1);   // node planes kz0 .. kz1
+#pragma unroll
+    for (int r = 0; r < NR; ++r) idx[r] = kz0 * Pi + min(max(cj0 * ry + r - p.offy, 0), p.fny - 1) * p.fnx + ic;
+#pragma unroll
+    for (int r = 0; r < RY; ++r) {
+        const int j = cj0 * ry + r - p.offy;
+        My[r] = m_of(__ldg(p.wy + min(max(j, 0), p.fny - 2)));
+        rowv[r] = (j >= 0 && j < p.fny - 1) ? 0.125f : 0.f;   // (times the 1/8 of the element mean)
+    }
+    // carried from plane to plane: the node values (GRAD) and the in-plane stage results of every element row
+    struct Carry {
+        float ap[NR], anp[NR];                                // GRAD: node values (own column, next column)
+        float q0[RY], q1[RY], q2[RY], q3[RY], csp[RY];        // GRAD: Px[0], Px[1], Py[0], Py[1]; MASS: P[cx][cy] = q[cx * 2 + cy]
+    };
+    // raw node values of one plane: all loads of a plane are independent (one memory round trip per plane), and the next
+    // plane's are issued before the current plane is worked on
+    struct Raw { float a[NR], b[NR], t[NR], s[NR]; };
+    constexpr bool PREFETCH = RY <= 6;
+    float S[MC][NACC];                // running sums per parent y-cell of the band
+#pragma unroll
+    for (int t = 0; t < MC; ++t)
+#pragma unroll
+        for (int c = 0; c < NACC; ++c) S[t][c] = 0.f;
+    int ck = ck0;
+    int knext = __ldg(p.fsz + ck0 + 1);                              // plane at which cell ck is complete
+    const bool hasB = FAST ? MODE == 1 : p.A2 != nullptr, hasC = FAST ? false : p.coef != nullptr;
+    auto load_raw = [&](Raw& w) {   // the plane idx[] points at; then idx[] moves on
+#pragma unroll
+        for (int r = 0; r < NR; ++r) w.a[r] = __ldg(p.A + idx[r]);
+        if (hasB) {
+#pragma unroll
+            for (int r = 0; r < NR; ++r) w.b[r] = __ldg(p.A2 + idx[r]);
+        }
+        if (hasC) {
+#pragma unroll
+            for (int r = 0; r < NR; ++r) w.t[r] = __ldg(p.coef + idx[r]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                w.t[r] = __ldg(p.cT + idx[r]);
+                w.s[r] = __ldg(p.cS1 + idx[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < NR; ++r) idx[r] += Pi;
+    };
+    auto flush = [&]() {
+        // parent cell layer ck is complete: corner sums, x reduction over the cell's r_x lanes, store
+#pragma unroll
+        for (int t = 0; t < MC; ++t) {
+            float* s = S[t];
+            float o[8];    // hex8 local order: 0 (000) 1 (100) 2 (110) 3 (010) 4 (001) 5 (101) 6 (111) 7 (011), bits = (x, y, z)
+            if (MODE == 1) {
+                const float f = colv ? -(p.sw * p.inv_cvol) : 0.f;
+                // s[(cx * 2 + cy) * 2 + cz]
+                o[0] = f * s[0]; o[1] = f * s[4]; o[2] = f * s[6]; o[3] = f * s[2];
+                o[4] = f * s[1]; o[5] = f * s[5]; o[6] = f * s[7]; o[7] = f * s[3];
+            } else {
+                const float f = colv ? -(p.sw * p.inv_cvol) * 2.0f : 0.f;
+                const float gx = f * p.inv_hfx, gy = f * p.inv_hfy, gz = f * p.inv_hfz;
+                // out[cx][cy][cz] = sgn(cx) gx AX[cy][cz] + sgn(cy) gy AY[cx][cz] + sgn(cz) gz AZ[cx][cy]
+                float ax[4], ay[4], az[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { ax[c] = gx * s[c]; ay[c] = gy * s[4 + c]; az[c] = gz * s[8 + c]; }
+#define GM_OUT(cx, cy, cz) ((cx ? ax[cy * 2 + cz] : -ax[cy * 2 + cz]) + (cy ? ay[cx * 2 + cz] : -ay[cx * 2 + cz]) + (cz ? az[cx * 2 + cy] : -az[cx * 2 + cy]))
+                o[0] = GM_OUT(0, 0, 0); o[1] = GM_OUT(1, 0, 0); o[2] = GM_OUT(1, 1, 0); o[3] = GM_OUT(0, 1, 0);
+                o[4] = GM_OUT(0, 0, 1); o[5] = GM_OUT(1, 0, 1); o[6] = GM_OUT(1, 1, 1); o[7] = GM_OUT(0, 1, 1);
+#undef GM_OUT
+            }
+            for (int d = 1; d < p.rx; d <<= 1) {
+                const bool take = seg + d < p.rx;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float v = __shfl_down_sync(0xffffffffu, o[c], d);
+                    o[c] += take ? v : 0.f;
+                }
+            }
+            const int cj = cj0 + t;
+            if (seg == 0 && lane < p.epw && ci < p.ncx && cj < p.ncy) {
+                float4* dst = reinterpret_cast<float4*>(p.cellsum + (((long long)ck * p.ncy + cj) * p.ncx + ci) * 8);
+                dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+                dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+            }
+#pragma unroll
+            for (int c = 0; c < NACC; ++c) s[c] = 0.f;
+        }
+    };
+    // one node plane: cur = its raw values, cp = what the previous plane left, cn = what this plane leaves (the same
+    // object: every entry is read before it is overwritten)
+    auto plane = [&](int k, const Raw& cur, const Carry& cp, Carry& cn) {
+        // substrate nodes: flat id < cnsub (cF:2589-2590), as a threshold on idx[], which already points `ahead` planes
+        // past this one (its own load and, unless this is the last plane, the prefetch)
+        const int ahead = (PREFETCH && k < kz1) ? 2 : 1;
+        long long left = p.cnsub - (long long)k * Pi;
+        left = left < 0 ? 0 : (left > Pi ? Pi : left);
+        const int sub_thr = (int)left + (k + ahead) * Pi;
+        float a[NR], an[NR], cs2[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            a[r] = hasB ? cur.a[r] - cur.b[r] : cur.a[r];
+            if (hasC) {
+                cs2[r] = cur.t[r];
+            } else {
+                float kk, rr;
+                bool b1, b2;
+                node_props(p.pk, cur.t[r], cur.s[r], idx[r] < sub_thr, kk, rr, b1, b2);
+                cs2[r] = MODE == 1 ? rr : kk;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            an[r] = __shfl_down_sync(0xffffffffu, a[r], 1);
+            cs2[r] += __shfl_down_sync(0xffffffffu, cs2[r], 1);
+        }
+        const bool have_prev = k > kz0;
+        M22 Mz;
+        if (have_prev) Mz = m_of(__ldg(p.wz + (k - 1)));
+        if (MODE == 1) {
+            float tn0[NR], tn1[NR];   // x stage per node row: tn[cx] = Mx[cx][0] a + Mx[cx][1] an
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                tn0[r] = Mx.m00 * a[r] + Mx.m01 * an[r];
+                tn1[r] = Mx.m10 * a[r] + Mx.m11 * an[r];
+            }
+#pragma unroll
+            for (int t = 0; t < MC; ++t) {
+                float L[4] = {0.f, 0.f, 0.f, 0.f}, U[4] = {0.f, 0.f, 0.f, 0.f};   // sum over the cell's rows of cbar P, lower / upper plane
+#pragma unroll
+                for (int rr = 0; rr < ry; ++rr) {
+                    const int r = t * ry + rr;
+                    const float cs = cs2[r] + cs2[r + 1];
+                    // P[cx][cy] = My[cy][0] tn[r][cx] + My[cy][1] tn[r + 1][cx]
+                    const float p00 = My[r].m00 * tn0[r] + My[r].m01 * tn0[r + 1], p01 = My[r].m10 * tn0[r] + My[r].m11 * tn0[r + 1];
+                    const float p10 = My[r].m00 * tn1[r] + My[r].m01 * tn1[r + 1], p11 = My[r].m10 * tn1[r] + My[r].m11 * tn1[r + 1];
+                    if (have_prev) {
+                        const float cb = (cs + cp.csp[r]) * rowv[r];
+                        L[0] += cb * cp.q0[r]; L[1] += cb * cp.q1[r]; L[2] += cb * cp.q2[r]; L[3] += cb * cp.q3[r];
+                        U[0] += cb * p00; U[1] += cb * p01; U[2] += cb * p10; U[3] += cb * p11;
+                    }
+                    cn.q0[r] = p00; cn.q1[r] = p01; cn.q2[r] = p10; cn.q3[r] = p11; cn.csp[r] = cs;
+                }
+                if (have_prev) {
+                    float* s = S[t];   // s[(cx * 2 + cy) * 2 + cz] += Mz[cz][0] L + Mz[cz][1] U
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        s[2 * c] += Mz.m00 * L[c] + Mz.m01 * U[c];
+                        s[2 * c + 1] += Mz.m10 * L[c] + Mz.m11 * U[c];
+                    }
+                }
+            }
+        } else {
+            float tz0[NR], tz1[NR];   // z-difference, x stage per node row
+            if (have_prev) {
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    const float d = a[r] - cp.ap[r], dn = an[r] - cp.anp[r];
+                    tz0[r] = Mx.m00 * d + Mx.m01 * dn;
+                    tz1[r] = Mx.m10 * d + Mx.m11 * dn;
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < MC; ++t) {
+                // sums over the cell's rows of kbar times the in-plane stage results: x term [cy], y term [cx], lower / upper plane
+                float LX[2] = {0.f, 0.f}, UX[2] = {0.f, 0.f}, LY[2] = {0.f, 0.f}, UY[2] = {0.f, 0.f};
+                float* s = S[t];
+#pragma unroll
+                for (int rr = 0; rr < ry; ++rr) {
+                    const int r = t * ry + rr;
+                    const float cs = cs2[r] + cs2[r + 1];
+                    const float dx0 = an[r] - a[r], dx1 = an[r + 1] - a[r + 1];
+                    const float dy0 = a[r + 1] - a[r], dy1 = an[r + 1] - an[r];
+                    const float px0 = My[r].m00 * dx0 + My[r].m01 * dx1, px1 = My[r].m10 * dx0 + My[r].m11 * dx1;   // Px[cy]
+                    const float py0 = Mx.m00 * dy0 + Mx.m01 * dy1, py1 = Mx.m10 * dy0 + Mx.m11 * dy1;               // Py[cx]
+                    if (have_prev) {
+                        const float kb = (cs + cp.csp[r]) * rowv[r];
+                        LX[0] += kb * cp.q0[r]; LX[1] += kb * cp.q1[r]; UX[0] += kb * px0; UX[1] += kb * px1;
+                        LY[0] += kb * cp.q2[r]; LY[1] += kb * cp.q3[r]; UY[0] += kb * py0; UY[1] += kb * py1;
+                        // AZ[cx][cy] = s[8 + cx * 2 + cy] += kbar (My[cy][0] tz[r][cx] + My[cy][1] tz[r + 1][cx])
+                        const float k00 = kb * My[r].m00, k01 = kb * My[r].m01, k10 = kb * My[r].m10, k11 = kb * My[r].m11;
+                        s[8] += k00 * tz0[r] + k01 * tz0[r + 1]; s[9] += k10 * tz0[r] + k11 * tz0[r + 1];
+                        s[10] += k00 * tz1[r] + k01 * tz1[r + 1]; s[11] += k10 * tz1[r] + k11 * tz1[r + 1];
+                    }
+                    cn.q0[r] = px0; cn.q1[r] = px1; cn.q2[r] = py0; cn.q3[r] = py1; cn.csp[r] = cs;
+                }
+                if (have_prev) {
+                    // AX[cy][cz] = s[cy * 2 + cz], AY[cx][cz] = s[4 + cx * 2 + cz]: z stage once per cell and plane
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        s[2 * c] += Mz.m00 * LX[c] + Mz.m01 * UX[c];
+                        s[2 * c + 1] += Mz.m10 * LX[c] + Mz.m11 * UX[c];
+                        s[4 + 2 * c] += Mz.m00 * LY[c] + Mz.m01 * UY[c];
+                        s[4 + 2 * c + 1] += Mz.m10 * LY[c] + Mz.m11 * UY[c];
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < NR; ++r) { cn.ap[r] = a[r]; cn.anp[r] = an[r]; }
+        }
+        while (ck < ck1 && k == knext) {
+            flush();
+            ++ck;
+            if (ck < ck1) knext = __ldg(p.fsz + ck + 1);
+        }
+    };
+    Raw cur, nxt;
+    Carry cy;
+    load_raw(cur);
+    for (int k = kz0; k <= kz1; ++k) {
+        if (PREFETCH) {
+            if (k < kz1) load_raw(nxt);
+        } else if (k > kz0) {   // (the tall bands have no registers to spare for a second raw plane)
+            load_raw(cur);
+        }
+        plane(k, cur, cy, cy);
+        if (PREFETCH) cur = nxt;
+    }
+}
+
+template <int MODE, bool FAST>
+static bool launch_march_f(const MarchParams& mp, dim3 grid, cudaStream_t st) {
+    const dim3 blk(32 * MARCH_WARPS);
+    switch (mp.ry) {
+        case 1: project_march_kernel<MODE, 4, 4, FAST><<<grid, blk, 0, st>>>(mp); break;
+        case 2: project_march_kernel<MODE, 4, 2, FAST><<<grid, blk, 0, st>>>(mp); break;
+        case 3: project_march_kernel<MODE, 3, 1, FAST><<<grid, blk, 0, st>>>(mp); break;
+        case 4: project_march_kernel<MODE, 4, 1, FAST><<<grid, blk, 0, st>>>(mp); break;
+        case 5: project_march_kernel<MODE, 5, 1, FAST><<<grid, blk, 0, st>>>(mp); break;
+        case 6: project_march_kernel<MODE, 6, 1, FAST><<<grid, blk, 0, st>>>(mp); break;
+        case 8: project_march_kernel<MODE, 8, 1, FAST><<<grid, blk, 0, st>>>(mp); break;
+        case 10: project_march_kernel<MODE, 10, 1, FAST><<<grid, blk, 0, st>>>(mp); break;
+        default: return false;
+    }
+    count_launch();
+    return true;
+}
+template <int MODE>
+static bool launch_march(const MarchParams& mp, dim3 grid, cudaStream_t st) {
+    const bool fast = !mp.coef && ((MODE == 1) == (mp.A2 != nullptr));
+    return fast ? launch_march_f<MODE, true>(mp, grid, st) : launch_march_f<MODE, false>(mp, grid, st);
+}
+static inline int march_cells_per_band(int ry) { return ry == 1 ? 4 : (ry == 2 ? 2 : 1); }
+static inline bool march_ry_ok(int ry) { return ry == 1 || ry == 2 || ry == 3 || ry == 4 || ry == 5 || ry == 6 || ry == 8 || ry == 10; }
+
 // parent node (gi,gj,gk) of the box [c0, c0 + nc] (nodes) <- its <= 8 adjacent cells, increasing cell id
 __global__ void project_nodes_kernel(const float* __restrict__ cellsum, int c0x, int c0y, int c0z, int ncx, int ncy,
                                      int ncz, int pnx, int pny, float* __restrict__ V, int accumulate) {
@@ -1106,8 +1426,49 @@ extern "C" int gomelt_project_f32(const gomelt_project_args_t* a, void* stream) 
     const long long ncell = (long long)p.ncx * p.ncy * p.ncz;
     cudaStream_t st = (cudaStream_t)stream;
     bool tiled = a->wtab_x && a->wtab_y && a->wtab_z && a->rmax[0] >= 1 && a->rmax[1] >= 1 && a->rmax[2] >= 1;
+    // marching form: uniform integer ratio in x and y (every cell of the box holds exactly rmax fine elements: the counts
+    // sum to the number of fine elements), any grouping in z; elems_per_cell_hint < 0 asks for the tile kernel (A/B)
+    bool marched = false;
+    const int offx = a->uniform_off[0], offy = a->uniform_off[1];
+    const bool nest_x = offx > 0 ? offx < a->rmax[0] : (offx == 0 && (long long)a->rmax[0] * p.ncx == a->fine[0].n - 1);
+    const bool nest_y = offy > 0 ? offy < a->rmax[1] : (offy == 0 && (long long)a->rmax[1] * p.ncy == a->fine[1].n - 1);
+    const long long fnn = (long long)a->fine[0].n * a->fine[1].n * a->fine[2].n;
+    if (tiled && a->elems_per_cell_hint >= 0 && nest_x && nest_y && a->rmax[0] <= 31 && march_ry_ok(a->rmax[1]) &&
+        fnn + 2LL * a->fine[0].n * a->fine[1].n < 2147483647LL) {
+        MarchParams mp;
+        mp.fnx = a->fine[0].n; mp.fny = a->fine[1].n; mp.fnz = a->fine[2].n;
+        mp.A = a->A; mp.A2 = a->A2; mp.coef = a->coef; mp.cT = a->coef_T; mp.cS1 = a->coef_S1; mp.cnsub = a->coef_n_substrate;
+        if (!a->coef) mp.pk = fold_props(*a->coef_props);
+        mp.wx = reinterpret_cast<const float4*>(a->wtab_x); mp.wy = reinterpret_cast<const float4*>(a->wtab_y);
+        mp.wz = reinterpret_cast<const float4*>(a->wtab_z);
+        mp.fsz = a->first_z;
+        mp.ncx = p.ncx; mp.ncy = p.ncy; mp.ncz = p.ncz;
+        mp.rx = a->rmax[0]; mp.ry = a->rmax[1];
+        mp.offx = offx; mp.offy = offy;
+        mp.epw = (31 / mp.rx) * mp.rx;
+        const float wq = (a->hf[0] * a->hf[1] * a->hf[2]) * 0.125f;
+        mp.sw = a->mode == 1 ? a->scale * wq : wq;
+        mp.inv_hfx = 1.0f / a->hf[0]; mp.inv_hfy = 1.0f / a->hf[1]; mp.inv_hfz = 1.0f / a->hf[2];
+        mp.inv_cvol = 1.0f / ((a->hc[0] * a->hc[1]) * a->hc[2]);
+        mp.cellsum = a->cellsum;
+        const int cpw = mp.epw / mp.rx;
+        const int nwx = (p.ncx + cpw - 1) / cpw;
+        const int mc = march_cells_per_band(mp.ry);
+        const int nby = (p.ncy + mc - 1) / mc;
+        // z-chunks of whole parent cells: enough warps for ~2.5 resident sets of 8 per SM
+        const long long target = 20LL * sm_count();
+        long long nzc = (target + (long long)nwx * nby - 1) / ((long long)nwx * nby);
+        if (nzc > p.ncz) nzc = p.ncz;
+        if (nzc < 1) nzc = 1;
+        mp.czn = (int)((p.ncz + nzc - 1) / nzc);
+        const dim3 grid((nwx + MARCH_WARPS - 1) / MARCH_WARPS, nby, (p.ncz + mp.czn - 1) / mp.czn);
+        if (grid.y <= 65535u && grid.z <= 65535u)
+            marched = a->mode == 1 ? launch_march<1>(mp, grid, st) : launch_march<0>(mp, grid, st);
+    }
     TileParams tp;
-    if (tiled) {
+    if (marched) {
+        tiled = true;
+    } else if (tiled) {
         // parent cells per CTA: about 32 x 8 x 4 fine elements, the node box within the shared-memory capacity
         int pc[3] = {32 / a->rmax[0], 8 / a->rmax[1], 4 / a->rmax[2]};
         for (int d = 0; d < 3; ++d) pc[d] = pc[d] < 1 ? 1 : pc[d];
@@ -1144,7 +1505,7 @@ extern "C" int gomelt_project_f32(const gomelt_project_args_t* a, void* stream) 
     }
     if (tiled) {
         // (cellsum is complete: fall through to the node pass)
-    } else if (a->elems_per_cell_hint <= 16) {
+    } else if ((a->elems_per_cell_hint < 0 ? -a->elems_per_cell_hint : a->elems_per_cell_hint) <= 16) {
         const long long threads = ncell * 8;
         project_cells_kernel<8><<<(int)((threads + 127) / 128), 128, 0, st>>>(p), count_launch();
     } else {

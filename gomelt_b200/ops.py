@@ -269,7 +269,8 @@ def coarse_source_tables(props, fine_coords, parent_coords, laser_xyz, laserP, t
 def project(fine_coords, parent_coords, A, coef, V, cells, *, mode, scale=1.0, A2=None, accumulate=True, tiled=True,
             coef_from=None):
     """gomelt_project_f32.  ``cells`` = dict(cell0, ncell, first (3 int32 device arrays), cellsum, hint, wtab, rmax, hf,
-    hc).  ``tiled=False`` forces the general kernel (A/B).  ``coef_from`` = (props, T, S1, n_substrate) evaluates the
+    hc).  ``tiled=False`` forces the general kernel, ``tiled="tile"`` the shared-memory tile kernel instead of the marching
+    kernel that nested windows get (A/B and parity tests).  ``coef_from`` = (props, T, S1, n_substrate) evaluates the
     coefficient in the kernel (then ``coef`` is None)."""
     lib = _lib.load()
     a = _lib.ProjectArgs()
@@ -284,12 +285,13 @@ def project(fine_coords, parent_coords, A, coef, V, cells, *, mode, scale=1.0, A
     a.cell0 = (C.c_int32 * 3)(*[int(v) for v in cells["cell0"]])
     a.ncell = (C.c_int32 * 3)(*[int(v) for v in cells["ncell"]])
     a.first_x, a.first_y, a.first_z = (t.data_ptr() for t in cells["first"])
-    a.elems_per_cell_hint = int(cells["hint"])
+    a.elems_per_cell_hint = -int(cells["hint"]) if tiled == "tile" else int(cells["hint"])
     if tiled and cells.get("wtab") is not None:
         a.wtab_x, a.wtab_y, a.wtab_z = (t.data_ptr() for t in cells["wtab"])
         a.rmax = (C.c_int32 * 3)(*[int(v) for v in cells["rmax"]])
         a.hf = (C.c_float * 3)(*cells["hf"])
         a.hc = (C.c_float * 3)(*cells["hc"])
+        a.uniform_off = (C.c_int32 * 3)(*[int(v) for v in cells.get("off", (0, 0, 0))])
     a.cellsum, a.V, a.accumulate = cells["cellsum"].data_ptr(), V.data_ptr(), int(bool(accumulate))
     _lib.check(lib.gomelt_project_f32(C.byref(a), _lib.stream_ptr()), "gomelt_project_f32")
     _count(2)

@@ -279,10 +279,20 @@ typedef struct gomelt_project_args {
      * points, wtab_d[4 e .. 4 e + 3] = (x1 - xq0, xq0 - x0, x1 - xq1, xq1 - x0) with [x0, x1] the parent cell that holds
      * each Gauss point (device arrays, 16-byte aligned, built once per window position); rmax = the largest number of
      * fine elements per parent cell along each axis; hf / hc = element sizes of the fine / parent level.  All NULL / 0:
-     * the general kernel derives everything from the coordinate arrays. */
+     * the general kernel derives everything from the coordinate arrays.  With the tables, windows that nest in x and y
+     * (every parent cell of the box holds exactly rmax[0] x rmax[1] element columns; any grouping in z) take the marching
+     * kernel (no staging, plane-shared sum factorisation: csrc/k_transfer.cu project_march_kernel), the others the
+     * shared-memory tile kernel; elems_per_cell_hint < 0 (magnitude = the hint) asks for the tile kernel (A/B). */
     const float  *wtab_x, *wtab_y, *wtab_z;
     int32_t       rmax[3];
     float         hf[3], hc[3];
+    /* Nested grouping along x and y, stated by the caller (the first_d tables live on the device): parent cell i of the
+     * box holds the fine elements [i * rmax[d] - uniform_off[d], (i + 1) * rmax[d] - uniform_off[d]) clipped to the
+     * fine grid, i.e. uniform_off[d] (0 <= off < rmax[d]) elements are missing from the first cell - a window that
+     * starts inside a parent cell, as the Level-3 window does relative to Level 1.  0: the library itself checks
+     * ncell[d] * rmax[d] == number of fine elements; -1: not nested (tile / general kernel).  [2] is ignored (z follows
+     * first_z). */
+    int32_t       uniform_off[3];
 } gomelt_project_args_t;
 
 int gomelt_project_f32(const gomelt_project_args_t *args, void *stream);
@@ -347,6 +357,7 @@ typedef struct gomelt_pair {     /* fine -> parent element grouping of one level
     int32_t       elems_per_cell_hint;
     const float  *wtab_x, *wtab_y, *wtab_z;   /* see gomelt_project_args_t (may be NULL) */
     int32_t       rmax[3];
+    int32_t       uniform_off[3];             /* see gomelt_project_args_t */
 } gomelt_pair_t;
 
 typedef struct gomelt_overlap {  /* parent nodes under a window: index vectors and their coordinates            */

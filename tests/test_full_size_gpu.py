@@ -200,3 +200,56 @@ def test_level1_slab_size_cut_out_and_general_kernel(gm, example_props):
     keep = keep.reshape(-1)
     got = cut(outs[0])
     assert _rel(got[keep], Tref[keep]) <= RTOL, _rel(got[keep], Tref[keep])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# K3 at C2 size: the marching projection kernel (nested windows) against the tile kernel, plus a property the
+# domain offers at any size - the parent's shape functions are a partition of unity, so the projected MASS vector
+# sums to -scale * integral(rho*cp A) and the projected GRAD vector sums to 0
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ratio", [2, 5, 10])
+def test_projection_march_vs_tile_at_full_size(gm, example_props, ratio):
+    import torch
+
+    P = cF.SetupProperties(example_props)
+    cf = gm.computeFunctions
+    ne = (500, 500, 40)
+    hf = 0.02
+    hc = hf * ratio
+    fine = make_level(ne, ((4.0, 4.0 + ne[0] * hf), (4.0, 4.0 + ne[1] * hf), (-ne[2] * hf, 0.0)))
+    npar = (int(np.ceil(ne[0] / ratio)) + 8 * 2, int(np.ceil(ne[1] / ratio)) + 8 * 2, int(np.ceil(ne[2] / ratio)) + 2)
+    parent = make_level(npar, ((4.0 - 8 * hc, 4.0 - 8 * hc + npar[0] * hc), (4.0 - 8 * hc, 4.0 - 8 * hc + npar[1] * hc),
+                               (-npar[2] * hc, 0.0)))
+    cells = cf._pair_cells(fine, parent)
+    assert [int(v) for v in cells["rmax"]] == [ratio] * 3
+    Tf, S1 = _fields(torch, fine["nodes"], 5)
+    g = torch.Generator(device="cuda").manual_seed(6)
+    Tp0 = 60.0 * torch.rand(fine["nn"], device="cuda", generator=g) - 30.0
+    Tp1 = Tp0 + 4.0 * torch.rand(fine["nn"], device="cuda", generator=g)
+    props = gm._lib.make_props(P)
+    dt = 1e-5
+    out = {}
+    for how in (True, "tile"):
+        V = torch.zeros(parent["nn"], device="cuda")
+        cf._project(cells, Tp0, None, V, mode=0, coef_from=(props, Tf, S1, 0), tiled=how)
+        g0 = V.clone()
+        cf._project(cells, Tp1, None, V, mode=1, scale=1.0 / dt, A2=Tp0, coef_from=(props, Tf, S1, 0), tiled=how)
+        out[how] = (g0, V - g0)
+    for q in (0, 1):
+        a, b = out[True][q].double(), out["tile"][q].double()
+        assert float((a - b).abs().max() / b.abs().max()) <= 3e-5, (ratio, q)
+    # partition of unity: sum_c Nc = 1, sum_c grad Nc = 0
+    g0, m1 = out[True]
+    assert abs(float(g0.double().sum())) <= 1e-4 * float(g0.double().abs().sum())
+    _, _, _, rc = cf.computeStateProperties(Tf, S1, P, 0)
+    # integral of (element-mean rho*cp) * (trilinear dA) with the 2x2x2 rule = wq * cbar * sum_q N[q,:] . dA = V_e * cbar * mean_8(dA)
+    nx, ny, nz = fine["nodes"]
+    dA = (Tp1 - Tp0).double().reshape(nz, ny, nx)
+    rc3 = rc.double().reshape(nz, ny, nx)
+
+    def mean8(f):
+        return (f[:-1, :-1, :-1] + f[:-1, :-1, 1:] + f[:-1, 1:, :-1] + f[:-1, 1:, 1:] + f[1:, :-1, :-1] + f[1:, :-1, 1:]
+                + f[1:, 1:, :-1] + f[1:, 1:, 1:]) / 8.0
+
+    want = -(1.0 / dt) * float((mean8(rc3) * mean8(dA)).sum()) * hf ** 3
+    assert abs(float(m1.double().sum()) - want) <= 2e-5 * abs(want), (float(m1.double().sum()), want)

@@ -257,6 +257,9 @@ PROJ = {
     "L3->L2 shifted (3, -5, 0)": (lambda: _L3(0.12, -0.2, 0.0), lambda: _L2()),
     "L2->L1 shifted 7, 2 cells and one 0.04 layer in z (unequal counts per cell in z)": (lambda: _L2(1.4, 0.4, 0.04), _L1),
     "L2->L1 clipped at the +x,+y edge": (lambda: _L2(6.0, 0.0, 0.0), _L1),
+    # Level 3 moves in Level-2 cells: relative to Level 1 it starts inside a parent cell (partial first and last cells)
+    "L3->L1 shifted by (3, -5) Level-2 cells": (lambda: _L3(0.12, -0.2, 0.0), _L1),
+    "L3->L1 shifted by (1, 2) Level-2 cells and one layer": (lambda: _L3(0.04, 0.08, 0.04), _L1),
     "non-integer ratio 2.5 (2 or 3 fine elements per cell)": (
         lambda: _lv((25, 20, 9), ((0.5, 3.0), (0.5, 2.5), (-0.9, 0.0))),
         lambda: _lv((16, 12, 6), ((0.0, 4.0), (0.0, 3.0), (-1.5, 0.0)))),
@@ -297,6 +300,11 @@ def test_project_grad_and_mass_terms(gm, T, pair, example_props):
     cf._project(cells, T.f(Tp0), T.f(k), V3, mode=0, tiled=False)
     cf._project(cells, T.f(Tp1), T.f(rc), V3, mode=1, scale=1.0 / dt, A2=T.f(Tp0), tiled=False)
     assert _relmax(T.h(V3), want0 + want1) <= TOL_P, pair
+    # ... the shared-memory tile kernel (the fast path of windows that do not nest; nested ones take the marching kernel above)
+    V5 = T.torch_.zeros(parent["nn"], device="cuda")
+    cf._project(cells, T.f(Tp0), T.f(k), V5, mode=0, tiled="tile")
+    cf._project(cells, T.f(Tp1), T.f(rc), V5, mode=1, scale=1.0 / dt, A2=T.f(Tp0), tiled="tile")
+    assert _relmax(T.h(V5), want0 + want1) <= TOL_P, pair
     # ... and so does the form the steppers use: k / rho*cp evaluated inside the kernel from (T, S1) - no coefficient array
     props = gm._lib.make_props(P)
     V4 = T.torch_.zeros(parent["nn"], device="cuda")

@@ -134,6 +134,7 @@ class Hier(C.Structure):
         ("nz_active_L1", C.c_int32),
         ("L1_spare", C.c_void_p),
         ("work", C.c_void_p), ("work_floats", C.c_int64),
+        ("l1_solve", C.c_void_p), ("l1_user", C.c_void_p),
     ]
 
 
@@ -163,6 +164,8 @@ STEP_BC_CONST, STEP_SKIP_FACES, STEP_ACCUM = 0x08, 0x10, 0x20
 STEP_FUSED_FLUX = 0x40
 STEP_GENERAL_KERNEL = 0x80
 STEP_NO_COLD_PLANES = 0x100
+L1_CLAMP_AFTER = 0x10000
+L1_SOLVE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int32)
 
 # name -> (restype, argtypes); kept in one table so tests can check every header symbol loads
 SIGNATURES = {
@@ -201,6 +204,9 @@ SIGNATURES = {
                                               C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "gomelt_shift_window_f32": (C.c_int, [C.POINTER(ShiftArgs), C.c_void_p]),
     "gomelt_clamp_min_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
+    "gomelt_patch_copy_f32": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32 * 3), C.POINTER(C.c_int32 * 3), C.c_void_p,
+                                        C.POINTER(C.c_int32 * 3), C.POINTER(C.c_int32 * 3), C.POINTER(C.c_int32 * 3),
+                                        C.c_void_p]),
     "gomelt_hier_work_floats": (C.c_longlong, [C.POINTER(Hier), C.c_int32, C.c_int32]),
     "gomelt_subcycle_f32": (C.c_int, [C.POINTER(Props), C.POINTER(Hier), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                       C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),

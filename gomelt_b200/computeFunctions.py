@@ -103,10 +103,86 @@ def _grid(L):
 # ----------------------------------------------------------------------------------------------
 # setup (host geometry + device fields)
 # ----------------------------------------------------------------------------------------------
+_DIST_CONFIG = None
+
+
+def enable_distributed(rank, world, owner=None, symmetric=None):
+    """Slab-decompose Level 1 over the ranks of the default torch.distributed process group for every ``Levels`` built
+    from now on (dist.py; one process per GPU, every rank runs the same driver).  ``enable_distributed(0, 1)`` runs the
+    same machinery on one rank; ``disable_distributed()`` turns it off."""
+    global _DIST_CONFIG
+    _DIST_CONFIG = {"rank": int(rank), "world": int(world), "owner": owner, "symmetric": symmetric}
+
+
+def disable_distributed():
+    global _DIST_CONFIG
+    _DIST_CONFIG = None
+
+
+def distOf(Levels):
+    """The Level1Dist of a distributed ``Levels`` list, else None."""
+    return Levels[0].get("_gomelt_dist") if isinstance(Levels[0], dict) else None
+
+
+def isWorker(Levels):
+    """True on the ranks that hold only a Level-1 slab (no windows, no Level 0)."""
+    d = distOf(Levels)
+    return d is not None and not d.is_owner
+
+
+def gatherL1(Levels, what="T0"):
+    """Full Level-1 temperature / state on the laser owner (None on the other ranks); collective."""
+    d = distOf(Levels)
+    if d is None:
+        return Levels[1][what]
+    return d.gather(d.slab.T if what == "T0" else d.slab.S1)
+
+
+def layerShiftL1(Levels, tmp_coords, state_idx, T_amb):
+    """gm:215-224 for a slab-decomposed Level 1 (dist.Level1Dist.layer_shift)."""
+    distOf(Levels).layer_shift(Levels[1], tmp_coords, state_idx)
+    Levels[1]["node_coords"] = copy.deepcopy(tmp_coords)
+    return Levels
+
+
+def _setup_distributed(L, properties):
+    import gomelt_b200 as gm
+
+    from . import dist as _dist
+
+    torch = _torch()
+    cfg = _DIST_CONFIG
+    d = _dist.Level1Dist(gm, L, properties, cfg["rank"], cfg["world"], owner=cfg["owner"], symmetric=cfg["symmetric"])
+    L[0]["_gomelt_dist"] = d
+    L[1]["S1_storage"] = None  # slab-local: d.S1_storage
+    if d.is_owner:
+        nn1 = L[1]["nn"]
+        # full-size mirrors, valid on the box under the Level-2 window (uniform at the start: valid everywhere)
+        L[1]["T0"] = torch.full((nn1,), float(F32(properties["T_amb"])), device="cuda", dtype=torch.float32)
+        L[1]["S1"] = torch.zeros(nn1, device="cuda", dtype=torch.float32)
+        for i in (2, 3):
+            nn = L[i]["nn"]
+            L[i]["T0"] = torch.full((nn,), float(F32(properties["T_amb"])), device="cuda", dtype=torch.float32)
+            L[i]["S1"] = torch.zeros(nn, device="cuda", dtype=torch.float32)
+            L[i]["S2"] = torch.zeros(nn, device="cuda", dtype=torch.bool)
+            L[i]["Tprime0"] = torch.zeros(nn, device="cuda", dtype=torch.float32)
+        L[0]["S1"] = torch.zeros(L[0]["nn"], device="cuda", dtype=torch.float32)
+        L[0]["S2"] = torch.zeros(L[0]["nn"], device="cuda", dtype=torch.bool)
+    else:
+        for i in (1, 2, 3):
+            L[i]["T0"] = L[i]["S1"] = L[i]["S2"] = None
+        for i in (2, 3):
+            L[i]["Tprime0"] = None
+        L[0]["S1"] = L[0]["S2"] = None
+    return L
+
+
 def SetupLevels(solver_input, properties):
     """cF:115-264.  Unused reference fields (T, k, rhocp, Tprime: cF:150-157, 172) are not allocated."""
     torch = _torch()
     L = levels.build_levels(solver_input, properties)
+    if _DIST_CONFIG is not None:
+        return _setup_distributed(L, properties)
     for i in (1, 2, 3):
         nn = L[i]["nn"]
         L[i]["T0"] = torch.full((nn,), float(F32(properties["T_amb"])), device="cuda", dtype=torch.float32)
@@ -436,7 +512,24 @@ def _hier(Levels, Shapes, tmp_ne_nn, substrate, properties, N2=1, N3=1, windows=
         need = 0 if spare is not None else int(L1["nn"])
     work = ws.work_for(max(need, 64))
     h.work, h.work_floats = work.data_ptr(), int(work.numel())
+    d = distOf(Levels)
+    if d is not None:  # slab-decomposed Level 1: the steppers' Level-1 solves go through the hook (dist.py)
+        cb = d.hook()
+        h.l1_solve = _lib.C.cast(cb, _lib.C.c_void_p)
+        keep.append(cb)
     return h, keep, ws
+
+
+def _native(d, fn, *args):
+    """A native stepper call; an exception raised inside the Level-1 hook (dist.py) is re-raised here."""
+    if d is not None:
+        d._hook_error = None
+    try:
+        return fn(*args)
+    except _lib.GomeltError:
+        if d is not None and getattr(d, "_hook_error", None) is not None:
+            raise d._hook_error
+        raise
 
 
 def _swap_l1(Levels, ws, in_spare):
@@ -450,18 +543,33 @@ def _swap_l1(Levels, ws, in_spare):
 def stepGOMELT(Levels, ne_nn, tmp_ne_nn, Shapes, LInterp, v, properties, dt, laserP, substrate):
     """cF:2304-2397: one single-step predictor / corrector update of Levels 1-3 (gomelt_step_f32)."""
     torch = _torch()
+    d = distOf(Levels)
+    if d is not None:
+        d.begin_call(Levels, tmp_ne_nn, substrate)
+        if not d.is_owner:  # the Level-1 side of the two solves of cF:2355 / 2375
+            flags = _lib.STEP_BC_CONST | _lib.STEP_FUSED_FLUX | _lib.L1_CLAMP_AFTER | 0x20000
+            d.solve(float(F32(_host(dt))), flags)
+            d.solve(float(F32(_host(dt))), flags)
+            d.finish(clamp_after=True)
+            return Levels, None
     _ensure_fields(Levels)
     row = np.zeros(7, F32)
     row[:3] = np.asarray(_host(v), F32)[:3]
     row[5], row[6] = F32(_host(dt)), F32(_host(laserP))
     h, keep, ws = _hier(Levels, Shapes, tmp_ne_nn, substrate, properties)
     resetmask = torch.empty(int(Levels[3]["nn"]), device="cuda", dtype=torch.bool)
-    _swap_l1(Levels, ws, ops.step(_props(properties), h, row, resetmask))
+    _swap_l1(Levels, ws, _native(d, ops.step, _props(properties), h, row, resetmask))
+    if d is not None:
+        d.finish(clamp_after=True, final_mirror=Levels[1]["T0"])
     return Levels, resetmask
 
 
 def stepGOMELTDwellTime(Levels, tmp_ne_nn, ne_nn, properties, dt, substrate):
     """cF:2617-2664: Level 1 only, no clamp (gomelt_dwell_step_f32)."""
+    d = distOf(Levels)
+    if d is not None:  # every rank sweeps its slab; the owner's mirror is refreshed by the next moveEverything
+        d.dwell(float(F32(_host(dt))), tmp_ne_nn, substrate)
+        return Levels
     L1 = Levels[1]
     L1["T0"], L1["S1"] = _f(L1["T0"]), _f(L1["S1"])
     h, keep, ws = _hier(Levels, None, tmp_ne_nn, substrate, properties, windows=False)
@@ -474,13 +582,27 @@ def subcycleGOMELT(Levels, ne_nn, Shapes, substrate, LInterp, tmp_ne_nn, laser_p
     """cF:3224-3632: Level 1 once, Level 2 x N2, Level 3 x N2*N3, predictor pass then corrector pass
     (gomelt_subcycle_f32).  ``max_accum_L3`` / ``accum_L3`` (the melt-time windows, gm:448-449) are updated in place when
     they are CUDA tensors and returned."""
-    _ensure_fields(Levels)
     rows = np.array(_host(laser_position), F32, copy=True).reshape(-1, 7)
     rows[:, 6] = np.asarray(_host(laserP), F32)
     N2, N3 = int(subcycle[0]), int(subcycle[1])
+    d = distOf(Levels)
+    if d is not None:
+        d.begin_call(Levels, tmp_ne_nn, substrate)
+        if not d.is_owner:  # the Level-1 side of cF:3306 / 3456: dt_all summed in the order of the native call
+            dt_all = F32(0)
+            for r in range(N2 * N3):
+                dt_all = F32(dt_all + rows[r, 5])
+            flags = _lib.STEP_BC_CONST | _lib.STEP_FUSED_FLUX | _lib.STEP_CLAMP | 0x20000
+            d.solve(float(dt_all), flags)
+            d.solve(float(dt_all), flags)
+            d.finish(clamp_after=False)
+            return Levels, None, None, None, max_accum_L3, accum_L3
+    _ensure_fields(Levels)
     mx, ac = _f(max_accum_L3), _f(accum_L3)
     h, keep, ws = _hier(Levels, Shapes, tmp_ne_nn, substrate, properties, N2, N3)
-    _swap_l1(Levels, ws, ops.subcycle(_props(properties), h, rows, N2, N3, mx, ac))
+    _swap_l1(Levels, ws, _native(d, ops.subcycle, _props(properties), h, rows, N2, N3, mx, ac))
+    if d is not None:
+        d.finish(clamp_after=False, final_mirror=Levels[1]["T0"])
     return Levels, None, None, None, mx, ac
 
 
@@ -500,24 +622,24 @@ def _constrain(vtot, L):
 def moveEverything(v, vstart, Levels, move_v, LInterp, L1L2Eratio, L2L3Eratio, height):
     """cF:2400-2510: integer-cell shift of the Level-3 / Level-2 windows; T0 / T'0 re-interpolated at the new
     window nodes (one launch per window: gomelt_shift_window_f32); overlap index sets updated; S1 / S2 regathered from
-    Level 0.  ``Shapes`` = per-pair fine-element -> parent-cell grouping (three small int arrays each)."""
+    Level 0.  ``Shapes`` = per-pair fine-element -> parent-cell grouping (three small int arrays each).
+    With a slab-decomposed Level 1 (dist.py) the geometry below is evaluated on every rank, the device part on the
+    laser owner only, after the Level-1 box under the old and the new window positions has come up from the slabs."""
     torch = _torch()
-    _ensure_fields(Levels)
-    ws = _workspace(Levels)
+    d = distOf(Levels)
+    worker = d is not None and not d.is_owner
+    if not worker:
+        _ensure_fields(Levels)
     L0, L1, L2, L3 = Levels
     vtot = np.asarray(_host(v), F32) - np.asarray(_host(vstart), F32)
-    c1, c2_old, c3_old = _coords(L1["node_coords"]), _coords(L2["node_coords"]), _coords(L3["node_coords"])
+    old2, old3 = L2["node_coords"], L3["node_coords"]
     # ---- Level 3 (shifts in Level-2 cells) ----
     v3 = _constrain(vtot, L3)
     h2 = L2["h"]
     s3 = [_trunc_shift(v3[i], h2[i]) for i in range(3)]
     new3 = [(np.asarray(L3["init_node_coors"][i], F32) + F32(h2[i]) * s3[i]).astype(F32) for i in range(3)]
-    L3["overlapNodes"] = [np.asarray(L3["orig_overlap_nodes"][i]) + s3[i] for i in range(3)]
-    L3["overlapCoords"] = [(np.asarray(L3["orig_overlap_coors"][i], F32) + F32(h2[i]) * s3[i]).astype(F32)
-                           for i in range(3)]
-    # T'3 <- I_3(T'3), T3 <- I_1(T1) + (I_2(T'2) + T'3) at the new nodes (cF:2439-2443), with the OLD Level-2 window
-    Tp3n, T3n = ops.shift_window(c1, L1["T0"], c3_old, L3["Tprime0"], _coords(new3), ws.buffer("Tp3", L3["Tprime0"]),
-                                 ws.buffer("T3", L3["T0"]), mid_coords=c2_old, Tp_mid=L2["Tprime0"])
+    ov3_nodes = [np.asarray(L3["orig_overlap_nodes"][i]) + s3[i] for i in range(3)]
+    ov3_coords = [(np.asarray(L3["orig_overlap_coors"][i], F32) + F32(h2[i]) * s3[i]).astype(F32) for i in range(3)]
     # ---- Level 2 (shifts in Level-1 cells in x, y; whole layers in z) ----
     v2 = _constrain(vtot, L2)
     h1 = [L1["h"][0], L1["h"][1], F32(height)]
@@ -526,21 +648,36 @@ def moveEverything(v, vstart, Levels, move_v, LInterp, L1L2Eratio, L2L3Eratio, h
     move_v = [s2[i] * int(L1L2Eratio[i]) for i in range(3)]
     sz1 = _trunc_shift(v2[2], L1["h"][2])
     o, c = L2["orig_overlap_nodes"], L2["orig_overlap_coors"]
-    L2["overlapNodes"] = [np.asarray(o[0]) + s2[0], np.asarray(o[1]) + s2[1], np.asarray(o[2]) + sz1]
-    L2["overlapCoords"] = [(np.asarray(c[0], F32) + F32(L1["h"][0]) * s2[0]).astype(F32),
-                           (np.asarray(c[1], F32) + F32(L1["h"][1]) * s2[1]).astype(F32),
-                           (np.asarray(c[2], F32) + F32(height) * _trunc_shift(v2[2], height)).astype(F32)]
-    Tp2n, T2n = ops.shift_window(c1, L1["T0"], c2_old, L2["Tprime0"], _coords(new2), ws.buffer("Tp2", L2["Tprime0"]),
-                                 ws.buffer("T2", L2["T0"]))
-    # the new fields become the Levels' fields, the old tensors become the spare buffers of the next move
-    ws.alt["Tp3"], L3["Tprime0"] = L3["Tprime0"], Tp3n
-    ws.alt["T3"], L3["T0"] = L3["T0"], T3n
-    ws.alt["Tp2"], L2["Tprime0"] = L2["Tprime0"], Tp2n
-    ws.alt["T2"], L2["T0"] = L2["T0"], T2n
+    ov2_nodes = [np.asarray(o[0]) + s2[0], np.asarray(o[1]) + s2[1], np.asarray(o[2]) + sz1]
+    ov2_coords = [(np.asarray(c[0], F32) + F32(L1["h"][0]) * s2[0]).astype(F32),
+                  (np.asarray(c[1], F32) + F32(L1["h"][1]) * s2[1]).astype(F32),
+                  (np.asarray(c[2], F32) + F32(height) * _trunc_shift(v2[2], height)).astype(F32)]
+    if d is not None:
+        # the Level-1 temperature under the new window positions (and the old Level-2 one): slabs -> the owner's mirror
+        from .dist import Box, footprint_box
+
+        boxes = [footprint_box({"node_coords": cc}, L1) for cc in (new2, new3, old2)]
+        lo = [min(b.lo[k] for b in boxes) for k in range(3)]
+        hi = [max(b.lo[k] + b.n[k] for b in boxes) for k in range(3)]
+        d.up(Box(lo, [hi[k] - lo[k] for k in range(3)]), d.slab.T, None if worker else L1["T0"])
+    if not worker:
+        ws = _workspace(Levels)
+        c1, c2_old, c3_old = _coords(L1["node_coords"]), _coords(old2), _coords(old3)
+        # T'3 <- I_3(T'3), T3 <- I_1(T1) + (I_2(T'2) + T'3) at the new nodes (cF:2439-2443), with the OLD Level-2 window
+        Tp3n, T3n = ops.shift_window(c1, L1["T0"], c3_old, L3["Tprime0"], _coords(new3), ws.buffer("Tp3", L3["Tprime0"]),
+                                     ws.buffer("T3", L3["T0"]), mid_coords=c2_old, Tp_mid=L2["Tprime0"])
+        Tp2n, T2n = ops.shift_window(c1, L1["T0"], c2_old, L2["Tprime0"], _coords(new2), ws.buffer("Tp2", L2["Tprime0"]),
+                                     ws.buffer("T2", L2["T0"]))
+        # the new fields become the Levels' fields, the old tensors become the spare buffers of the next move
+        ws.alt["Tp3"], L3["Tprime0"] = L3["Tprime0"], Tp3n
+        ws.alt["T3"], L3["T0"] = L3["T0"], T3n
+        ws.alt["Tp2"], L2["Tprime0"] = L2["Tprime0"], Tp2n
+        ws.alt["T2"], L2["T0"] = L2["T0"], T2n
+    L3["overlapCoords"], L2["overlapNodes"], L2["overlapCoords"] = ov3_coords, ov2_nodes, ov2_coords
     L3["node_coords"], L2["node_coords"] = new3, new2
     LInterp = [interpolatePointsMatrix(L1, new2), None]
     # Level-3 overlap indices are relative to Level 2, which has itself moved
-    L3["overlapNodes"] = [L3["overlapNodes"][i] - move_v[i] for i in range(3)]
+    L3["overlapNodes"] = [ov3_nodes[i] - move_v[i] for i in range(3)]
     # ---- Level 0 index sets of the two windows ----
     r3 = [int(x) for x in L2L3Eratio]
     L0["overlapNodes"] = [np.asarray(L0["orig_overlap_nodes"][i]) + r3[i] * s3[i] for i in range(3)]
@@ -556,12 +693,14 @@ def moveEverything(v, vstart, Levels, move_v, LInterp, L1L2Eratio, L2L3Eratio, h
     L0["overlapNodes_L2"][2] = L0["overlapNodes_L2"][2] - move_v[2] * r3[2]
     L0["idx"] = BoxIndex(L0["overlapNodes"], L0["nodes"][0], L0["nodes"][1])
     L0["idx_L2"] = BoxIndex(L0["overlapNodes_L2"], L0["nodes"][0], L0["nodes"][1])
+    LInterp[1] = interpolatePointsMatrix(L2, new3)
+    if worker:
+        return Levels, None, LInterp, move_v
     # ---- state regather from Level 0 (cF:2500-2502), in place: every node of the windows is overwritten ----
     i3, i2 = L0["idx"].device(), L0["idx_L2"].device()
     ops.box_copy(L0["S1"], L2["S1"], i2, L0["nodes"][0], L0["nodes"][1], scatter=False)
     ops.box_copy(L0["S1"], L3["S1"], i3, L0["nodes"][0], L0["nodes"][1], scatter=False)
     ops.box_copy(L0["S2"], L3["S2"], i3, L0["nodes"][0], L0["nodes"][1], scatter=False)
-    LInterp[1] = interpolatePointsMatrix(L2, new3)
     Shapes = {"L2L1": _pair_cells(L2, L1), "L3L1": _pair_cells(L3, L1), "L3L2": _pair_cells(L3, L2)}
     return Levels, Shapes, LInterp, move_v
 

@@ -122,6 +122,11 @@ struct Ctx {
 // fused level step of one level (gomelt_level_step_f32)
 int k1(const Ctx& c, const gomelt_level_t& L, const float* T0, const float* S1, float* Tout, float dt, const float* rhs,
        const float* tables, float coef, int flags, float* S1_out = nullptr) {
+    if (&L == &c.h->L1 && c.h->l1_solve) {  // slab-decomposed Level 1: the hook sweeps the slabs of every rank
+        const int rc = c.h->l1_solve(c.h->l1_user, T0, S1, Tout, dt, rhs, flags);
+        if (rc) set_error("Level-1 solve hook returned %d", rc);
+        return rc;
+    }
     gomelt_step_args_t s;
     memset(&s, 0, sizeof s);
     s.grid = L.grid;
@@ -333,7 +338,7 @@ extern "C" int gomelt_step_f32(const gomelt_props_t* props, const gomelt_hier_t*
     for (int pass = 0; pass < 2; ++pass) {
         // computeSolutions cF:2135-2204: the parents are prolonged UNCLAMPED onto the child faces, the
         // jnp.maximum(T_amb, .) of cF:2360-2362 / 2380-2382 follows
-        GM_TRY(k1(c, L1, L1.T0, L1.S1, T1n, dt, w.rhs1, nullptr, 0.f, F_L1));
+        GM_TRY(k1(c, L1, L1.T0, L1.S1, T1n, dt, w.rhs1, nullptr, 0.f, F_L1 | (h->l1_solve ? GOMELT_L1_CLAMP_AFTER : 0)));
         GM_TRY(k1(c, L2, L2.T0, L2.S1, w.T2a, dt, w.rhs2, nullptr, 0.f, F_CHILD));
         GM_TRY(faces(c, c.a1, T1n, nullptr, 1.f, 0.f, L2, w.T2a, false));
         // Level 3: same T0, F, k, rho*cp and Corr = 0 in both passes (cF:2199-2201): the corrector re-uses the
@@ -499,6 +504,39 @@ extern "C" int gomelt_subcycle_f32(const gomelt_props_t* props, const gomelt_hie
         GM_TRY(copy_f32(c, L1.T0, L1fin, n1));
     }
     return scatter_L0(c);
+}
+
+__global__ void patch_copy_kernel(const float* __restrict__ src, int snx, int sny, int sx, int sy, int sz, float* __restrict__ dst,
+                                  int dnx, int dny, int dx, int dy, int dz, int nx, int ny, int nz) {
+    // one block row per (y, z) line of the box, threads along x
+    for (int line = blockIdx.x; line < ny * nz; line += gridDim.x) {
+        const int j = line % ny, k = line / ny;
+        const float* s = src + ((long long)(sz + k) * sny + (sy + j)) * snx + sx;
+        float* d = dst + ((long long)(dz + k) * dny + (dy + j)) * dnx + dx;
+        for (int i = threadIdx.x; i < nx; i += blockDim.x) d[i] = s[i];
+    }
+}
+
+extern "C" int gomelt_patch_copy_f32(const float* src, const int32_t sdims[3], const int32_t slo[3], float* dst,
+                                     const int32_t ddims[3], const int32_t dlo[3], const int32_t n[3], void* stream) {
+    if (!src || !dst || !sdims || !slo || !ddims || !dlo || !n) {
+        set_error("gomelt_patch_copy_f32: NULL argument");
+        return GOMELT_E_NULL;
+    }
+    for (int d = 0; d < 3; ++d)
+        if (n[d] < 0 || slo[d] < 0 || dlo[d] < 0 || slo[d] + n[d] > sdims[d] || dlo[d] + n[d] > ddims[d]) {
+            set_error("gomelt_patch_copy_f32: box [%d, %d) of axis %d outside the source (%d) or the destination (%d at %d)",
+                      slo[d], slo[d] + n[d], d, sdims[d], ddims[d], dlo[d]);
+            return GOMELT_E_SIZE;
+        }
+    if (n[0] == 0 || n[1] == 0 || n[2] == 0) return 0;
+    const long long lines = (long long)n[1] * n[2];
+    const int threads = n[0] >= 256 ? 256 : (n[0] >= 128 ? 128 : (n[0] >= 64 ? 64 : 32));
+    const long long cap = 16LL * sm_count();
+    patch_copy_kernel<<<(int)(lines < cap ? lines : cap), threads, 0, (cudaStream_t)stream>>>(
+        src, sdims[0], sdims[1], slo[0], slo[1], slo[2], dst, ddims[0], ddims[1], dlo[0], dlo[1], dlo[2], n[0], n[1], n[2]),
+        count_launch();
+    return check_launch("gomelt_patch_copy_f32");
 }
 
 extern "C" int gomelt_accum_single_step_f32(const float* T3, const uint8_t* resetmask, float dt, float T_liquidus, float* accum0,

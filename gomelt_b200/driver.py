@@ -157,8 +157,12 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
     t_output = 0.0
     laser_prev_z = float("inf")
     dwell_count = 0.0
+    # slab-decomposed Level 1 (computeFunctions.enable_distributed): every rank runs this loop; `worker` ranks hold only a
+    # Level-1 slab - no windows, no Level 0, no melt-time arrays - and serve the Level-1 side of every call
+    dist_on = hasattr(cf, "distOf") and cf.distOf(Levels) is not None
+    worker = dist_on and cf.isWorker(Levels)
     nn0 = int(Levels[0]["nn"])
-    accum_time, max_accum_time = xp.zeros(nn0), xp.zeros(nn0)
+    accum_time, max_accum_time = (None, None) if worker else (xp.zeros(nn0), xp.zeros(nn0))
     move_hist = [0, 0, 0]
     force_move = move_vert = new_checkpoint = load_chkpt = False
     ongoing = True
@@ -208,7 +212,9 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
                         while not np.isclose(np.asarray(tmp_coords[2]) - laser_pos[2], 0, atol=1e-4).any():
                             tmp_coords[2] = (np.asarray(tmp_coords[2], F32) + F32(Properties["layer_height"])).astype(F32)
                             state_idx += 1
-                        if not load_chkpt:
+                        if not load_chkpt and dist_on:
+                            Levels = cf.layerShiftL1(Levels, tmp_coords, state_idx, F32(T_amb))
+                        elif not load_chkpt:
                             Levels[1]["T0"] = xp.maximum(xp.f32(cf.interpolatePoints(Levels[1], Levels[1]["T0"], tmp_coords)),
                                                          F32(T_amb))
                             Levels[1]["S1_storage"] = xp.set_row(xp.f32(Levels[1]["S1_storage"]), state_idx - 1,
@@ -223,7 +229,7 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
                         wait_inc = 0
                         move_vert = True
                         counts["layers"] += 1
-                        if not load_chkpt:
+                        if not load_chkpt and not worker:
                             if "on_layer_state" in hooks:  # saveState(Level0) gm:245
                                 hooks["on_layer_state"](Levels, Nonmesh)
                             accum_time = xp.maximum(accum_time, max_accum_time)
@@ -248,13 +254,16 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
                         if move_vert:
                             move_vert = False
                             substrate = cf.getSubstrateNodes(Levels)
-                            Levels[0]["S1"] = xp.fill_prefix(xp.f32(Levels[0]["S1"]), substrate[0], 1.0)
+                            if not worker:
+                                Levels[0]["S1"] = xp.fill_prefix(xp.f32(Levels[0]["S1"]), substrate[0], 1.0)
                     if wait_inc <= Nonmesh["wait_time"]:
                         Levels, all_reset = cf.stepGOMELT(Levels, ne_nn, tmp_ne_nn, Shapes, LInterp, laser_pos, Properties,
                                                           laser_pos[5], laser_pos[6], substrate)
                         counts["stepGOMELT"] += 1
                         tprime_test_done = False
-                        if hasattr(cf, "accumSingleStepFused"):  # gm:339-357 + melting_temp as one kernel, in place
+                        if worker:
+                            pass
+                        elif hasattr(cf, "accumSingleStepFused"):  # gm:339-357 + melting_temp as one kernel, in place
                             accum_time, max_accum_time = cf.accumSingleStepFused(
                                 Levels, all_reset, accum_time, max_accum_time, laser_pos[5], Properties["T_liquidus"])
                         else:
@@ -267,7 +276,7 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
                     else:
                         # gm:360-368.  The outcome of this test (a device -> host round trip) can only change when a
                         # stepper has written T'0 again, so it is evaluated once per run of dwell rows.
-                        if not tprime_test_done:
+                        if not tprime_test_done and not worker:
                             tprime_test_done = True
                             if not xp.all_zero(xp.f32(Levels[2]["Tprime0"])) and not xp.all_zero(xp.f32(Levels[3]["Tprime0"])):
                                 dwell_count = Nonmesh["wait_time"] * Nonmesh["timestep_L3"]
@@ -298,12 +307,14 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
                 counts["moveEverything"] += 1
                 idx = Levels[0]["idx"]
                 res = cf.subcycleGOMELT(Levels, ne_nn, Shapes, substrate, LInterp, tmp_ne_nn, laser_all, Properties,
-                                        laser_all[:, 6], subcycle, xp.take(max_accum_time, idx), xp.take(accum_time, idx))
+                                        laser_all[:, 6], subcycle, None if worker else xp.take(max_accum_time, idx),
+                                        None if worker else xp.take(accum_time, idx))
                 Levels, _max_accum, _accum = res[0], res[4], res[5]
                 counts["subcycleGOMELT"] += 1
                 tprime_test_done = False
-                max_accum_time = xp.put(max_accum_time, idx, xp.f32(_max_accum))
-                accum_time = xp.put(accum_time, idx, xp.f32(_accum))
+                if not worker:
+                    max_accum_time = xp.put(max_accum_time, idx, xp.f32(_max_accum))
+                    accum_time = xp.put(accum_time, idx, xp.f32(_accum))
                 time_inc += t_add
                 record_inc += t_add
             t_output += float(laser_all[:, 5].sum(dtype=F32))
@@ -320,10 +331,20 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
                        1000 * (tend - tstart) / max(time_inc, 1)))
     finally:
         fh.close()
-    accum_time = xp.maximum(accum_time, max_accum_time)  # gm:512
+    if not worker:
+        accum_time = xp.maximum(accum_time, max_accum_time)  # gm:512
     if hasattr(xp, "sync"):
         xp.sync()
     wall = time.time() - tstart
+    L1_full = None
+    if dist_on:  # the owner's Level-1 arrays are mirrors of the box under the windows: assemble the part-scale field
+        L1_full = cf.gatherL1(Levels)
+        if worker:
+            return {"Levels": Levels, "accum_time": None, "time_inc": time_inc, "total_t_inc": total_t_inc,
+                    "sim_seconds": t_output, "wall_seconds": wall, "counts": counts, "Properties": Properties,
+                    "Nonmesh": Nonmesh, "ne_nn": ne_nn, "dwell_seconds": dwell_count, "worker": True,
+                    "stopped_at_layer_check": stopped_at_layer_check}
+        Levels[1]["T0"] = L1_full
     if "on_final" in hooks and not stopped_at_layer_check:  # saveState(Level 0) + saveResultsFinal gm:501-502
         hooks["on_final"](Levels, Nonmesh)
     if write_final and not stopped_at_layer_check:  # gm:504-516

@@ -133,14 +133,16 @@ def _axes(coords):
 
 
 def interp(src_coords, u, tgt_coords, out, *, mode=_lib.INTERP_SET, u2=None, alpha=1.0, beta=0.0, faces_only=False,
-           clamp_min=None, index_map=None, base=None):
+           clamp_min=None, index_map=None, base=None, u_offset=0):
     """gomelt_interp_f32: trilinear interpolation of ``u`` (on the level with device coordinate arrays
     ``src_coords``) at the tensor-product target grid ``tgt_coords`` -> ``out`` (see gomelt_abi.h).
-    ``index_map`` = (mx, my, mz, big_nx, big_ny) scatters the result through a tensor-product index set."""
+    ``index_map`` = (mx, my, mz, big_nx, big_ny) scatters the result through a tensor-product index set.
+    ``u_offset`` = number of leading nodes of the source level that ``u`` does NOT hold (a z-slab's local array used
+    with the global coordinate arrays: the caller guarantees that only nodes it holds are read)."""
     lib = _lib.load()
     a = _lib.InterpArgs()
     a.src = _axes(src_coords)
-    a.u, a.u2 = u.data_ptr(), (u2.data_ptr() if u2 is not None else None)
+    a.u, a.u2 = u.data_ptr() - 4 * int(u_offset), (u2.data_ptr() if u2 is not None else None)
     a.alpha, a.beta = float(alpha), float(beta)
     a.tx, a.ty, a.tz = (t.data_ptr() for t in tgt_coords)
     a.ntx, a.nty, a.ntz = (int(t.numel()) for t in tgt_coords)
@@ -334,6 +336,19 @@ def clamp_min(x, lo):
     _lib.check(lib.gomelt_clamp_min_f32(_lib.ptr(x), int(x.numel()), float(lo), _lib.stream_ptr()), "gomelt_clamp_min_f32")
     _count()
     return x
+
+
+def patch_copy(src, sdims, slo, dst, ddims, dlo, n):
+    """gomelt_patch_copy_f32: box [slo, slo + n) of the (nx, ny, nz) array ``src`` -> box at ``dlo`` of ``dst``.  ``src`` /
+    ``dst`` are float32 tensors or raw device addresses (a peer-mapped array of another rank)."""
+    lib = _lib.load()
+    v3 = lambda t: (C.c_int32 * 3)(*[int(q) for q in t])
+    a = src if isinstance(src, int) else src.data_ptr()
+    b = dst if isinstance(dst, int) else dst.data_ptr()
+    _lib.check(lib.gomelt_patch_copy_f32(C.c_void_p(a), C.byref(v3(sdims)), C.byref(v3(slo)), C.c_void_p(b), C.byref(v3(ddims)),
+                                         C.byref(v3(dlo)), C.byref(v3(n)), _lib.stream_ptr()), "gomelt_patch_copy_f32")
+    _count()
+    return dst
 
 
 def hier_work_floats(hier, N2, N3):

@@ -49,16 +49,27 @@ def local_extent(rank, world, k0, k1):
     return k0 - lo, (k1 - k0) + lo + hi, lo, lo + (k1 - k0)
 
 
+def boundary_transfers(field, plane, z_begin, z_end, rank, world):
+    """(sends, recvs) = [(tensor, peer)] of one ghost exchange of ``field`` (flat, x-fastest, local planes): the first /
+    last owned plane goes to the lower / upper neighbour's ghost plane, theirs come back."""
+    sends, recvs = [], []
+    if rank > 0:
+        sends.append((field[z_begin * plane:(z_begin + 1) * plane], rank - 1))
+        recvs.append((field[(z_begin - 1) * plane:z_begin * plane], rank - 1))
+    if rank < world - 1:
+        sends.append((field[(z_end - 1) * plane:z_end * plane], rank + 1))
+        recvs.append((field[z_end * plane:(z_end + 1) * plane], rank + 1))
+    return sends, recvs
+
+
 def exchange_planes(field, plane, z_begin, z_end, rank, world, group=None):
     """Send the first / last owned plane of ``field`` (flat, x-fastest, local planes) to the lower /
     upper neighbour's ghost plane and receive theirs.  Returns the list of Work handles."""
+    sends, recvs = boundary_transfers(field, plane, z_begin, z_end, rank, world)
     ops = []
-    if rank > 0:
-        ops.append(dist.P2POp(dist.isend, field[z_begin * plane:(z_begin + 1) * plane], rank - 1, group))
-        ops.append(dist.P2POp(dist.irecv, field[(z_begin - 1) * plane:z_begin * plane], rank - 1, group))
-    if rank < world - 1:
-        ops.append(dist.P2POp(dist.isend, field[(z_end - 1) * plane:z_end * plane], rank + 1, group))
-        ops.append(dist.P2POp(dist.irecv, field[z_end * plane:(z_end + 1) * plane], rank + 1, group))
+    for (t, q), (u, _) in zip(sends, recvs):  # per neighbour: send, then receive
+        ops.append(dist.P2POp(dist.isend, t, q, group))
+        ops.append(dist.P2POp(dist.irecv, u, q, group))
     return dist.batch_isend_irecv(ops) if ops else []
 
 
@@ -110,6 +121,39 @@ class Level1Slab:
         self.S1 = torch.empty(n, dtype=torch.float32, device=device)
         self.comm = torch.cuda.Stream(device=device) if (device is not None and world > 1 and not self.symmetric) else None
         self.sweeps = 0
+        self.transport = None  # dist.Transport: ghost exchanges staged through the host (gloo with device tensors)
+
+    def _exchange(self, field):
+        """One blocking ghost exchange of ``field`` (stream-ordered on device tensors)."""
+        if self.world == 1:
+            return
+        if self.transport is not None:
+            self.transport.exchange(*boundary_transfers(field, self.plane, self.zb, self.ze, self.rank, self.world))
+        else:
+            for w in exchange_planes(field, self.plane, self.zb, self.ze, self.rank, self.world):
+                w.wait()
+
+    def swap(self):
+        """Make the spare buffer the current field (its owned planes were written by the caller)."""
+        if self.symmetric:
+            self._cur = (self._cur + 1) % self._nbuf
+            self.T, self.Tn = self._halves[self._cur], self._halves[(self._cur + 1) % self._nbuf]
+        else:
+            self.T, self.Tn = self.Tn, self.T
+
+    def unswap(self):
+        """Undo the buffer swap of the last sweep: the next sweep starts from the same field again (predictor /
+        corrector pairs) and overwrites the last result.  The halo protocol keeps counting sweeps."""
+        if self.symmetric:
+            self._cur = (self._cur - 1) % self._nbuf
+            self.T, self.Tn = self._halves[self._cur], self._halves[(self._cur + 1) % self._nbuf]
+        else:
+            self.T, self.Tn = self.Tn, self.T
+
+    def refresh_ghosts_T(self):
+        """Ghost planes of the current temperature from the neighbours, ordered on the stream (the owned boundary planes
+        were modified outside a sweep: clamp, injected child solution)."""
+        self._exchange(self.T)
 
     def set_active(self, nz_active_global, n_substrate_global):
         """tmp_ne_nn / substrate of the whole grid (cF:495-517, 562-579) -> this slab's local planes / node ids."""
@@ -133,8 +177,7 @@ class Level1Slab:
         if self.world == 1:
             return
         for f in (self.T, self.S1):
-            for w in exchange_planes(f, self.plane, self.zb, self.ze, self.rank, self.world):
-                w.wait()
+            self._exchange(f)
         if self.device is not None:
             torch.cuda.synchronize(self.device)
         if self.symmetric:
@@ -198,6 +241,9 @@ class Level1Slab:
         zb, ze = self.zb, self.ze
         if self.world == 1:
             self._k1(dt, zb, ze, top, rhs, clamp)
+        elif self.transport is not None:   # staged transport: the whole slab, then the ghost planes of the new field
+            self._k1(dt, zb, ze, top, rhs, clamp)
+            self._exchange(self.Tn)
         else:
             lo = zb + 1 if self.rank > 0 else zb
             hi = ze - 1 if self.rank < self.world - 1 else ze

@@ -366,6 +366,13 @@ typedef struct gomelt_overlap {  /* parent nodes under a window: index vectors a
     int32_t       n[3];
 } gomelt_overlap_t;
 
+/* see gomelt_hier_t.l1_solve: flags = the GOMELT_STEP_* bits of the Level-1 solve it replaces, rhs may be NULL.
+ * GOMELT_L1_CLAMP_AFTER: the stepper prolongs the UNCLAMPED field onto the child faces and applies max(T_amb, .)
+ * afterwards (computeSolutions cF:2184-2196, then cF:2360-2362): the slabs do the same once the box has been shipped. */
+#define GOMELT_L1_CLAMP_AFTER 0x10000
+typedef int (*gomelt_l1_solve_fn)(void *user, const float *T0, const float *S1, float *T_out, float dt, const float *rhs,
+                                  int32_t flags);
+
 typedef struct gomelt_hier {
     gomelt_level_t   L1, L2, L3;
     gomelt_pair_t    L2L1, L3L1, L3L2;
@@ -381,6 +388,15 @@ typedef struct gomelt_hier {
                                               copy of the part-scale field); NULL = copy back into L1.T0             */
     float           *work;                 /* device scratch                                                           */
     int64_t          work_floats;          /* >= gomelt_hier_work_floats(...)                                          */
+    /* Slab-decomposed Level 1 (gomelt_b200/dist.py): when set, every Level-1 solve of the steppers
+     * (computeSolutions cF:2172-2185, computeL1Temperature cF:2813-2854, stepGOMELTDwellTime cF:2617-2664) is handed to
+     * this function instead of gomelt_level_step_f32 on the arrays of L1.  On the rank that owns the laser, L1.T0 / L1.S1
+     * / the load vector are full-size MIRRORS that are valid on the Level-1 box under the Level-2 window only; the hook
+     * ships that box of S1 and of the load to the slab owners (gomelt_patch_copy + the transport of the host side),
+     * all ranks sweep their slabs, and the box of the new temperature comes back into T_out.  It runs on the calling
+     * host thread, between kernels issued on `stream`; a non-zero return aborts the stepper with that code. */
+    gomelt_l1_solve_fn l1_solve;
+    void            *l1_user;
 } gomelt_hier_t;
 
 long long gomelt_hier_work_floats(const gomelt_hier_t *h, int32_t N2, int32_t N3);
@@ -400,6 +416,15 @@ int gomelt_dwell_step_f32(const gomelt_props_t *props, const gomelt_hier_t *h, f
 int gomelt_accum_single_step_f32(const float *T3, const uint8_t *resetmask, float dt, float T_liquidus, float *accum0,
                                  float *max_accum0, const int32_t *ix, const int32_t *iy, const int32_t *iz, int32_t nx,
                                  int32_t ny, int32_t nz, int32_t big_nx, int32_t big_ny, void *stream);
+
+/* Patch exchange, device side (SURVEY.md 8b gomelt_patch_exchange; 8e "fine <-> coarse across ranks"): copy the box
+ * [lo, lo + n) of a 3-D x-fastest float32 array into the box of the same size at dlo of another one.  Either side may be
+ * a contiguous staging buffer (dims = n, lo = 0: pack / unpack around a send / recv) or a peer-mapped array of another
+ * rank (symmetric memory: the copy then IS the exchange, over NVLink).  Used for the Level-1 box under the Level-2
+ * window: T old / new down and up, injected T, S1 and the load vector (getNewTprime cF:2060-2099,
+ * computeCoarseTprimeTerm_jax cF:1477-1565, updateStateProperties cF:2546-2556). */
+int gomelt_patch_copy_f32(const float *src, const int32_t sdims[3], const int32_t slo[3], float *dst, const int32_t ddims[3],
+                          const int32_t dlo[3], const int32_t n[3], void *stream);
 
 /* Monitor (printLevelMaxMin cF:3635-3665): out3 = {min, max over the finite values, number of non-finite values}
  * of x[0..n) in one reduction (device memory, 3 floats; read it back when convenient). */

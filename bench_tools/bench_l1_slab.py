@@ -222,12 +222,18 @@ def run_gomelt_multi(args, read_peaks, ClockSampler, host_properties, single_gpu
     # same-workload single-GPU reference (one slab of the same size, no neighbours), timed on rank 0 outside
     # the timed region, so that a weak-scaling efficiency can be read off this one line; plus the round-1
     # configuration (25 planes per GPU) and the round-1 mechanism (push kernel + barrier launch) for comparison
-    one_gpu, alt, par = None, {}, None
+    one_gpu, alt, par, drop_in = None, {}, None, None
     if world > 1:
         if rank == 0:
             one_gpu = one_gpu_reference(torch, gm, props, P, SLAB_PLANES, K, W, device)
         dist.barrier()
         par = parity_check(torch, dist, gm, props, P, sl, rank, world, device)
+        try:
+            from bench_tools.dist_check import run as drop_in_check
+
+            drop_in = drop_in_check(torch, dist, gm, rank, world)
+        except Exception as exc:  # reported, not fatal for the timing line
+            drop_in = {"ok": False, "error": repr(exc)}
         del sl
         torch.cuda.empty_cache()
         for name, planes, fused in (("slab_50_planes", 50, True), ("slab_25_planes", 25, True),
@@ -275,7 +281,7 @@ def run_gomelt_multi(args, read_peaks, ClockSampler, host_properties, single_gpu
                 "weak_scaling_efficiency": one_gpu / (total_s / K),
                 "note": f"one {SLAB_PLANES}-plane slab on rank 0, no neighbours, timed right after the N-GPU region; the "
                         "driver's own `efficiency` divides by the N=1 line, which is a different metric (Level-3 window)"},
-            "parity_check": par, "other_configurations": alt,
+            "parity_check": par, "drop_in_parity": drop_in, "other_configurations": alt,
             "halo_bytes_per_step_per_gpu": 4 * L1_NX * L1_NY * (2 if world > 2 else (1 if world == 2 else 0)),
             "halo": ("exchange kernel after the step: peer stores + release / acquire counters (symmetric memory)"
                      if symmetric else "NCCL send/recv") if world > 1 else "none",

@@ -150,3 +150,16 @@ def serpentine_input(tmp):
                           wait_time=4, dwell_time=8e-5, dwell_time_multiplier=1, subcycle_num_L2=2,
                           subcycle_num_L3=2, record_step=4, info_T=0, laser_velocity=500)
     return inp
+
+
+def wide_part_input(tmp):
+    """examples/example.json with a part-scale level wide enough for the fast level-step kernel (72 x 20 x 30 elements:
+    73 nodes per row) - the Level-1 sweeps of the slab-decomposed runs then go through level_step_v3 with the fused
+    halo exchange - driven by a short two-layer G-code with a pause that reaches the dwell mode (the bench's N>1 line
+    runs the same case: bench_tools/dist_check.py)."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench_tools.dist_check import wide_part_input as make
+
+    return make(tmp)

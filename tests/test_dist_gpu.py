@@ -54,7 +54,7 @@ def _check(want, out):
     return got
 
 
-@pytest.mark.parametrize("case", ["small_two_layer_input", "serpentine_input"])
+@pytest.mark.parametrize("case", ["small_two_layer_input", "serpentine_input", "wide_part_input"])
 def test_one_rank_distributed_equals_plain(gm, tmp_path, case):
     import torch
 
@@ -89,25 +89,26 @@ def _spawn(world, out, case, backend, one_device):
                 raise
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_ranks_sharing_one_gpu_equal_plain(gm, tmp_path, world):
-    want = _plain(gm, str(tmp_path / "plain"), "small_two_layer_input")
+@pytest.mark.parametrize("world,case", [(2, "small_two_layer_input"), (3, "small_two_layer_input"), (3, "wide_part_input")])
+def test_ranks_sharing_one_gpu_equal_plain(gm, tmp_path, world, case):
+    want = _plain(gm, str(tmp_path / "plain"), case)
     out = str(tmp_path / "dist")
     os.makedirs(out)
-    _spawn(world, out, "small_two_layer_input", "gloo", True)
+    _spawn(world, out, case, "gloo", True)
     got = _check(want, out)
     assert int(got["boxes_down"]) > 0
 
 
-def test_one_rank_per_gpu_equals_plain(gm, tmp_path):
+@pytest.mark.parametrize("case", ["small_two_layer_input", "wide_part_input"])
+def test_one_rank_per_gpu_equals_plain(gm, tmp_path, case):
     import torch
 
     ngpu = torch.cuda.device_count()
     if ngpu < 2:
         pytest.skip("needs >= 2 GPUs (the same protocol runs under gloo on one GPU in the test above)")
     world = min(ngpu, 4)
-    want = _plain(gm, str(tmp_path / "plain"), "small_two_layer_input")
+    want = _plain(gm, str(tmp_path / "plain"), case)
     out = str(tmp_path / "dist")
     os.makedirs(out)
-    _spawn(world, out, "small_two_layer_input", "nccl", False)
+    _spawn(world, out, case, "nccl", False)
     _check(want, out)

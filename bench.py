@@ -329,15 +329,22 @@ def example_json_run():
     import gomelt_b200 as gm
     from bench_tools.run_example import load_input
 
-    res = None
+    res = eager = None
     for _ in range(2):  # the first pass warms up module loading / allocator / kernel images
-        l0 = gm.ops.LAUNCHES
+        eager = gm.driver.go_melt(load_input(tempfile.mkdtemp()), write_final=False, graphs=False)
+    for _ in range(2):
+        l0, g0 = gm.ops.LAUNCHES, gm.ops.GRAPH_LAUNCHES
         res = gm.driver.go_melt(load_input(tempfile.mkdtemp()), write_final=False)
     torch.cuda.synchronize()
-    return {"workload": "examples/example.json + example.gcode, whole run, device-resident state, no file output",
+    same = all(torch.equal(res["Levels"][i]["T0"], eager["Levels"][i]["T0"]) for i in (1, 2, 3))
+    return {"workload": "examples/example.json + example.gcode, whole run, device-resident state, no file output; the "
+                        "499 rows of the pause replay a CUDA graph of two rows (computeFunctions.dwellRows)",
             "wall_s": res["wall_seconds"], "sim_s": res["sim_seconds"],
             "wall_s_per_sim_s": res["wall_seconds"] / res["sim_seconds"], "toolpath_rows": res["time_inc"],
-            "counts": res["counts"], "lib_launches": gm.ops.LAUNCHES - l0}
+            "counts": res["counts"], "lib_launches": gm.ops.LAUNCHES - l0,
+            "kernels_replayed_from_graphs": gm.ops.GRAPH_LAUNCHES - g0,
+            "row_by_row": {"wall_s": eager["wall_seconds"], "wall_s_per_sim_s": eager["wall_seconds"] / eager["sim_seconds"],
+                           "fields_bit_equal_to_the_graph_run": bool(same)}}
 
 
 def run_e2e_hostbuffers(blk, K):

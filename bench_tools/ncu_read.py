@@ -23,11 +23,12 @@ st = {k: float(v) for k, v in d.items() if re.match(r"smsp__average_warps_issue_
 print("stalls/issue:", ", ".join(f"{k.split('stalled_')[1].split('_per_')[0]}={v:.2f}" for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:9]))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hdr = rows[1]
+heads = [i for i, r in enumerate(rows) if "Instructions Executed" in r]   # one table per captured launch: the first
+hdr = rows[heads[0]]
 iS, iE = hdr.index("Source"), hdr.index("Instructions Executed")
 ops, tot = collections.Counter(), 0
-for r in rows[2:]:
-    if len(r) <= iE:
+for r in rows[heads[0] + 1:(heads[1] - 1 if len(heads) > 1 else len(rows))]:
+    if len(r) <= iE or not r[iE].isdigit() or not r[iS].split():
         continue
     p = r[iS].split()
     b = p[1] if p[0].startswith("@") else p[0]

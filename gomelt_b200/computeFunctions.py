@@ -706,6 +706,97 @@ def moveEverything(v, vstart, Levels, move_v, LInterp, L1L2Eratio, L2L3Eratio, h
 
 
 # ----------------------------------------------------------------------------------------------
+# runs of identical dwell rows as CUDA-graph replays
+# ----------------------------------------------------------------------------------------------
+class _DwellGraph:
+    def __init__(self):
+        self.key = self.graph = self.p0 = None
+        self.keep = []
+        self.launches = 0
+        self.replays = 0
+
+
+def _pointer_state(Levels, ws):
+    """Addresses of every device buffer a dwell row reads or writes, in their current roles."""
+    t = [Levels[1]["T0"], Levels[1]["S1"], ws.l1_spare, Levels[0]["S1"], Levels[0]["S2"]]
+    for i in (2, 3):
+        t += [Levels[i]["T0"], Levels[i]["Tprime0"], Levels[i]["S1"]]
+    t += [Levels[3]["S2"]] + [ws.alt.get(k) for k in ("Tp3", "T3", "Tp2", "T2")]
+    return tuple(0 if x is None else x.data_ptr() for x in t)
+
+
+def dwellRows(Levels, n, v, vstart, move_v, LInterp, L1L2Eratio, L2L3Eratio, height, tmp_ne_nn, ne_nn, properties, dt,
+              substrate, graphs=True):
+    """``n`` consecutive IDENTICAL Level-1-only rows of the driver (gm:292-370 in dwell mode): n x [moveEverything
+    cF:2400-2510 at the same laser position + stepGOMELTDwellTime cF:2617-2664 with the same dt].  Such a row is ~10
+    small launches whose host issue costs several times their run time, and the windows do not move, so after two rows
+    every buffer is back in its role (the window fields and the Level-1 field ping-pong): the first two rows run
+    eagerly, the next two are captured as ONE CUDA graph, and the rest of the run - also in later calls with the same
+    arguments - replays it.  Returns what the last moveEverything returned: (Levels, Shapes, LInterp, move_v)."""
+    torch = _torch()
+    Shapes = None
+
+    def one():
+        nonlocal Levels, Shapes, LInterp, move_v
+        Levels, Shapes, LInterp, move_v = moveEverything(v, vstart, Levels, move_v, LInterp, L1L2Eratio, L2L3Eratio, height)
+        Levels = stepGOMELTDwellTime(Levels, tmp_ne_nn, ne_nn, properties, dt, substrate)
+
+    ws = _workspace(Levels)
+    done = 0
+    if not graphs or distOf(Levels) is not None or n < 3:
+        for _ in range(n):
+            one()
+        return Levels, Shapes, LInterp, move_v
+    key = (np.asarray(_host(v), F32).tobytes(), np.asarray(_host(vstart), F32).tobytes(), float(F32(_host(dt))),
+           tuple(int(q) for q in tmp_ne_nn), tuple(int(q) for q in substrate), float(F32(height)))
+    g = getattr(ws, "dwell_graph", None)
+    if g is None or g.key != key:
+        g = ws.dwell_graph = _DwellGraph()
+        g.key = key
+        before = _pointer_state(Levels, ws)
+        one()
+        one()
+        done = 2
+        if _pointer_state(Levels, ws) != before:   # first rows after a window move: the roles settle one pair later
+            before = _pointer_state(Levels, ws)
+            if n - done >= 2:
+                one()
+                one()
+                done += 2
+        if n - done >= 2 and _pointer_state(Levels, ws) == before:
+            l0 = ops.LAUNCHES
+            keep_from = len(_CACHE.store)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                one()
+                one()
+            if _pointer_state(Levels, ws) == before and len(_CACHE.store) == keep_from:
+                g.graph, g.p0, g.launches = graph, before, ops.LAUNCHES - l0
+                g.keep = [list(_CACHE.store.values()), Shapes, LInterp]   # everything the graph's kernels point at
+                graph.replay()   # (capturing does not execute; the library counted these launches at capture)
+                g.replays += 1
+                done += 2
+            else:   # a cache filled during the capture: nothing ran, run the pair now
+                one()
+                one()
+                done += 2
+    if g.graph is not None:
+        if n - done >= 1 and _pointer_state(Levels, ws) != g.p0:
+            one()   # an odd row count left the buffers in their other roles
+            done += 1
+        while n - done >= 2 and _pointer_state(Levels, ws) == g.p0:
+            g.graph.replay()
+            ops.GRAPH_LAUNCHES += g.launches   # kernels executed by replays (not seen by the library's own counter)
+            g.replays += 1
+            done += 2
+    for _ in range(n - done):
+        one()
+    if Shapes is None:   # only replays ran in this call: the descriptors are those of the captured rows
+        Shapes, LInterp = g.keep[1], g.keep[2]
+    return Levels, Shapes, LInterp, move_v
+
+
+# ----------------------------------------------------------------------------------------------
 # melt-time bookkeeping and monitors
 # ----------------------------------------------------------------------------------------------
 def accumSingleStepFused(Levels, all_reset, accum_time, max_accum_time, dt, T_liquidus):

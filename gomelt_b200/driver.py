@@ -123,8 +123,60 @@ def _needs_single_step(laser_all, laser_prev_z, load_chkpt, wait_inc, nonmesh, s
     return bool((speed > F32(100 * nonmesh["laser_velocity"])).any())
 
 
-def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_final=True):
-    """Run the whole simulation.  Returns a dict: ``Levels``, ``accum_time``, counters and timings."""
+def plan_toolpath(toolpath_file, Nonmesh, subcycle):
+    """The stepping schedule of a toolpath file, computed on the host ahead of the run: the mode
+    predicate of gm:162-172 and the wait counter of gm:179 / 415-419 depend on the toolpath rows only (for a run that
+    does not restart from a checkpoint), so the sequence of calls the driver will make is known before the first kernel
+    is launched.  Returns a list of blocks: {"mode": "single" | "subcycle", "rows": n, "steps": s, "dwells": d,
+    "layer_changes": c, "dwell_runs": [lengths of runs of identical dwell rows: what dwellRows replays as graphs]}."""
+    nblock = subcycle[0] * subcycle[1]
+    blocks = []
+    wait_inc, laser_prev_z, ongoing, load_chkpt, time_inc = 0, float("inf"), True, False, 0
+    with open(toolpath_file, "r") as fh:
+        while ongoing:
+            laser_all, eof = _read_block(fh, nblock)
+            if eof:
+                ongoing = False
+                if laser_all.shape[0] == 0:
+                    break
+            if _needs_single_step(laser_all, laser_prev_z, load_chkpt, wait_inc, Nonmesh, subcycle, ongoing):
+                b = {"mode": "single", "rows": int(laser_all.shape[0]), "steps": 0, "dwells": 0, "layer_changes": 0,
+                     "dwell_runs": []}
+                new_checkpoint, prev, run = False, None, 0
+                for row in laser_all:
+                    wait_inc = wait_inc + 1 if row[4] == 0 else 0
+                    if row[2] != F32(laser_prev_z):
+                        if time_inc > 0 and not load_chkpt:
+                            new_checkpoint = True
+                        b["layer_changes"] += 1
+                        laser_prev_z = float(row[2])
+                        wait_inc = 0
+                    dwell = wait_inc > Nonmesh["wait_time"]
+                    b["dwells" if dwell else "steps"] += 1
+                    if dwell and prev is not None and np.array_equal(prev, row):
+                        run += 1
+                    else:
+                        if run > 1:
+                            b["dwell_runs"].append(run)
+                        run = 1 if dwell else 0
+                    prev = row if dwell else None
+                    time_inc += 1
+                if run > 1:
+                    b["dwell_runs"].append(run)
+                load_chkpt = new_checkpoint
+                blocks.append(b)
+            else:
+                off = laser_all[:, 4] == 0
+                wait_inc = wait_inc + len(laser_all) - int(laser_all[:, 4].sum()) if off.any() else 0
+                time_inc += laser_all.shape[0]
+                blocks.append({"mode": "subcycle", "rows": int(laser_all.shape[0]), "steps": 0, "dwells": 0,
+                               "layer_changes": 0, "dwell_runs": []})
+    return blocks
+
+
+def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_final=True, graphs=True):
+    """Run the whole simulation.  Returns a dict: ``Levels``, ``accum_time``, counters and timings.  ``graphs=False``
+    issues every row of a pause eagerly instead of replaying CUDA graphs (A/B; the results are identical)."""
     if cf is None:
         from . import computeFunctions as cf
     if xp is None:
@@ -161,6 +213,7 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
     # Level-1 slab - no windows, no Level 0, no melt-time arrays - and serve the Level-1 side of every call
     dist_on = hasattr(cf, "distOf") and cf.distOf(Levels) is not None
     worker = dist_on and cf.isWorker(Levels)
+    batch_dwell = bool(graphs) and hasattr(cf, "dwellRows") and not dist_on
     nn0 = int(Levels[0]["nn"])
     accum_time, max_accum_time = (None, None) if worker else (xp.zeros(nn0), xp.zeros(nn0))
     move_hist = [0, 0, 0]
@@ -202,7 +255,30 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
                     break
             single_step = _needs_single_step(laser_all, laser_prev_z, load_chkpt, wait_inc, Nonmesh, subcycle, ongoing)
             if single_step:
-                for laser_pos in laser_all:
+                jrow = 0
+                while jrow < laser_all.shape[0]:
+                    laser_pos = laser_all[jrow]
+                    jrow += 1
+                    # a run of identical rows in Level-1-only mode (the pause between tracks / layers): handed to the
+                    # stepper side as ONE call, which replays them as CUDA graphs (computeFunctions.dwellRows; N2)
+                    if (batch_dwell and laser_pos[4] == 0 and wait_inc + 1 > Nonmesh["wait_time"] and not move_vert
+                            and laser_pos[2] == F32(laser_prev_z) and tprime_test_done):
+                        m = 1
+                        while jrow - 1 + m < laser_all.shape[0] and np.array_equal(laser_all[jrow - 1 + m], laser_pos):
+                            m += 1
+                        if m >= 3:
+                            Levels, Shapes, LInterp, move_hist = cf.dwellRows(
+                                Levels, m, laser_pos, laser_start, move_hist, LInterp, L1L2Eratio, L2L3Eratio,
+                                Properties["layer_height"], tmp_ne_nn, ne_nn, Properties, laser_pos[5], substrate)
+                            counts["moveEverything"] += m
+                            counts["stepGOMELTDwellTime"] += m
+                            for _ in range(m):
+                                dwell_count += float(laser_pos[5])
+                            wait_inc += m
+                            time_inc += m
+                            record_inc += m
+                            jrow += m - 1
+                            continue
                     wait_inc = wait_inc + 1 if laser_pos[4] == 0 else 0
                     if laser_pos[2] != F32(laser_prev_z) and time_inc > 0 and not load_chkpt:
                         new_checkpoint = True

@@ -10,6 +10,7 @@ from ._lib import (STEP_ACCUM, STEP_BC_CONST, STEP_CLAMP, STEP_FUSED_FLUX, STEP_
                    STEP_WRITE_S1, STEP_WRITE_S2)
 
 LAUNCHES = 0  # kernels launched by the library in this process (bench.py reports the difference as gpu_launches)
+GRAPH_LAUNCHES = 0  # kernels executed through CUDA-graph replays (computeFunctions.dwellRows)
 
 
 def _count(n=1):

@@ -36,6 +36,49 @@ def test_mode_sequence_on_the_example_toolpath(tmp_path):
     calls = [x for x in stub.calls if x != "move"]
     assert calls[:25] == ["step"] * 25 and calls[25:55] == ["subcycle"] * 30
     assert calls[55:80] == ["step"] * 25 and calls[80:] == ["dwell"] * 499
+    # the same schedule computed ahead of the run from the toolpath file alone (N2: host-side block scheduler)
+    plan = drv.plan_toolpath(out["Nonmesh"]["toolpath"], out["Nonmesh"], sc.getStaticSubcycle(out["Nonmesh"]))
+    assert sum(b["rows"] for b in plan) == 1299
+    assert [b["mode"] for b in plan[:32]] == ["single"] + ["subcycle"] * 30 + ["single"]
+    assert sum(b["steps"] for b in plan) == 50 and sum(b["dwells"] for b in plan) == 499
+    assert sum(b["layer_changes"] for b in plan) == 1
+    # the pause is runs of identical rows (one per 25-row block): what dwellRows replays as CUDA graphs
+    assert sum(sum(b["dwell_runs"]) for b in plan) >= 490
+
+
+@pytest.mark.gpu
+def test_graph_replay_of_dwell_runs_is_bit_identical(tmp_path):
+    """N2: runs of identical dwell rows go through computeFunctions.dwellRows (two eager rows, two captured as one
+    CUDA graph, the rest replayed); the run must equal the row-by-row run bit for bit on every level."""
+    import torch
+
+    import gomelt_b200 as gm
+
+    drv = importlib.import_module("gomelt_b200.driver")
+    inp = json.load(open(os.path.join(ROOT, "examples", "example.json")))
+
+    def run(sub, graphs):
+        d = tmp_path / sub
+        d.mkdir()
+        i = json.loads(json.dumps(inp))
+        i["nonmesh"].update(save_path=str(d) + "/", toolpath=str(d / "toolpath.txt"), output_files=0, info_T=0,
+                            gcode=os.path.join(ROOT, "examples", "gcodefiles", "example.gcode"))
+        g0 = gm.ops.GRAPH_LAUNCHES
+        res = drv.go_melt(i, write_final=False, graphs=graphs)
+        torch.cuda.synchronize()
+        return res, gm.ops.GRAPH_LAUNCHES - g0
+
+    a, ga = run("graphs", True)
+    b, gb = run("eager", False)
+    assert a["counts"] == b["counts"] and a["time_inc"] == b["time_inc"] == 1299
+    assert abs(a["dwell_seconds"] - b["dwell_seconds"]) < 1e-12
+    assert gb == 0 and ga > 2000, (ga, gb)   # most of the 499 x ~6 launches of the pause ran as replays
+    for lvl in (1, 2, 3):
+        for f in ("T0", "S1"):
+            assert torch.equal(a["Levels"][lvl][f], b["Levels"][lvl][f]), (lvl, f)
+    for lvl in (2, 3):
+        assert torch.equal(a["Levels"][lvl]["Tprime0"], b["Levels"][lvl]["Tprime0"])
+    assert torch.equal(a["accum_time"], b["accum_time"])
 
 
 @pytest.mark.gpu

@@ -8,6 +8,8 @@
 // weights are evaluated in registers from the levels' 1-D node-coordinate arrays with the reference's
 // own float32 formulas (floor((x-x0)/h) cell search, compute3DN cF:1361-1393 products, the +-1e-2
 // validity window), so that cell decisions are identical and values agree to rounding.
+#include <math.h>
+
 #include "common.cuh"
 
 namespace gomelt {
@@ -1080,27 +1082,58 @@ __global__ void __launch_bounds__(32 * MARCH_WARPS) project_march_kernel(const M
     }
 }
 
+// z-chunks of whole parent cells: all warps of a launch do the same work, (planes of a chunk + the one it re-reads), and
+// run in ceil(warps / resident warp slots) rounds - pick the chunk that minimises rounds x planes (fsz is on the device,
+// so the planes of a chunk are estimated from the mean number of fine layers per parent cell).
+template <typename K>
+static int march_blocks_per_sm(K kernel) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * MARCH_WARPS, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+    return per_sm;
+}
+static int march_pick_chunk(int per_sm, MarchParams& mp, int nwx, int nby, int fine_layers) {
+    const double slots = (double)per_sm * MARCH_WARPS * sm_count();
+    const double lpc = (double)fine_layers / mp.ncz;          // fine layers per parent cell
+    const long long warps_xy = (long long)nwx * nby;
+    int best = mp.ncz;
+    double best_cost = 1e300;
+    for (int czn = 1; czn <= mp.ncz; ++czn) {
+        const int nzc = (mp.ncz + czn - 1) / czn;
+        const double rounds = ceil((double)(warps_xy * nzc) / slots);
+        const double cost = rounds * (czn * lpc + 1.0 + 1.5);   // + ~1.5 planes of prologue / flush per warp
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = czn; }
+    }
+    return best;
+}
+
+template <int MODE, int RY, int MC, bool FAST>
+static void launch_march_i(MarchParams& mp, int nwx, int nby, int fine_layers, cudaStream_t st) {
+    static const int per_sm = march_blocks_per_sm(project_march_kernel<MODE, RY, MC, FAST>);   // (once per instance)
+    mp.czn = march_pick_chunk(per_sm, mp, nwx, nby, fine_layers);
+    const dim3 grid((nwx + MARCH_WARPS - 1) / MARCH_WARPS, nby, (mp.ncz + mp.czn - 1) / mp.czn);
+    project_march_kernel<MODE, RY, MC, FAST><<<grid, 32 * MARCH_WARPS, 0, st>>>(mp);
+}
+
 template <int MODE, bool FAST>
-static bool launch_march_f(const MarchParams& mp, dim3 grid, cudaStream_t st) {
-    const dim3 blk(32 * MARCH_WARPS);
+static bool launch_march_f(MarchParams& mp, int nwx, int nby, int fine_layers, cudaStream_t st) {
     switch (mp.ry) {
-        case 1: project_march_kernel<MODE, 4, 4, FAST><<<grid, blk, 0, st>>>(mp); break;
-        case 2: project_march_kernel<MODE, 4, 2, FAST><<<grid, blk, 0, st>>>(mp); break;
-        case 3: project_march_kernel<MODE, 3, 1, FAST><<<grid, blk, 0, st>>>(mp); break;
-        case 4: project_march_kernel<MODE, 4, 1, FAST><<<grid, blk, 0, st>>>(mp); break;
-        case 5: project_march_kernel<MODE, 5, 1, FAST><<<grid, blk, 0, st>>>(mp); break;
-        case 6: project_march_kernel<MODE, 6, 1, FAST><<<grid, blk, 0, st>>>(mp); break;
-        case 8: project_march_kernel<MODE, 8, 1, FAST><<<grid, blk, 0, st>>>(mp); break;
-        case 10: project_march_kernel<MODE, 10, 1, FAST><<<grid, blk, 0, st>>>(mp); break;
+        case 1: launch_march_i<MODE, 4, 4, FAST>(mp, nwx, nby, fine_layers, st); break;
+        case 2: launch_march_i<MODE, 4, 2, FAST>(mp, nwx, nby, fine_layers, st); break;
+        case 3: launch_march_i<MODE, 3, 1, FAST>(mp, nwx, nby, fine_layers, st); break;
+        case 4: launch_march_i<MODE, 4, 1, FAST>(mp, nwx, nby, fine_layers, st); break;
+        case 5: launch_march_i<MODE, 5, 1, FAST>(mp, nwx, nby, fine_layers, st); break;
+        case 6: launch_march_i<MODE, 6, 1, FAST>(mp, nwx, nby, fine_layers, st); break;
+        case 8: launch_march_i<MODE, 8, 1, FAST>(mp, nwx, nby, fine_layers, st); break;
+        case 10: launch_march_i<MODE, 10, 1, FAST>(mp, nwx, nby, fine_layers, st); break;
         default: return false;
     }
     count_launch();
     return true;
 }
 template <int MODE>
-static bool launch_march(const MarchParams& mp, dim3 grid, cudaStream_t st) {
+static bool launch_march(MarchParams& mp, int nwx, int nby, int fine_layers, cudaStream_t st) {
     const bool fast = !mp.coef && ((MODE == 1) == (mp.A2 != nullptr));
-    return fast ? launch_march_f<MODE, true>(mp, grid, st) : launch_march_f<MODE, false>(mp, grid, st);
+    return fast ? launch_march_f<MODE, true>(mp, nwx, nby, fine_layers, st) : launch_march_f<MODE, false>(mp, nwx, nby, fine_layers, st);
 }
 static inline int march_cells_per_band(int ry) { return ry == 1 ? 4 : (ry == 2 ? 2 : 1); }
 static inline bool march_ry_ok(int ry) { return ry == 1 || ry == 2 || ry == 3 || ry == 4 || ry == 5 || ry == 6 || ry == 8 || ry == 10; }
@@ -1455,15 +1488,8 @@ extern "C" int gomelt_project_f32(const gomelt_project_args_t* a, void* stream) 
         const int nwx = (p.ncx + cpw - 1) / cpw;
         const int mc = march_cells_per_band(mp.ry);
         const int nby = (p.ncy + mc - 1) / mc;
-        // z-chunks of whole parent cells: enough warps for ~2.5 resident sets of 8 per SM
-        const long long target = 20LL * sm_count();
-        long long nzc = (target + (long long)nwx * nby - 1) / ((long long)nwx * nby);
-        if (nzc > p.ncz) nzc = p.ncz;
-        if (nzc < 1) nzc = 1;
-        mp.czn = (int)((p.ncz + nzc - 1) / nzc);
-        const dim3 grid((nwx + MARCH_WARPS - 1) / MARCH_WARPS, nby, (p.ncz + mp.czn - 1) / mp.czn);
-        if (grid.y <= 65535u && grid.z <= 65535u)
-            marched = a->mode == 1 ? launch_march<1>(mp, grid, st) : launch_march<0>(mp, grid, st);
+        if (nby <= 65535 && p.ncz <= 65535)
+            marched = a->mode == 1 ? launch_march<1>(mp, nwx, nby, a->fine[2].n - 1, st) : launch_march<0>(mp, nwx, nby, a->fine[2].n - 1, st);
     }
     TileParams tp;
     if (marched) {

@@ -20,14 +20,15 @@ for label, hot in (("40% of the nodes molten, scattered", 2000.0), ("0.8% molten
     Tout = torch.empty_like(T0); S2 = torch.zeros(nn, device="cuda", dtype=torch.uint8); acc = torch.zeros(nn, device="cuda"); mx = torch.zeros(nn, device="cuda")
     tx = torch.rand(nx, device="cuda"); ty = torch.rand(ny, device="cuda"); tz = torch.rand(nz, device="cuda")
     flush = torch.empty(64 * 1024 * 1024, device="cuda")
-    for name, extra in (("fast", 0), ("general", ops.STEP_GENERAL_KERNEL)):
+    queue = torch.zeros(2 + 2 * (nn // 120 + 1024), device="cuda", dtype=torch.int32)
+    for name, extra, q in (("fast", 0, None), ("fast + hot-plane queue", 0, queue), ("general", ops.STEP_GENERAL_KERNEL, None)):
         ts = []
         for it in range(9):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             ops.level_step(props, grid, T0, S1, Tout, 1e-5, src=(tx, ty, tz, 1e-3), n_substrate=2*nx*ny, S1_out=S1, S2_out=S2, S2_prev=S2, accum=acc, max_accum=mx,
-                           flags=ops.STEP_SKIP_FACES | ops.STEP_CLAMP | ops.STEP_WRITE_S1 | ops.STEP_WRITE_S2 | ops.STEP_ACCUM | ops.STEP_FUSED_FLUX | extra)
+                           flags=ops.STEP_SKIP_FACES | ops.STEP_CLAMP | ops.STEP_WRITE_S1 | ops.STEP_WRITE_S2 | ops.STEP_ACCUM | ops.STEP_FUSED_FLUX | extra, bk_queue=q)
             e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
         t = np.median(ts[3:]) * 1e-3
         print(f"  Part-2 shape {name}: {t*1e6:.1f} us  ({nn*33/t/1e9:.0f} GB/s at the 33 B/DOF of SURVEY 8d)")

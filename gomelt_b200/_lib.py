@@ -46,6 +46,7 @@ class StepArgs(C.Structure):
         ("peer_lo", C.c_void_p), ("peer_hi", C.c_void_p),
         ("halo_sync", C.c_void_p), ("halo_sync_lo", C.c_void_p), ("halo_sync_hi", C.c_void_p),
         ("halo_seq", C.c_uint32),
+        ("bk_queue", C.c_void_p), ("bk_queue_words", C.c_int64), ("bk_queue_keep", C.c_int32),
     ]
 
 
@@ -153,6 +154,7 @@ class SubstepsArgs(C.Structure):
         ("faces", C.POINTER(InterpArgs)),
         ("faces_n", C.c_float),
         ("T_last", C.POINTER(C.c_void_p)),
+        ("bk_queue", C.c_void_p), ("bk_queue_words", C.c_int64),
         ("faces_scratch", C.c_void_p),
     ]
 

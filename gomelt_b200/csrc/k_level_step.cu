@@ -144,6 +144,10 @@ static void launch_v3(const StepParams& sp, int nch, cudaStream_t st) {
 
 // v3 (k_level_step_v3.cuh) serves the Dirichlet-side-face shapes of the steppers on grids that hold a full tile.
 // Returns false when the call is not one of them (v2 takes it).
+static bool gridDim_fits_u16(const StepParams& sp) {  // queue entries pack the tile indices into 16 bits each
+    return (sp.nx - 2 + 2 * K1_TX - 1) / (2 * K1_TX) < 65536 && (sp.ny - 2 + 4 - 1) / 4 < 65536;
+}
+
 static bool try_launch_v3(StepParams& sp, int nch, cudaStream_t st) {
     constexpr int RY = 4;
     const int f = sp.feat;
@@ -174,10 +178,16 @@ static bool try_launch_v3(StepParams& sp, int nch, cudaStream_t st) {
             if (sp.S1out == sp.S1) GM_V3(V3_L3_SUB | K1F_S1INPLACE);
             else GM_V3(V3_L3_SUB);
             break;
-        case V3_L3_SUB2:
+        case V3_L3_SUB2: {
+            const bool queue = sp.bkq != nullptr && sp.bkq_cap > 0 && gridDim_fits_u16(sp);
+            if (!queue) sp.bkq = nullptr;
+            else if (sp.bkq_reset && cudaMemsetAsync(sp.bkq, 0, 8, st) != cudaSuccess) return false;
             if (sp.S1out == sp.S1) GM_V3(V3_L3_SUB2 | K1F_S1INPLACE);
             else GM_V3(V3_L3_SUB2);
+            if (queue)  // the hot planes the step queued: one warp per (tile, plane), spread over the GPU
+                bookkeep_queue_kernel<RY, true, true><<<sm_count(), 128, 0, st>>>(sp), count_launch();
             break;
+        }
         case V3_L3_STEP: GM_V3(V3_L3_STEP); break;
         case V3_RHS: GM_V3(V3_RHS); break;  // (the rhs rows are fetched a plane ahead into registers there)
         case V3_RHS_NC: GM_V3(V3_RHS_NC); break;
@@ -343,6 +353,9 @@ extern "C" int gomelt_level_step_f32(const gomelt_props_t* props, const gomelt_s
     sp.peer_lo = a->peer_lo; sp.peer_hi = a->peer_hi;
     sp.exp = GM_DEV_SWITCH("GOMELT_K1_EXP", 0);
     sp.hsync = a->halo_sync; sp.hsync_lo = a->halo_sync_lo; sp.hsync_hi = a->halo_sync_hi;
+    sp.bkq = a->bk_queue;
+    sp.bkq_cap = (a->bk_queue && a->bk_queue_words > 2) ? (unsigned)((a->bk_queue_words - 2) / 2) : 0u;
+    sp.bkq_reset = a->bk_queue_keep ? 0 : 1;
     if (sp.hsync) {
         if ((a->peer_lo != nullptr) != (a->halo_sync_lo != nullptr) || (a->peer_hi != nullptr) != (a->halo_sync_hi != nullptr) ||
             !(a->flags & GOMELT_STEP_BC_CONST)) {

@@ -63,6 +63,9 @@ struct StepParams {
     unsigned* hsync_hi;
     unsigned hseq;
     int ran_v3;            // set by the launcher: the fast kernel took the call (its Dirichlet faces come from a face pass)
+    unsigned* bkq;         // hot-plane work queue of the melt-time bookkeeping (gomelt_step_args_t.bk_queue) or nullptr
+    unsigned bkq_cap;      // its capacity in entries
+    int bkq_reset;         // zero its header before the step (0: the previous sweep left it zeroed)
     // v3 normalisation: stiffness modes divided by s = lambda'[2], masses by cdt * s, loads by s (so that
     // T_new = T + (rr/s - KT/s) / (mnode/(cdt s)) needs neither the lambda'[2] nor the cdt multiply)
     float n_ca0, n_ca1, n_cmushy, n_cfluid, n_inv_s, n_wq;

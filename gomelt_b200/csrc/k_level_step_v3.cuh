@@ -409,6 +409,32 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
         static_assert(NR == 6, "bookkeep_planes takes the six row offsets of RY = 4");
         unsigned long long m = hotmask;  // warp-uniform
         hotmask = 0;
+        if (p.bkq && m) {
+            // With a work queue the hot planes are handed to bookkeep_queue_kernel, which follows on the stream: the few
+            // warps over the melt pool are the tail of a single-wave launch, and their bookkeeping - two dependent memory
+            // round trips per pair of planes, serial in this warp - is spread over the whole GPU instead.
+            const unsigned n = (unsigned)__popcll(m);
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(p.bkq, n);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + n <= p.bkq_cap) {
+                if (lane == 0) {
+                    unsigned* q = p.bkq + 2 + 2 * (size_t)base;
+                    const unsigned tile = (unsigned)blockIdx.x | ((unsigned)blockIdx.y << 16);
+                    while (m) {
+                        const int b = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        q[0] = tile;
+                        q[1] = (unsigned)(lfirst + b);
+                        q += 2;
+                    }
+                }
+                return;
+            }
+            // queue full: this warp keeps its planes; the slots it reserved below the capacity are marked empty
+            if (lane == 0)
+                for (unsigned e = base; e < p.bkq_cap; ++e) p.bkq[3 + 2 * (size_t)e] = 0xffffffffu;
+        }
 #pragma unroll 1
         while (m) {  // two hot planes per pass
             size_t pl[2];
@@ -753,6 +779,50 @@ __global__ void __launch_bounds__(32, MINB) level_step_v3(const __grid_constant_
         char* out = (char*)(p.Tout + (size_t)f * P);
 #pragma unroll
         for (int r = 0; r < RY; ++r) st2(out + off[r + 1], owna, ownb, splat(p.pk.T_amb));
+    }
+}
+
+// Melt-time bookkeeping of the hot planes that level_step_v3 queued (StepParams::bkq: word 0 = number of entries, word 1
+// = blocks of this kernel that have finished, then (tile, plane) pairs): one warp per entry, with the tile geometry formed exactly as the step kernel forms it
+// (one owner per node: the owned lanes / rows that are not the overlap of a shifted tile, plus the face column / row of the
+// outermost tiles).  Entries beyond the capacity were handled by the step kernel itself.
+template <int RY, bool F_S2, bool F_ACC>
+__global__ void __launch_bounds__(128) bookkeep_queue_kernel(const __grid_constant__ StepParams p) {
+    static_assert(RY == 4, "bookkeep_planes takes the six row offsets of RY = 4");
+    constexpr int NR = RY + 2;
+    const unsigned n = min(p.bkq[0], p.bkq_cap);
+    const int lane = threadIdx.x & 31;
+    const int nx = p.nx, ny = p.ny;
+    const size_t P = (size_t)nx * ny;
+    for (unsigned e = blockIdx.x * 4u + (threadIdx.x >> 5); e < n; e += gridDim.x * 4u) {
+        const unsigned tile = p.bkq[2 + 2 * (size_t)e], l = p.bkq[3 + 2 * (size_t)e];
+        if (l == 0xffffffffu) continue;  // reserved by a warp that found the queue full and kept its planes
+        const int bx = (int)(tile & 0xffffu), by = (int)(tile >> 16);
+        const int c0 = min(bx * (2 * K1_TX), nx - (2 * K1_TX + 2));
+        const int j0 = min(1 + by * RY, ny - 1 - RY);
+        const int ia = c0 + lane, ib = ia + K1_TX;
+        const int own = (lane >= 1 && lane <= K1_TX) ? 1 : 0;
+        const int x_new = bx * (2 * K1_TX) + 1, y_new = by * RY + 1;
+        const int qa = ((own && ia >= x_new) || ia == 0) ? 1 : 0, qb = ((own && ib >= x_new) || ib == nx - 1) ? 1 : 0;
+        unsigned off[NR], rows_mine = 0;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int j = j0 - 1 + r;
+            off[r] = 4u * (unsigned)(j * nx + ib);
+            if ((r >= 1 && r <= RY) ? (j >= y_new) : (r == 0 ? j == 0 : j == ny - 1)) rows_mine |= 1u << r;
+        }
+        const size_t pl[1] = {(size_t)l * P};
+        const unsigned rm[1] = {rows_mine};
+        bookkeep_planes<F_S2, F_ACC, 1>(p, pl, rm, qa, qb, off[0], off[1], off[2], off[3], off[4], off[5]);
+    }
+    // the last block to finish leaves the header zeroed for the next sweep (every block has read the count by then)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(p.bkq + 1, 1u) == gridDim.x - 1) {
+            p.bkq[0] = 0u;
+            p.bkq[1] = 0u;
+        }
     }
 }
 

@@ -53,6 +53,8 @@ struct Work {
     float *T3a, *T3b, *S13p, *Tp3c, *Tp3h, *tables3, *faces3;
     float *ptab, *cs21, *cs31, *cs32;
     uint8_t* preS2;
+    uint32_t* bkq;
+    long long bkq_words;
 };
 
 long long carve(const gomelt_hier_t& h, int N2, int N3, float* base, long long have, Work* w) {
@@ -69,6 +71,8 @@ long long carve(const gomelt_hier_t& h, int N2, int N3, float* base, long long h
     t.ptab = c.take((long long)GOMELT_MAX_SUBSTEPS * ps);
     t.cs21 = c.take(cells_of(h.L2L1)); t.cs31 = c.take(cells_of(h.L3L1)); t.cs32 = c.take(cells_of(h.L3L2));
     t.preS2 = reinterpret_cast<uint8_t*>(c.take((n3 + 3) / 4));
+    t.bkq_words = 2 + 2 * (n3 / 120 + 1024);   // hot-plane queue of the corrector substeps (gomelt_step_args_t.bk_queue)
+    t.bkq = reinterpret_cast<uint32_t*>(c.take(t.bkq_words));
     if (w) *w = t;
     return c.ok ? have - c.left : -1;
 }
@@ -427,7 +431,7 @@ extern "C" int gomelt_subcycle_f32(const gomelt_props_t* props, const gomelt_hie
         s.n_substrate = L3.n_substrate;
         s.flags = GOMELT_STEP_SKIP_FACES | GOMELT_STEP_CLAMP | (bookkeeping ? (GOMELT_STEP_WRITE_S2 | GOMELT_STEP_ACCUM) : 0);
         s.tables = w.tables3;
-        if (bookkeeping) { s.S2 = L3.S2; s.accum = accum; s.max_accum = max_accum; }
+        if (bookkeeping) { s.S2 = L3.S2; s.accum = accum; s.max_accum = max_accum; s.bk_queue = w.bkq; s.bk_queue_words = w.bkq_words; }
         s.faces = &fa; s.faces_n = fN3;
         s.T_last = Tlast;
         s.faces_scratch = N3 > 1 ? w.faces3 : nullptr;

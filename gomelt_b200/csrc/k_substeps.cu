@@ -64,6 +64,9 @@ extern "C" int gomelt_l3_substeps_f32(const gomelt_props_t* props, const gomelt_
         s.S2_prev = a->S2;
         s.accum = a->accum;
         s.max_accum = a->max_accum;
+        s.bk_queue = a->bk_queue;
+        s.bk_queue_words = a->bk_queue_words;
+        s.bk_queue_keep = i > 0 ? 1 : 0;   // (the first substep zeroes the header, every sweep leaves it zeroed)
         rc = gomelt_level_step_f32(props, &s, stream);
         if (rc) return rc;
         if (compact_faces) {

@@ -122,6 +122,16 @@ typedef struct gomelt_step_args {
     uint32_t     *halo_sync_lo; /* the lower neighbour's counter block (peer-mapped), NULL on the lowest rank           */
     uint32_t     *halo_sync_hi; /* the upper neighbour's, NULL on the highest rank                                       */
     uint32_t      halo_seq;     /* number of sweeps this slab has done under the protocol before this one               */
+    /* Optional scratch of the melt-time bookkeeping (GOMELT_STEP_ACCUM on the fast kernel): with it the step kernel only
+     * QUEUES the planes of a tile that hold molten nodes and a second launch does their accum / max_accum / S2 update with
+     * one warp per (tile, plane) - the warps over the melt pool are otherwise the tail of a one-wave launch (72.6 -> ~55 us
+     * per 10 M-node corrector sweep with one melt pool).  bk_queue_words >= 2 + 2 * entries uint32 words; one entry per
+     * (60 x 4-node tile, plane) that is hot: nn / 120 + 1024 entries always suffice.  NULL: everything inside the step. */
+    uint32_t     *bk_queue;
+    int64_t       bk_queue_words;
+    int32_t       bk_queue_keep;  /* 0: the call zeroes the queue's two header words first; 1: the caller guarantees they
+                                   * are zero - every call that uses the queue leaves them zeroed (saves a memset node
+                                   * per sweep inside a block of substeps) */
 } gomelt_step_args_t;
 
 int gomelt_level_step_f32(const gomelt_props_t *props, const gomelt_step_args_t *args, void *stream);
@@ -328,6 +338,8 @@ typedef struct gomelt_substeps_args {
                                      faces_only are set per substep by the call                                */
     float         faces_n;        /* fN3 (float, as the reference divides: alpha = (i+1)/fN3, beta = 1-alpha) */
     float       **T_last;         /* HOST out: buffer holding the newest temperature (may be NULL)            */
+    uint32_t     *bk_queue;       /* NULL, or the scratch of gomelt_step_args_t.bk_queue (used by the ACCUM substeps)   */
+    int64_t       bk_queue_words;
     float        *faces_scratch;  /* NULL, or device scratch [2 * gomelt_faces_count(nx, ny, nz)]: the two parent
                                      fields are interpolated at the face nodes ONCE per call (gomelt_faces_gather_f32)
                                      and every substep blends them (gomelt_faces_blend_f32) instead of

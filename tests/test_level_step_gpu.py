@@ -506,16 +506,24 @@ def test_fast_kernel_melt_time_bookkeeping_has_one_owner_per_node(gm, example_pr
     v = np.array([0.01 * ex, 0.01 * ey, 0.0], np.float32)
     coef = ops.source_tables(props, grid, coords, v, 285.0, tx, ty, tz)
     outs = []
-    for extra in (0, ops.STEP_GENERAL_KERNEL):
+    # the fast kernel on its own, the general kernel, and the fast kernel with the hot-plane work queue
+    # (gomelt_step_args_t.bk_queue: ample, and with room for 3 entries only so that most warps keep their planes)
+    for extra, qwords in ((0, 0), (ops.STEP_GENERAL_KERNEL, 0), (0, 2 + 2 * (nn // 120 + 1024)), (0, 2 + 2 * 3)):
         dS2, dacc, dmx = _dev(prev.astype(np.uint8)), _dev(acc), _dev(mx)
         Tout = torch.full((nn,), -7.0, device="cuda")
         S1o = torch.empty(nn, device="cuda")
+        queue = torch.full((qwords,), 12345, device="cuda", dtype=torch.int32) if qwords else None
+        l0 = ops.LAUNCHES
         ops.level_step(props, grid, _dev(T0), _dev(S1), Tout, 1e-5, src=(tx, ty, tz, coef), n_substrate=nsub,
                        flags=ops.STEP_SKIP_FACES | ops.STEP_CLAMP | ops.STEP_WRITE_S1 | ops.STEP_WRITE_S2 |
                        ops.STEP_ACCUM | ops.STEP_FUSED_FLUX | extra,
-                       S1_out=S1o, S2_out=dS2, S2_prev=dS2, accum=dacc, max_accum=dmx, z_chunk=z_chunk)
+                       S1_out=S1o, S2_out=dS2, S2_prev=dS2, accum=dacc, max_accum=dmx, z_chunk=z_chunk, bk_queue=queue)
         torch.cuda.synchronize()
+        if qwords and nx >= 62:  # the fast kernel took the call: step + queue kernel, which leaves the header zeroed
+            assert ops.LAUNCHES - l0 == 2 and int(queue[0]) == 0 and int(queue[1]) == 0
         outs.append([t.cpu().numpy() for t in (Tout, S1o, dS2, dacc, dmx)])
+    for k in range(5):  # the queue changes who does the bookkeeping, not a single bit of any output
+        assert np.array_equal(outs[2][k], outs[0][k]) and np.array_equal(outs[3][k], outs[0][k])
     for T, S1o, s2, a, m in outs:
         assert np.array_equal(s2.astype(bool), S2)
         assert np.array_equal(m, mx_ref)

@@ -314,6 +314,16 @@ def run_gomelt_single(args):
         line["example_json"] = example_json_run()
     except Exception as exc:
         line["example_json"] = {"error": repr(exc)}
+    try:  # BASELINE.json configs[3] at full size (50 M-node Level 1, three layers): wall-s per sim-s through the driver
+        import torch
+
+        torch.cuda.empty_cache()
+        from bench_tools.run_config4 import run as config4_run
+
+        line["config4_full_size"] = config4_run()
+        torch.cuda.empty_cache()
+    except Exception as exc:
+        line["config4_full_size"] = {"error": repr(exc)}
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_sample()
     print(json.dumps(line))

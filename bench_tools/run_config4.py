@@ -1,0 +1,78 @@
+"""BASELINE.json configs[3] at full size: a multi-layer build with powder-layer activation, convection + radiation +
+evaporation surface terms and a 50 M-node part-scale level (Level 1 800 x 400 x 155 elements, h = 0.2 mm: 50.1 M nodes;
+Level 2 / Level 3 = the example's 100 x 100 x 10-element windows at 0.04 / 0.02 mm; Level 0 = 8001 x 4001 x 21 state
+nodes) through the drop-in driver on cuda:0.  Three layers x two short tracks, a pause after every layer that reaches
+the Level-1-only mode (the layer change then re-interpolates the part-scale field, rotates S1_storage, shifts Level 0).
+Parity of this control path is checked on its down-scaled twin (tests/test_driver.py: two_layers vs the oracle and the
+reference driver's golden run); this script reports what the full size costs.
+
+    python bench_tools/run_config4.py            -> one JSON object
+"""
+import importlib
+import json
+import os
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+L1_ELEMENTS = [800, 400, 155]
+
+
+def config4_input(tmp, layers=3):
+    with open(os.path.join(ROOT, "examples", "example.json")) as fh:
+        inp = json.load(fh)
+    inp["Level1"]["elements"] = list(L1_ELEMENTS)
+    inp["Level1"]["bounds"] = {"x": [0, 160.0], "y": [0, 80.0], "z": [-28.0, 3.0]}
+    # the windows of the example, placed in the middle of the plate
+    inp["Level2"]["bounds"] = {"x": [78.0, 82.0], "y": [38.0, 42.0], "z": [-0.4, 0.0]}
+    inp["Level3"]["bounds"] = {"x": [79.0, 81.0], "y": [39.0, 41.0], "z": [-0.2, 0.0]}
+    inp["properties"]["laser_center"] = [80.0, 40.0, 0.0, 0, 0, 0, 0]
+    g = os.path.join(tmp, "config4.gcode")
+    with open(g, "w") as fh:
+        for k in range(1, layers + 1):
+            z = 0.04 * k
+            fh.write(f"G0 X80.0 Y40.0 Z{z:.2f}\nG1 X80.5 Y40.0 Z{z:.2f}\nG0 X80.5 Y40.1 Z{z:.2f}\nG1 X80.0 Y40.1 Z{z:.2f}\n")
+    inp["nonmesh"].update(save_path=tmp + "/", toolpath=os.path.join(tmp, "toolpath.txt"), gcode=g, use_txt=0,
+                          wait_time=10, dwell_time=2e-2, dwell_time_multiplier=8, subcycle_num_L2=5, subcycle_num_L3=5,
+                          record_step=100000, info_T=0, output_files=0)
+    return inp
+
+
+def run(layers=3):
+    import numpy as np
+    import torch
+
+    import gomelt_b200 as gm
+
+    drv = importlib.import_module("gomelt_b200.driver")
+    drv.go_melt(config4_input(tempfile.mkdtemp(), 1), write_final=False)   # warm-up: module / kernel loading, allocator
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    t0 = time.time()
+    res = drv.go_melt(config4_input(tempfile.mkdtemp(), layers), write_final=False)
+    torch.cuda.synchronize()
+    total = time.time() - t0
+    L = res["Levels"]
+    nn1, nn3 = int(L[1]["nn"]), int(L[3]["nn"])
+    c = res["counts"]
+    # Level-1 sweeps: 2 per stepGOMELT, 2 per subcycleGOMELT, 1 per dwell row
+    l1_sweeps = 2 * c["stepGOMELT"] + 2 * c["subcycleGOMELT"] + c["stepGOMELTDwellTime"]
+    out = {"workload": f"Level 1 {L1_ELEMENTS[0]} x {L1_ELEMENTS[1]} x {L1_ELEMENTS[2]} elements ({nn1} nodes), windows of the "
+                       f"example ({nn3} nodes each), {layers} layers x 2 tracks + pauses, powder-layer activation, all surface terms",
+           "wall_s": res["wall_seconds"], "wall_s_with_setup": total, "sim_s": res["sim_seconds"],
+           "wall_s_per_sim_s": res["wall_seconds"] / res["sim_seconds"], "toolpath_rows": res["time_inc"], "counts": c,
+           "level1_sweeps": l1_sweeps, "level1_DOF_updates": l1_sweeps * nn1,
+           "level1_DOF_updates_per_wall_s": l1_sweeps * nn1 / res["wall_seconds"],
+           "max_T_K": {f"L{i}": float(L[i]["T0"].max()) for i in (1, 2, 3)},
+           "min_T_K": {f"L{i}": float(L[i]["T0"].min()) for i in (1, 2, 3)},
+           "finite": bool(all(torch.isfinite(L[i]["T0"]).all() for i in (1, 2, 3))),
+           "active_planes_at_the_end": int(np.sum(np.asarray(L[1]["node_coords"][2]) <= 0.04 * layers + 1e-5)),
+           "peak_device_memory_GB": torch.cuda.max_memory_allocated() / 1e9}
+    return out
+
+
+if __name__ == "__main__":
+    print(json.dumps(run(int(sys.argv[1]) if len(sys.argv) > 1 else 3)))

@@ -131,6 +131,7 @@ class Hier(C.Structure):
         ("L0_S1", C.c_void_p), ("L0_S2", C.c_void_p),
         ("L0_nx", C.c_int32), ("L0_ny", C.c_int32), ("L0_nz", C.c_int32),
         ("l0_ix", C.c_void_p), ("l0_iy", C.c_void_p), ("l0_iz", C.c_void_p),
+        ("l0p_ix", C.c_void_p), ("l0p_iy", C.c_void_p), ("l0p_iz", C.c_void_p), ("l0p_n", C.c_int32 * 3),
         ("bc5", C.c_float * 5),
         ("nz_active_L1", C.c_int32),
         ("L1_spare", C.c_void_p),

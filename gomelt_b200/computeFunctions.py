@@ -507,6 +507,14 @@ def _hier(Levels, Shapes, tmp_ne_nn, substrate, properties, N2=1, N3=1, windows=
         i3 = _index3(L0["overlapNodes"])
         h.l0_ix, h.l0_iy, h.l0_iz = (t.data_ptr() for t in i3)
         keep.append(i3)
+        # Level-0 S2 is zero outside the index set of the last scatter into THIS tensor: clear that set, not the grid
+        prev = getattr(ws, "l0_prev", None)
+        if prev is not None and prev[0] == L0["S2"].data_ptr():
+            h.l0p_ix, h.l0p_iy, h.l0p_iz = (t.data_ptr() for t in prev[1])
+            for dd in range(3):
+                h.l0p_n[dd] = int(prev[1][dd].numel())
+            keep.append(prev[1])
+        ws.l0_prev = (L0["S2"].data_ptr(), i3)
         need = ops.hier_work_floats(h, N2, N3)
     else:
         need = 0 if spare is not None else int(L1["nn"])

@@ -101,6 +101,24 @@ __global__ void accum_single_step_kernel(const float* __restrict__ T3, const uin
         acc[g] = an;
     }
 }
+// dst[ix[i] + iy[j] * bnx + iz[k] * bnx * bny] = 0 over a tensor-product index set (one block row per (j, k) line)
+__global__ void box_zero_u8_kernel(uint8_t* __restrict__ dst, const int* __restrict__ ix, const int* __restrict__ iy,
+                                   const int* __restrict__ iz, int nx, int ny, int nz, int bnx, int bny) {
+    for (int line = blockIdx.x; line < ny * nz; line += gridDim.x) {
+        const int j = line % ny, k = line / ny;
+        uint8_t* d = dst + (long long)iy[j] * bnx + (long long)iz[k] * bnx * bny;
+        for (int i = threadIdx.x; i < nx; i += blockDim.x) d[ix[i]] = 0;
+    }
+}
+// x = max(x, lo) on the node box [b0, b0 + bn) of an (nx, ny, nz) array
+__global__ void box_clamp_min_kernel(float* __restrict__ x, int nx, int ny, int b0x, int b0y, int b0z, int bnx, int bny, int bnz,
+                                     float lo) {
+    for (int line = blockIdx.x; line < bny * bnz; line += gridDim.x) {
+        const int j = line % bny, k = line / bny;
+        float* d = x + ((long long)(b0z + k) * ny + (b0y + j)) * nx + b0x;
+        for (int i = threadIdx.x; i < bnx; i += blockDim.x) d[i] = fmaxf(d[i], lo);
+    }
+}
 inline int blocks_for(long long n) {
     long long b = (n + 255) / 256;
     const long long cap = 8LL * sm_count();
@@ -235,8 +253,40 @@ int scatter_L0(const Ctx& c) {
     const gomelt_hier_t& h = *c.h;
     const gomelt_grid_t& g = h.L3.grid;
     GM_TRY(gomelt_box_copy(h.L3.S1, h.L0_S1, 4, h.l0_ix, h.l0_iy, h.l0_iz, g.nx, g.ny, g.nz, h.L0_nx, h.L0_ny, 1, c.stream));
-    if (cudaMemsetAsync(h.L0_S2, 0, (size_t)h.L0_nx * h.L0_ny * h.L0_nz, c.st) != cudaSuccess) return check_launch("scatter_L0");
+    // cF:2391: Level-0 S2 = 0 everywhere, then the window.  The only nodes that can be non-zero are the ones the previous
+    // call scattered: with their index set given, clear those instead of the whole state grid (672 MB at config-4 size)
+    if (h.l0p_ix && h.l0p_iy && h.l0p_iz && h.l0p_n[0] > 0 && h.l0p_n[1] > 0 && h.l0p_n[2] > 0) {
+        const long long lines = (long long)h.l0p_n[1] * h.l0p_n[2];
+        const long long cap = 16LL * sm_count();
+        box_zero_u8_kernel<<<(int)(lines < cap ? lines : cap), 256, 0, c.st>>>(h.L0_S2, h.l0p_ix, h.l0p_iy, h.l0p_iz, h.l0p_n[0],
+                                                                              h.l0p_n[1], h.l0p_n[2], h.L0_nx, h.L0_ny), count_launch();
+        GM_TRY(check_launch("scatter_L0"));
+    } else if (cudaMemsetAsync(h.L0_S2, 0, (size_t)h.L0_nx * h.L0_ny * h.L0_nz, c.st) != cudaSuccess) {
+        return check_launch("scatter_L0");
+    }
     return gomelt_box_copy(h.L3.S2, h.L0_S2, 1, h.l0_ix, h.l0_iy, h.l0_iz, g.nx, g.ny, g.nz, h.L0_nx, h.L0_ny, 1, c.stream);
+}
+
+// max(T_amb, .) on the Level-1 nodes that Level 2 can see (the parent cells under the window, one node wider): what the
+// predictor pass needs of the clamp of cF:2360 - its Level-1 field is only prolonged / injected there and then discarded
+int clamp_l1_box(const Ctx& c, float* T1) {
+    const gomelt_hier_t& h = *c.h;
+    const gomelt_grid_t& g = h.L1.grid;
+    const int dims[3] = {g.nx, g.ny, g.nz};
+    int lo[3], n[3];
+    for (int d = 0; d < 3; ++d) {
+        int a = h.L2L1.cell0[d] - 1, b = h.L2L1.cell0[d] + h.L2L1.ncell[d] + 1;
+        a = a < 0 ? 0 : a;
+        b = b > dims[d] - 1 ? dims[d] - 1 : b;
+        lo[d] = a;
+        n[d] = b - a + 1;
+        if (n[d] < 1) return 0;
+    }
+    const long long lines = (long long)n[1] * n[2];
+    const long long cap = 16LL * sm_count();
+    box_clamp_min_kernel<<<(int)(lines < cap ? lines : cap), 128, 0, c.st>>>(T1, g.nx, g.ny, lo[0], lo[1], lo[2], n[0], n[1], n[2],
+                                                                              c.T_amb), count_launch();
+    return check_launch("clamp_l1_box");
 }
 
 int copy_f32(const Ctx& c, float* dst, const float* src, long long n) {
@@ -349,7 +399,10 @@ extern "C" int gomelt_step_f32(const gomelt_props_t* props, const gomelt_hier_t*
         // predictor interior and only the faces change
         if (pass == 0) GM_TRY(k1(c, L3, L3.T0, L3.S1, w.T3a, dt, nullptr, w.tables3, coef3, F_CHILD | GOMELT_STEP_CLAMP));
         GM_TRY(faces(c, c.a2, w.T2a, nullptr, 1.f, 0.f, L3, w.T3a, true));
-        GM_TRY(gomelt_clamp_min_f32(T1n, n1, c.T_amb, stream));
+        // (predictor: only the box under Level 2 is looked at again; with a slab-decomposed Level 1 the field is a mirror of
+        // that box in both passes and the slabs clamp themselves)
+        if (pass == 0 || h->l1_solve) GM_TRY(clamp_l1_box(c, T1n));
+        else GM_TRY(gomelt_clamp_min_f32(T1n, n1, c.T_amb, stream));
         GM_TRY(gomelt_clamp_min_f32(w.T2a, n2, c.T_amb, stream));
         if (pass == 0) {
             // getBothNewTprimes cF:2102-2132, then computeCoarseTprimeMassTerm_jax cF:1396-1474

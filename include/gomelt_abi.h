@@ -393,6 +393,10 @@ typedef struct gomelt_hier {
     uint8_t         *L0_S2;
     int32_t          L0_nx, L0_ny, L0_nz;
     const int32_t   *l0_ix, *l0_iy, *l0_iz; /* the Level-3 window's nodes in Level 0 (lengths = Level-3 nx, ny, nz)    */
+    const int32_t   *l0p_ix, *l0p_iy, *l0p_iz; /* NULL, or the index set the PREVIOUS stepper call scattered Level-3 S2 to:
+                                              the only Level-0 S2 entries that can be non-zero (cF:2391 zeroes the grid
+                                              before every scatter) - cleared instead of the whole state grid           */
+    int32_t          l0p_n[3];
     float            bc5[5];               /* Level-1 Dirichlet values y-, y+, x-, x+, z-                              */
     int32_t          nz_active_L1;         /* active Level-1 planes (tmp_ne_nn, cF:495-517)                            */
     float           *L1_spare;             /* [nn1] second Level-1 temperature buffer: the new Level-1 field is left

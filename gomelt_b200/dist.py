@@ -34,7 +34,7 @@ the rank that owns the top active plane of the first layer; transfers stay corre
 import numpy as np
 
 from . import _lib, ops
-from .slab import Level1Slab, local_extent, partition_planes
+from .slab import Level1Slab, local_extent, partition_active_planes
 
 F32 = np.float32
 
@@ -131,7 +131,11 @@ class Level1Dist:
         nx, ny, nz = (int(v) for v in L1["nodes"])
         self.nodes = (nx, ny, nz)
         self.plane = nx * ny
-        self.parts = partition_planes(nz, self.world)
+        # slabs balance the planes that are active when the build starts (those up to the first layer); the planes above
+        # the powder bed go to the last rank on top of its share (they cost a store per node until the build reaches them)
+        z1 = np.asarray(L1["node_coords"][2], F32)
+        active0 = int((z1 <= F32(properties.get("layer_height", 0.0)) + F32(1e-5)).sum())
+        self.parts = partition_active_planes(nz, active0, self.world)
         self.extents = [local_extent(q, self.world, *self.parts[q]) for q in range(self.world)]  # (g0, nzl, zb, ze)
         self.props = _lib.make_props(properties)
         self.T_amb = float(F32(properties["T_amb"]))
@@ -146,7 +150,7 @@ class Level1Dist:
         else:
             self.tr, symmetric = None, False
         self.slab = Level1Slab(gm, self.props, self.nodes, L1["h"], self.rank, self.world, self.bc5, device=self.device,
-                               symmetric=bool(symmetric))
+                               symmetric=bool(symmetric), parts=self.parts)
         if self.world > 1 and not self.slab.symmetric and self.tr.backend == "gloo":
             self.slab.transport = self.tr  # ghost planes through the staged transport as well
         self.slab.T.fill_(self.T_amb)

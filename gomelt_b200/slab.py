@@ -42,6 +42,16 @@ def partition_planes(nz, world):
     return out
 
 
+def partition_active_planes(nz, nz_active, world):
+    """Plane ranges that balance the ACTIVE planes [0, nz_active): the planes above the powder bed cost a store per
+    node and no stencil, so they all go to the last rank on top of its share (layer activation, cF:495-517: a z-slab
+    decomposition of all nz planes would leave the upper ranks idle until the build reaches them)."""
+    nz_active = max(min(int(nz_active), nz), world)
+    parts = partition_planes(nz_active, world)
+    parts[-1] = (parts[-1][0], nz)
+    return parts
+
+
 def local_extent(rank, world, k0, k1):
     """(first stored global plane, stored plane count, z_begin, z_end) of a rank's local array."""
     lo = 1 if rank > 0 else 0
@@ -78,13 +88,14 @@ class Level1Slab:
     vector and the clamp (the Level-1 sweeps of stepGOMELT / subcycleGOMELT, cF:2172-2185, 2813-2854)."""
 
     def __init__(self, gm, props, nodes, h, rank, world, bc5, nz_active=None, n_substrate=0, device=None,
-                 symmetric=False, fused=True):
+                 symmetric=False, fused=True, parts=None):
         self.gm, self.ops, self.props = gm, gm.ops, props
         self.rank, self.world = rank, world
         nx, ny, nz = (int(v) for v in nodes)
         self.nodes_global = (nx, ny, nz)
         self.plane = nx * ny
-        self.k0, self.k1 = partition_planes(nz, world)[rank]
+        parts = list(parts) if parts is not None else partition_planes(nz, world)
+        self.k0, self.k1 = parts[rank]
         self.g0, self.nzl, self.zb, self.ze = local_extent(rank, world, self.k0, self.k1)
         self.grid = gm._lib.make_grid((nx, ny, self.nzl), h)
         self.bc5 = list(bc5)
@@ -98,7 +109,6 @@ class Level1Slab:
 
             # one symmetric allocation of two buffers, sized for the largest slab so that every rank's layout is
             # the same (buffer b of rank q starts at ptrs[q] + 4 * b * nmax), followed by the counter block
-            parts = partition_planes(nz, world)
             # (rounded up to 128 bytes: K1's TMA plane ring wants 16-byte aligned field pointers for every buffer)
             self._nmax = -(-self.plane * (max(b - a for a, b in parts) + 2) // 32) * 32
             self._nbuf = 2

@@ -180,3 +180,17 @@ def test_slab_sweeps_match_single_domain(tmp_path, world):
     assert got.shape == ref.shape
     # the slab-local oracle sums element contributions in a different order at slab edges: f32 round-off only
     assert np.max(np.abs(got - ref) / np.abs(ref)) < 2e-6
+
+
+def test_active_plane_partition_balances_the_powder_bed():
+    """dist.py cuts the slabs over the planes that are active when the build starts; the planes above the powder bed
+    (a store per node, no stencil) ride on the last rank."""
+    from gomelt_b200.slab import partition_active_planes, partition_planes
+
+    for nz, act, world in ((156, 141, 8), (31, 22, 4), (7, 5, 3), (40, 40, 4), (9, 2, 4)):
+        parts = partition_active_planes(nz, act, world)
+        assert parts[0][0] == 0 and parts[-1][1] == nz and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+        assert all(b > a for a, b in parts)
+        active = [max(0, min(b, max(act, world)) - a) for a, b in parts]
+        assert max(active) - min(active) <= 1   # the active planes are balanced
+    assert partition_active_planes(40, 40, 4) == partition_planes(40, 4)

@@ -179,7 +179,9 @@ static bool try_launch_v3(StepParams& sp, int nch, cudaStream_t st) {
             else GM_V3(V3_L3_SUB);
             break;
         case V3_L3_SUB2: {
-            const bool queue = sp.bkq != nullptr && sp.bkq_cap > 0 && gridDim_fits_u16(sp);
+            // (only where the launch fills the GPU: on a small window the second launch costs more than the tail it removes)
+            const long long tiles = (long long)((sp.nx - 2 + 2 * K1_TX - 1) / (2 * K1_TX)) * ((sp.ny - 2 + RY - 1) / RY) * nch;
+            const bool queue = sp.bkq != nullptr && sp.bkq_cap > 0 && gridDim_fits_u16(sp) && (tiles >= 4LL * sm_count() || sp.bkq_force);
             if (!queue) sp.bkq = nullptr;
             else if (sp.bkq_reset && cudaMemsetAsync(sp.bkq, 0, 8, st) != cudaSuccess) return false;
             if (sp.S1out == sp.S1) GM_V3(V3_L3_SUB2 | K1F_S1INPLACE);
@@ -355,7 +357,8 @@ extern "C" int gomelt_level_step_f32(const gomelt_props_t* props, const gomelt_s
     sp.hsync = a->halo_sync; sp.hsync_lo = a->halo_sync_lo; sp.hsync_hi = a->halo_sync_hi;
     sp.bkq = a->bk_queue;
     sp.bkq_cap = (a->bk_queue && a->bk_queue_words > 2) ? (unsigned)((a->bk_queue_words - 2) / 2) : 0u;
-    sp.bkq_reset = a->bk_queue_keep ? 0 : 1;
+    sp.bkq_reset = (a->bk_queue_keep & 1) ? 0 : 1;
+    sp.bkq_force = (a->bk_queue_keep & 2) ? 1 : 0;
     if (sp.hsync) {
         if ((a->peer_lo != nullptr) != (a->halo_sync_lo != nullptr) || (a->peer_hi != nullptr) != (a->halo_sync_hi != nullptr) ||
             !(a->flags & GOMELT_STEP_BC_CONST)) {
@@ -387,6 +390,19 @@ extern "C" int gomelt_level_step_f32(const gomelt_props_t* props, const gomelt_s
         sp.feat = f;
     }
     sp.zchunk = a->z_chunk > 0 ? a->z_chunk : (zend - zbeg);
+    if (a->z_chunk <= 0) {
+        // Small grids (the example's levels: 6 .. 50 tiles) are a handful of warps that each march the whole column, one
+        // dependent plane after the other: cut the march into z-chunks (bit-identical results; a chunk re-reads one plane)
+        // until there are about two warps per SM, at least 4 planes per chunk.
+        const long long tiles = (long long)((g.nx - 2 + 2 * K1_TX - 1) / (2 * K1_TX)) * ((g.ny - 2 + 3) / 4);
+        const int planes = zend - zbeg;
+        const long long want = 2LL * sm_count();
+        if (tiles > 0 && tiles < want && planes >= 8) {
+            long long nch = (want + tiles - 1) / tiles;
+            if (nch > planes / 4) nch = planes / 4;
+            if (nch > 1) sp.zchunk = (int)((planes + nch - 1) / nch);
+        }
+    }
     if (any_src && sp.zchunk > K1_SRCZ_MAX) sp.zchunk = K1_SRCZ_MAX;  // the chunk's z-factors live in shared memory
     if ((sp.feat & (K1F_S2OUT | K1F_ACCUM)) && sp.zchunk > 62) sp.zchunk = 62;  // v3 keeps a 64-bit mask of hot planes per chunk
     return launch_step(sp, (cudaStream_t)stream);

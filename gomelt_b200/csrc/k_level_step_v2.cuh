@@ -66,6 +66,7 @@ struct StepParams {
     unsigned* bkq;         // hot-plane work queue of the melt-time bookkeeping (gomelt_step_args_t.bk_queue) or nullptr
     unsigned bkq_cap;      // its capacity in entries
     int bkq_reset;         // zero its header before the step (0: the previous sweep left it zeroed)
+    int bkq_force;         // use the queue on small grids too (tests)
     // v3 normalisation: stiffness modes divided by s = lambda'[2], masses by cdt * s, loads by s (so that
     // T_new = T + (rr/s - KT/s) / (mnode/(cdt s)) needs neither the lambda'[2] nor the cdt multiply)
     float n_ca0, n_ca1, n_cmushy, n_cfluid, n_inv_s, n_wq;

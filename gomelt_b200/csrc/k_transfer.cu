@@ -118,8 +118,9 @@ __global__ void interp3_kernel(const InterpParams p) {
     const Ax1 X = ax1_of(p.sx, g.hx, p.tx[i]);
     const int k = blockIdx.z;
     const Ax1 Z = ax1_of(p.sz, g.hz, p.tz[k]);
-    const int j1 = min(p.nty, (int)(blockIdx.y + 1) * ROWS3);
-    for (int j = blockIdx.y * ROWS3; j < j1; ++j) {
+    const int rpb = (p.nty + (int)gridDim.y - 1) / (int)gridDim.y;   // rows per block: ROWS3, or 1 on small grids (rows_per_block)
+    const int j1 = min(p.nty, (int)(blockIdx.y + 1) * rpb);
+    for (int j = blockIdx.y * rpb; j < j1; ++j) {
         const Ax1 Y = ax1_of(p.sy, g.hy, p.ty[j]);
         const float acc = tri_eval<BLEND>(p.u, p.u2, p.alpha, p.beta, g, X, Y, Z);
         const size_t o = ((size_t)k * p.nty + j) * p.ntx + i;
@@ -316,7 +317,8 @@ __global__ void box_copy_kernel(const T* __restrict__ src, T* __restrict__ dst, 
     // blockIdx.y / .z = window row / plane (launched that way when ny, nz <= 65535), else a flat grid-stride loop
     if (gridDim.y > 1 || gridDim.z > 1) {
         const int k = blockIdx.z;
-        for (int j = blockIdx.y * ROWS3; j < min(ny, (int)(blockIdx.y + 1) * ROWS3); ++j) {
+        const int rpb = (ny + (int)gridDim.y - 1) / (int)gridDim.y;
+        for (int j = blockIdx.y * rpb; j < min(ny, (int)(blockIdx.y + 1) * rpb); ++j) {
             const long long gb = (long long)iy[j] * big_nx + (long long)iz[k] * big_nx * big_ny;
             const long long tb = ((long long)k * ny + j) * nx;
             for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x) {
@@ -1245,8 +1247,9 @@ __global__ void shift_window_kernel(const ShiftParams p) {
         Xm = ax1_of(p.mx, gm.hx, x);
         Zm = ax1_of(p.mz, gm.hz, z);
     }
-    const int j1 = min(p.nty, (int)(blockIdx.y + 1) * ROWS3);
-    for (int j = blockIdx.y * ROWS3; j < j1; ++j) {
+    const int rpb = (p.nty + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int j1 = min(p.nty, (int)(blockIdx.y + 1) * rpb);
+    for (int j = blockIdx.y * rpb; j < j1; ++j) {
         const float y = p.ty[j];
         const size_t w = ((size_t)k * p.nty + j) * p.ntx + i;
         const float tp = tri_eval<false>(p.Tpo, nullptr, 1.f, 0.f, go, Xo, ax1_of(p.oy, go.hy, y), Zo);
@@ -1256,6 +1259,14 @@ __global__ void shift_window_kernel(const ShiftParams p) {
         p.Tp_new[w] = tp;
         p.T_new[w] = __fadd_rn(t1, rest);
     }
+}
+
+// Row groups of the 3-D launch forms (blockIdx.y): ROWS3 rows per block on large grids; one row per block where that
+// would leave the GPU with fewer than ~4 blocks per SM (the example's 101 x 101 x 11-node windows: the rows of a block run
+// one after the other, each with its chain of dependent loads).
+static inline int row_groups(int nx_blocks, int ny, int nz) {
+    const long long blocks = (long long)nx_blocks * ((ny + ROWS3 - 1) / ROWS3) * nz;
+    return blocks >= 4LL * sm_count() ? (ny + ROWS3 - 1) / ROWS3 : ny;
 }
 
 static inline int grid_for(long long n, int threads) {
@@ -1300,7 +1311,7 @@ extern "C" int gomelt_interp_f32(const gomelt_interp_args_t* a, void* stream) {
     const long long src_nn = (long long)a->src[0].n * a->src[1].n * a->src[2].n;
     if (!a->faces_only && !a->map_x && a->ntz <= 65535 && src_nn < 2000000000LL) {
         const int threads = a->ntx >= 256 ? 256 : (a->ntx >= 128 ? 128 : 64);
-        const dim3 grid((a->ntx + threads - 1) / threads, (a->nty + ROWS3 - 1) / ROWS3, a->ntz);
+        const dim3 grid((a->ntx + threads - 1) / threads, row_groups((a->ntx + threads - 1) / threads, a->nty, a->ntz), a->ntz);
         if (a->u2) interp3_kernel<true><<<grid, threads, 0, (cudaStream_t)stream>>>(p), count_launch();
         else interp3_kernel<false><<<grid, threads, 0, (cudaStream_t)stream>>>(p), count_launch();
     } else {
@@ -1365,7 +1376,7 @@ extern "C" int gomelt_box_copy(const void* src, void* dst, int32_t elem_size, co
     const long long total = (long long)nx * ny * nz;
     cudaStream_t st = (cudaStream_t)stream;
     const bool g3 = nz <= 65535 && (ny > ROWS3 || nz > 1);
-    const dim3 grid = g3 ? dim3((nx + 255) / 256, (ny + ROWS3 - 1) / ROWS3, nz) : dim3(grid_for(total, 256));
+    const dim3 grid = g3 ? dim3((nx + 255) / 256, row_groups((nx + 255) / 256, ny, nz), nz) : dim3(grid_for(total, 256));
     if (elem_size == 4)
         box_copy_kernel<float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, ix, iy, iz, nx, ny,
                                                      nz, big_nx, big_ny, scatter), count_launch();
@@ -1606,7 +1617,7 @@ extern "C" int gomelt_shift_window_f32(const gomelt_shift_args_t* a, void* strea
         set_error("gomelt_shift_window_f32: target grid too large (ntz <= 65535)");
         return GOMELT_E_SIZE;
     }
-    shift_window_kernel<<<dim3((a->ntx + 255) / 256, (a->nty + ROWS3 - 1) / ROWS3, a->ntz), 256, 0, (cudaStream_t)stream>>>(p),
+    shift_window_kernel<<<dim3((a->ntx + 255) / 256, row_groups((a->ntx + 255) / 256, a->nty, a->ntz), a->ntz), 256, 0, (cudaStream_t)stream>>>(p),
         count_launch();
     return check_launch("gomelt_shift_window_f32");
 }

@@ -30,7 +30,7 @@ def _chk_f32(t, n, name):
 
 def level_step(props, grid, T0, S1, T_out, dt, *, rhs=None, src=None, topflux=None, nz_active=None,
                n_substrate=0, flags=0, bc5=None, S1_out=None, S2_out=None, S2_prev=None, accum=None,
-               max_accum=None, z_chunk=0, z_range=None, peer_lo=None, peer_hi=None, halo=None, bk_queue=None):
+               max_accum=None, z_chunk=0, z_range=None, peer_lo=None, peer_hi=None, halo=None, bk_queue=None, bk_queue_force=False):
     """K1 (gomelt_level_step_f32): one explicit sweep of one level.  ``src`` = (tx, ty, tz, coef).
     ``peer_lo`` / ``peer_hi`` = raw device addresses (int) of the z-neighbours' ghost planes in peer-mapped
     memory.  ``halo`` = (sync, sync_lo, sync_hi, seq): the fused halo protocol of gomelt_abi.h (raw addresses of this
@@ -70,6 +70,7 @@ def level_step(props, grid, T0, S1, T_out, dt, *, rhs=None, src=None, topflux=No
         a.halo_seq = int(seq)
     if bk_queue is not None:  # int32 / uint32 scratch: the hot-plane queue of the melt-time bookkeeping (gomelt_abi.h)
         a.bk_queue, a.bk_queue_words = bk_queue.data_ptr(), int(bk_queue.numel())
+        a.bk_queue_keep = 2 if bk_queue_force else 0
     _lib.check(lib.gomelt_level_step_f32(C.byref(props), C.byref(a), _lib.stream_ptr()), "gomelt_level_step_f32")
     _count()
     return T_out

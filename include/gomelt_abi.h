@@ -129,9 +129,11 @@ typedef struct gomelt_step_args {
      * (60 x 4-node tile, plane) that is hot: nn / 120 + 1024 entries always suffice.  NULL: everything inside the step. */
     uint32_t     *bk_queue;
     int64_t       bk_queue_words;
-    int32_t       bk_queue_keep;  /* 0: the call zeroes the queue's two header words first; 1: the caller guarantees they
-                                   * are zero - every call that uses the queue leaves them zeroed (saves a memset node
-                                   * per sweep inside a block of substeps) */
+    int32_t       bk_queue_keep;  /* bit 0 clear: the call zeroes the queue's two header words first; set: the caller
+                                   * guarantees they are zero - every call that uses the queue leaves them zeroed (saves a
+                                   * memset node per sweep inside a block of substeps).  Bit 1: use the queue whatever the
+                                   * grid size (by default only launches that fill the GPU use it: on a small window the
+                                   * second launch costs more than the tail it removes) */
 } gomelt_step_args_t;
 
 int gomelt_level_step_f32(const gomelt_props_t *props, const gomelt_step_args_t *args, void *stream);

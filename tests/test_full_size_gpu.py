@@ -253,3 +253,42 @@ def test_projection_march_vs_tile_at_full_size(gm, example_props, ratio):
 
     want = -(1.0 / dt) * float((mean8(rc3) * mean8(dA)).sum()) * hf ** 3
     assert abs(float(m1.double().sum()) - want) <= 2e-5 * abs(want), (float(m1.double().sum()), want)
+
+
+def test_melt_time_work_queue_at_full_size(gm, example_props):
+    """The corrector-substep shape (SKIP_FACES + WRITE_S2 + ACCUM, in place) on the 10.26 M-node window with one melt pool:
+    with the hot-plane work queue (what the steppers pass; used by default at this size) every output equals the
+    in-kernel bookkeeping bit for bit, and S2 / accum / max_accum equal the closed form."""
+    import torch
+
+    ops = gm.ops
+    P = cF.SetupProperties(example_props)
+    props = gm._lib.make_props(P)
+    nx, ny, nz = L3_NODES
+    nn = nx * ny * nz
+    grid = gm._lib.make_grid(L3_NODES, (H3, H3, H3))
+    T0, S1 = _fields(torch, L3_NODES, 3, hot=2600.0)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    prev = (torch.rand(nn, device="cuda", generator=g) > 0.5).to(torch.uint8)
+    acc = torch.rand(nn, device="cuda", generator=g) * 1e-3
+    mx = torch.rand(nn, device="cuda", generator=g) * 1e-3
+    tx, ty, tz = (torch.rand(n, device="cuda", generator=g) for n in L3_NODES)
+    outs = []
+    for queue in (None, torch.zeros(2 + 2 * (nn // 120 + 1024), device="cuda", dtype=torch.int32)):
+        dS2, dacc, dmx, dS1 = prev.clone(), acc.clone(), mx.clone(), S1.clone()
+        Tout = torch.full((nn,), -7.0, device="cuda")   # (the step leaves the Dirichlet faces alone)
+        l0 = ops.LAUNCHES
+        ops.level_step(props, grid, T0, dS1, Tout, 1e-5, src=(tx, ty, tz, 1e-3), n_substrate=2 * nx * ny,
+                       flags=ops.STEP_SKIP_FACES | ops.STEP_CLAMP | ops.STEP_WRITE_S1 | ops.STEP_WRITE_S2 | ops.STEP_ACCUM |
+                       ops.STEP_FUSED_FLUX, S1_out=dS1, S2_out=dS2, S2_prev=dS2, accum=dacc, max_accum=dmx, bk_queue=queue)
+        torch.cuda.synchronize()
+        assert ops.LAUNCHES - l0 == (1 if queue is None else 2)
+        outs.append((Tout, dS1, dS2, dacc, dmx))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    S2 = T0 >= float(np.float32(P["T_liquidus"]))
+    assert 100 < int(S2.sum()) < nn // 50   # one pool
+    reset = acc * ((prev == 0) & S2)
+    assert torch.equal(outs[1][2].bool(), S2)
+    assert torch.equal(outs[1][4], torch.maximum(reset, mx))
+    assert torch.equal(outs[1][3], (acc + torch.where(S2, torch.full_like(acc, 1e-5), torch.zeros_like(acc))) - reset)

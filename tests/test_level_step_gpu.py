@@ -517,7 +517,7 @@ def test_fast_kernel_melt_time_bookkeeping_has_one_owner_per_node(gm, example_pr
         ops.level_step(props, grid, _dev(T0), _dev(S1), Tout, 1e-5, src=(tx, ty, tz, coef), n_substrate=nsub,
                        flags=ops.STEP_SKIP_FACES | ops.STEP_CLAMP | ops.STEP_WRITE_S1 | ops.STEP_WRITE_S2 |
                        ops.STEP_ACCUM | ops.STEP_FUSED_FLUX | extra,
-                       S1_out=S1o, S2_out=dS2, S2_prev=dS2, accum=dacc, max_accum=dmx, z_chunk=z_chunk, bk_queue=queue)
+                       S1_out=S1o, S2_out=dS2, S2_prev=dS2, accum=dacc, max_accum=dmx, z_chunk=z_chunk, bk_queue=queue, bk_queue_force=True)
         torch.cuda.synchronize()
         if qwords and nx >= 62:  # the fast kernel took the call: step + queue kernel, which leaves the header zeroed
             assert ops.LAUNCHES - l0 == 2 and int(queue[0]) == 0 and int(queue[1]) == 0

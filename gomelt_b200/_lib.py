@@ -156,6 +156,7 @@ class SubstepsArgs(C.Structure):
         ("faces_n", C.c_float),
         ("T_last", C.POINTER(C.c_void_p)),
         ("bk_queue", C.c_void_p), ("bk_queue_words", C.c_int64),
+        ("step_events", C.c_void_p),
         ("faces_scratch", C.c_void_p),
     ]
 

@@ -67,7 +67,9 @@ extern "C" int gomelt_l3_substeps_f32(const gomelt_props_t* props, const gomelt_
         s.bk_queue = a->bk_queue;
         s.bk_queue_words = a->bk_queue_words;
         s.bk_queue_keep = i > 0 ? 1 : 0;   // (the first substep zeroes the header, every sweep leaves it zeroed)
+        if (a->step_events) cudaEventRecord((cudaEvent_t)a->step_events[2 * i], (cudaStream_t)stream);
         rc = gomelt_level_step_f32(props, &s, stream);
+        if (a->step_events) cudaEventRecord((cudaEvent_t)a->step_events[2 * i + 1], (cudaStream_t)stream);
         if (rc) return rc;
         if (compact_faces) {
             const float alpha = (float)(i + 1) / a->faces_n;  // cF:3386-3387, float32 like the traced scalars

@@ -193,7 +193,7 @@ def faces_scratch(grid, device):
 
 
 def l3_substeps(props, grid, coords, rows, T_in, T_a, T_b, S1, tables, *, S1_in=None, n_substrate=0, flags=0,
-                S2=None, accum=None, max_accum=None, faces=None, compact_faces=True):
+                S2=None, accum=None, max_accum=None, faces=None, compact_faces=True, step_events=None):
     """gomelt_l3_substeps_f32: the inner scan of subcycleGOMELT (cF:3367-3412 / 3530-3590) as one call.
     ``rows`` = host float32 array [n, 7] of toolpath rows; ``faces`` = None or
     (parent_coords, parent_new, parent_old, fN3, clamp_min).  Returns the tensor (T_a or T_b) that holds the
@@ -229,6 +229,13 @@ def l3_substeps(props, grid, coords, rows, T_in, T_a, T_b, S1, tables, *, S1_in=
         a.faces_n = float(fN)
         if compact_faces and pold is not None and n > 1:  # parents interpolated once per block, blended per substep
             a.faces_scratch = faces_scratch(grid, T_a.device).data_ptr()
+    ev = None
+    if step_events is not None:  # 2 n torch.cuda.Event(enable_timing=True): recorded around every fused level step
+        torch = _lib.require_cuda()
+        for e in step_events:
+            e.record()           # (creates the handle; re-recorded inside the call)
+        ev = (C.c_void_p * (2 * n))(*[C.c_void_p(int(e.cuda_event)) for e in step_events])
+        a.step_events = C.cast(ev, C.c_void_p)
     last = C.c_void_p(0)
     a.T_last = C.pointer(last)
     _lib.check(lib.gomelt_l3_substeps_f32(C.byref(props), C.byref(a), _lib.stream_ptr()), "gomelt_l3_substeps_f32")

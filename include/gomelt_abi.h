@@ -342,6 +342,9 @@ typedef struct gomelt_substeps_args {
     float       **T_last;         /* HOST out: buffer holding the newest temperature (may be NULL)            */
     uint32_t     *bk_queue;       /* NULL, or the scratch of gomelt_step_args_t.bk_queue (used by the ACCUM substeps)   */
     int64_t       bk_queue_words;
+    void * const *step_events;    /* NULL, or HOST array of 2 n cudaEvent_t: recorded on `stream` right before / after the
+                                     fused level step of every substep (measurement: the kernel's duration as it runs
+                                     inside the block, without a caller's issue path between the records)             */
     float        *faces_scratch;  /* NULL, or device scratch [2 * gomelt_faces_count(nx, ny, nz)]: the two parent
                                      fields are interpolated at the face nodes ONCE per call (gomelt_faces_gather_f32)
                                      and every substep blends them (gomelt_faces_blend_f32) instead of

@@ -382,8 +382,29 @@ def run_e2e_hostbuffers(blk, K):
         pipe.drain()
         out[name] = K * N3 * nn / (time.perf_counter() - t0)
         del pipe
+    # What a user of the drop-in does instead (the reference keeps Levels on the device between jitted calls): the state
+    # stays resident, a step's inputs are its toolpath rows (host -> kernel arguments), its result the monitor the driver
+    # reads back (printLevelMaxMin gm:473-474: min / max / non-finite count of the field, one fused reduction)
+    mm = torch.empty(3, device="cuda")
+    host_mm = torch.empty(3).pin_memory()
+    for _ in range(2):
+        blk.block()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(K):
+        cur = blk.block()
+        gm.ops.minmax(cur, out=mm)
+        host_mm.copy_(mm, non_blocking=True)
+        torch.cuda.synchronize()   # the monitor value is needed before the next block is issued
+    resident = K * N3 * nn / (time.perf_counter() - t0)
     return {"value": out["pipelined"], "unit": "DOF-updates/s", "h2d_bytes_per_step": 8 * nn,
             "d2h_bytes_per_step": 8 * nn, "serial_value": out["serial"],
+            "resident_state": {"value": resident, "unit": "DOF-updates/s", "h2d_bytes_per_step": 4 * 7 * N3,
+                               "d2h_bytes_per_step": 12,
+                               "api": "state device-resident as in the drop-in driver: per step the N3 toolpath rows from "
+                                      "the host, the block through gomelt_l3_substeps_f32, and the min / max monitor "
+                                      "(gomelt_minmax_f32) read back to pinned host memory before the next step is issued",
+                               "monitor_min_max_nonfinite": [float(v) for v in host_mm]},
             "api": "gomelt_b200.hostpipe.HostBlockPipeline.submit: upload T0,S1 (pinned host); N3 substeps through "
                    "gomelt_l3_substeps_f32; download T,S1 - two steps in flight on three streams (serial_value: one)"}
 

@@ -214,6 +214,12 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
     dist_on = hasattr(cf, "distOf") and cf.distOf(Levels) is not None
     worker = dist_on and cf.isWorker(Levels)
     batch_dwell = bool(graphs) and hasattr(cf, "dwellRows") and not dist_on
+    if dist_on and Nonmesh["layer_num"] > 0:
+        raise RuntimeError("restart from a checkpoint (nonmesh.layer_num > 0) is not supported with a slab-decomposed "
+                           "Level 1: checkpoints hold the whole part-scale field (run the restart on one GPU)")
+    if dist_on and any(k in hooks for k in ("on_record", "on_checkpoint", "on_layer_state")):
+        raise RuntimeError("file-output hooks see the laser owner's Level-1 MIRROR (valid under the windows only) in a "
+                           "distributed run: only on_info / on_final are supported; the assembled field is returned")
     nn0 = int(Levels[0]["nn"])
     accum_time, max_accum_time = (None, None) if worker else (xp.zeros(nn0), xp.zeros(nn0))
     move_hist = [0, 0, 0]

@@ -7,7 +7,8 @@ inside a 120 x 120 x 30-element Level 1 (h = 0.2 mm), Level 0 = 1201 x 1201 x 81
     gather / scatter of the melt-time windows (gm:448-455);
   * one *single step* = moveEverything + stepGOMELT (cF:2304-2397) + the melt-time update (gm:339-357).
 
-Timed with CUDA events over whole calls (device-resident state, host issue included); the per-kernel table comes from
+Timed with CUDA events over whole calls (device-resident state, host issue included; the median call is reported, every call listed);
+the per-kernel table comes from
 a CUPTI trace of one block and one step (torch.profiler sees every kernel of the process).  Returns a dict for the
 bench line; run as a script it prints it.
 """
@@ -119,15 +120,21 @@ def run(props_in, peaks_gbs, blocks=5, warm=2):
             fn()
         torch.cuda.synchronize()
         l0 = gm.ops.LAUNCHES
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
         t = time.perf_counter()
-        e0.record()
-        for _ in range(n):
+        evs[0].record()
+        for i in range(n):
             fn()
-        e1.record()
+            evs[i + 1].record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) * 1e-3 / n, (time.perf_counter() - t) / n, (gm.ops.LAUNCHES - l0) / n
+        wall = (time.perf_counter() - t) / n
+        each = sorted(evs[i].elapsed_time(evs[i + 1]) * 1e-3 for i in range(n))
+        per_call.append([round(1e3 * v, 3) for v in each])
+        # the median call: a call that lands on a first-time allocation of the caching allocator (a new window position
+        # brings a new 41 MB cell-sum buffer) or a host hiccup takes several times longer and would own the mean
+        return each[n // 2], wall, (gm.ops.LAUNCHES - l0) / n
 
+    per_call = []
     # heat the window up first (a few steps with the laser on), so that the melt pool exists in what is timed
     for _ in range(3):
         step()
@@ -141,7 +148,7 @@ def run(props_in, peaks_gbs, blocks=5, warm=2):
         "subcycle_block": {
             "what": "moveEverything + subcycleGOMELT (one native call: 50 L3 + 10 L2 + 2 L1 sweeps, projections, "
                     "getNewTprime, faces, bookkeeping) + gather / scatter of the melt-time windows",
-            "ms": blk_s * 1e3, "host_wall_ms": blk_wall * 1e3, "lib_launches": blk_launch,
+            "ms": blk_s * 1e3, "ms_each_call_sorted": per_call[0], "host_wall_ms_mean": blk_wall * 1e3, "lib_launches": blk_launch,
             "L3_DOF_updates_per_s": 2 * N2 * N3 * nn[3] / blk_s,
             "all_levels_DOF_updates_per_s": (2 * N2 * N3 * nn[3] + 2 * N2 * nn[2] + 2 * nn[1]) / blk_s,
             "algorithmic_GBps": (2 * N2 * N3 * nn[3] * 16 + 2 * N2 * nn[2] * 20 + 2 * nn[1] * 16) / blk_s / 1e9,
@@ -151,7 +158,7 @@ def run(props_in, peaks_gbs, blocks=5, warm=2):
         "single_step": {
             "what": "moveEverything + stepGOMELT (one native call: 2 x (L1 + L2 solves, faces), 1 L3 solve, 6 projections, "
                     "4 getNewTprime) + melt-time update",
-            "ms": stp_s * 1e3, "host_wall_ms": stp_wall * 1e3, "lib_launches": stp_launch,
+            "ms": stp_s * 1e3, "ms_each_call_sorted": per_call[1], "host_wall_ms_mean": stp_wall * 1e3, "lib_launches": stp_launch,
             "wall_s_per_sim_s": stp_s / DT,
         },
     }

@@ -296,6 +296,25 @@ def _pair_cells(fine, parent):
     return hit
 
 
+class _CellSum:
+    """Lazily allocated, size-shared scratch [ncell * 8] of gomelt_project_f32 (``.data_ptr()`` like a tensor)."""
+    _pool = {}
+
+    def __init__(self, n):
+        self.n = int(n)
+
+    def tensor(self):
+        t = _CellSum._pool.get(self.n)
+        if t is None:
+            if len(_CellSum._pool) > 8:
+                _CellSum._pool.clear()
+            t = _CellSum._pool[self.n] = _torch().empty(self.n, device="cuda", dtype=_torch().float32)
+        return t
+
+    def data_ptr(self):
+        return self.tensor().data_ptr()
+
+
 def _pair_cells_build(fine, parent):
     torch = _torch()
     g = F32(0.57735026918962576)
@@ -325,8 +344,10 @@ def _pair_cells_build(fine, parent):
         e1 = np.clip(np.floor((xq1 - xc[0]) / hc).astype(np.int64), 0, xc.size - 2)
         tab = np.stack([xc[ec + 1] - xq0, xq0 - xc[ec], xc[e1 + 1] - xq1, xq1 - xc[e1]], axis=1).astype(F32)
         wtab.append(_CACHE.get(tab.reshape(-1), np.float32))
-    cellsum = torch.empty(ncell[0] * ncell[1] * ncell[2] * 8, device="cuda", dtype=torch.float32)
-    return {"cell0": cell0, "ncell": ncell, "first": first, "hint": hint, "cellsum": cellsum, "wtab": wtab, "rmax": rmax,
+    # (the per-cell scratch of a stand-alone projection is shared by size: the steppers carve theirs from the work block,
+    # and a cached grouping per window position must not pin 41 MB each at C2 size)
+    return {"cell0": cell0, "ncell": ncell, "first": first, "hint": hint, "cellsum": _CellSum(ncell[0] * ncell[1] * ncell[2] * 8),
+            "wtab": wtab, "rmax": rmax,
             "off": off,
             "hf": [float(F32(v)) for v in fine["h"]], "hc": [float(F32(v)) for v in parent["h"]],
             "fine": _coords(fine["node_coords"]), "parent": _coords(parent["node_coords"])}

@@ -369,16 +369,19 @@ def run_e2e_hostbuffers(blk, K):
                             else torch.as_tensor(src).clone().pin_memory())
     hT, hS = [pin(blk.T0_host), pin(blk.T0_host)], [pin(blk.S1_host), pin(blk.S1_host)]
     oT, oS = [pin(), pin()], [pin(), pin()]
+    pin8 = lambda src=None: (torch.empty(nn, dtype=torch.uint8).pin_memory() if src is None
+                             else torch.as_tensor(src).to(torch.uint8).pin_memory())
+    hS8, oS8 = [pin8(blk.S1_host), pin8(blk.S1_host)], [pin8(), pin8()]
     out = {}
-    for name, depth in (("serial", 1), ("pipelined", 2)):
+    for name, depth, sin, sout in (("serial", 1, hS, oS), ("pipelined", 2, hS, oS), ("pipelined_u8_state", 2, hS8, oS8)):
         pipe = gm.hostpipe.HostBlockPipeline(gm.ops, blk.props, blk.grid, blk.coords, depth=depth, n_rows=N3,
                                              n_substrate=blk.n_sub, flags=blk.step_flags, faces=blk.faces)
         for i in range(2):  # warm-up (allocator, first-touch of the pinned buffers)
-            pipe.submit(hT[i % 2], hS[i % 2], blk._rows(), oT[i % 2], oS[i % 2])
+            pipe.submit(hT[i % 2], sin[i % 2], blk._rows(), oT[i % 2], sout[i % 2])
         pipe.drain()
         t0 = time.perf_counter()
         for i in range(K):
-            pipe.submit(hT[i % 2], hS[i % 2], blk._rows(), oT[i % 2], oS[i % 2])
+            pipe.submit(hT[i % 2], sin[i % 2], blk._rows(), oT[i % 2], sout[i % 2])
         pipe.drain()
         out[name] = K * N3 * nn / (time.perf_counter() - t0)
         del pipe
@@ -397,16 +400,19 @@ def run_e2e_hostbuffers(blk, K):
         host_mm.copy_(mm, non_blocking=True)
         torch.cuda.synchronize()   # the monitor value is needed before the next block is issued
     resident = K * N3 * nn / (time.perf_counter() - t0)
-    return {"value": out["pipelined"], "unit": "DOF-updates/s", "h2d_bytes_per_step": 8 * nn,
-            "d2h_bytes_per_step": 8 * nn, "serial_value": out["serial"],
+    return {"value": out["pipelined_u8_state"], "unit": "DOF-updates/s", "h2d_bytes_per_step": 5 * nn,
+            "d2h_bytes_per_step": 5 * nn, "serial_value": out["serial"], "f32_state_value": out["pipelined"],
+            "f32_state_bytes_per_step_each_way": 8 * nn,
             "resident_state": {"value": resident, "unit": "DOF-updates/s", "h2d_bytes_per_step": 4 * 7 * N3,
                                "d2h_bytes_per_step": 12,
                                "api": "state device-resident as in the drop-in driver: per step the N3 toolpath rows from "
                                       "the host, the block through gomelt_l3_substeps_f32, and the min / max monitor "
                                       "(gomelt_minmax_f32) read back to pinned host memory before the next step is issued",
                                "monitor_min_max_nonfinite": [float(v) for v in host_mm]},
-            "api": "gomelt_b200.hostpipe.HostBlockPipeline.submit: upload T0,S1 (pinned host); N3 substeps through "
-                   "gomelt_l3_substeps_f32; download T,S1 - two steps in flight on three streams (serial_value: one)"}
+            "api": "gomelt_b200.hostpipe.HostBlockPipeline.submit: upload T0 (f32) and S1 (uint8 on the host and on the "
+                   "wire: the state of a window level is 0 / 1; widened to the kernels' float32 on the device) from pinned "
+                   "host memory; N3 substeps through gomelt_l3_substeps_f32; download T, S1 - two steps in flight on three "
+                   "streams (f32_state_value: S1 as float32 on the wire; serial_value: that with one step in flight)"}
 
 
 def read_peaks():

@@ -9,6 +9,11 @@ Every block still makes the one C-ABI call subcycleGOMELT makes (``gomelt_l3_sub
 
 All host tensors must be pinned (``torch.Tensor.pin_memory``); results are valid after ``drain()`` or after the
 event returned by ``submit`` has completed.
+
+The state S1 of a window level is 0 / 1 by construction (it is re-thresholded by every computeStateProperties, cF:2589;
+fractional values exist on Level 1 only), so the host side may hold it as ``uint8``: a quarter of the bytes on the
+wire, widened / narrowed on the device (the kernels keep the reference's float32 state).  ``submit`` takes either
+dtype for ``hS1`` / ``oS1``.
 """
 import torch
 
@@ -21,7 +26,8 @@ class HostBlockPipeline:
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
         mk = lambda: torch.empty(self.nn, dtype=torch.float32, device=dev)
-        self.slots = [{"Ta": mk(), "Tb": mk(), "S1": mk(), "free": None} for _ in range(depth)]
+        mk8 = lambda: torch.empty(self.nn, dtype=torch.uint8, device=dev)
+        self.slots = [{"Ta": mk(), "Tb": mk(), "S1": mk(), "S8": None, "mk8": mk8, "free": None} for _ in range(depth)]
         self.tables = torch.empty(n_rows * (grid.nx + grid.ny + grid.nz), dtype=torch.float32, device=dev)
         self.k = 0
 
@@ -34,7 +40,13 @@ class HostBlockPipeline:
             self.s_in.wait_event(slot["free"])
         with torch.cuda.stream(self.s_in):
             slot["Ta"].copy_(hT, non_blocking=True)
-            slot["S1"].copy_(hS1, non_blocking=True)
+            if hS1.dtype == torch.uint8:   # bytes on the wire, float32 state on the device
+                if slot["S8"] is None:
+                    slot["S8"] = slot["mk8"]()
+                slot["S8"].copy_(hS1, non_blocking=True)
+                slot["S1"].copy_(slot["S8"])
+            else:
+                slot["S1"].copy_(hS1, non_blocking=True)
             up = torch.cuda.Event()
             up.record()
         self.s_run.wait_event(up)
@@ -47,7 +59,13 @@ class HostBlockPipeline:
         self.s_out.wait_event(ran)
         with torch.cuda.stream(self.s_out):
             oT.copy_(T, non_blocking=True)
-            oS1.copy_(slot["S1"], non_blocking=True)
+            if oS1.dtype == torch.uint8:
+                if slot["S8"] is None:
+                    slot["S8"] = slot["mk8"]()
+                slot["S8"].copy_(slot["S1"])   # exact: the state is 0.0 / 1.0
+                oS1.copy_(slot["S8"], non_blocking=True)
+            else:
+                oS1.copy_(slot["S1"], non_blocking=True)
             done = torch.cuda.Event()
             done.record()
         slot["free"] = done

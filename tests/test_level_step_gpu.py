@@ -595,10 +595,14 @@ def test_fast_kernel_in_place_state_on_a_mostly_cold_field(gm, example_props, el
     assert np.array_equal(Sc, S1ref)
 
 
-def test_host_block_pipeline_equals_device_blocks(gm, example_props):
+@pytest.mark.parametrize("state", ["float32", "uint8"])
+def test_host_block_pipeline_equals_device_blocks(gm, example_props, state):
     """hostpipe.HostBlockPipeline (host buffers, two blocks in flight on three streams) returns, for every block,
-    exactly what the same gomelt_l3_substeps_f32 call returns on device-resident fields."""
+    exactly what the same gomelt_l3_substeps_f32 call returns on device-resident fields - with the state as float32 or
+    as bytes on the host side and on the wire."""
     import torch
+
+    sdt = torch.float32 if state == "float32" else torch.uint8
 
     ops = gm.ops
     elements = (75, 23, 7)
@@ -619,8 +623,8 @@ def test_host_block_pipeline_equals_device_blocks(gm, example_props):
             rows[i] = (0.5 + 0.05 * j + 0.01 * i, 0.23, 0.0, 1, 1, 1e-5, 285.0)
         Tj = (T0 * (0.6 + 0.1 * j)).astype(np.float32)
         Sj = (rng.random(lv["nn"]) > 0.4).astype(np.float32)
-        hT, hS = torch.as_tensor(Tj).pin_memory(), torch.as_tensor(Sj).pin_memory()
-        oT, oS = torch.empty(lv["nn"]).pin_memory(), torch.empty(lv["nn"]).pin_memory()
+        hT, hS = torch.as_tensor(Tj).pin_memory(), torch.as_tensor(Sj).to(sdt).pin_memory()
+        oT, oS = torch.empty(lv["nn"]).pin_memory(), torch.empty(lv["nn"], dtype=sdt).pin_memory()
         pipe.submit(hT, hS, rows, oT, oS)
         jobs.append((rows, Tj, Sj, oT, oS))
     pipe.drain()
@@ -631,4 +635,4 @@ def test_host_block_pipeline_equals_device_blocks(gm, example_props):
         last = ops.l3_substeps(props, grid, coords, rows, A, B, A, S, tables, n_substrate=nsub, flags=flags)
         torch.cuda.synchronize()
         assert np.array_equal(oT.numpy(), last.cpu().numpy())
-        assert np.array_equal(oS.numpy(), S.cpu().numpy())
+        assert np.array_equal(oS.numpy().astype(np.float32), S.cpu().numpy())

@@ -318,13 +318,35 @@ __global__ void box_copy_kernel(const T* __restrict__ src, T* __restrict__ dst, 
     if (gridDim.y > 1 || gridDim.z > 1) {
         const int k = blockIdx.z;
         const int rpb = (ny + (int)gridDim.y - 1) / (int)gridDim.y;
-        for (int j = blockIdx.y * rpb; j < min(ny, (int)(blockIdx.y + 1) * rpb); ++j) {
-            const long long gb = (long long)iy[j] * big_nx + (long long)iz[k] * big_nx * big_ny;
-            const long long tb = ((long long)k * ny + j) * nx;
-            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x) {
-                if (scatter) dst[gb + ix[i]] = src[tb + i];
-                else dst[tb + i] = src[gb + ix[i]];
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (the 3-D launch covers x with blockIdx.x)
+        if (i >= nx) return;
+        const int xi = ix[i];
+        const long long gz = (long long)iz[k] * big_nx * big_ny;
+        if (rpb == ROWS3) {
+            // a group of ROWS3 rows: all loads of the group in flight before the first store (the copy is latency-bound
+            // otherwise: one element per thread and row)
+            const int j0 = blockIdx.y * ROWS3;
+            T v[ROWS3];
+            long long go[ROWS3];
+#pragma unroll
+            for (int q = 0; q < ROWS3; ++q) {
+                const int j = min(j0 + q, ny - 1);
+                go[q] = (long long)iy[j] * big_nx + gz + xi;
+                v[q] = scatter ? src[((long long)k * ny + j) * nx + i] : src[go[q]];
             }
+#pragma unroll
+            for (int q = 0; q < ROWS3; ++q) {
+                if (j0 + q >= ny) break;
+                if (scatter) dst[go[q]] = v[q];
+                else dst[((long long)k * ny + j0 + q) * nx + i] = v[q];
+            }
+            return;
+        }
+        for (int j = blockIdx.y * rpb; j < min(ny, (int)(blockIdx.y + 1) * rpb); ++j) {
+            const long long gb = (long long)iy[j] * big_nx + gz;
+            const long long tb = ((long long)k * ny + j) * nx;
+            if (scatter) dst[gb + xi] = src[tb + i];
+            else dst[tb + i] = src[gb + xi];
         }
         return;
     }

@@ -341,14 +341,19 @@ def example_json_run():
     res = eager = None
     for _ in range(2):  # the first pass warms up module loading / allocator / kernel images
         eager = gm.driver.go_melt(load_input(tempfile.mkdtemp()), write_final=False, graphs=False)
-    for _ in range(2):
+    walls, best = [], None
+    for _ in range(4):   # host-issue-bound: the fastest of the repeats is reported, all are listed
         l0, g0 = gm.ops.LAUNCHES, gm.ops.GRAPH_LAUNCHES
         res = gm.driver.go_melt(load_input(tempfile.mkdtemp()), write_final=False)
+        walls.append(round(res["wall_seconds"], 4))
+        if best is None or res["wall_seconds"] < best["wall_seconds"]:
+            best = res
+    res = best
     torch.cuda.synchronize()
     same = all(torch.equal(res["Levels"][i]["T0"], eager["Levels"][i]["T0"]) for i in (1, 2, 3))
     return {"workload": "examples/example.json + example.gcode, whole run, device-resident state, no file output; the "
                         "499 rows of the pause replay a CUDA graph of two rows (computeFunctions.dwellRows)",
-            "wall_s": res["wall_seconds"], "sim_s": res["sim_seconds"],
+            "wall_s": res["wall_seconds"], "wall_s_of_every_repeat": walls, "sim_s": res["sim_seconds"],
             "wall_s_per_sim_s": res["wall_seconds"] / res["sim_seconds"], "toolpath_rows": res["time_inc"],
             "counts": res["counts"], "lib_launches": gm.ops.LAUNCHES - l0,
             "kernels_replayed_from_graphs": gm.ops.GRAPH_LAUNCHES - g0,

@@ -74,5 +74,49 @@ def run(layers=3):
     return out
 
 
+def run_distributed(layers=3):
+    """The same run with Level 1 in z-slabs over the ranks of a torchrun launch (one rank per GPU); rank 0 prints."""
+    import torch
+    import torch.distributed as dist
+
+    import gomelt_b200 as gm
+
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    gm.load()
+    cf = gm.computeFunctions
+    drv = importlib.import_module("gomelt_b200.driver")
+    cf.enable_distributed(rank, world)
+    out = None
+    try:
+        drv.go_melt(config4_input(tempfile.mkdtemp(), 1), write_final=False)   # warm-up
+        torch.cuda.synchronize()
+        dist.barrier()
+        res = drv.go_melt(config4_input(tempfile.mkdtemp(), layers), write_final=False)
+        torch.cuda.synchronize()
+        d = cf.distOf(res["Levels"])
+        walls, stats = [None] * world, [None] * world
+        dist.all_gather_object(walls, res["wall_seconds"])
+        dist.all_gather_object(stats, dict(d.stats))
+        owner_stats = stats[d.owner]
+        if rank == 0:
+            out = {"ranks": world, "owner_rank": d.owner, "slabs": d.parts, "wall_s_max_over_ranks": max(walls),
+                   "sim_s": res["sim_seconds"], "wall_s_per_sim_s": max(walls) / res["sim_seconds"], "counts": res["counts"],
+                   "level1_solves": owner_stats["solves"], "boxes": owner_stats["boxes_down"] + owner_stats["boxes_up"],
+                   "box_bytes": owner_stats["bytes"],
+                   "note": "windows on the laser owner, Level 1 (50.1 M nodes) in z-slabs; the pause rows are not graph replays "
+                           "in a distributed run"}
+    finally:
+        cf.disable_distributed()
+        dist.destroy_process_group()
+    return out
+
+
 if __name__ == "__main__":
-    print(json.dumps(run(int(sys.argv[1]) if len(sys.argv) > 1 else 3)))
+    if "--dist" in sys.argv:
+        r = run_distributed()
+        if r is not None:
+            print(json.dumps(r))
+    else:
+        print(json.dumps(run(int(sys.argv[1]) if len(sys.argv) > 1 else 3)))

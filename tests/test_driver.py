@@ -97,6 +97,13 @@ def test_whole_run_matches_oracle(tmp_path, case):
     ref = drv.go_melt(make(str(tmp_path / "cpu")), cf=cF, xp=NumpyArrays(), write_final=False)
     assert got["counts"] == ref["counts"] and got["time_inc"] == ref["time_inc"]
     c = got["counts"]
+    # the schedule computed ahead of the run from the toolpath alone (driver.plan_toolpath) is the one that was executed
+    sc = importlib.import_module("gomelt_b200.schema")
+    plan = drv.plan_toolpath(got["Nonmesh"]["toolpath"], got["Nonmesh"], sc.getStaticSubcycle(got["Nonmesh"]))
+    assert sum(b["rows"] for b in plan) == got["time_inc"]
+    assert sum(b["steps"] for b in plan) == c["stepGOMELT"] and sum(b["dwells"] for b in plan) == c["stepGOMELTDwellTime"]
+    assert sum(b["mode"] == "subcycle" for b in plan) == c["subcycleGOMELT"]
+    assert sum(b["layer_changes"] for b in plan) == c["layers"]
     assert c["stepGOMELT"] > 0 and c["subcycleGOMELT"] > 0 and c["stepGOMELTDwellTime"] > 0
     assert c["layers"] == (2 if case == "two_layers" else 1)
     host = lambda a: a.detach().cpu().numpy() if hasattr(a, "detach") else np.asarray(a)

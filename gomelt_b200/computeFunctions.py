@@ -163,6 +163,26 @@ def gatherL1(Levels, what="T0"):
     return d.gather(d.slab.T if what == "T0" else d.slab.S1)
 
 
+def outputView(Levels, with_storage=False):
+    """What the file-output hooks of a distributed run see (collective; None on the ranks without windows): a shallow
+    copy of ``Levels`` whose Level-1 temperature / state - and, for checkpoints, ``S1_storage`` - are assembled from the
+    slabs on the laser owner instead of its mirrors (which are valid under the windows only)."""
+    d = distOf(Levels)
+    if d is None:
+        return Levels
+    T = d.gather(d.slab.T)
+    S = d.gather(d.slab.S1)
+    rows = [d.gather(d.S1_storage[i].contiguous()) for i in range(d.S1_storage.shape[0])] if with_storage else None
+    if not d.is_owner:
+        return None
+    view = list(Levels)
+    view[1] = dict(Levels[1], T0=T, S1=S)
+    if rows is not None:
+        view[1]["S1_storage"] = _torch().stack(rows) if rows else _torch().zeros((0, T.numel()), device="cuda")
+    view[0] = {k: v for k, v in Levels[0].items() if not k.startswith("_gomelt")}
+    return view
+
+
 def layerShiftL1(Levels, tmp_coords, state_idx, T_amb):
     """gm:215-224 for a slab-decomposed Level 1 (dist.Level1Dist.layer_shift)."""
     distOf(Levels).layer_shift(Levels[1], tmp_coords, state_idx)

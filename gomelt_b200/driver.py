@@ -217,9 +217,18 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
     if dist_on and Nonmesh["layer_num"] > 0:
         raise RuntimeError("restart from a checkpoint (nonmesh.layer_num > 0) is not supported with a slab-decomposed "
                            "Level 1: checkpoints hold the whole part-scale field (run the restart on one GPU)")
-    if dist_on and any(k in hooks for k in ("on_record", "on_checkpoint", "on_layer_state")):
-        raise RuntimeError("file-output hooks see the laser owner's Level-1 MIRROR (valid under the windows only) in a "
-                           "distributed run: only on_info / on_final are supported; the assembled field is returned")
+
+    def call(name, *args, storage=False):
+        """A file-output hook.  In a distributed run the Level-1 fields it sees are assembled from the slabs first (a
+        collective: every rank passes here; the ranks without windows then skip the hook)."""
+        if name not in hooks:
+            return
+        if dist_on:
+            view = cf.outputView(Levels, with_storage=storage)
+            if view is None:
+                return
+            args = (view,) + args[1:]
+        hooks[name](*args)
     nn0 = int(Levels[0]["nn"])
     accum_time, max_accum_time = (None, None) if worker else (xp.zeros(nn0), xp.zeros(nn0))
     move_hist = [0, 0, 0]
@@ -228,8 +237,7 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
     stopped_at_layer_check = False
     tprime_test_done = False
     layer_check = Nonmesh["layer_num"] + Nonmesh["restart_layer_num"]
-    if "on_record" in hooks:  # the initial saveResults(Levels, Nonmesh, 1) of gm:83-84
-        hooks["on_record"](Levels, Nonmesh, int(time_inc / Nonmesh["record_step"]) + 1)
+    call("on_record", Levels, Nonmesh, int(time_inc / Nonmesh["record_step"]) + 1)  # the initial saveResults of gm:83-84
     counts = {"stepGOMELT": 0, "subcycleGOMELT": 0, "stepGOMELTDwellTime": 0, "moveEverything": 0, "layers": 0}
     Shapes = tmp_ne_nn = substrate = None
     nblock = subcycle[0] * subcycle[1]
@@ -312,7 +320,7 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
                         move_vert = True
                         counts["layers"] += 1
                         if not load_chkpt and not worker:
-                            if "on_layer_state" in hooks:  # saveState(Level0) gm:245
+                            if "on_layer_state" in hooks:  # saveState(Level0) gm:245 (Level 0 lives on the owner)
                                 hooks["on_layer_state"](Levels, Nonmesh)
                             accum_time = xp.maximum(accum_time, max_accum_time)
                             if "on_layer_accum" in hooks:  # accum_time<layer_num>.npz gm:253-261, before the shift
@@ -371,8 +379,8 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
                     record_inc += 1
                 if new_checkpoint:
                     Nonmesh["layer_num"] += 1
-                    if "on_checkpoint" in hooks:  # dill dump gm:390-402
-                        hooks["on_checkpoint"](Levels, accum_time, max_accum_time, time_inc, record_inc, Nonmesh)
+                    call("on_checkpoint", Levels, accum_time, max_accum_time, time_inc, record_inc, Nonmesh,
+                         storage=True)  # dill dump gm:390-402
                     if Nonmesh["layer_num"] == layer_check:  # gm:405-406: return right here, no final output
                         stopped_at_layer_check = True
                         break
@@ -402,10 +410,9 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
             t_output += float(laser_all[:, 5].sum(dtype=F32))
             if record_inc >= Nonmesh["record_step"]:
                 record_inc = 0
-                if "on_record" in hooks:  # saveResults gm:467-470
-                    hooks["on_record"](Levels, Nonmesh, int(time_inc / Nonmesh["record_step"]) + 1)
-            if Nonmesh["info_T"] and "on_info" in hooks:  # printLevelMaxMin gm:473-474 (forces a sync)
-                hooks["on_info"](Levels)
+                call("on_record", Levels, Nonmesh, int(time_inc / Nonmesh["record_step"]) + 1)  # saveResults gm:467-470
+            if Nonmesh["info_T"]:  # printLevelMaxMin gm:473-474 (forces a sync)
+                call("on_info", Levels)
             if verbose:
                 tend = time.time()
                 say("%d/%d, Real: %.6f s, Wall: %.2f s, Loop: %5.2f ms, Avg: %5.2f ms/dt"
@@ -418,6 +425,8 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
     if hasattr(xp, "sync"):
         xp.sync()
     wall = time.time() - tstart
+    if not stopped_at_layer_check:  # saveState(Level 0) + saveResultsFinal gm:501-502
+        call("on_final", Levels, Nonmesh)
     L1_full = None
     if dist_on:  # the owner's Level-1 arrays are mirrors of the box under the windows: assemble the part-scale field
         L1_full = cf.gatherL1(Levels)
@@ -427,8 +436,6 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
                     "Nonmesh": Nonmesh, "ne_nn": ne_nn, "dwell_seconds": dwell_count, "worker": True,
                     "stopped_at_layer_check": stopped_at_layer_check}
         Levels[1]["T0"] = L1_full
-    if "on_final" in hooks and not stopped_at_layer_check:  # saveState(Level 0) + saveResultsFinal gm:501-502
-        hooks["on_final"](Levels, Nonmesh)
     if write_final and not stopped_at_layer_check:  # gm:504-516
         np.savez(f"{Nonmesh['save_path']}FinalTemperatureFields", L1T=xp.host(Levels[1]["T0"]),
                  L2T=xp.host(Levels[2]["T0"]), L3T=xp.host(Levels[3]["T0"]))

@@ -112,3 +112,36 @@ def test_one_rank_per_gpu_equals_plain(gm, tmp_path, case):
     os.makedirs(out)
     _spawn(world, out, case, "nccl", False)
     _check(want, out)
+
+
+def test_output_hooks_of_a_distributed_run_see_the_assembled_level1(gm, tmp_path):
+    """Records, checkpoints and the final output of a distributed run go through computeFunctions.outputView: the hooks
+    get the Level-1 temperature / state / S1_storage assembled from the slabs, equal to what the plain run's hooks get."""
+    import torch
+
+    cf = gm.computeFunctions
+    seen = {}
+
+    def hooks(tag):
+        seen[tag] = {"rec": [], "ckpt": [], "final": []}
+        s = seen[tag]
+        return {"on_record": lambda L, N, i: s["rec"].append((i, L[1]["T0"].clone(), L[1]["S1"].clone(), L[3]["T0"].clone())),
+                "on_checkpoint": lambda L, a, m, t, r, N: s["ckpt"].append((t, L[1]["T0"].clone(), L[1]["S1_storage"].clone())),
+                "on_final": lambda L, N: s["final"].append(L[1]["T0"].clone())}
+
+    try:
+        for tag in ("plain", "dist"):
+            (cf.enable_distributed(0, 1) if tag == "dist" else cf.disable_distributed())
+            d = str(tmp_path / tag)
+            os.makedirs(d)
+            gm.driver.go_melt(driver_support.small_two_layer_input(d), write_final=False, hooks=hooks(tag))
+            torch.cuda.synchronize()
+    finally:
+        cf.disable_distributed()
+    a, b = seen["plain"], seen["dist"]
+    assert len(a["rec"]) == len(b["rec"]) > 3 and len(a["ckpt"]) == len(b["ckpt"]) >= 1 and len(a["final"]) == len(b["final"]) == 1
+    for x, y in zip(a["rec"], b["rec"]):
+        assert x[0] == y[0] and all(torch.equal(p, q) for p, q in zip(x[1:], y[1:]))
+    for x, y in zip(a["ckpt"], b["ckpt"]):
+        assert x[0] == y[0] and torch.equal(x[1], y[1]) and torch.equal(x[2], y[2])
+    assert torch.equal(a["final"][0], b["final"][0])

@@ -183,6 +183,35 @@ def outputView(Levels, with_storage=False):
     return view
 
 
+def adoptCheckpoint(Levels, loaded):
+    """Restart of a distributed run (gm:108-129): ``loaded`` = the Levels list of a checkpoint (single-GPU format: whole
+    Level-1 fields; every rank has read it), ``Levels`` = the freshly set-up distributed list.  Every rank cuts its slab
+    (ghost planes included) out of the whole fields, the laser owner keeps the rest, the other ranks drop it."""
+    torch = _torch()
+    d = distOf(Levels)
+    sl = d.slab
+    g0, nzl, _, _ = d.extents[d.rank]
+    lo, hi = g0 * d.plane, (g0 + nzl) * d.plane
+    sl.T.copy_(_f(loaded[1]["T0"])[lo:hi])
+    sl.S1.copy_(_f(loaded[1]["S1"])[lo:hi])
+    st = loaded[1].get("S1_storage")
+    if st is not None and d.S1_storage.shape[0] > 0:
+        d.S1_storage.copy_(_f(st).reshape(d.S1_storage.shape[0], -1)[:, lo:hi])
+    sl.fill_ghosts()   # (collective: restarts the halo protocol on the new field)
+    loaded[0]["_gomelt_dist"] = d
+    loaded[1]["S1_storage"] = None
+    if d.is_owner:
+        loaded[1]["T0"], loaded[1]["S1"] = _f(loaded[1]["T0"]), _f(loaded[1]["S1"])   # the mirrors: valid everywhere now
+    else:
+        for i in (1, 2, 3):
+            loaded[i]["T0"] = loaded[i]["S1"] = loaded[i]["S2"] = None
+        for i in (2, 3):
+            loaded[i]["Tprime0"] = None
+        loaded[0]["S1"] = loaded[0]["S2"] = None
+    torch.cuda.synchronize()
+    return loaded
+
+
 def layerShiftL1(Levels, tmp_coords, state_idx, T_amb):
     """gm:215-224 for a slab-decomposed Level 1 (dist.Level1Dist.layer_shift)."""
     distOf(Levels).layer_shift(Levels[1], tmp_coords, state_idx)

@@ -214,9 +214,6 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
     dist_on = hasattr(cf, "distOf") and cf.distOf(Levels) is not None
     worker = dist_on and cf.isWorker(Levels)
     batch_dwell = bool(graphs) and hasattr(cf, "dwellRows") and not dist_on
-    if dist_on and Nonmesh["layer_num"] > 0:
-        raise RuntimeError("restart from a checkpoint (nonmesh.layer_num > 0) is not supported with a slab-decomposed "
-                           "Level 1: checkpoints hold the whole part-scale field (run the restart on one GPU)")
 
     def call(name, *args, storage=False):
         """A file-output hook.  In a distributed run the Level-1 fields it sees are assembled from the slabs first (a
@@ -251,9 +248,11 @@ def go_melt(solver_input, cf=None, xp=None, hooks=None, verbose=False, write_fin
                                f"Checkpoint{str(Nonmesh['layer_num']).zfill(4)}, but no 'load_checkpoint' hook was given "
                                "(use hooks=output.driver_hooks())")
         say(f"Checkpoint loading for start of Layer {Nonmesh['layer_num']}")
-        Levels, accum_time, max_accum_time, time_inc_loaded, record_inc = hooks["load_checkpoint"](
-            Nonmesh, "cuda" if isinstance(xp, TorchArrays) else None)
-        accum_time, max_accum_time = xp.f32(accum_time), xp.f32(max_accum_time)
+        loaded, accum_time, max_accum_time, time_inc_loaded, record_inc = hooks["load_checkpoint"](
+            Nonmesh, "cuda" if (isinstance(xp, TorchArrays) and not worker) else None)
+        # (a checkpoint holds the whole part-scale field: a distributed run cuts its slabs out of it)
+        Levels = cf.adoptCheckpoint(Levels, loaded) if dist_on else loaded
+        accum_time, max_accum_time = (None, None) if worker else (xp.f32(accum_time), xp.f32(max_accum_time))
         load_chkpt = True
         line_len = len(fh.readline())
         fh.seek(int(time_inc_loaded) * line_len)

@@ -145,3 +145,34 @@ def test_output_hooks_of_a_distributed_run_see_the_assembled_level1(gm, tmp_path
     for x, y in zip(a["ckpt"], b["ckpt"]):
         assert x[0] == y[0] and torch.equal(x[1], y[1]) and torch.equal(x[2], y[2])
     assert torch.equal(a["final"][0], b["final"][0])
+
+
+def test_distributed_restart_from_a_checkpoint_equals_the_uninterrupted_plain_run(gm, tmp_path):
+    """gm:108-129 + 390-411 with a slab-decomposed Level 1: a distributed run stopped at its first checkpoint (written in
+    the single-GPU format from the assembled fields) and restarted - again distributed: every rank cuts its slab out of
+    the checkpoint - ends bit for bit where the uninterrupted plain run ends."""
+    import torch
+
+    cf = gm.computeFunctions
+    out = gm.output
+    hooks = {k: v for k, v in out.driver_hooks().items() if k in ("on_checkpoint", "load_checkpoint", "on_layer_accum")}
+    want = _plain(gm, str(tmp_path / "plain"), "small_two_layer_input")
+    d = str(tmp_path / "split")
+    os.makedirs(d)
+    try:
+        cf.enable_distributed(0, 1)
+        inp = driver_support.small_two_layer_input(d)
+        inp["nonmesh"]["restart_layer_num"] = 1
+        first = gm.driver.go_melt(inp, hooks=hooks, write_final=False)
+        assert first["stopped_at_layer_check"] and os.path.exists(os.path.join(d, "checkpoint", "Checkpoint0001", "header.json"))
+        inp = driver_support.small_two_layer_input(d)
+        inp["nonmesh"].update(layer_num=1, use_txt=1)
+        second = gm.driver.go_melt(inp, hooks=hooks, write_final=False)
+        torch.cuda.synchronize()
+        L = second["Levels"]
+        assert cf.distOf(L) is not None
+        got = {"L1T": L[1]["T0"], "L2T": L[2]["T0"], "L3T": L[3]["T0"], "accum": second["accum_time"], "S1": cf.gatherL1(L, "S1")}
+        for k, t in got.items():
+            assert np.array_equal(t.cpu().numpy(), want[k]), k
+    finally:
+        cf.disable_distributed()

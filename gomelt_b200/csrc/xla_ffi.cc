@@ -130,7 +130,7 @@ const size_t kStep[] = {OFF(gomelt_step_args_t, T0), OFF(gomelt_step_args_t, S1)
                         OFF(gomelt_step_args_t, src_x), OFF(gomelt_step_args_t, src_y), OFF(gomelt_step_args_t, src_z),
                         OFF(gomelt_step_args_t, topflux), OFF(gomelt_step_args_t, T_out), OFF(gomelt_step_args_t, S1_out),
                         OFF(gomelt_step_args_t, S2_out), OFF(gomelt_step_args_t, S2_prev), OFF(gomelt_step_args_t, accum),
-                        OFF(gomelt_step_args_t, max_accum)};
+                        OFF(gomelt_step_args_t, max_accum), OFF(gomelt_step_args_t, bk_queue)};
 const size_t kInterp[] = {AXIS3(gomelt_interp_args_t, src), OFF(gomelt_interp_args_t, u), OFF(gomelt_interp_args_t, u2),
                           OFF(gomelt_interp_args_t, tx), OFF(gomelt_interp_args_t, ty), OFF(gomelt_interp_args_t, tz),
                           OFF(gomelt_interp_args_t, map_x), OFF(gomelt_interp_args_t, map_y), OFF(gomelt_interp_args_t, map_z),
@@ -149,7 +149,8 @@ const size_t kSubsteps[] = {OFF(gomelt_substeps_args_t, x), OFF(gomelt_substeps_
                             OFF(gomelt_substeps_args_t, T_in), OFF(gomelt_substeps_args_t, T_a), OFF(gomelt_substeps_args_t, T_b),
                             OFF(gomelt_substeps_args_t, S1_in), OFF(gomelt_substeps_args_t, S1), OFF(gomelt_substeps_args_t, tables),
                             OFF(gomelt_substeps_args_t, S2), OFF(gomelt_substeps_args_t, accum),
-                            OFF(gomelt_substeps_args_t, max_accum), OFF(gomelt_substeps_args_t, faces_scratch)};
+                            OFF(gomelt_substeps_args_t, max_accum), OFF(gomelt_substeps_args_t, faces_scratch),
+                            OFF(gomelt_substeps_args_t, bk_queue)};
 #define LEVEL_PTRS(L) OFF(gomelt_hier_t, L.x), OFF(gomelt_hier_t, L.y), OFF(gomelt_hier_t, L.z), OFF(gomelt_hier_t, L.T0), \
                       OFF(gomelt_hier_t, L.S1), OFF(gomelt_hier_t, L.Tprime0), OFF(gomelt_hier_t, L.S2)
 #define PAIR_PTRS(P) OFF(gomelt_hier_t, P.first_x), OFF(gomelt_hier_t, P.first_y), OFF(gomelt_hier_t, P.first_z), \
@@ -158,7 +159,9 @@ const size_t kSubsteps[] = {OFF(gomelt_substeps_args_t, x), OFF(gomelt_substeps_
                    OFF(gomelt_hier_t, O.cy), OFF(gomelt_hier_t, O.cz)
 const size_t kHier[] = {LEVEL_PTRS(L1), LEVEL_PTRS(L2), LEVEL_PTRS(L3), PAIR_PTRS(L2L1), PAIR_PTRS(L3L1), PAIR_PTRS(L3L2),
                         OV_PTRS(ov2), OV_PTRS(ov3), OFF(gomelt_hier_t, L0_S1), OFF(gomelt_hier_t, L0_S2), OFF(gomelt_hier_t, l0_ix),
-                        OFF(gomelt_hier_t, l0_iy), OFF(gomelt_hier_t, l0_iz), OFF(gomelt_hier_t, L1_spare), OFF(gomelt_hier_t, work)};
+                        OFF(gomelt_hier_t, l0_iy), OFF(gomelt_hier_t, l0_iz), OFF(gomelt_hier_t, l0p_ix), OFF(gomelt_hier_t, l0p_iy),
+                        OFF(gomelt_hier_t, l0p_iz), OFF(gomelt_hier_t, L1_spare), OFF(gomelt_hier_t, work)};
+const size_t kPatchCopy[] = {OFF(gomelt_ffi_patch_copy_t, src), OFF(gomelt_ffi_patch_copy_t, dst)};
 
 // generic body: A = argument struct type; OFFS = its device-pointer offsets; CALL(frame, args, props, stream) -> rc
 #define GOMELT_HANDLER(NAME, A, OFFS, NEEDS_PROPS, WHAT, CALL)                                              \
@@ -235,6 +238,8 @@ GOMELT_HANDLER(GomeltFacesBlendFfi, gomelt_ffi_faces_blend_t, kFacesBlend, false
                rc = gomelt_faces_blend_f32(a.face_a, a.face_b, a.ntx, a.nty, a.ntz, a.alpha, a.beta, a.has_clamp, a.clamp_min, a.out, st))
 GOMELT_HANDLER(GomeltBoxCopyFfi, gomelt_ffi_box_copy_t, kBoxCopy, false, "gomelt_box_copy",
                rc = gomelt_box_copy(a.src, a.dst, a.elem_size, a.ix, a.iy, a.iz, a.nx, a.ny, a.nz, a.big_nx, a.big_ny, a.scatter, st))
+GOMELT_HANDLER(GomeltPatchCopyFfi, gomelt_ffi_patch_copy_t, kPatchCopy, false, "gomelt_patch_copy_f32",
+               rc = gomelt_patch_copy_f32(a.src, a.sdims, a.slo, a.dst, a.ddims, a.dlo, a.n, st))
 GOMELT_HANDLER(GomeltRank1Ffi, gomelt_ffi_rank1_t, kRank1, false, "gomelt_rank1_f32",
                rc = gomelt_rank1_f32(a.F, a.tx, a.ty, a.tz, a.nx, a.ny, a.nz, a.coef, a.accumulate, st))
 GOMELT_HANDLER(GomeltCoarseSourceTablesFfi, gomelt_ffi_coarse_source_tables_t, kCoarseTables, true, "gomelt_coarse_source_tables_f32",
@@ -278,6 +283,7 @@ extern "C" void* GomeltL3SubstepsFfi(void* call_frame) {
     const float* rows = fr.f32_array("rows", 7 * (size_t)a.substeps.n);
     if (!rows) return fr.fail(XLA_FFI_Error_Code_INVALID_ARGUMENT, fr.err);
     a.substeps.rows = rows;
+    a.substeps.step_events = nullptr;   // host-side measurement hook: not reachable from an XLA computation
     a.substeps.faces = a.has_faces ? &a.faces : nullptr;
     a.substeps.T_last = nullptr;
     void* st = nullptr;
@@ -304,6 +310,8 @@ extern "C" void* GomeltSubcycleFfi(void* call_frame) {
     void* st = nullptr;
     if (XLA_FFI_Error* e = fr.stream(&st)) return e;
     int32_t in_spare = 0;
+    a.hier.l1_solve = nullptr;   // (a host callback: the slab-decomposed drop-in drives the C ABI directly)
+    a.hier.l1_user = nullptr;
     return fr.from_rc(gomelt_subcycle_f32(&props, &a.hier, rows, a.N2, a.N3, a.max_accum, a.accum, &in_spare, st), "gomelt_subcycle_f32");
 }
 extern "C" void* GomeltStepFfi(void* call_frame) {
@@ -321,6 +329,8 @@ extern "C" void* GomeltStepFfi(void* call_frame) {
     void* st = nullptr;
     if (XLA_FFI_Error* e = fr.stream(&st)) return e;
     int32_t in_spare = 0;
+    a.hier.l1_solve = nullptr;   // (a host callback: the slab-decomposed drop-in drives the C ABI directly)
+    a.hier.l1_user = nullptr;
     return fr.from_rc(gomelt_step_f32(&props, &a.hier, row, a.resetmask, &in_spare, st), "gomelt_step_f32");
 }
 extern "C" void* GomeltDwellStepFfi(void* call_frame) {
@@ -334,6 +344,8 @@ extern "C" void* GomeltDwellStepFfi(void* call_frame) {
     void* st = nullptr;
     if (XLA_FFI_Error* e = fr.stream(&st)) return e;
     int32_t in_spare = 0;
+    a.hier.l1_solve = nullptr;   // (a host callback: the slab-decomposed drop-in drives the C ABI directly)
+    a.hier.l1_user = nullptr;
     return fr.from_rc(gomelt_dwell_step_f32(&props, &a.hier, a.dt, &in_spare, st), "gomelt_dwell_step_f32");
 }
 

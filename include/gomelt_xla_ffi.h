@@ -39,6 +39,7 @@ typedef struct { gomelt_grid_t grid; const float *T0; int32_t nz_active, add; fl
 typedef struct { gomelt_grid_t grid; const float *x, *y, *z; float laserP; float *tx, *ty, *tz; } gomelt_ffi_source_tables_t;
 typedef struct { gomelt_grid_t grid; const float *x, *y, *z; int32_t n; float *tables; } gomelt_ffi_source_tables_batch_t;
 typedef struct { const void *src; void *dst; int32_t elem_size; const int32_t *ix, *iy, *iz; int32_t nx, ny, nz, big_nx, big_ny, scatter; } gomelt_ffi_box_copy_t;
+typedef struct { const float *src; int32_t sdims[3], slo[3]; float *dst; int32_t ddims[3], dlo[3], n[3]; } gomelt_ffi_patch_copy_t;
 typedef struct { float *F; const float *tx, *ty, *tz; int32_t nx, ny, nz; float coef; int32_t accumulate; } gomelt_ffi_rank1_t;
 typedef struct { gomelt_axis_t fine[3], parent[3]; float laserP; float *tx, *ty, *tz; } gomelt_ffi_coarse_source_tables_t;
 typedef struct { gomelt_axis_t fine[3], parent[3]; float wq_fine; int32_t n; float *tables, *F; int32_t accumulate; } gomelt_ffi_projected_source_t;
@@ -58,7 +59,8 @@ typedef struct { gomelt_hier_t hier; float dt; } gomelt_ffi_dwell_step_t;
     X(GomeltLevelStepFfi) X(GomeltStatePropsFfi) X(GomeltSurfaceFluxFfi) X(GomeltSourceTablesFfi) X(GomeltSourceTablesBatchFfi) \
     X(GomeltInterpFfi) X(GomeltFacesGatherFfi) X(GomeltFacesBlendFfi) X(GomeltBoxCopyFfi) X(GomeltRank1Ffi) \
     X(GomeltCoarseSourceTablesFfi) X(GomeltProjectedSourceFfi) X(GomeltProjectFfi) X(GomeltShiftWindowFfi) X(GomeltClampMinFfi) \
-    X(GomeltMinMaxFfi) X(GomeltAccumSingleStepFfi) X(GomeltL3SubstepsFfi) X(GomeltSubcycleFfi) X(GomeltStepFfi) X(GomeltDwellStepFfi)
+    X(GomeltMinMaxFfi) X(GomeltAccumSingleStepFfi) X(GomeltL3SubstepsFfi) X(GomeltSubcycleFfi) X(GomeltStepFfi) X(GomeltDwellStepFfi) \
+    X(GomeltPatchCopyFfi)
 #define GOMELT_FFI_DECLARE(name) void* name(void* call_frame);
 GOMELT_FFI_HANDLERS(GOMELT_FFI_DECLARE)
 #undef GOMELT_FFI_DECLARE

@@ -1,6 +1,6 @@
 // Builds XLA_FFI_CallFrames by hand - the way the XLA runtime does - and calls the handlers of libgomelt_sm100.so:
 //   1. registration-time metadata query, non-EXECUTE stages, a malformed frame (error object through the API table);
-//   2. (GPU) GomeltLevelStepFfi, GomeltInterpFfi and GomeltDwellStepFfi against the direct C-ABI calls on the same
+//   2. (GPU) GomeltLevelStepFfi, GomeltInterpFfi, GomeltPatchCopyFfi and GomeltDwellStepFfi against the direct C-ABI calls on the same
 //      inputs, bit for bit, on the stream the fake runtime hands out.
 // usage: ffi_callframe_test [--no-gpu]      exit code 0 = all checks passed
 #include <cuda_runtime.h>
@@ -120,7 +120,7 @@ static gomelt_props_t example_props() {
 static void host_only_checks(const XLA_FFI_Api& api) {
     // 1. metadata query: every handler reports the API version and does nothing else
     for (int i = 0; i < gomelt_xla_ffi_handler_count(); ++i) CHECK(gomelt_xla_ffi_handler_name(i) != nullptr, "handler name %d", i);
-    CHECK(gomelt_xla_ffi_handler_count() == 21, "handler count %d", gomelt_xla_ffi_handler_count());
+    CHECK(gomelt_xla_ffi_handler_count() == 22, "handler count %d", gomelt_xla_ffi_handler_count());
     XLA_FFI_Metadata md;
     memset(&md, 0xff, sizeof md);
     XLA_FFI_Metadata_Extension ext;
@@ -240,6 +240,28 @@ static void gpu_checks(const XLA_FFI_Api& api) {
     {
         auto x = d2h(dO1, mn), y = d2h(dO2, mn);
         CHECK(memcmp(x.data(), y.data(), mn * 4) == 0 && x[mn / 2] >= 500.f, "interp through the FFI differs from the direct call");
+    }
+    // ---- gomelt_patch_copy_f32 (box transfers of the slab-decomposed drop-in) through its handler ----
+    {
+        const int32_t sd[3] = {nx, ny, nz}, lo[3] = {2, 1, 1}, n[3] = {nx - 5, ny - 3, nz - 2};
+        const size_t bn = (size_t)n[0] * n[1] * n[2];
+        float *dP1, *dP2;
+        cudaMalloc(&dP1, bn * 4); cudaMalloc(&dP2, bn * 4);
+        const int32_t zero[3] = {0, 0, 0};
+        CHECK(gomelt_patch_copy_f32(dT0, sd, lo, dP1, n, zero, n, st) == 0, "direct patch copy: %s", gomelt_last_error());
+        FrameBuilder fb;
+        gomelt_ffi_patch_copy_t blob;
+        memset(&blob, 0, sizeof blob);
+        for (int d = 0; d < 3; ++d) { blob.sdims[d] = sd[d]; blob.slo[d] = lo[d]; blob.ddims[d] = n[d]; blob.n[d] = n[d]; }
+        set_slot(blob.src, fb.arg(dT0, XLA_FFI_DataType_F32, nn));
+        set_slot(blob.dst, fb.ret(dP2, XLA_FFI_DataType_F32, bn));
+        fb.attr_array("args", XLA_FFI_DataType_U8, &blob, sizeof blob);
+        XLA_FFI_Error* e = static_cast<XLA_FFI_Error*>(GomeltPatchCopyFfi(fb.build(&api, &ctx, XLA_FFI_ExecutionStage_EXECUTE)));
+        CHECK(e == nullptr, "GomeltPatchCopyFfi: %s", e ? e->msg.c_str() : "");
+        cudaStreamSynchronize(st);
+        auto x = d2h(dP1, bn), y = d2h(dP2, bn);
+        CHECK(memcmp(x.data(), y.data(), bn * 4) == 0 && x[bn / 2] > 100.f, "patch copy through the FFI differs from the direct call");
+        cudaFree(dP1); cudaFree(dP2);
     }
     // ---- stepGOMELTDwellTime as one FFI call (the hierarchy struct, Level 1 only), result left in L1_spare ----
     gomelt_hier_t h;

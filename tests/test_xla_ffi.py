@@ -31,7 +31,7 @@ def _build(tmp_path, gm):
 def test_every_handler_is_exported(gm):
     lib = gm.load()
     names = _handlers()
-    assert len(names) == 21 and lib.gomelt_xla_ffi_available() == 1
+    assert len(names) == 22 and lib.gomelt_xla_ffi_available() == 1
     raw = C.CDLL(gm._lib.lib_path())
     raw.gomelt_xla_ffi_handler_count.restype = C.c_int
     raw.gomelt_xla_ffi_handler_name.restype = C.c_char_p

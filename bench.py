@@ -10,12 +10,23 @@ N = 1  workload "L3-10M": BASELINE.json configs[1] — single laser track, Level
        from the Level-2 parent (assignBCsFine), laser advancing along +x.  metric = Level-3 DOF-updates/s (1 DOF-update = one node advanced one sweep).
 N > 1  workload "L1-slab": BASELINE.json configs[4] — part-scale Level-1 mesh z-slab-decomposed, one
        rank per GPU, dwell sweeps (stepGOMELTDwellTime cF:2617-2664) with a one-plane halo exchange
-       per sweep (boundary planes stored into the neighbours' ghost planes over NVLink peer memory;
-       GOMELT_SLAB_NCCL=1: NCCL send/recv); weak scaling (fixed slab per GPU).  metric = Level-1 DOF-updates/s.
+       per sweep (one C-ABI call = the fused level step + an exchange kernel: boundary planes into the neighbours'
+       ghost planes over NVLink peer memory, release / acquire counters, no NCCL and no barrier launch in the sweep;
+       GOMELT_SLAB_NCCL=1: NCCL send/recv); weak scaling (100 planes of 1001 x 1001 per GPU).  metric = Level-1 DOF-updates/s.
 
-`--impl reference` times the reference algorithm on the host cores: the NumPy float32 oracle
-(oracle/, "restated reference, not JAX/XLA": JAX is not installable here or on the GPU box) on a
-bounded sample of the same workload, one process per core.
+`--impl reference` times the reference algorithm on the host cores: element gather, 8 x 8 apply, scatter-add as
+dense tensor operations on all host threads (oracle/torch_cpu.py, pinned to the NumPy oracle; "restated
+reference, not JAX/XLA": JAX is not installable here or on the GPU box) on the SAME 10 M-node window, a bounded
+number of blocks.
+
+Beyond the contract keys the N = 1 line carries: `roofline` with K1's duration from CUDA events recorded inside the
+native call; `e2e` (host buffers, state as bytes on the wire, three steps in flight) with `f32_state_value`,
+`serial_value` and `resident_state` (state on the device as in the driver, toolpath rows in, monitor out);
+`l1_slab_1gpu` (the N > 1 workload on one GPU); `whole_step` (a whole subcycleGOMELT / stepGOMELT + moveEverything at
+C2 scale with a per-kernel table); `example_json` (config 0 through the driver: wall-s per sim-s, graph replays against
+row by row); `config4_full_size` (config 3 at full size).  Every N > 1 line carries `weak_scaling_efficiency`
+(against the same slab alone), `parity_check` (slab boundaries bit for bit) and `drop_in_parity` (the whole driver on
+N ranks against the plain run, bit for bit).
 """
 import argparse
 import json

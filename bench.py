@@ -525,9 +525,58 @@ def cpu_baseline_sample():
                                             f"oracle (np.add.at scatter)"}}
 
 
+def _torch_cpu_dwell(nodes, sweeps, h=0.2, dt=2e-3):
+    """``sweeps`` Level-1 dwell sweeps (stepGOMELTDwellTime cF:2617-2664) of the reference algorithm on the host threads,
+    on an (nx, ny, nz)-node slab of the N > 1 workload."""
+    import numpy as np
+    import torch
+
+    from oracle import computeFunctions as cF
+    from oracle.torch_cpu import L3SubstepCPU
+    from oracle.util import make_level
+
+    P = cF.SetupProperties(EXAMPLE_PROPS)
+    nx, ny, nz = nodes
+    lv = make_level((nx - 1, ny - 1, nz - 1), ((0.0, (nx - 1) * h), (0.0, (ny - 1) * h), (-(nz - 1) * h, 0.0)))
+    port = L3SubstepCPU(lv, P)
+    nn = lv["nn"]
+    T = torch.full((nn,), float(P["T_amb"]) + 200.0)
+    S1 = torch.ones(nn)
+    port.dwell_step(T[:0].new_full((nn,), float(P["T_amb"]) + 200.0), S1, dt, [float(P["T_amb"])] * 5)   # warm-up
+    t0 = time.perf_counter()
+    for _ in range(sweeps):
+        T = port.dwell_step(T, S1, dt, [float(P["T_amb"])] * 5)
+    return sweeps * nn, time.perf_counter() - t0, torch.get_num_threads()
+
+
+def run_reference_multi(args):
+    """--impl reference under the N > 1 launch: the arm's metric there is Level-1 DOF-updates/s of dwell sweeps, so the
+    CPU arm times dwell sweeps too - a bounded slab of the same grid (1001 x 1001 x 10 nodes) on all host threads."""
+    nodes = (1001, 1001, 10)
+    Kb = max(1, min(args.steps, 3))
+    dofs, secs, threads = _torch_cpu_dwell(nodes, Kb)
+    value = dofs / secs
+    sample = (f"{Kb} dwell sweep(s) of a {nodes[0]}x{nodes[1]}x{nodes[2]}-node slab of the part-scale grid with the multi-threaded "
+              f"tensor port of the reference algorithm ({threads} threads); the GPU arm sweeps {args.gpus} x 100 planes of the same "
+              "grid.  JAX is not installable on this box.")
+    line = {
+        "impl": "reference", "metric": "Level-1 DOF-updates/s", "value": value, "unit": "DOF-updates/s", "n_gpus": args.gpus,
+        "steps": Kb, "warmup": args.warmup, "ms_per_step": 1e3 * secs / Kb, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "L1-slab dwell sweeps (bounded sample: one 10-plane slab on the host cores)", "sample": sample,
+                   "nodes": nodes[0] * nodes[1] * nodes[2]},
+        "cpu_baseline": {"value": value, "unit": "DOF-updates/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "DOF-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        run_reference_multi(args)
         return
     import multiprocessing as mp
 

@@ -119,3 +119,19 @@ class L3SubstepCPU:
         aT = Me * Te - (self.K0 @ Te) * kbar[None, :]                       # (diag(Me) - Ke) @ T_e
         Tn = (self._scatter_add(aT) + F) / self._scatter_add(Me)
         return torch.clamp_min(Tn, float(self.p["T_amb"])), S1n
+
+    def dwell_step(self, T, S1, dt, bc5, n_substrate=0):
+        """stepGOMELTDwellTime cF:2617-2664 on a part-scale level: surface flux -> properties -> solve (no source, no
+        correction, no clamp) -> the five Dirichlet faces (assignBCs cF:1568-1595: y-, y+, x-, x+, z-; later wins)."""
+        _, k, rc = self.state_properties(T, S1, n_substrate)
+        F = torch.zeros_like(T)
+        F[-self.nx * self.ny:] += self.surface_flux(T)
+        Te = self._gather(T)
+        kbar = self._gather(k).mean(dim=0)
+        mbar = self._gather(rc).mean(dim=0) / float(dt)
+        Me = self.m0[:, None] * mbar[None, :]
+        aT = Me * Te - (self.K0 @ Te) * kbar[None, :]
+        Tn = ((self._scatter_add(aT) + F) / self._scatter_add(Me)).view(self.nz, self.ny, self.nx)
+        Tn[:, 0, :] = float(bc5[0]); Tn[:, -1, :] = float(bc5[1]); Tn[:, :, 0] = float(bc5[2]); Tn[:, :, -1] = float(bc5[3])
+        Tn[0] = float(bc5[4])
+        return Tn.view(-1)

@@ -164,3 +164,30 @@ def test_torch_cpu_port_matches_the_numpy_oracle():
     assert (T0 >= P["T_liquidus"]).sum() > 10
     assert np.array_equal(S1g.numpy(), S1r)
     assert float(np.max(np.abs(got.numpy() - want) / np.abs(want))) <= 1e-5
+
+
+def test_torch_cpu_dwell_step_matches_the_numpy_oracle():
+    """The CPU arm of the N > 1 bench line (oracle/torch_cpu.py dwell_step: stepGOMELTDwellTime cF:2617-2664 as dense
+    tensor operations) against the NumPy oracle's flux -> properties -> solve -> assignBCs on a part-scale grid."""
+    import torch
+
+    from oracle import computeFunctions as cF
+    from oracle.torch_cpu import L3SubstepCPU
+    from oracle.util import make_level, smooth_field
+
+    props_in = {"laser_radius": 0.1, "laser_depth": 0.1, "laser_absorptivity": 0.45, "T_amb": 298.15, "T_solidus": 1533,
+                "T_liquidus": 1609, "h_conv": 1.5e-05, "emissivity": 0.3, "latent_heat_evap": 6457000.0}
+    P = cF.SetupProperties(props_in)
+    lv = make_level((14, 9, 6), ((0.0, 2.8), (0.0, 1.8), (-1.2, 0.0)))
+    rng = np.random.default_rng(4)
+    T0 = smooth_field(lv, rng)
+    S1 = (rng.random(lv["nn"]) > 0.3).astype(np.float32)
+    dt = 2e-3
+    bc5 = [301.0, 302.0, 303.0, 304.0, 305.0]
+    _, _, k, rc = cF.computeStateProperties(T0, S1, P, 0)
+    F = cF.computeConvRadBC(lv, T0, lv["ne"], lv["nn"], P, np.zeros(lv["nn"], np.float32))
+    want = cF.solveMatrixFreeFE(lv, lv["nn"], lv["ne"], k, rc, dt, T0, F, 0).reshape(lv["nodes"][2], lv["nodes"][1], lv["nodes"][0])
+    want[:, 0, :] = bc5[0]; want[:, -1, :] = bc5[1]; want[:, :, 0] = bc5[2]; want[:, :, -1] = bc5[3]; want[0] = bc5[4]
+    got = L3SubstepCPU(lv, P, threads=2).dwell_step(torch.from_numpy(T0), torch.from_numpy(S1), dt, bc5).numpy()
+    assert float(np.max(np.abs(got - want.reshape(-1)) / np.abs(want.reshape(-1)))) <= 1e-5
+    assert np.abs(got - T0).max() > 0.1

@@ -9,6 +9,7 @@
 // own float32 formulas (floor((x-x0)/h) cell search, compute3DN cF:1361-1393 products, the +-1e-2
 // validity window), so that cell decisions are identical and values agree to rounding.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -69,7 +70,7 @@ __device__ __forceinline__ Ax1 ax1_of(const AxisView& ax, float h, float x) {
 }
 struct SrcGeom {  // per source level, formed once per thread
     float hx, hy, hz, inv_vol;
-    int nnx, nnxy;
+    int nnx, nnxy, nny;
 };
 __device__ __forceinline__ SrcGeom geom_of(const AxisView& sx, const AxisView& sy, const AxisView& sz) {
     SrcGeom g;
@@ -79,6 +80,7 @@ __device__ __forceinline__ SrcGeom geom_of(const AxisView& sx, const AxisView& s
     g.inv_vol = __fdiv_rn(1.0f, __fmul_rn(__fmul_rn(g.hx, g.hy), g.hz));
     g.nnx = sx.n;
     g.nnxy = sx.n * sy.n;
+    g.nny = sy.n;
     return g;
 }
 template <bool BLEND>
@@ -109,7 +111,9 @@ __device__ __forceinline__ float tri_eval(const float* __restrict__ u, const flo
     return acc;
 }
 
-// full target grid, no index map: blockIdx.y = group of ROWS3 target rows, blockIdx.z = target plane
+// full target grid, no index map: blockIdx.y = group of ROWS3 target rows, blockIdx.z = target plane.  The plain form: every
+// target evaluates all of its weights and loads its 8 parent values (kept as the A/B partner of interp3_march_kernel,
+// GOMELT_TRANSFER_PLAIN=1)
 template <bool BLEND>
 __global__ void interp3_kernel(const InterpParams p) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -130,6 +134,172 @@ __global__ void interp3_kernel(const InterpParams p) {
         else r = __fsub_rn(p.base[o], acc);
         if (p.has_clamp) r = fmaxf(r, p.clamp_min);
         p.out[o] = r;
+    }
+}
+
+// ---- marching form ---------------------------------------------------------------------------------------------------
+// A thread owns one target column and walks ROWSM rows of one target plane.  Three things make it cheaper than the
+// plain form while producing the SAME bits:
+//  * the y part of a row (cell, distances), the z part of the plane and 1 / (hx hy hz) are formed once per block into
+//    shared memory (SrcShared), the x part once per thread; the field the result is combined with (ADD / RSUB) is
+//    requested for all rows before anything else;
+//  * the 8 parent values stay in registers while consecutive rows lie in the same parent cell (r_y - 1 rows out of r_y),
+//    and when the row moves up one cell the upper four become the lower four: 8 / r_y .. 4 / r_y loads per target, not 8;
+//  * for a target inside the parent (every distance >= -1e-4 h) the validity window needs one product: rounding is
+//    monotonic, so max_a N_a = ((max ax * max ay) * max az) * inv_vol bit for bit, and min_a N_a >= -1e-4 holds by
+//    construction.  Distances clamped at 0 beforehand give exactly the zeros the reference's clip(N, 0, 1) gives for
+//    a target a hair outside its cell (x = c[e] - 1 ulp with floor() landing in e: one factor negative -> N <= 0 -> 0;
+//    two such axes at once give N <= 1e-8 instead of 0: seen as 1-ulp differences at ~1e-4 of the nodes when parent and
+//    target have the SAME spacing, never for a coarser parent - tests/test_transfer_gpu.py compares the two forms bit for bit).
+// Targets outside the parent (overhanging windows) take tri_eval as before.  At C2 size (10.3 M targets): T' = child -
+// I(parent) 67.6 -> 57.4 us (ratio 2), 66.4 -> 51.2 us (ratio 5), the blended form 74.6 -> 56.2 us; both forms are bound by
+// instruction issue (71-78 % issue-active), not by DRAM (82 MB in 57 us).
+struct AxC {
+    int e;
+    float c0, c1, mx;  // max(a0, 0), max(a1, 0), max(a0, a1)
+    bool ok;           // inside the parent along this axis
+};
+__device__ __forceinline__ AxC axc_of(const AxisView& ax, float h, float x) {
+    const Ax1 a = ax1_of(ax, h, x);
+    AxC r;
+    r.e = a.e;
+    r.c0 = fmaxf(a.a0, 0.f);
+    r.c1 = fmaxf(a.a1, 0.f);
+    r.mx = fmaxf(a.a0, a.a1);
+    r.ok = fminf(a.a0, a.a1) >= -1e-4f * h;
+    return r;
+}
+__device__ __forceinline__ float4 row_pack(const AxC& Y) { return make_float4(__int_as_float(Y.ok ? Y.e : ~Y.e), Y.c0, Y.c1, Y.mx); }
+// Parent values of one parent row at a column's x pair and z pair: (x0,z0), (x1,z0), (x0,z1), (x1,z1).
+template <bool BLEND>
+__device__ __forceinline__ void row4_load(float v[4], const float* __restrict__ u, const float* __restrict__ u2, float alpha, float beta,
+                                          const SrcGeom& g, int bxz, int row) {
+    const int b = bxz + row * g.nnx;
+    v[0] = __ldg(u + b); v[1] = __ldg(u + b + 1); v[2] = __ldg(u + b + g.nnxy); v[3] = __ldg(u + b + 1 + g.nnxy);
+    if (BLEND) {
+        const float w0 = __ldg(u2 + b), w1 = __ldg(u2 + b + 1), w2 = __ldg(u2 + b + g.nnxy), w3 = __ldg(u2 + b + 1 + g.nnxy);
+        v[0] = __fadd_rn(__fmul_rn(alpha, v[0]), __fmul_rn(beta, w0));
+        v[1] = __fadd_rn(__fmul_rn(alpha, v[1]), __fmul_rn(beta, w1));
+        v[2] = __fadd_rn(__fmul_rn(alpha, v[2]), __fmul_rn(beta, w2));
+        v[3] = __fadd_rn(__fmul_rn(alpha, v[3]), __fmul_rn(beta, w3));
+    }
+}
+struct Rows2 {   // the two parent rows of the current cell
+    int E;
+    float lo[4], hi[4];
+};
+template <bool BLEND>
+__device__ __forceinline__ void rows_enter(Rows2& c, const float* __restrict__ u, const float* __restrict__ u2, float alpha, float beta,
+                                           const SrcGeom& g, int bxz, int e) {
+    if (e == c.E + 1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) c.lo[q] = c.hi[q];
+    } else {
+        row4_load<BLEND>(c.lo, u, u2, alpha, beta, g, bxz, e);
+    }
+    row4_load<BLEND>(c.hi, u, u2, alpha, beta, g, bxz, e + 1);
+    c.E = e;
+}
+__device__ __forceinline__ float tri_fast(const float lo[4], const float hi[4], float inv_vol, const AxC& X, float yc0, float yc1, float ymx,
+                                          const AxC& Z) {
+    const float xy00 = __fmul_rn(X.c0, yc0), xy10 = __fmul_rn(X.c1, yc0), xy11 = __fmul_rn(X.c1, yc1), xy01 = __fmul_rn(X.c0, yc1);
+    const float top = __fmul_rn(__fmul_rn(__fmul_rn(X.mx, ymx), Z.mx), inv_vol);
+    float acc = 0.f;   // hex8 local order, as tri_eval
+    acc = __fadd_rn(acc, __fmul_rn(fminf(__fmul_rn(__fmul_rn(xy00, Z.c0), inv_vol), 1.f), lo[0]));
+    acc = __fadd_rn(acc, __fmul_rn(fminf(__fmul_rn(__fmul_rn(xy10, Z.c0), inv_vol), 1.f), lo[1]));
+    acc = __fadd_rn(acc, __fmul_rn(fminf(__fmul_rn(__fmul_rn(xy11, Z.c0), inv_vol), 1.f), hi[1]));
+    acc = __fadd_rn(acc, __fmul_rn(fminf(__fmul_rn(__fmul_rn(xy01, Z.c0), inv_vol), 1.f), hi[0]));
+    acc = __fadd_rn(acc, __fmul_rn(fminf(__fmul_rn(__fmul_rn(xy00, Z.c1), inv_vol), 1.f), lo[2]));
+    acc = __fadd_rn(acc, __fmul_rn(fminf(__fmul_rn(__fmul_rn(xy10, Z.c1), inv_vol), 1.f), lo[3]));
+    acc = __fadd_rn(acc, __fmul_rn(fminf(__fmul_rn(__fmul_rn(xy11, Z.c1), inv_vol), 1.f), hi[3]));
+    acc = __fadd_rn(acc, __fmul_rn(fminf(__fmul_rn(__fmul_rn(xy01, Z.c1), inv_vol), 1.f), hi[2]));
+    return top <= 1.0f + 1e-2f ? acc : 0.f;
+}
+// a target outside the parent: the plain evaluation, out of line (rare; keeps the unrolled row bodies small)
+template <bool BLEND>
+__device__ __noinline__ float tri_plain(const float* __restrict__ u, const float* __restrict__ u2, float alpha, float beta, AxisView sx,
+                                        AxisView sy, AxisView sz, float x, float y, float z) {
+    const SrcGeom g = geom_of(sx, sy, sz);
+    return tri_eval<BLEND>(u, u2, alpha, beta, g, ax1_of(sx, g.hx, x), ax1_of(sy, g.hy, y), ax1_of(sz, g.hz, z));
+}
+
+constexpr int ROWSM = 8;   // target rows per thread of the marching forms
+
+// What a block shares about one parent: the y part of its R rows, the z part of its plane, 1 / (hx hy hz) - formed by
+// R + 2 threads of the block, read by all after one barrier (none of it depends on the column).
+struct SrcShared {
+    float4 row[ROWSM];
+    float4 z;
+    float inv_vol;
+    float pad[3];
+};
+__device__ __forceinline__ void src_to_shared(SrcShared& s, int t, const AxisView& sx, const AxisView& sy, const AxisView& sz,
+                                              const float* __restrict__ ty, int j0, int nrows, float z) {
+    if (t < 0 || t > ROWSM + 1) return;
+    if (t < ROWSM) {
+        if (t < nrows) s.row[t] = row_pack(axc_of(sy, __fsub_rn(sy.c[1], sy.c[0]), ty[j0 + t]));
+    } else if (t == ROWSM) {
+        s.z = row_pack(axc_of(sz, __fsub_rn(sz.c[1], sz.c[0]), z));
+    } else {
+        s.inv_vol = geom_of(sx, sy, sz).inv_vol;
+    }
+}
+__device__ __forceinline__ AxC row_unpack(const float4& r) {
+    AxC a;
+    const int e = __float_as_int(r.x);
+    a.ok = e >= 0;
+    a.e = a.ok ? e : ~e;
+    a.c0 = r.y; a.c1 = r.z; a.mx = r.w;
+    return a;
+}
+
+template <bool BLEND, int MODE>
+__global__ void __launch_bounds__(256, 4) interp3_march_kernel(const InterpParams p, const int rpb) {   // rpb: rows per block (R, or 1 on small grids)
+    constexpr int R = ROWSM;
+    __shared__ SrcShared sh;
+    const int j0 = blockIdx.y * rpb, j1 = min(p.nty, j0 + rpb);
+    const int i = min((int)(blockIdx.x * blockDim.x + threadIdx.x), p.ntx - 1);   // the last block's spare threads shadow the last column
+    const bool owner = (int)(blockIdx.x * blockDim.x + threadIdx.x) < p.ntx;
+    const int k = blockIdx.z;
+    const size_t o0 = ((size_t)k * p.nty + j0) * p.ntx + i;
+    // everything that waits for memory is requested before the barrier: the field the result is combined with (all
+    // rows), this column's x part, the block's shared parts
+    float prev[R];
+    if (MODE != GOMELT_INTERP_SET) {
+        const float* __restrict__ b = MODE == GOMELT_INTERP_ADD ? p.out : p.base;
+#pragma unroll
+        for (int q = 0; q < R; ++q) prev[q] = j0 + q < j1 ? b[o0 + (size_t)q * p.ntx] : 0.f;
+    }
+    SrcGeom g;
+    g.nnx = p.sx.n; g.nnxy = p.sx.n * p.sy.n; g.nny = p.sy.n;
+    const AxC X = axc_of(p.sx, __fsub_rn(p.sx.c[1], p.sx.c[0]), p.tx[i]);
+    src_to_shared(sh, threadIdx.x, p.sx, p.sy, p.sz, p.ty, j0, j1 - j0, p.tz[k]);
+    __syncthreads();
+    if (!owner) return;
+    const AxC Z = row_unpack(sh.z);
+    g.inv_vol = sh.inv_vol;
+    const bool xz = X.ok && Z.ok;
+    const int bxz = X.e + Z.e * g.nnxy;
+    Rows2 c;
+    c.E = -(1 << 30);
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+        if (j0 + q >= j1) break;
+        const float4 r = sh.row[q];
+        const int e = __float_as_int(r.x);
+        float acc;
+        if (xz && e >= 0) {
+            if (e != c.E) rows_enter<BLEND>(c, p.u, p.u2, p.alpha, p.beta, g, bxz, e);
+            acc = tri_fast(c.lo, c.hi, g.inv_vol, X, r.y, r.z, r.w, Z);
+        } else {
+            acc = tri_plain<BLEND>(p.u, p.u2, p.alpha, p.beta, p.sx, p.sy, p.sz, p.tx[i], p.ty[j0 + q], p.tz[k]);
+        }
+        float res;
+        if (MODE == GOMELT_INTERP_SET) res = acc;
+        else if (MODE == GOMELT_INTERP_ADD) res = __fadd_rn(prev[q], acc);
+        else res = __fsub_rn(prev[q], acc);
+        if (p.has_clamp) res = fmaxf(res, p.clamp_min);
+        p.out[o0 + (size_t)q * p.ntx] = res;
     }
 }
 
@@ -1254,30 +1424,53 @@ struct ShiftParams {
     int ntx, nty, ntz;
     float *Tp_new, *T_new;
 };
-__global__ void shift_window_kernel(const ShiftParams p) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // blockIdx.y = group of ROWS3 target rows, blockIdx.z = target plane
-    if (i >= p.ntx) return;
+// The y part of the block's rows and the z part of its plane do not depend on the column: one warp per parent forms them
+// (lane q < rows: row q, lane ROWS3: the plane) and the block reads them after one barrier, instead of every thread
+// repeating the cell searches (IEEE divisions) of its rows: 144 -> 130 us (Level 3), 104 -> 97 us (Level 2) at C2 size.
+// Tried on top of it and dropped (bench_tools/quick_interp.py, one box): the marching form of interp3_march_kernel with
+// a register cache per parent - the window's own old field has the SAME spacing, every row enters a new cell and its
+// loads come from DRAM: 190 / 143 us even with the next parent row requested a row ahead; the short form of the weights
+// (tri_fast) with per-target loads: 138 / 106 us at 64 registers, 137 / 104 with a 48-register cap.
+__device__ __forceinline__ float4 ax1_pack(const Ax1& a) { return make_float4(__int_as_float(a.e), a.a0, a.a1, 0.f); }
+__device__ __forceinline__ Ax1 ax1_unpack(const float4& r) {
+    Ax1 a;
+    a.e = __float_as_int(r.x); a.a0 = r.y; a.a1 = r.z;
+    return a;
+}
+__global__ void __launch_bounds__(256) shift_window_kernel(const ShiftParams p, const int rpb) {
+    __shared__ float4 s_ax[3][ROWS3 + 1];
+    const int i = min((int)(blockIdx.x * blockDim.x + threadIdx.x), p.ntx - 1);  // blockIdx.y = group of rpb target rows, blockIdx.z = target plane
+    const bool owner = (int)(blockIdx.x * blockDim.x + threadIdx.x) < p.ntx;
     const int k = blockIdx.z;
-    const float x = p.tx[i], z = p.tz[k];
+    const int j0 = blockIdx.y * rpb, j1 = min(p.nty, j0 + rpb);
+    const float x = p.tx[i];
     const SrcGeom g1 = geom_of(p.ax, p.ay, p.az), go = geom_of(p.ox, p.oy, p.oz);
-    const Ax1 X1 = ax1_of(p.ax, g1.hx, x), Z1 = ax1_of(p.az, g1.hz, z);
-    const Ax1 Xo = ax1_of(p.ox, go.hx, x), Zo = ax1_of(p.oz, go.hz, z);
+    const Ax1 X1 = ax1_of(p.ax, g1.hx, x), Xo = ax1_of(p.ox, go.hx, x);
     SrcGeom gm = go;
-    Ax1 Xm = Xo, Zm = Zo;
+    Ax1 Xm = Xo;
     if (p.Tpm) {
         gm = geom_of(p.mx, p.my, p.mz);
         Xm = ax1_of(p.mx, gm.hx, x);
-        Zm = ax1_of(p.mz, gm.hz, z);
     }
-    const int rpb = (p.nty + (int)gridDim.y - 1) / (int)gridDim.y;
-    const int j1 = min(p.nty, (int)(blockIdx.y + 1) * rpb);
-    for (int j = blockIdx.y * rpb; j < j1; ++j) {
-        const float y = p.ty[j];
+    {
+        const int which = threadIdx.x >> 5, t = threadIdx.x & 31;
+        if (which < (p.Tpm ? 3 : 2) && (t < j1 - j0 || t == ROWS3)) {
+            const AxisView& ay = which == 0 ? p.oy : which == 1 ? p.ay : p.my;
+            const AxisView& az = which == 0 ? p.oz : which == 1 ? p.az : p.mz;
+            const SrcGeom& g = which == 0 ? go : which == 1 ? g1 : gm;
+            s_ax[which][t] = t == ROWS3 ? ax1_pack(ax1_of(az, g.hz, p.tz[k])) : ax1_pack(ax1_of(ay, g.hy, p.ty[j0 + t]));
+        }
+    }
+    __syncthreads();
+    if (!owner) return;
+    const Ax1 Zo = ax1_unpack(s_ax[0][ROWS3]), Z1 = ax1_unpack(s_ax[1][ROWS3]);
+    const Ax1 Zm = p.Tpm ? ax1_unpack(s_ax[2][ROWS3]) : Zo;
+    for (int j = j0; j < j1; ++j) {
         const size_t w = ((size_t)k * p.nty + j) * p.ntx + i;
-        const float tp = tri_eval<false>(p.Tpo, nullptr, 1.f, 0.f, go, Xo, ax1_of(p.oy, go.hy, y), Zo);
-        const float t1 = tri_eval<false>(p.T1, nullptr, 1.f, 0.f, g1, X1, ax1_of(p.ay, g1.hy, y), Z1);
+        const float tp = tri_eval<false>(p.Tpo, nullptr, 1.f, 0.f, go, Xo, ax1_unpack(s_ax[0][j - j0]), Zo);
+        const float t1 = tri_eval<false>(p.T1, nullptr, 1.f, 0.f, g1, X1, ax1_unpack(s_ax[1][j - j0]), Z1);
         float rest = tp;
-        if (p.Tpm) rest = __fadd_rn(tri_eval<false>(p.Tpm, nullptr, 1.f, 0.f, gm, Xm, ax1_of(p.my, gm.hy, y), Zm), tp);  // T1on3 + (Tp2on3 + Tp3)
+        if (p.Tpm) rest = __fadd_rn(tri_eval<false>(p.Tpm, nullptr, 1.f, 0.f, gm, Xm, ax1_unpack(s_ax[2][j - j0]), Zm), tp);  // T1on3 + (Tp2on3 + Tp3)
         p.Tp_new[w] = tp;
         p.T_new[w] = __fadd_rn(t1, rest);
     }
@@ -1289,6 +1482,15 @@ __global__ void shift_window_kernel(const ShiftParams p) {
 static inline int row_groups(int nx_blocks, int ny, int nz) {
     const long long blocks = (long long)nx_blocks * ((ny + ROWS3 - 1) / ROWS3) * nz;
     return blocks >= 4LL * sm_count() ? (ny + ROWS3 - 1) / ROWS3 : ny;
+}
+
+static inline int row_groups_march(int nx_blocks, int ny, int nz) {
+    const long long blocks = (long long)nx_blocks * ((ny + ROWSM - 1) / ROWSM) * nz;
+    return blocks >= 4LL * sm_count() ? (ny + ROWSM - 1) / ROWSM : ny;
+}
+static inline bool transfer_plain() {   // A/B switch: the plain per-target interpolation kernel instead of the marching form
+    const char* e = getenv("GOMELT_TRANSFER_PLAIN");   // read per call: a test flips it inside one process
+    return e && e[0] == '1';
 }
 
 static inline int grid_for(long long n, int threads) {
@@ -1333,9 +1535,30 @@ extern "C" int gomelt_interp_f32(const gomelt_interp_args_t* a, void* stream) {
     const long long src_nn = (long long)a->src[0].n * a->src[1].n * a->src[2].n;
     if (!a->faces_only && !a->map_x && a->ntz <= 65535 && src_nn < 2000000000LL) {
         const int threads = a->ntx >= 256 ? 256 : (a->ntx >= 128 ? 128 : 64);
-        const dim3 grid((a->ntx + threads - 1) / threads, row_groups((a->ntx + threads - 1) / threads, a->nty, a->ntz), a->ntz);
-        if (a->u2) interp3_kernel<true><<<grid, threads, 0, (cudaStream_t)stream>>>(p), count_launch();
-        else interp3_kernel<false><<<grid, threads, 0, (cudaStream_t)stream>>>(p), count_launch();
+        const int nxb = (a->ntx + threads - 1) / threads;
+        if (transfer_plain()) {
+            const dim3 grid(nxb, row_groups(nxb, a->nty, a->ntz), a->ntz);
+            if (a->u2) interp3_kernel<true><<<grid, threads, 0, (cudaStream_t)stream>>>(p), count_launch();
+            else interp3_kernel<false><<<grid, threads, 0, (cudaStream_t)stream>>>(p), count_launch();
+        } else {
+            const int threads_m = threads, nxm = nxb;
+            const int groups = row_groups_march(nxm, a->nty, a->ntz);
+            const int rpb = (a->nty + groups - 1) / groups;
+            const dim3 grid(nxm, groups, a->ntz);
+            cudaStream_t st = (cudaStream_t)stream;
+#define GOMELT_I3M(B, M) interp3_march_kernel<B, M><<<grid, threads_m, 0, st>>>(p, rpb)
+            if (a->u2) {
+                if (a->mode == GOMELT_INTERP_SET) GOMELT_I3M(true, GOMELT_INTERP_SET);
+                else if (a->mode == GOMELT_INTERP_ADD) GOMELT_I3M(true, GOMELT_INTERP_ADD);
+                else GOMELT_I3M(true, GOMELT_INTERP_RSUB);
+            } else {
+                if (a->mode == GOMELT_INTERP_SET) GOMELT_I3M(false, GOMELT_INTERP_SET);
+                else if (a->mode == GOMELT_INTERP_ADD) GOMELT_I3M(false, GOMELT_INTERP_ADD);
+                else GOMELT_I3M(false, GOMELT_INTERP_RSUB);
+            }
+#undef GOMELT_I3M
+            count_launch();
+        }
     } else {
         interp_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p), count_launch();
     }
@@ -1639,7 +1862,7 @@ extern "C" int gomelt_shift_window_f32(const gomelt_shift_args_t* a, void* strea
         set_error("gomelt_shift_window_f32: target grid too large (ntz <= 65535)");
         return GOMELT_E_SIZE;
     }
-    shift_window_kernel<<<dim3((a->ntx + 255) / 256, row_groups((a->ntx + 255) / 256, a->nty, a->ntz), a->ntz), 256, 0, (cudaStream_t)stream>>>(p),
-        count_launch();
+    const int nxb = (a->ntx + 255) / 256, groups = row_groups(nxb, a->nty, a->ntz);
+    shift_window_kernel<<<dim3(nxb, groups, a->ntz), 256, 0, (cudaStream_t)stream>>>(p, (a->nty + groups - 1) / groups), count_launch();
     return check_launch("gomelt_shift_window_f32");
 }

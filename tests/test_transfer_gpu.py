@@ -138,6 +138,26 @@ def test_interp_set_add_rsub_clamp(gm, T, pair):
     assert _relmax(got, np.maximum(want, F32(cl))) <= TOL_I
 
 
+@pytest.mark.parametrize("pair", list(PAIRS))
+def test_interp_marching_form_equals_the_plain_form_bit_for_bit(gm, T, pair, monkeypatch):
+    """The full-grid interpolation runs a marching kernel (parent values kept in registers along y, the validity window
+    from one product); GOMELT_TRANSFER_PLAIN=1 selects the plain per-target kernel.  Same bits, every mode, incl. the
+    pairs whose targets hang over the parent (those targets take the plain evaluation inside the marching kernel)."""
+    src, tgt = (f() for f in PAIRS[pair])
+    u, u2, base = T.f(_field(src, 11)), T.f(_field(src, 12, hi=1400.0)), T.f(_field(tgt, 13))
+    sc, tc = T.coords(src), T.coords(tgt)
+    res = {}
+    for plain in ("1", "0"):
+        monkeypatch.setenv("GOMELT_TRANSFER_PLAIN", plain)
+        e = lambda: T.torch_.empty(tgt["nn"], device="cuda")
+        res[plain] = [gm.ops.interp(sc, u, tc, e()).clone(),
+                      gm.ops.interp(sc, u, tc, e(), u2=u2, alpha=0.4, beta=0.6).clone(),
+                      gm.ops.interp(sc, u, tc, e(), mode=gm._lib.INTERP_RSUB, base=base).clone(),
+                      gm.ops.interp(sc, u, tc, base.clone(), mode=gm._lib.INTERP_ADD, clamp_min=500.0).clone()]
+    for a, b in zip(res["1"], res["0"]):
+        assert T.torch_.equal(a, b)
+
+
 @pytest.mark.parametrize("pair", ["L1->L2 (ratio 5)", "L2->L3 shifted (3, -5, 0) parent cells",
                                   "parent coarser by 2.5 (non-integer ratio)"])
 def test_interp_faces_only_and_blend(gm, T, pair):

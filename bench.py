@@ -482,6 +482,15 @@ def _oracle_block(elements, nblocks, seed=0):
     return nblocks * N3 * nn, time.perf_counter() - t0
 
 
+def _host_threads():
+    """The host cores this process may use.  Under torchrun OMP_NUM_THREADS is preset to 1; the CPU arms set their thread
+    count explicitly (torch.set_num_threads) so that the baseline is the same with and without the launcher."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def _torch_cpu_block(elements, nblocks, threads=None):
     """nblocks x N3 Level-3 substeps of the reference algorithm as dense tensor operations on all host threads
     (oracle/torch_cpu.py: what a multi-threaded CPU array runtime makes of the reference; pinned to the NumPy oracle by
@@ -496,7 +505,7 @@ def _torch_cpu_block(elements, nblocks, threads=None):
     P = cF.SetupProperties(EXAMPLE_PROPS)
     ex, ey, ez = elements
     lv = make_level(elements, ((0.0, ex * L3_H), (0.0, ey * L3_H), (-ez * L3_H, 0.0)))
-    port = L3SubstepCPU(lv, P, threads=threads)
+    port = L3SubstepCPU(lv, P, threads=threads or _host_threads())
     nn = lv["nn"]
     T = torch.full((nn,), float(P["T_amb"]) + 51.0)
     S1 = torch.from_numpy(np.repeat((lv["node_coords"][2] <= -0.04 + 1e-6).astype(np.float32), lv["nodes"][0] * lv["nodes"][1]))
@@ -538,7 +547,7 @@ def _torch_cpu_dwell(nodes, sweeps, h=0.2, dt=2e-3):
     P = cF.SetupProperties(EXAMPLE_PROPS)
     nx, ny, nz = nodes
     lv = make_level((nx - 1, ny - 1, nz - 1), ((0.0, (nx - 1) * h), (0.0, (ny - 1) * h), (-(nz - 1) * h, 0.0)))
-    port = L3SubstepCPU(lv, P)
+    port = L3SubstepCPU(lv, P, threads=_host_threads())
     nn = lv["nn"]
     T = torch.full((nn,), float(P["T_amb"]) + 200.0)
     S1 = torch.ones(nn)

@@ -311,6 +311,13 @@ def run_gomelt_single(args):
         line["l1_slab_1gpu"]["workload"] = ref["config"]["workload"]
     except Exception as exc:  # the headline line must still print
         line["l1_slab_1gpu"] = {"error": repr(exc)}
+    # the reference's default run end to end (before the whole-step block: that one traces its kernels through CUPTI,
+    # which stays attached to the process and taxes every later launch of this host-issue-bound run)
+    try:
+        torch.cuda.empty_cache()
+        line["example_json"] = example_json_run()
+    except Exception as exc:
+        line["example_json"] = {"error": repr(exc)}
     # whole steps through the drop-in entry points at the same scale (10 M-node Level 3 WITH its Level 2 / Level 1:
     # subcycleGOMELT, stepGOMELT, moveEverything, the T' projections ...) and the reference's default run end to end
     try:
@@ -320,10 +327,6 @@ def run_gomelt_single(args):
         line["whole_step"] = whole_step(EXAMPLE_PROPS, peaks["hbm_gbs"])
     except Exception as exc:
         line["whole_step"] = {"error": repr(exc)}
-    try:
-        line["example_json"] = example_json_run()
-    except Exception as exc:
-        line["example_json"] = {"error": repr(exc)}
     try:  # BASELINE.json configs[3] at full size (50 M-node Level 1, three layers): wall-s per sim-s through the driver
         import torch
 
@@ -353,7 +356,12 @@ def example_json_run():
     for _ in range(2):  # the first pass warms up module loading / allocator / kernel images
         eager = gm.driver.go_melt(load_input(tempfile.mkdtemp()), write_final=False, graphs=False)
     walls, best = [], None
+    cf = gm.computeFunctions
     for _ in range(4):   # host-issue-bound: the fastest of the repeats is reported, all are listed
+        # every repeat starts like a first run: no coordinate array on the device, no per-position pair descriptor,
+        # no captured graph (those live in the run's own workspace) - only the loaded library and the warm allocator
+        cf._PAIR_CACHE.clear()
+        cf._CACHE.store.clear()
         l0, g0 = gm.ops.LAUNCHES, gm.ops.GRAPH_LAUNCHES
         res = gm.driver.go_melt(load_input(tempfile.mkdtemp()), write_final=False)
         walls.append(round(res["wall_seconds"], 4))
@@ -363,7 +371,8 @@ def example_json_run():
     torch.cuda.synchronize()
     same = all(torch.equal(res["Levels"][i]["T0"], eager["Levels"][i]["T0"]) for i in (1, 2, 3))
     return {"workload": "examples/example.json + example.gcode, whole run, device-resident state, no file output; the "
-                        "499 rows of the pause replay a CUDA graph of two rows (computeFunctions.dwellRows)",
+                        "499 rows of the pause replay a CUDA graph of two rows (computeFunctions.dwellRows); the host-side caches "
+                        "(device copies of coordinate arrays, per-position pair descriptors) are emptied before every repeat",
             "wall_s": res["wall_seconds"], "wall_s_of_every_repeat": walls, "sim_s": res["sim_seconds"],
             "wall_s_per_sim_s": res["wall_seconds"] / res["sim_seconds"], "toolpath_rows": res["time_inc"],
             "counts": res["counts"], "lib_launches": gm.ops.LAUNCHES - l0,

@@ -22,6 +22,8 @@ There is no CPU path: every entry point raises ``GomeltError`` without the libra
 """
 import copy  # noqa: F401  (re-exported: gm:200 uses ``copy`` through the star import)
 import math
+import os
+import sys
 
 import numpy as np
 
@@ -866,6 +868,10 @@ def dwellRows(Levels, n, v, vstart, move_v, LInterp, L1L2Eratio, L2L3Eratio, hei
                 one()
                 one()
                 done += 2
+        if os.environ.get("GOMELT_DWELL_TRACE"):
+            now = _pointer_state(Levels, ws)
+            print("dwellRows: n=%d done=%d roles_back=%s differing_slots=%s" % (
+                n, done, now == before, [i for i, (a, b) in enumerate(zip(now, before)) if a != b]), file=sys.stderr)
         if n - done >= 2 and _pointer_state(Levels, ws) == before:
             l0 = ops.LAUNCHES
             keep_from = len(_CACHE.store)
@@ -891,6 +897,9 @@ def dwellRows(Levels, n, v, vstart, move_v, LInterp, L1L2Eratio, L2L3Eratio, hei
                 g.replays += 1
                 done += 2
             else:   # a cache filled during the capture: nothing ran, run the pair now
+                if os.environ.get("GOMELT_DWELL_TRACE"):
+                    print("dwellRows: capture dropped: roles_back=%s cache %d -> %d" % (
+                        _pointer_state(Levels, ws) == before, keep_from, len(_CACHE.store)), file=sys.stderr)
                 one()
                 one()
                 done += 2

@@ -1036,17 +1036,22 @@ __device__ __forceinline__ M22 m_of(const float4 w) {  // w = (W[q0][c0], W[q0][
 
 // FAST: the steppers' call shape (coefficient evaluated from (T, S1); A2 given exactly in MASS mode) without the run-time
 // selects of the general shape.
-template <int MODE, int RY, int MC, bool FAST>   // RY element rows per thread = MC parent y-cells of r_y = RY / MC rows each
+// SPLIT = 2: a band is HALF a parent cell row (r_y = 2 RY element rows per cell; MC = 1): the tall ratio (10) otherwise
+// needs ~255 registers for its 10 carried rows and has none left for the plane prefetch.  The two halves of a cell add
+// their corner sums into a zeroed cellsum with atomicAdd - two terms onto 0, so the result does not depend on their order.
+template <int MODE, int RY, int MC, bool FAST, int SPLIT = 1>   // RY element rows per thread = MC parent y-cells of r_y = RY / MC rows each
 __global__ void __launch_bounds__(32 * MARCH_WARPS) project_march_kernel(const MarchParams p) {
     constexpr int NR = RY + 1;
     constexpr int ry = RY / MC;
+    static_assert(SPLIT == 1 || MC == 1, "half bands hold part of one cell");
     constexpr int NACC = MODE == 1 ? 8 : 12;
     static_assert(RY % MC == 0, "a band holds whole parent cells");
     const int lane = threadIdx.x & 31;
     const int wchunk = blockIdx.x * MARCH_WARPS + (threadIdx.x >> 5);
     const int cpw = p.epw / p.rx;                 // parent x-cells per warp
     if (wchunk * cpw >= p.ncx) return;            // (whole warp)
-    const int cj0 = blockIdx.y * MC;
+    const int cj0 = SPLIT > 1 ? (int)blockIdx.y / SPLIT : (int)blockIdx.y * MC;
+    const int row0 = (int)blockIdx.y * RY;        // first element row of the band (before the window's offset)
     const int ck0 = blockIdx.z * p.czn, ck1 = min(ck0 + p.czn, p.ncz);
     const int ex = wchunk * p.epw + lane - p.offx;    // element column = node column of this lane
     const bool colv = lane < p.epw && ex >= 0 && ex < p.fnx - 1;
@@ -1060,10 +1065,10 @@ __global__ void __launch_bounds__(32 * MARCH_WARPS) project_march_kernel(const M
     const int Pi = p.fnx * p.fny;
     const int kz0 = __ldg(p.fsz + ck0), kz1 = __ldg(p.fsz + ck1);   // node planes kz0 .. kz1
 #pragma unroll
-    for (int r = 0; r < NR; ++r) idx[r] = kz0 * Pi + min(max(cj0 * ry + r - p.offy, 0), p.fny - 1) * p.fnx + ic;
+    for (int r = 0; r < NR; ++r) idx[r] = kz0 * Pi + min(max(row0 + r - p.offy, 0), p.fny - 1) * p.fnx + ic;
 #pragma unroll
     for (int r = 0; r < RY; ++r) {
-        const int j = cj0 * ry + r - p.offy;
+        const int j = row0 + r - p.offy;
         My[r] = m_of(__ldg(p.wy + min(max(j, 0), p.fny - 2)));
         rowv[r] = (j >= 0 && j < p.fny - 1) ? 0.125f : 0.f;   // (times the 1/8 of the element mean)
     }
@@ -1137,9 +1142,15 @@ __global__ void __launch_bounds__(32 * MARCH_WARPS) project_march_kernel(const M
             }
             const int cj = cj0 + t;
             if (seg == 0 && lane < p.epw && ci < p.ncx && cj < p.ncy) {
-                float4* dst = reinterpret_cast<float4*>(p.cellsum + (((long long)ck * p.ncy + cj) * p.ncx + ci) * 8);
-                dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-                dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+                float* cs = p.cellsum + (((long long)ck * p.ncy + cj) * p.ncx + ci) * 8;
+                if (SPLIT > 1) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) atomicAdd(cs + c, o[c]);
+                } else {
+                    float4* dst = reinterpret_cast<float4*>(cs);
+                    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+                    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+                }
             }
 #pragma unroll
             for (int c = 0; c < NACC; ++c) s[c] = 0.f;
@@ -1287,14 +1298,20 @@ static int march_pick_chunk(MarchParams& mp, int nwx, int nby) {
     return (int)((mp.ncz + nzc - 1) / nzc);
 }
 
-template <int MODE, int RY, int MC, bool FAST>
+template <int MODE, int RY, int MC, bool FAST, int SPLIT = 1>
 static void launch_march_i(MarchParams& mp, int nwx, int nby, int fine_layers, cudaStream_t st) {
     (void)fine_layers;
+    nby *= SPLIT;
+    if (SPLIT > 1) cudaMemsetAsync(mp.cellsum, 0, (size_t)mp.ncx * mp.ncy * mp.ncz * 8 * sizeof(float), st);   // the halves add
     mp.czn = march_pick_chunk(mp, nwx, nby);
     const dim3 grid((nwx + MARCH_WARPS - 1) / MARCH_WARPS, nby, (mp.ncz + mp.czn - 1) / mp.czn);
-    project_march_kernel<MODE, RY, MC, FAST><<<grid, 32 * MARCH_WARPS, 0, st>>>(mp);
+    project_march_kernel<MODE, RY, MC, FAST, SPLIT><<<grid, 32 * MARCH_WARPS, 0, st>>>(mp);
 }
 
+static inline bool march_split() {   // A/B switch: GOMELT_MARCH_SPLIT=0 keeps the ratio-10 band in one thread
+    const char* e = getenv("GOMELT_MARCH_SPLIT");
+    return !(e && e[0] == '0');
+}
 template <int MODE, bool FAST>
 static bool launch_march_f(MarchParams& mp, int nwx, int nby, int fine_layers, cudaStream_t st) {
     switch (mp.ry) {
@@ -1305,7 +1322,10 @@ static bool launch_march_f(MarchParams& mp, int nwx, int nby, int fine_layers, c
         case 5: launch_march_i<MODE, 5, 1, FAST>(mp, nwx, nby, fine_layers, st); break;
         case 6: launch_march_i<MODE, 6, 1, FAST>(mp, nwx, nby, fine_layers, st); break;
         case 8: launch_march_i<MODE, 8, 1, FAST>(mp, nwx, nby, fine_layers, st); break;
-        case 10: launch_march_i<MODE, 10, 1, FAST>(mp, nwx, nby, fine_layers, st); break;
+        case 10:
+            if (march_split()) launch_march_i<MODE, 5, 1, FAST, 2>(mp, nwx, nby, fine_layers, st);
+            else launch_march_i<MODE, 10, 1, FAST>(mp, nwx, nby, fine_layers, st);
+            break;
         default: return false;
     }
     count_launch();

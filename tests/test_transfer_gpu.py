@@ -287,7 +287,7 @@ PROJ = {
 
 
 @pytest.mark.parametrize("pair", list(PROJ))
-def test_project_grad_and_mass_terms(gm, T, pair, example_props):
+def test_project_grad_and_mass_terms(gm, T, pair, example_props, monkeypatch):
     fine, parent = (f() for f in PROJ[pair])
     P = cF.SetupProperties(example_props)
     Tp0 = (_field(fine, 8, lo=-40.0, hi=60.0)).astype(F32)
@@ -332,6 +332,15 @@ def test_project_grad_and_mass_terms(gm, T, pair, example_props):
     cf._project(cells, T.f(Tp0), None, V4, mode=0, coef_from=(props, dT, dS, 0))
     cf._project(cells, T.f(Tp1), None, V4, mode=1, scale=1.0 / dt, A2=T.f(Tp0), coef_from=(props, dT, dS, 0))
     assert _relmax(T.h(V4), want0 + want1) <= TOL_P, pair
+    # ratio 10 runs half a parent cell row per thread (two halves added onto a zeroed cell sum: order-independent, hence the
+    # bit-identical V2 above); GOMELT_MARCH_SPLIT=0 keeps the whole row in one thread
+    if "ratio 10" in pair or "L3->L1" in pair:
+        monkeypatch.setenv("GOMELT_MARCH_SPLIT", "0")
+        V6 = T.torch_.zeros(parent["nn"], device="cuda")
+        cf._project(cells, T.f(Tp0), None, V6, mode=0, coef_from=(props, dT, dS, 0))
+        cf._project(cells, T.f(Tp1), None, V6, mode=1, scale=1.0 / dt, A2=T.f(Tp0), coef_from=(props, dT, dS, 0))
+        assert _relmax(T.h(V6), want0 + want1) <= TOL_P, pair
+        assert _relmax(T.h(V6), T.h(V4)) <= 2e-6, pair
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -1426,6 +1426,9 @@ __global__ void rank_n_kernel(float* __restrict__ F, const float* __restrict__ t
     for (int r = 0; r < sb.n; ++r) {  // laser rows in order, like the row-by-row accumulation of gomelt_rank1_f32
         const float* tb = tables + (size_t)r * stride;
         const float txv = tb[i], tzv = tb[nx + ny + k], c = sb.c[r];
+        // the tables are Gaussians that underflow to exactly 0 some 6 laser radii away (all but ~8 % of the columns and most
+        // planes of a C2-size parent): there the row adds c * ((0 * ty) * tz) = 0, i.e. nothing
+        if (txv == 0.f || tzv == 0.f) continue;
 #pragma unroll
         for (int q = 0; q < ROWS3; ++q)
             if (j0 + q < j1) f[q] = f[q] + c * ((txv * tb[nx + j0 + q]) * tzv);

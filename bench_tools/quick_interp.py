@@ -1,6 +1,6 @@
 """Full-grid interpolation (getNewTprime's T' = child - I(parent), cF:2060-2099) and the window shift of moveEverything
-(cF:2439-2443 / 2460-2464) at C2 size, one call at a time: the marching kernels against the plain per-target kernels
-(GOMELT_TRANSFER_PLAIN=1), and whether they give the same bits.  CUDA events, L2 flushed between calls.
+(cF:2439-2443 / 2460-2464) at C2 size, one call at a time: the marching kernel against the per-target kernel (the same
+call with an identity index map), and whether they give the same bits.  CUDA events, L2 flushed between calls.
 python bench_tools/quick_interp.py"""
 import json
 import os
@@ -60,30 +60,28 @@ def main():
     c1, c2, c3, c3n, c2n = dev(L1), dev(L2), dev(L3), dev(L3n), dev(L2n)
     out3, out2 = torch.empty(L3["nn"], device="cuda"), torch.empty(L2["nn"], device="cuda")
     a3, b3, a2, b2 = (torch.empty(L3["nn"], device="cuda") for _ in range(4))
+    ident3 = [torch.arange(n, dtype=torch.int32, device="cuda") for n in L3["nodes"]] + [L3["nodes"][0], L3["nodes"][1]]
+    ident2 = [torch.arange(n, dtype=torch.int32, device="cuda") for n in L2["nodes"]] + [L2["nodes"][0], L2["nodes"][1]]
     cases = {
-        "tprime_L2_to_L3 (ratio 2, RSUB)": (lambda: ops.interp(c2, T2, c3, out3, mode=lib.INTERP_RSUB, base=T3), (out3,), 8 * L3["nn"]),
-        "tprime_L1_to_L2 (ratio 5, RSUB)": (lambda: ops.interp(c1, T1, c2, out2, mode=lib.INTERP_RSUB, base=T2), (out2,), 8 * L2["nn"]),
-        "blend_L2_to_L3 (SET, two parents)": (lambda: ops.interp(c2, T2, c3, out3, u2=Tp2, alpha=0.4, beta=0.6), (out3,), 4 * L3["nn"]),
-        "shift_L3 (old window + L1 + L2)": (lambda: ops.shift_window(c1, T1, c3, Tp3, c3n, a3, b3, mid_coords=c2, Tp_mid=Tp2), (a3, b3), 12 * L3["nn"]),
-        "shift_L2 (old window + L1)": (lambda: ops.shift_window(c1, T1, c2, Tp2, c2n, a2, b2), (a2, b2), 12 * L2["nn"]),
+        "tprime_L2_to_L3 (ratio 2, RSUB)": (lambda **kw: ops.interp(c2, T2, c3, out3, mode=lib.INTERP_RSUB, base=T3, **kw), ident3, out3, 8 * L3["nn"]),
+        "tprime_L1_to_L2 (ratio 5, RSUB)": (lambda **kw: ops.interp(c1, T1, c2, out2, mode=lib.INTERP_RSUB, base=T2, **kw), ident2, out2, 8 * L2["nn"]),
+        "blend_L2_to_L3 (SET, two parents)": (lambda **kw: ops.interp(c2, T2, c3, out3, u2=Tp2, alpha=0.4, beta=0.6, **kw), ident3, out3, 4 * L3["nn"]),
     }
     res = {}
-    for name, (fn, outs, nbytes) in cases.items():
+    for name, (fn, ident, out, nbytes) in cases.items():
         r = {}
-        keep = {}
-        for plain in ("1", "0"):
-            os.environ["GOMELT_TRANSFER_PLAIN"] = plain
-            us = timed(fn, flush)
-            key = "plain" if plain == "1" else "march"
-            r[key + "_us"] = us
-            r[key + "_GBps"] = round(nbytes / us * 1e-3, 1)
-            keep[plain] = [o.clone() for o in outs]
-        r["same_bits"] = all(torch.equal(x, y) for x, y in zip(keep["1"], keep["0"]))
-        if not r["same_bits"]:
-            r["max_abs_diff"] = max(float((x - y).abs().max()) for x, y in zip(keep["1"], keep["0"]))
-            r["n_diff"] = int(sum(int((x != y).sum()) for x, y in zip(keep["1"], keep["0"])))
+        us = timed(lambda: fn(index_map=tuple(ident)), flush)
+        r["per_target_us"], r["per_target_GBps"] = us, round(nbytes / us * 1e-3, 1)
+        ref = out.clone()
+        us = timed(fn, flush)
+        r["march_us"], r["march_GBps"] = us, round(nbytes / us * 1e-3, 1)
+        r["same_bits"] = bool(torch.equal(ref, out))
         res[name] = r
-    os.environ.pop("GOMELT_TRANSFER_PLAIN", None)
+    for name, fn, nbytes in (
+            ("shift_L3 (old window + L1 + L2)", lambda: ops.shift_window(c1, T1, c3, Tp3, c3n, a3, b3, mid_coords=c2, Tp_mid=Tp2), 12 * L3["nn"]),
+            ("shift_L2 (old window + L1)", lambda: ops.shift_window(c1, T1, c2, Tp2, c2n, a2, b2), 12 * L2["nn"])):
+        us = timed(fn, flush)
+        res[name] = {"us": us, "GBps": round(nbytes / us * 1e-3, 1)}
     print(json.dumps(res))
 
 

@@ -8,6 +8,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("GOMELT_DWELL_TRACE", "1")
 import numpy as np  # noqa: E402
 
 import gomelt_b200 as gm  # noqa: E402

@@ -813,6 +813,9 @@ def moveEverything(v, vstart, Levels, move_v, LInterp, L1L2Eratio, L2L3Eratio, h
 # ----------------------------------------------------------------------------------------------
 # runs of identical dwell rows as CUDA-graph replays
 # ----------------------------------------------------------------------------------------------
+_DWELL_TRACE = bool(os.environ.get("GOMELT_DWELL_TRACE"))   # print the capture decisions of dwellRows (read once, at import)
+
+
 class _DwellGraph:
     def __init__(self):
         self.key = self.graph = self.p0 = None
@@ -868,7 +871,7 @@ def dwellRows(Levels, n, v, vstart, move_v, LInterp, L1L2Eratio, L2L3Eratio, hei
                 one()
                 one()
                 done += 2
-        if os.environ.get("GOMELT_DWELL_TRACE"):
+        if _DWELL_TRACE:
             now = _pointer_state(Levels, ws)
             print("dwellRows: n=%d done=%d roles_back=%s differing_slots=%s" % (
                 n, done, now == before, [i for i, (a, b) in enumerate(zip(now, before)) if a != b]), file=sys.stderr)
@@ -897,7 +900,7 @@ def dwellRows(Levels, n, v, vstart, move_v, LInterp, L1L2Eratio, L2L3Eratio, hei
                 g.replays += 1
                 done += 2
             else:   # a cache filled during the capture: nothing ran, run the pair now
-                if os.environ.get("GOMELT_DWELL_TRACE"):
+                if _DWELL_TRACE:
                     print("dwellRows: capture dropped: roles_back=%s cache %d -> %d" % (
                         _pointer_state(Levels, ws) == before, keep_from, len(_CACHE.store)), file=sys.stderr)
                 one()

@@ -9,7 +9,6 @@
 // own float32 formulas (floor((x-x0)/h) cell search, compute3DN cF:1361-1393 products, the +-1e-2
 // validity window), so that cell decisions are identical and values agree to rounding.
 #include <math.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -111,35 +110,10 @@ __device__ __forceinline__ float tri_eval(const float* __restrict__ u, const flo
     return acc;
 }
 
-// full target grid, no index map: blockIdx.y = group of ROWS3 target rows, blockIdx.z = target plane.  The plain form: every
-// target evaluates all of its weights and loads its 8 parent values (kept as the A/B partner of interp3_march_kernel,
-// GOMELT_TRANSFER_PLAIN=1)
-template <bool BLEND>
-__global__ void interp3_kernel(const InterpParams p) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.ntx) return;
-    const SrcGeom g = geom_of(p.sx, p.sy, p.sz);
-    const Ax1 X = ax1_of(p.sx, g.hx, p.tx[i]);
-    const int k = blockIdx.z;
-    const Ax1 Z = ax1_of(p.sz, g.hz, p.tz[k]);
-    const int rpb = (p.nty + (int)gridDim.y - 1) / (int)gridDim.y;   // rows per block: ROWS3, or 1 on small grids (rows_per_block)
-    const int j1 = min(p.nty, (int)(blockIdx.y + 1) * rpb);
-    for (int j = blockIdx.y * rpb; j < j1; ++j) {
-        const Ax1 Y = ax1_of(p.sy, g.hy, p.ty[j]);
-        const float acc = tri_eval<BLEND>(p.u, p.u2, p.alpha, p.beta, g, X, Y, Z);
-        const size_t o = ((size_t)k * p.nty + j) * p.ntx + i;
-        float r;
-        if (p.mode == GOMELT_INTERP_SET) r = acc;
-        else if (p.mode == GOMELT_INTERP_ADD) r = __fadd_rn(p.out[o], acc);
-        else r = __fsub_rn(p.base[o], acc);
-        if (p.has_clamp) r = fmaxf(r, p.clamp_min);
-        p.out[o] = r;
-    }
-}
-
 // ---- marching form ---------------------------------------------------------------------------------------------------
-// A thread owns one target column and walks ROWSM rows of one target plane.  Three things make it cheaper than the
-// plain form while producing the SAME bits:
+// Full target grid, no index map (interp3_march_kernel): a thread owns one target column and walks ROWSM rows of one
+// target plane.  Three things make it cheaper than evaluating every target on its own (interp_kernel, which the
+// mapped / faces-only calls still use, and which the tests reach with an identity index map) while producing the SAME bits:
 //  * the y part of a row (cell, distances), the z part of the plane and 1 / (hx hy hz) are formed once per block into
 //    shared memory (SrcShared), the x part once per thread; the field the result is combined with (ADD / RSUB) is
 //    requested for all rows before anything else;
@@ -150,10 +124,10 @@ __global__ void interp3_kernel(const InterpParams p) {
 //    construction.  Distances clamped at 0 beforehand give exactly the zeros the reference's clip(N, 0, 1) gives for
 //    a target a hair outside its cell (x = c[e] - 1 ulp with floor() landing in e: one factor negative -> N <= 0 -> 0;
 //    two such axes at once give N <= 1e-8 instead of 0: seen as 1-ulp differences at ~1e-4 of the nodes when parent and
-//    target have the SAME spacing, never for a coarser parent - tests/test_transfer_gpu.py compares the two forms bit for bit).
+//    target have the SAME spacing, never for a coarser parent - tests/test_transfer_gpu.py compares the two kernels bit for bit).
 // Targets outside the parent (overhanging windows) take tri_eval as before.  At C2 size (10.3 M targets): T' = child -
-// I(parent) 67.6 -> 57.4 us (ratio 2), 66.4 -> 51.2 us (ratio 5), the blended form 74.6 -> 56.2 us; both forms are bound by
-// instruction issue (71-78 % issue-active), not by DRAM (82 MB in 57 us).
+// I(parent) 67.6 -> 57.4 us (ratio 2), 66.4 -> 51.2 us (ratio 5), the blended form 74.6 -> 56.2 us against the per-target 3-D
+// kernel this replaced (profiles/r02_quick_interp.json); bound by instruction issue (71-78 % issue-active), not by DRAM.
 struct AxC {
     int e;
     float c0, c1, mx;  // max(a0, 0), max(a1, 0), max(a0, a1)
@@ -1308,10 +1282,6 @@ static void launch_march_i(MarchParams& mp, int nwx, int nby, int fine_layers, c
     project_march_kernel<MODE, RY, MC, FAST, SPLIT><<<grid, 32 * MARCH_WARPS, 0, st>>>(mp);
 }
 
-static inline bool march_split() {   // A/B switch: GOMELT_MARCH_SPLIT=0 keeps the ratio-10 band in one thread
-    const char* e = getenv("GOMELT_MARCH_SPLIT");
-    return !(e && e[0] == '0');
-}
 template <int MODE, bool FAST>
 static bool launch_march_f(MarchParams& mp, int nwx, int nby, int fine_layers, cudaStream_t st) {
     switch (mp.ry) {
@@ -1322,10 +1292,7 @@ static bool launch_march_f(MarchParams& mp, int nwx, int nby, int fine_layers, c
         case 5: launch_march_i<MODE, 5, 1, FAST>(mp, nwx, nby, fine_layers, st); break;
         case 6: launch_march_i<MODE, 6, 1, FAST>(mp, nwx, nby, fine_layers, st); break;
         case 8: launch_march_i<MODE, 8, 1, FAST>(mp, nwx, nby, fine_layers, st); break;
-        case 10:
-            if (march_split()) launch_march_i<MODE, 5, 1, FAST, 2>(mp, nwx, nby, fine_layers, st);
-            else launch_march_i<MODE, 10, 1, FAST>(mp, nwx, nby, fine_layers, st);
-            break;
+        case 10: launch_march_i<MODE, 5, 1, FAST, 2>(mp, nwx, nby, fine_layers, st); break;   // two half-cell bands
         default: return false;
     }
     count_launch();
@@ -1511,11 +1478,6 @@ static inline int row_groups_march(int nx_blocks, int ny, int nz) {
     const long long blocks = (long long)nx_blocks * ((ny + ROWSM - 1) / ROWSM) * nz;
     return blocks >= 4LL * sm_count() ? (ny + ROWSM - 1) / ROWSM : ny;
 }
-static inline bool transfer_plain() {   // A/B switch: the plain per-target interpolation kernel instead of the marching form
-    const char* e = getenv("GOMELT_TRANSFER_PLAIN");   // read per call: a test flips it inside one process
-    return e && e[0] == '1';
-}
-
 static inline int grid_for(long long n, int threads) {
     long long b = (n + threads - 1) / threads;
     const long long cap = (long long)sm_count() * 16;
@@ -1559,29 +1521,22 @@ extern "C" int gomelt_interp_f32(const gomelt_interp_args_t* a, void* stream) {
     if (!a->faces_only && !a->map_x && a->ntz <= 65535 && src_nn < 2000000000LL) {
         const int threads = a->ntx >= 256 ? 256 : (a->ntx >= 128 ? 128 : 64);
         const int nxb = (a->ntx + threads - 1) / threads;
-        if (transfer_plain()) {
-            const dim3 grid(nxb, row_groups(nxb, a->nty, a->ntz), a->ntz);
-            if (a->u2) interp3_kernel<true><<<grid, threads, 0, (cudaStream_t)stream>>>(p), count_launch();
-            else interp3_kernel<false><<<grid, threads, 0, (cudaStream_t)stream>>>(p), count_launch();
+        const int groups = row_groups_march(nxb, a->nty, a->ntz);
+        const int rpb = (a->nty + groups - 1) / groups;
+        const dim3 grid(nxb, groups, a->ntz);
+        cudaStream_t st = (cudaStream_t)stream;
+#define GOMELT_I3M(B, M) interp3_march_kernel<B, M><<<grid, threads, 0, st>>>(p, rpb)
+        if (a->u2) {
+            if (a->mode == GOMELT_INTERP_SET) GOMELT_I3M(true, GOMELT_INTERP_SET);
+            else if (a->mode == GOMELT_INTERP_ADD) GOMELT_I3M(true, GOMELT_INTERP_ADD);
+            else GOMELT_I3M(true, GOMELT_INTERP_RSUB);
         } else {
-            const int threads_m = threads, nxm = nxb;
-            const int groups = row_groups_march(nxm, a->nty, a->ntz);
-            const int rpb = (a->nty + groups - 1) / groups;
-            const dim3 grid(nxm, groups, a->ntz);
-            cudaStream_t st = (cudaStream_t)stream;
-#define GOMELT_I3M(B, M) interp3_march_kernel<B, M><<<grid, threads_m, 0, st>>>(p, rpb)
-            if (a->u2) {
-                if (a->mode == GOMELT_INTERP_SET) GOMELT_I3M(true, GOMELT_INTERP_SET);
-                else if (a->mode == GOMELT_INTERP_ADD) GOMELT_I3M(true, GOMELT_INTERP_ADD);
-                else GOMELT_I3M(true, GOMELT_INTERP_RSUB);
-            } else {
-                if (a->mode == GOMELT_INTERP_SET) GOMELT_I3M(false, GOMELT_INTERP_SET);
-                else if (a->mode == GOMELT_INTERP_ADD) GOMELT_I3M(false, GOMELT_INTERP_ADD);
-                else GOMELT_I3M(false, GOMELT_INTERP_RSUB);
-            }
-#undef GOMELT_I3M
-            count_launch();
+            if (a->mode == GOMELT_INTERP_SET) GOMELT_I3M(false, GOMELT_INTERP_SET);
+            else if (a->mode == GOMELT_INTERP_ADD) GOMELT_I3M(false, GOMELT_INTERP_ADD);
+            else GOMELT_I3M(false, GOMELT_INTERP_RSUB);
         }
+#undef GOMELT_I3M
+        count_launch();
     } else {
         interp_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p), count_launch();
     }

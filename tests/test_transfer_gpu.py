@@ -139,23 +139,25 @@ def test_interp_set_add_rsub_clamp(gm, T, pair):
 
 
 @pytest.mark.parametrize("pair", list(PAIRS))
-def test_interp_marching_form_equals_the_plain_form_bit_for_bit(gm, T, pair, monkeypatch):
-    """The full-grid interpolation runs a marching kernel (parent values kept in registers along y, the validity window
-    from one product); GOMELT_TRANSFER_PLAIN=1 selects the plain per-target kernel.  Same bits, every mode, incl. the
-    pairs whose targets hang over the parent (those targets take the plain evaluation inside the marching kernel)."""
+def test_interp_marching_kernel_equals_the_per_target_kernel_bit_for_bit(gm, T, pair):
+    """A full-grid interpolation runs the marching kernel (parent values kept in registers along y, the validity window
+    from one product); with an index map - here the identity - the same call runs the per-target kernel.  Same bits in
+    every mode, incl. the pairs whose targets hang over the parent (those take the plain evaluation inside the marching
+    kernel) and the non-nested pair."""
+    import torch
+
     src, tgt = (f() for f in PAIRS[pair])
     u, u2, base = T.f(_field(src, 11)), T.f(_field(src, 12, hi=1400.0)), T.f(_field(tgt, 13))
     sc, tc = T.coords(src), T.coords(tgt)
-    res = {}
-    for plain in ("1", "0"):
-        monkeypatch.setenv("GOMELT_TRANSFER_PLAIN", plain)
-        e = lambda: T.torch_.empty(tgt["nn"], device="cuda")
-        res[plain] = [gm.ops.interp(sc, u, tc, e()).clone(),
-                      gm.ops.interp(sc, u, tc, e(), u2=u2, alpha=0.4, beta=0.6).clone(),
-                      gm.ops.interp(sc, u, tc, e(), mode=gm._lib.INTERP_RSUB, base=base).clone(),
-                      gm.ops.interp(sc, u, tc, base.clone(), mode=gm._lib.INTERP_ADD, clamp_min=500.0).clone()]
-    for a, b in zip(res["1"], res["0"]):
-        assert T.torch_.equal(a, b)
+    ident = [torch.arange(n, dtype=torch.int32, device="cuda") for n in tgt["nodes"]]
+    e = lambda: torch.empty(tgt["nn"], device="cuda")
+    for kw in ({}, {"u2": u2, "alpha": 0.4, "beta": 0.6}, {"mode": gm._lib.INTERP_RSUB, "base": base}, {"clamp_min": 500.0}):
+        a = gm.ops.interp(sc, u, tc, e(), **kw)
+        b = gm.ops.interp(sc, u, tc, e(), index_map=(ident[0], ident[1], ident[2], tgt["nodes"][0], tgt["nodes"][1]), **kw)
+        assert torch.equal(a, b), kw
+    a = gm.ops.interp(sc, u, tc, base.clone(), mode=gm._lib.INTERP_ADD)
+    b = gm.ops.interp(sc, u, tc, base.clone(), mode=gm._lib.INTERP_ADD, index_map=(ident[0], ident[1], ident[2], tgt["nodes"][0], tgt["nodes"][1]))
+    assert torch.equal(a, b)
 
 
 @pytest.mark.parametrize("pair", ["L1->L2 (ratio 5)", "L2->L3 shifted (3, -5, 0) parent cells",
@@ -287,7 +289,7 @@ PROJ = {
 
 
 @pytest.mark.parametrize("pair", list(PROJ))
-def test_project_grad_and_mass_terms(gm, T, pair, example_props, monkeypatch):
+def test_project_grad_and_mass_terms(gm, T, pair, example_props):
     fine, parent = (f() for f in PROJ[pair])
     P = cF.SetupProperties(example_props)
     Tp0 = (_field(fine, 8, lo=-40.0, hi=60.0)).astype(F32)
@@ -332,15 +334,8 @@ def test_project_grad_and_mass_terms(gm, T, pair, example_props, monkeypatch):
     cf._project(cells, T.f(Tp0), None, V4, mode=0, coef_from=(props, dT, dS, 0))
     cf._project(cells, T.f(Tp1), None, V4, mode=1, scale=1.0 / dt, A2=T.f(Tp0), coef_from=(props, dT, dS, 0))
     assert _relmax(T.h(V4), want0 + want1) <= TOL_P, pair
-    # ratio 10 runs half a parent cell row per thread (two halves added onto a zeroed cell sum: order-independent, hence the
-    # bit-identical V2 above); GOMELT_MARCH_SPLIT=0 keeps the whole row in one thread
-    if "ratio 10" in pair or "L3->L1" in pair:
-        monkeypatch.setenv("GOMELT_MARCH_SPLIT", "0")
-        V6 = T.torch_.zeros(parent["nn"], device="cuda")
-        cf._project(cells, T.f(Tp0), None, V6, mode=0, coef_from=(props, dT, dS, 0))
-        cf._project(cells, T.f(Tp1), None, V6, mode=1, scale=1.0 / dt, A2=T.f(Tp0), coef_from=(props, dT, dS, 0))
-        assert _relmax(T.h(V6), want0 + want1) <= TOL_P, pair
-        assert _relmax(T.h(V6), T.h(V4)) <= 2e-6, pair
+    # (ratio 10 runs half a parent cell row per thread, the two halves added onto a zeroed cell sum: order-independent,
+    # hence the bit-identical V2 above)
 
 
 # ------------------------------------------------------------------------------------------------------------

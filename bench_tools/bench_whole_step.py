@@ -43,7 +43,7 @@ def _kernel_table(prof, total_us):
             continue
         name = ev.name
         us = float(getattr(ev, "device_time", 0.0) or getattr(ev, "cuda_time", 0.0) or 0.0)
-        short = name.split("<")[0].split("(")[0].replace("gomelt::", "").replace("void ", "")
+        short = name.replace("(anonymous namespace)::", "").split("<")[0].split("(")[0].replace("gomelt::", "").replace("void ", "")
         if short.startswith("at::") or "elementwise" in name or "vectorized" in name:
             short = "torch:" + short[:48]
         r = rows.setdefault(short, [0, 0.0])

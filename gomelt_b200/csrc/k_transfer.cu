@@ -85,6 +85,17 @@ __device__ __forceinline__ SrcGeom geom_of(const AxisView& sx, const AxisView& s
 template <bool BLEND>
 __device__ __forceinline__ float tri_eval(const float* __restrict__ u, const float* __restrict__ u2, float alpha, float beta,
                                           const SrcGeom& g, const Ax1& X, const Ax1& Y, const Ax1& Z) {
+    // the 8 parent values are requested first and unconditionally (the cell is clamped into the parent, so the addresses
+    // are valid for every target), the validity window is a select at the end: no branch stands between the loads of
+    // one interpolation and the next, so a caller with several parents (the window shift) has all of them in flight at once
+    const int b = X.e + Y.e * g.nnx + Z.e * g.nnxy;
+    const int nd[8] = {b, b + 1, b + 1 + g.nnx, b + g.nnx, b + g.nnxy, b + 1 + g.nnxy, b + 1 + g.nnx + g.nnxy, b + g.nnx + g.nnxy};
+    float v[8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        v[a] = __ldg(u + nd[a]);
+        if (BLEND) v[a] = __fadd_rn(__fmul_rn(alpha, v[a]), __fmul_rn(beta, __ldg(u2 + nd[a])));
+    }
     const float xy00 = __fmul_rn(X.a0, Y.a0), xy10 = __fmul_rn(X.a1, Y.a0), xy11 = __fmul_rn(X.a1, Y.a1), xy01 = __fmul_rn(X.a0, Y.a1);
     float N[8];  // hex8 local order
     N[0] = __fmul_rn(__fmul_rn(xy00, Z.a0), g.inv_vol);
@@ -97,17 +108,10 @@ __device__ __forceinline__ float tri_eval(const float* __restrict__ u, const flo
     N[7] = __fmul_rn(__fmul_rn(xy01, Z.a1), g.inv_vol);
     const float lo = fminf(fminf(fminf(N[0], N[1]), fminf(N[2], N[3])), fminf(fminf(N[4], N[5]), fminf(N[6], N[7])));
     const float hi = fmaxf(fmaxf(fmaxf(N[0], N[1]), fmaxf(N[2], N[3])), fmaxf(fmaxf(N[4], N[5]), fmaxf(N[6], N[7])));
-    if (!(lo >= -1e-2f && hi <= 1.0f + 1e-2f)) return 0.f;
-    const int b = X.e + Y.e * g.nnx + Z.e * g.nnxy;
-    const int nd[8] = {b, b + 1, b + 1 + g.nnx, b + g.nnx, b + g.nnxy, b + 1 + g.nnxy, b + 1 + g.nnx + g.nnxy, b + g.nnx + g.nnxy};
     float acc = 0.f;
 #pragma unroll
-    for (int a = 0; a < 8; ++a) {
-        float v = __ldg(u + nd[a]);
-        if (BLEND) v = __fadd_rn(__fmul_rn(alpha, v), __fmul_rn(beta, __ldg(u2 + nd[a])));
-        acc = __fadd_rn(acc, __fmul_rn(fminf(fmaxf(N[a], 0.f), 1.f), v));
-    }
-    return acc;
+    for (int a = 0; a < 8; ++a) acc = __fadd_rn(acc, __fmul_rn(fminf(fmaxf(N[a], 0.f), 1.f), v[a]));
+    return (lo >= -1e-2f && hi <= 1.0f + 1e-2f) ? acc : 0.f;
 }
 
 // ---- marching form ---------------------------------------------------------------------------------------------------
@@ -333,6 +337,16 @@ __global__ void interp_kernel(const InterpParams p) {
         const float ax0 = __fsub_rn(x1, x), ax1 = __fsub_rn(x, x0);
         const float ay0 = __fsub_rn(y1, y), ay1 = __fsub_rn(y, y0);
         const float az0 = __fsub_rn(z1, z), az1 = __fsub_rn(z, z0);
+        // the 8 parent values first, unconditionally (the cell is clamped into the parent): no branch before the loads
+        const long long b = ex + (long long)ey * nnx + (long long)ez * nnxy;
+        const long long nd[8] = {b, b + 1, b + 1 + nnx, b + nnx, b + nnxy, b + 1 + nnxy, b + 1 + nnx + nnxy,
+                                 b + nnx + nnxy};
+        float pv[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            pv[a] = p.u[nd[a]];
+            if (p.u2) pv[a] = __fadd_rn(__fmul_rn(p.alpha, pv[a]), __fmul_rn(p.beta, p.u2[nd[a]]));
+        }
         // compute3DN cF:1375-1391, hex8 local order
         float N[8];
         N[0] = __fmul_rn(__fmul_rn(__fmul_rn(ax0, ay0), az0), inv_vol);
@@ -346,19 +360,10 @@ __global__ void interp_kernel(const InterpParams p) {
         bool valid = true;
 #pragma unroll
         for (int a = 0; a < 8; ++a) valid = valid && (N[a] >= -1e-2f) && (N[a] <= 1.0f + 1e-2f);
-        const long long b = ex + (long long)ey * nnx + (long long)ez * nnxy;
-        const long long nd[8] = {b, b + 1, b + 1 + nnx, b + nnx, b + nnxy, b + 1 + nnxy, b + 1 + nnx + nnxy,
-                                 b + nnx + nnxy};
         float acc = 0.f;
-        if (valid) {
 #pragma unroll
-            for (int a = 0; a < 8; ++a) {
-                const float w = fminf(fmaxf(N[a], 0.f), 1.f);
-                float v = p.u[nd[a]];
-                if (p.u2) v = __fadd_rn(__fmul_rn(p.alpha, v), __fmul_rn(p.beta, p.u2[nd[a]]));
-                acc = __fadd_rn(acc, __fmul_rn(w, v));
-            }
-        }
+        for (int a = 0; a < 8; ++a) acc = __fadd_rn(acc, __fmul_rn(fminf(fmaxf(N[a], 0.f), 1.f), pv[a]));
+        if (!valid) acc = 0.f;
         long long o = t;
         if (p.mx) o = p.mx[i] + (long long)p.my[j] * p.map_nx + (long long)p.mz[k] * p.map_nx * p.map_ny;
         float r;
@@ -1416,7 +1421,9 @@ struct ShiftParams {
 };
 // The y part of the block's rows and the z part of its plane do not depend on the column: one warp per parent forms them
 // (lane q < rows: row q, lane ROWS3: the plane) and the block reads them after one barrier, instead of every thread
-// repeating the cell searches (IEEE divisions) of its rows: 144 -> 130 us (Level 3), 104 -> 97 us (Level 2) at C2 size.
+// repeating the cell searches (IEEE divisions) of its rows: 144 -> 130 us (Level 3), 104 -> 97 us (Level 2) at C2 size;
+// with tri_eval requesting its 8 parent values before anything else and deciding validity by a select, the loads of
+// all three interpolations of a target are in flight together: 119 / 87 us.
 // Tried on top of it and dropped (bench_tools/quick_interp.py, one box): the marching form of interp3_march_kernel with
 // a register cache per parent - the window's own old field has the SAME spacing, every row enters a new cell and its
 // loads come from DRAM: 190 / 143 us even with the next parent row requested a row ahead; the short form of the weights

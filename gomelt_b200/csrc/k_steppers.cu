@@ -85,20 +85,27 @@ __global__ void reset_mask_kernel(const uint8_t* __restrict__ pre, const uint8_t
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = (!pre[i] && now[i]) ? 1 : 0;  // ((1 - 2 preS2) * S2) == 1, cF:2394
 }
+// blockIdx.z = window plane, blockIdx.y = group of rpb window rows: the Level-0 row / plane offsets are formed once per row,
+// no index division per node (the flat grid-stride form with its 64-bit divisions ran 81 us per 10.3 M-node window)
 __global__ void accum_single_step_kernel(const float* __restrict__ T3, const uint8_t* __restrict__ mask, float dt, float Tliq,
                                          float* __restrict__ acc, float* __restrict__ mx, const int* __restrict__ ix,
                                          const int* __restrict__ iy, const int* __restrict__ iz, int nx, int ny, int nz, int bnx,
-                                         int bny) {
-    const long long total = (long long)nx * ny * nz;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(t % nx), j = (int)((t / nx) % ny), k = (int)(t / ((long long)nx * ny));
-        const long long g = ix[i] + (long long)iy[j] * bnx + (long long)iz[k] * bnx * bny;
-        const float a = acc[g];
-        const float reset = mask[t] ? a : a * 0.0f;        // accum * (all_reset > 0)
-        mx[g] = fmaxf(reset, mx[g]);
-        float an = __fadd_rn(a, -reset);
-        an = __fadd_rn(an, (T3[t] > Tliq) ? dt : 0.0f);   // melting_temp: accum[idx] += (T > T_melt) * dt
-        acc[g] = an;
+                                         int bny, int rpb) {
+    for (int k = blockIdx.z; k < nz; k += gridDim.z) {
+        const long long gk = (long long)iz[k] * bnx * bny;
+        const int j1 = min(ny, (int)(blockIdx.y + 1) * rpb);
+        for (int j = blockIdx.y * rpb; j < j1; ++j) {
+            const long long grow = gk + (long long)iy[j] * bnx, trow = ((long long)k * ny + j) * nx;
+            for (int i = threadIdx.x; i < nx; i += blockDim.x) {
+                const long long g = grow + ix[i], t = trow + i;
+                const float a = acc[g];
+                const float reset = mask[t] ? a : a * 0.0f;        // accum * (all_reset > 0)
+                mx[g] = fmaxf(reset, mx[g]);
+                float an = __fadd_rn(a, -reset);
+                an = __fadd_rn(an, (T3[t] > Tliq) ? dt : 0.0f);   // melting_temp: accum[idx] += (T > T_melt) * dt
+                acc[g] = an;
+            }
+        }
     }
 }
 // dst[ix[i] + iy[j] * bnx + iz[k] * bnx * bny] = 0 over a tensor-product index set (one block row per (j, k) line)
@@ -607,7 +614,9 @@ extern "C" int gomelt_accum_single_step_f32(const float* T3, const uint8_t* rese
         set_error("gomelt_accum_single_step_f32: empty window");
         return GOMELT_E_SIZE;
     }
-    accum_single_step_kernel<<<blocks_for((long long)nx * ny * nz), 256, 0, (cudaStream_t)stream>>>(
-        T3, resetmask, dt, T_liquidus, accum0, max_accum0, ix, iy, iz, nx, ny, nz, big_nx, big_ny), count_launch();
+    const int rpb = (long long)ny * nz >= 16LL * sm_count() ? 4 : 1;   // rows per block
+    const int threads = nx >= 256 ? 256 : (nx >= 128 ? 128 : 64);
+    accum_single_step_kernel<<<dim3(1, (ny + rpb - 1) / rpb, nz < 65535 ? nz : 65535), threads, 0, (cudaStream_t)stream>>>(
+        T3, resetmask, dt, T_liquidus, accum0, max_accum0, ix, iy, iz, nx, ny, nz, big_nx, big_ny, rpb), count_launch();
     return check_launch("gomelt_accum_single_step_f32");
 }

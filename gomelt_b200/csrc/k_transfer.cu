@@ -1531,7 +1531,7 @@ extern "C" int gomelt_interp_f32(const gomelt_interp_args_t* a, void* stream) {
     if (a->faces_only)
         total = (long long)a->ntx * a->nty + 2LL * a->ntx * (a->ntz - 1) + 2LL * (a->nty - 2) * (a->ntz - 1);
     const long long src_nn = (long long)a->src[0].n * a->src[1].n * a->src[2].n;
-    if (!a->faces_only && !a->map_x && a->ntz <= 65535 && src_nn < 2000000000LL) {
+    if (!a->faces_only && !a->map_x && a->ntz <= 65535 && a->nty <= 65535 && src_nn < 2000000000LL) {
         const int threads = a->ntx >= 256 ? 256 : (a->ntx >= 128 ? 128 : 64);
         const int nxb = (a->ntx + threads - 1) / threads;
         const int groups = row_groups_march(nxb, a->nty, a->ntz);

@@ -32,7 +32,6 @@ run("warm graphs")
 for _ in range(2):
     cf._PAIR_CACHE.clear()
     cf._CACHE.store.clear()
-    ws_clear = getattr(cf, "_drop_workspaces", None)
     run("cold caches, graphs")
 for _ in range(2):
     cf._PAIR_CACHE.clear()
